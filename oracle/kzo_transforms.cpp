@@ -1,0 +1,47 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see kzo.hpp). Transform dispatch (v2/transform/Factory.go:97-185).
+#include <algorithm>
+#include <cstring>
+
+#include "kzo.hpp"
+#include "kzo_transforms.hpp"
+
+namespace kzo {
+
+size_t transform_max_encoded_len(uint64_t type, size_t n) {
+    switch (type) {
+        case T_NONE: return n;                                   // NullTransform.go MaxEncodedLen
+        case T_BWT: return n + 33;                               // BWTBlockCodec.go:228-230 (_BWT_MAX_HEADER_SIZE = 8*4+1)
+        case T_LZ: case T_LZX: return lz_max_encoded_len(n);     // LZCodec.go:935-941
+        default: throw Error(ERR_CREATE_CODEC, "transform not restated in the oracle");
+    }
+}
+
+bool transform_forward(uint64_t type, Ctx& ctx, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n) {
+    switch (type) {
+        case T_NONE:  // NullTransform.Forward: plain copy, never fails for valid buffers
+            if (cap < n) return false;
+            std::memcpy(dst, src, n);
+            *out_n = n;
+            return true;
+        case T_BWT: return bwt_block_forward(ctx, src, n, dst, cap, out_n);
+        case T_LZ: return lz_forward(ctx, false, src, n, dst, cap, out_n);
+        case T_LZX: return lz_forward(ctx, true, src, n, dst, cap, out_n);
+        default: throw Error(ERR_CREATE_CODEC, "transform not restated in the oracle");
+    }
+}
+
+bool transform_inverse(uint64_t type, Ctx& ctx, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n) {
+    switch (type) {
+        case T_NONE:
+            if (cap < n) return false;
+            std::memcpy(dst, src, n);
+            *out_n = n;
+            return true;
+        case T_BWT: return bwt_block_inverse(ctx, src, n, dst, cap, out_n);
+        case T_LZ: return lz_inverse(ctx, false, src, n, dst, cap, out_n);
+        case T_LZX: return lz_inverse(ctx, true, src, n, dst, cap, out_n);
+        default: throw Error(ERR_INVALID_CODEC, "transform not restated in the oracle");
+    }
+}
+
+}  // namespace kzo

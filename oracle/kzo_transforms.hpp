@@ -1,0 +1,11 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see kzo.hpp). Internal declarations of the restated transforms.
+#pragma once
+#include "kzo.hpp"
+
+namespace kzo {
+bool bwt_block_forward(Ctx& ctx, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
+bool bwt_block_inverse(Ctx& ctx, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
+size_t lz_max_encoded_len(size_t n);
+bool lz_forward(Ctx& ctx, bool extra, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
+bool lz_inverse(Ctx& ctx, bool extra, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
+}  // namespace kzo
