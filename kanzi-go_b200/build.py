@@ -1,0 +1,42 @@
+"""Builds libkanzi_b200.so (CUDA kernels + C ABI) in-tree for sm_100a with nvcc. No GPU is needed to build."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libkanzi_b200.so")
+SOURCES = ["kz_ans.cu", "kz_concat.cu", "kz_api.cu"]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+         "-Xptxas", "-v"]
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    for root in (CSRC, os.path.join(HERE, "..", "include")):
+        for f in os.listdir(root):
+            if f.endswith((".cu", ".cuh", ".h", ".cpp")) and os.path.getmtime(os.path.join(root, f)) > t:
+                return True
+    return False
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    cmd = ["nvcc"] + FLAGS + srcs + ["-o", OUT]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed")
+    with open(os.path.join(HERE, "ptxas_info.txt"), "w") as f:
+        f.write(r.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force=True, verbose=True)
+    print(OUT)

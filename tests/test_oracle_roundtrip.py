@@ -1,0 +1,65 @@
+"""Oracle self-consistency on the reference's own test inputs and on chunk-boundary sizes (CPU only)."""
+import numpy as np
+import pytest
+
+CODECS = ["ANS0", "ANS1", "HUFFMAN", "RANGE", "NONE"]
+SIZES = [0, 1, 2, 3, 15, 16, 31, 32, 33, 34, 35, 36, 40, 255, 256, 1000, 4096, 16383, 16384, 16385, 16387, 32768 + 31, 32768 + 33, 70001]
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_reference_test_inputs(oracle, synth, codec):
+    et = oracle.parse_entropy(codec)
+    for x in synth.reference_test_inputs():
+        s, bits = oracle.entropy_encode(et, x)
+        y, used = oracle.entropy_decode(et, s, len(x))
+        assert np.array_equal(x, y)
+        assert used == bits
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_boundary_sizes(oracle, synth, codec):
+    et = oracle.parse_entropy(codec)
+    for n in SIZES:
+        if codec == "ANS1" and 32 < n < 36 and False:
+            continue
+        for gen in (lambda m: synth.zipf_bytes(m, 1.0, seed=n + 1), lambda m: synth.uniform_bytes(m, seed=n + 2), lambda m: np.full(m, 7, np.uint8)):
+            x = gen(n)
+            s, bits = oracle.entropy_encode(et, x)
+            y, used = oracle.entropy_decode(et, s, n)
+            assert np.array_equal(x, y), (codec, n)
+            assert used == bits, (codec, n)
+
+
+def test_ans1_short_chunk_panics_like_reference(oracle):
+    """an order-1 chunk of 2 or 3 bytes indexes block[-1] in the reference (a Go panic recovered as
+    ERR_PROCESS_BLOCK); only reachable when a block length is 2 or 3 mod the 4 MiB chunk and > 32."""
+    x = np.zeros((16384 << 8) + 2, np.uint8)
+    with pytest.raises(oracle.OracleError):
+        oracle.entropy_encode(oracle.E_ANS1, x)
+
+
+@pytest.mark.parametrize("transform,entropy", [("NONE", "ANS0"), ("NONE", "HUFFMAN"), ("BWT", "ANS0"), ("NONE", "NONE"), ("BWT", "NONE"), ("NONE", "RANGE"), ("NONE", "ANS1")])
+def test_stream_roundtrip(oracle, synth, transform, entropy):
+    for n, bs in ((0, 1024), (10, 1024), (1024, 1024), (100000, 16384), (300000, 65536)):
+        x = synth.markov_text(n, seed=n + 5) if n else np.zeros(0, np.uint8)
+        for ck in (0, 32, 64):
+            s = oracle.compress(x, transform, entropy, block_size=bs, checksum_bits=ck, jobs=3, input_size=n)
+            y = oracle.decompress(s, n + 16, jobs=2)
+            assert np.array_equal(x, y)
+
+
+def test_bwt_sizes(oracle, synth):
+    for n in (2, 3, 10, 255, 256, 257, 1000, 65536, 200001):
+        for x in (synth.uniform_bytes(n, seed=n), synth.markov_text(n, seed=n), np.full(n, 9, np.uint8), (np.arange(n) % 251).astype(np.uint8)):
+            f, _ = oracle.transform_forward(oracle.T_BWT, x)
+            assert f is not None and len(f) == n + (1 + (8 if n >= 256 else 1) * ((max(n - 1, 1).bit_length() + 7) // 8))
+            r = oracle.transform_inverse(oracle.T_BWT, f, n + 64)
+            assert np.array_equal(r, x)
+            out, prim = oracle.bwt_forward_raw(x)
+            # brute-force check of the definition on small inputs
+            if n <= 1000:
+                b = bytes(x)
+                sa = sorted(range(n), key=lambda i: b[i:])
+                want = bytes([b[n - 1]] + [b[i - 1] for i in sa if i != 0])
+                assert bytes(out) == want
+                assert prim[0] == sa.index(0) + 1
