@@ -489,205 +489,392 @@ __global__ void ans_walk_kernel(const uint32_t* __restrict__ words, const DecBlo
     if (st) status[b] = st;
 }
 
-// big-endian halves of a 16-byte block
-KZ_D void be_halves(const uint4 v, uint64_t& h0, uint64_t& h1) {
-    h0 = ((uint64_t)bswap32(v.x) << 32) | bswap32(v.y);
-    h1 = ((uint64_t)bswap32(v.z) << 32) | bswap32(v.w);
+// ------------------------------------------------------------------------------------------------------------
+// header walk v2 (order 0): one WARP per block. The chunk headers of a block form a serial chain (chunk k+1 starts
+// where chunk k's payload ends, at an arbitrary bit), so the walk is latency bound: 256 links per 4 MiB block. Per
+// link the warp stages a 512-byte window of the stream in shared memory with one coalesced load, counts the alphabet
+// with one popc per lane, and only the <= 32 frequency-group length nibbles are chased serially from shared memory.
+// ------------------------------------------------------------------------------------------------------------
+static const int WALK_WORDS = 128;
+
+__global__ void __launch_bounds__(32) ans0_walk_kernel(const uint32_t* __restrict__ words, uint64_t words_len, const DecBlock* __restrict__ blocks,
+                                                        int nblocks, uint64_t* __restrict__ chunk_hdr_bit, uint64_t* __restrict__ blk_end,
+                                                        int32_t* __restrict__ status) {
+    __shared__ uint32_t s_stage[WALK_WORDS + 4];
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (b >= nblocks) return;
+    const DecBlock blk = blocks[b];
+    if (blk.nchunks == 0) return;
+    uint64_t pos = blk.data_bit;
+    uint32_t remaining = blk.pre_len;
+    int32_t st = 0;
+    uint64_t prev_bits = 0;
+    for (uint32_t k = 0; k < blk.nchunks; k++) {
+        if (lane == 0) chunk_hdr_bit[blk.chunk_base + k] = pos;
+        if (st) continue;
+        const uint32_t clen = remaining < (uint32_t)ANS0_CHUNK ? remaining : (uint32_t)ANS0_CHUNK;
+        remaining -= clen;
+        const uint64_t w0 = pos >> 5;
+        // warm L2 around the predicted start of the next chunk while this header is parsed
+        if (prev_bits && lane < 8) {
+            const uint64_t pw = ((pos + prev_bits) >> 5) + (uint64_t)lane * 32 - 64;
+            if (pw < words_len) asm volatile("prefetch.global.L2 [%0];" ::"l"(words + pw));
+        }
+        for (int i = lane; i < WALK_WORDS + 2; i += 32) s_stage[i] = (w0 + i < words_len) ? bswap32(__ldg(words + w0 + i)) : 0u;
+        __syncwarp();
+        uint32_t q = (uint32_t)(pos & 31);
+        auto sbits = [&](uint32_t at, uint32_t n) -> uint32_t {  // n in 1..32, window relative bit position
+            const uint32_t w = at >> 5, o = at & 31;
+            return __funnelshift_l(s_stage[w + 1], s_stage[w], o) >> (32 - n);
+        };
+        const uint32_t lr = 8 + sbits(q, 3);
+        q += 3;
+        uint32_t llr = 3;
+        while ((1u << llr) <= lr) llr++;
+        int asz;
+        if (sbits(q, 1) == 0) {
+            asz = sbits(q + 1, 1) ? 0 : 256;
+            q += 2;
+        } else {
+            const uint32_t last = sbits(q + 1, 5);
+            q += 6;
+            uint32_t cnt = (uint32_t)lane <= last ? (uint32_t)__popc(sbits(q + 8 * lane, 8)) : 0u;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
+            asz = (int)cnt;
+            q += 8 * (last + 1);
+        }
+        if (asz == 0) st = -KZ_E_PROCESS_BLOCK;
+        if (st == 0 && lr > 12) st = -KZ_E_INVALID_CODEC;  // decode tables are sized for the encoder's fixed range (<= 12)
+        if (st == 0 && asz > 1) {
+            const int gs = asz < 64 ? 6 : 8;
+            for (int i = 1; i < asz; i += gs) {
+                const uint32_t log_max = sbits(q, llr);
+                if (log_max > lr) st = -KZ_E_PROCESS_BLOCK;
+                const int n = asz - i < gs ? asz - i : gs;
+                q += llr + (uint32_t)n * log_max;
+                if (q > 32u * (WALK_WORDS - 3)) {  // cannot happen for lr <= 12 (max 3453 header bits); guards corrupt input
+                    st = -KZ_E_PROCESS_BLOCK;
+                    break;
+                }
+            }
+            if (st == 0) {
+                // varint (EntropyUtils.go:278-296)
+                uint32_t sz = 0, shift = 0;
+                bool more = true;
+                for (int i = 0; i < 4 && more; i++) {
+                    const uint32_t v = sbits(q, 8);
+                    q += 8;
+                    sz |= (v & 0x7F) << shift;
+                    more = v >= 128;
+                    shift += 7;
+                }
+                if (more) {
+                    const uint32_t v = sbits(q, 8);
+                    q += 8;
+                    sz |= (v & 0x0F) << 28;
+                }
+                if (sz >= (uint32_t)ANS_MAX_CHUNK) st = -KZ_E_PROCESS_BLOCK;
+                const uint64_t next = (w0 << 5) + q + 128 + 8ull * sz;
+                prev_bits = next - pos;
+                pos = next;
+            }
+        } else if (st == 0) {
+            const uint64_t next = (w0 << 5) + q;
+            prev_bits = next - pos;
+            pos = next;
+        }
+        if (st == 0 && pos > blk.end_bit) st = -KZ_E_PROCESS_BLOCK;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        blk_end[b] = pos;
+        if (st) status[b] = st;
+    }
 }
 
-__global__ void __launch_bounds__(32) ans0_decode_kernel(const uint32_t* __restrict__ words, uint64_t words_len /*in 32-bit words*/,
-                                                          const DecChunk* __restrict__ chunks, int nchunks,
-                                                          const uint64_t* __restrict__ chunk_hdr_bit, uint8_t* __restrict__ out,
-                                                          int32_t* __restrict__ status) {
-    extern __shared__ uint32_t s_dec[];  // [DEC_BM_WORDS][32] bitmap+rank words, then [256][32] symbol entries
-    const int lane = threadIdx.x;
-    const int c = blockIdx.x * 32 + lane;
-    if (c >= nchunks) return;
-    const DecChunk ck = chunks[c];
-    if (status[ck.block] != 0) return;  // walk failed for this block
-    uint32_t* bm = s_dec + lane;                        // word w at bm[w*32]
-    uint32_t* symtab = s_dec + DEC_BM_WORDS * 32 + lane;  // entry i at symtab[i*32]
-    BitReader br(words, chunk_hdr_bit[c], ck.end_bit);
-    // ---- full header parse (decodeHeader :605-710)
-    const uint32_t lr = 8 + br.read(3);
-    const uint32_t scale = 1u << lr;
-    uint32_t llr = 3;
-    while ((1u << llr) <= lr) llr++;
-    int asz = 0;
-    if (br.read(1) == 0) {
-        if (br.read(1) == 0) {
-            asz = 256;
-            for (int i = 0; i < 256; i++) symtab[i * 32] = (uint32_t)i;
-        }
-    } else {
-        uint32_t last = br.read(5);
-        for (uint32_t i = 0; i <= last; i++) {
-            uint32_t m = br.read(8);
-            while (m) {
-                int j = __ffs((int)m) - 1;
-                m &= m - 1;
-                symtab[asz * 32] = 8 * i + (uint32_t)j;
-                asz++;
-            }
-        }
+// ------------------------------------------------------------------------------------------------------------
+// decode (v3): FOUR lanes per chunk (lane k owns rANS state k), 8 chunks per warp, 16 chunks per 64-thread CTA.
+//
+// History (profiles/): v1 = one thread per chunk with ILP over the 4 states: one warp per scheduler, 198 instructions
+// per step, stalled every step on some lane's stream refill. v2 = 4 lanes per chunk, 32 chunks per CTA: correct but
+// 72 KiB of shared memory per CTA -> 444 resident CTAs for the 512 of the 256 MiB workload (two waves of an
+// indivisible 4096-step chain) and a scoreboard wait at the warp-convergence point after the conditional refill.
+// v3 keeps the 4-lane layout and
+//   * shrinks the per-chunk tables to 1964 bytes (24-slot start-of-symbol buckets: bits 8..31 = start flags, low
+//     byte = rank-1; 256 symbol entries sym | freq << 8 | cum << 20; 256-byte payload ring) so that 7 CTAs x 16
+//     chunks = 112 chunks fit per SM: 16576 chunk slots >= the 16384 chunks of 64 x 4 MiB -> a single wave;
+//   * resolves the shared byte cursor with one __ballot_sync per step (order st3, st2, st1, st0,
+//     ANSRangeCodec.go:904-917) and reads the renormalisation word with one ld.shared.u16, branch free;
+//   * issues the ring refill loads unconditionally every 4 steps (clamped address) and consumes them one iteration
+//     later, so no step waits on a load issued in the same iteration;
+//   * transposes the decoded bytes across the 4 lanes with two shuffles per 4 steps and stores 16 bytes per chunk.
+// Table word w of chunk g lives at (w * 8 + g): the 8 chunks of a warp own disjoint groups of 4 banks.
+// ------------------------------------------------------------------------------------------------------------
+static const int RING_WORDS = 64;  // 32-bit words per chunk ring (256 bytes)
+
+KZ_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct DecLane {
+    uint32_t st;      // rANS state of this lane
+    uint32_t cur2;    // 2 * cursor (16-bit units, relative to the ring origin)
+    uint32_t acc;     // last 4 decoded symbols of this state
+};
+
+template <bool ALL_ACTIVE>
+KZ_D void dec_step(DecLane& L, const uint32_t* bm, const uint32_t* symtab, uint32_t ring_base, uint32_t mask, uint32_t lr, uint32_t hi_mask,
+                   uint32_t grp_mask, bool active) {
+    const uint32_t slot = L.st & mask;
+    const uint32_t w = (slot * 2731u) >> 16;  // slot / 24 (exact for slot < 4096)
+    const uint32_t b = bm[w * 8];
+    const uint32_t m = (0x200u << (slot - 24u * w)) - 0x100u;
+    const uint32_t idx = (b + __popc(b & m)) & 0xFFu;
+    const uint32_t e = symtab[idx * 8];
+    const uint32_t nst = ((e >> 8) & 0xFFFu) * (L.st >> lr) + slot - (e >> 20);  // D(x) (ANSRangeCodec.go:849)
+    bool need = nst < (uint32_t)ANS_TOP;
+    if (!ALL_ACTIVE) need = need && active;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, need);
+    const uint32_t t2 = L.cur2 + 2u * __popc(bal & hi_mask);
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(ring_base + ((t2 & (4 * RING_WORDS - 2)) ^ 2u)));
+    const uint32_t nst2 = (nst << 16) | v;
+    if (ALL_ACTIVE || active) {
+        L.st = need ? nst2 : nst;
+        L.cur2 += 2u * __popc(bal & grp_mask);
     }
-    uint8_t* dst = out + ck.out_off;
-    if (asz == 0 || lr > 12) {
-        atomicCAS(&status[ck.block], 0, asz == 0 ? -KZ_E_PROCESS_BLOCK : -KZ_E_INVALID_CODEC);
-        return;
-    }
-    if (asz == 1) {  // Read :737-741
-        const uint8_t v = (uint8_t)symtab[0];
-        for (uint32_t i = 0; i < ck.out_len; i++) dst[i] = v;
-        return;
-    }
-    {
-        const int gs = asz < 64 ? 6 : 8;
-        uint32_t sum = 0;
-        bool bad = false;
-        for (int i = 1; i < asz; i += gs) {
-            uint32_t log_max = br.read(llr);
-            if ((1u << log_max) > scale) bad = true;
-            int endj = i + gs < asz ? i + gs : asz;
-            for (int j = i; j < endj; j++) {
-                uint32_t freq = 1;
-                if (log_max > 0) {
-                    freq = 1 + br.read(log_max);
-                    if (freq >= scale) bad = true;
+    L.acc = __byte_perm(L.acc, e, 0x4321);  // acc = (acc >> 8) | (sym << 24)
+}
+
+__global__ void __launch_bounds__(64, 7) ans0_decode_kernel(const uint32_t* __restrict__ words, uint64_t words_len /*in 32-bit words*/,
+                                                            const DecChunk* __restrict__ chunks, int nchunks,
+                                                            const uint64_t* __restrict__ chunk_hdr_bit, uint8_t* __restrict__ out,
+                                                            int32_t* __restrict__ status) {
+    extern __shared__ uint32_t s_dec[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, k = lane & 3;  // chunk slot inside the warp, state index
+    uint32_t* wbase = s_dec + warp * DEC_WARP_WORDS;
+    uint32_t* bm = wbase + g;                                   // bucket w at bm[w*8]
+    uint32_t* symtab = wbase + DEC_BM_WORDS * 8 + g;            // entry i at symtab[i*8]
+    uint32_t* ring = wbase + (DEC_BM_WORDS + 256) * 8 + g * RING_WORDS;
+    const int c = blockIdx.x * DEC_CTA_CHUNKS + warp * 8 + g;
+    const uint32_t grp_mask = 0xFu << (lane & ~3);
+    const uint32_t hi_mask = grp_mask & ~((2u << lane) - 1u);  // lanes of my group with a higher state index (they read first)
+
+    // ---- per-chunk set-up by the group leader (k == 0): header parse, tables, chunk prologue
+    uint32_t lr = 12, nsteps = 0, tail = 0;
+    uint64_t pb = 0, pe = 0;
+    uint8_t* dst = nullptr;
+    int mode = 0;  // 0 = nothing to do, 1 = rANS decode
+    if (k == 0 && c < nchunks) {
+        const DecChunk ck = chunks[c];
+        dst = out + ck.out_off;
+        if (status[ck.block] == 0) {
+            BitReader br(words, chunk_hdr_bit[c], ck.end_bit);
+            lr = 8 + br.read(3);
+            const uint32_t scale = 1u << lr;
+            uint32_t llr = 3;
+            while ((1u << llr) <= lr) llr++;
+            int asz = 0;
+            if (br.read(1) == 0) {
+                if (br.read(1) == 0) {
+                    asz = 256;
+                    for (int i = 0; i < 256; i++) symtab[i * 8] = (uint32_t)i;
                 }
-                symtab[j * 32] |= freq << 8;
-                sum += freq;
+            } else {
+                uint32_t last = br.read(5);
+                for (uint32_t i = 0; i <= last; i++) {
+                    uint32_t m = br.read(8);
+                    while (m) {
+                        int j = __ffs((int)m) - 1;
+                        m &= m - 1;
+                        symtab[asz * 8] = 8 * i + (uint32_t)j;
+                        asz++;
+                    }
+                }
+            }
+            if (asz == 0 || lr > 12) {
+                atomicCAS(&status[ck.block], 0, asz == 0 ? -KZ_E_PROCESS_BLOCK : -KZ_E_INVALID_CODEC);
+            } else if (asz == 1) {  // Read :737-741
+                const uint8_t v = (uint8_t)symtab[0];
+                for (uint32_t i = 0; i < ck.out_len; i++) dst[i] = v;
+            } else {
+                const int gs = asz < 64 ? 6 : 8;
+                uint32_t sum = 0;
+                bool bad = false;
+                for (int i = 1; i < asz; i += gs) {
+                    uint32_t log_max = br.read(llr);
+                    if ((1u << log_max) > scale) bad = true;
+                    int endj = i + gs < asz ? i + gs : asz;
+                    for (int j = i; j < endj; j++) {
+                        uint32_t freq = 1;
+                        if (log_max > 0) {
+                            freq = 1 + br.read(log_max);
+                            if (freq >= scale) bad = true;
+                        }
+                        symtab[j * 8] |= freq << 8;
+                        sum += freq;
+                    }
+                }
+                if (scale <= sum) bad = true;
+                if (!bad) {
+                    symtab[0] |= (scale - sum) << 8;
+                    const uint32_t nb = (scale + 23) / 24;
+                    for (uint32_t w = 0; w < nb; w++) bm[w * 8] = 0;
+                    uint32_t cum = 0;
+                    for (int i = 0; i < asz; i++) {
+                        const uint32_t e = symtab[i * 8];
+                        const uint32_t f = (e >> 8) & 0xFFFu;  // every frequency is <= scale - 1 <= 4095 when asz >= 2 (decSymbol.reset :973-978)
+                        const uint32_t w = cum / 24;
+                        bm[w * 8] |= 0x100u << (cum - 24 * w);
+                        symtab[i * 8] = e | (cum << 20);
+                        cum += f;
+                    }
+                    uint32_t running = 0;
+                    for (uint32_t w = 0; w < nb; w++) {
+                        const uint32_t b = bm[w * 8];
+                        bm[w * 8] = b | ((running - 1u) & 0xFFu);
+                        running += __popc(b >> 8);
+                    }
+                    const uint32_t sz = br.read_varint();
+                    const uint32_t s0 = br.read(32), s1 = br.read(32), s2 = br.read(32), s3 = br.read(32);
+                    if (sz >= (uint32_t)ANS_MAX_CHUNK || br.overrun || br.pos + 8ull * sz > ck.end_bit) bad = true;
+                    if (!bad) {
+                        pb = br.pos;
+                        pe = pb + 8ull * sz;
+                        nsteps = ck.out_len >> 2;
+                        tail = ck.out_len & 3;
+                        mode = 1;
+                        ring[0] = s0;  // park the initial states where the other lanes can fetch them
+                        ring[1] = s1;
+                        ring[2] = s2;
+                        ring[3] = s3;
+                    }
+                }
+                if (bad || br.overrun) atomicCAS(&status[ck.block], 0, -KZ_E_PROCESS_BLOCK);
             }
         }
-        if (scale <= sum) bad = true;
-        if (bad || br.overrun) {
-            atomicCAS(&status[ck.block], 0, -KZ_E_PROCESS_BLOCK);
-            return;
-        }
-        symtab[0] |= (scale - sum) << 8;
     }
-    // ---- tables: 24 start-of-symbol bits + 8-bit (rank-1) per word; entries sym | freq << 8 | cum << 20
-    const uint32_t nwords = (scale + 23) / 24;
-    for (uint32_t w = 0; w < nwords; w++) bm[w * 32] = 0;
-    {
-        uint32_t cum = 0;
-        for (int i = 0; i < asz; i++) {
-            uint32_t e = symtab[i * 32];
-            uint32_t f = e >> 8;
-            uint32_t w = cum / 24, j = cum - 24 * w;
-            bm[w * 32] |= 1u << j;
-            uint32_t fc = f < scale - 1 ? f : scale - 1;  // decSymbol.reset :973-978
-            symtab[i * 32] = (e & 0xFF) | (fc << 8) | (cum << 20);
-            cum += f;
-        }
-        uint32_t running = 0;
-        for (uint32_t w = 0; w < nwords; w++) {
-            uint32_t b = bm[w * 32];
-            bm[w * 32] = b | (((running - 1u) & 0xFFu) << 24);
-            running += __popc(b);
-        }
+    __syncwarp();
+    const int leader = lane & ~3;
+    mode = __shfl_sync(0xFFFFFFFFu, mode, leader);
+    lr = __shfl_sync(0xFFFFFFFFu, lr, leader);
+    nsteps = __shfl_sync(0xFFFFFFFFu, nsteps, leader);
+    pb = __shfl_sync(0xFFFFFFFFu, pb, leader);
+    pe = __shfl_sync(0xFFFFFFFFu, pe, leader);
+    dst = (uint8_t*)(uintptr_t)__shfl_sync(0xFFFFFFFFu, (uint64_t)(uintptr_t)dst, leader);
+    DecLane L;
+    L.st = mode ? ring[k] : 0u;
+    L.acc = 0;
+    if (!mode) nsteps = 0;
+    __syncwarp();
+    uint32_t max_steps = nsteps, min_steps = nsteps;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        max_steps = max(max_steps, __shfl_xor_sync(0xFFFFFFFFu, max_steps, d));
+        min_steps = min(min_steps, __shfl_xor_sync(0xFFFFFFFFu, min_steps, d));
     }
-    // ---- chunk payload (decodeChunkV2 :860-957)
-    const uint32_t sz = br.read_varint();
-    uint32_t st0 = br.read(32), st1 = br.read(32), st2 = br.read(32), st3 = br.read(32);
-    if (sz >= (uint32_t)ANS_MAX_CHUNK || br.overrun || br.pos + 8ull * sz > ck.end_bit) {
-        atomicCAS(&status[ck.block], 0, -KZ_E_PROCESS_BLOCK);
-        return;
-    }
-    const uint64_t pb = br.pos;                 // first payload bit
-    const uint64_t pe = pb + 8ull * sz;         // one past the last payload bit
-    const uint4* blocks128 = reinterpret_cast<const uint4*>(words);
-    const uint64_t nblk128 = words_len >> 2;
-    uint64_t jn = pb >> 7;
-    const uint64_t jlast = sz ? ((pe - 1) >> 7) : 0;
-    auto load_blk = [&](uint64_t j) -> uint4 {
-        if (sz == 0 || j > jlast || j >= nblk128) return make_uint4(0, 0, 0, 0);  // zero guard (:888-893)
-        return __ldg(&blocks128[j]);
-    };
-    uint64_t q0, q1, c0, c1;
-    uint32_t cnt;
-    {
-        uint64_t h0, h1;
-        be_halves(load_blk(jn++), h0, h1);
-        const uint32_t off = (uint32_t)(pb & 127);
-        if (off >= 64) {
-            q0 = h1 << (off - 64);
-            q1 = 0;
-        } else {
-            q0 = off ? ((h0 << off) | (h1 >> (64 - off))) : h0;
-            q1 = h1 << off;
-        }
-        cnt = 128 - off;
-    }
-    be_halves(load_blk(jn++), c0, c1);
-    uint4 nxt = load_blk(jn++);
-    uint32_t pfh = 0;
-    const uint32_t mask = scale - 1;
-    const uint32_t end4 = ck.out_len & ~3u;
+    if (max_steps == 0) return;
 
-    // one interleaved step: decodes 4 symbols, returns them packed as block[i] | block[i+1] << 8 | ...
-    auto step = [&]() -> uint32_t {
-        if (cnt < 64) {  // top up the window with the next 64 bits
-            const uint64_t h = pfh ? c1 : c0;
-            q0 |= h >> cnt;
-            q1 = cnt ? (h << (64 - cnt)) : 0;
-            cnt += 64;
-            if (++pfh == 2) {
-                be_halves(nxt, c0, c1);
-                nxt = load_blk(jn++);
-                pfh = 0;
-            }
+    // ---- payload ring. Ring coordinates are relative to the 16-byte aligned source block holding the first payload
+    // bit: relative word r <-> source word base_w + r, re-aligned by s = pb & 31 bits; 16-bit unit t <-> word t >> 1.
+    const uint32_t s = (uint32_t)(pb & 31);
+    const uint64_t base_w = (pb >> 5) & ~3ull;
+    const uint64_t last_w = pe ? ((pe - 1) >> 5) : 0;  // last source word holding payload bits
+    uint32_t fill = 0;                                   // relative word index of the next refill round (multiple of 16)
+    L.cur2 = 4u * (uint32_t)((pb >> 5) - base_w);        // 2 * (16-bit units)
+    uint4 ld = make_uint4(0, 0, 0, 0);
+    uint32_t ld_next = 0;
+    bool ld_valid = false, pending = false;
+    const uint4* src128 = reinterpret_cast<const uint4*>(words);
+    auto issue = [&](bool want) {  // lane k loads relative words [fill + 4k, fill + 4k + 4]; always executes the loads
+        const uint64_t w0 = base_w + fill + 4u * k;
+        ld_valid = want && w0 <= last_w && w0 + 4 < words_len;
+        const uint64_t wa = ld_valid ? w0 : 0;
+        ld = __ldg(src128 + (wa >> 2));
+        ld_next = __ldg(words + wa + 4);
+    };
+    auto commit = [&]() {  // re-align to 16-bit units and store into the ring; zero guard past the payload (:888-893)
+        const uint32_t a0 = bswap32(ld.x), a1 = bswap32(ld.y), a2 = bswap32(ld.z), a3 = bswap32(ld.w), a4 = bswap32(ld_next);
+        uint4 r;
+        r.x = ld_valid ? __funnelshift_l(a1, a0, s) : 0u;
+        r.y = ld_valid ? __funnelshift_l(a2, a1, s) : 0u;
+        r.z = ld_valid ? __funnelshift_l(a3, a2, s) : 0u;
+        r.w = ld_valid ? __funnelshift_l(a4, a3, s) : 0u;
+        *reinterpret_cast<uint4*>(ring + ((fill + 4u * k) & (RING_WORDS - 1))) = r;
+    };
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {  // initial fill: the whole ring
+        issue(mode != 0);
+        commit();
+        fill += 16;
+    }
+    __syncwarp();
+    const uint32_t mask = (1u << lr) - 1u;
+    const uint32_t ring_base = smem_u32(ring);
+
+    // 4x4 byte transpose inside the group: after 4 steps lane k holds [a_k0 a_k1 a_k2 a_k3] (a_kj = symbol of state k in
+    // step j, output position 4j + 3 - k); lane j stores the word of step j: [a_3j a_2j a_1j a_0j].
+    auto transpose = [&](uint32_t acc) -> uint32_t {
+        const uint32_t o2 = __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+        const uint32_t t1 = (k & 2) ? __byte_perm(acc, o2, 0x3276) : __byte_perm(acc, o2, 0x5410);
+        const uint32_t o1 = __shfl_xor_sync(0xFFFFFFFFu, t1, 1);
+        return (k & 1) ? __byte_perm(t1, o1, 0x5173) : __byte_perm(t1, o1, 0x0426);
+    };
+    auto maintain = [&]() {  // uniform for the warp, every 4 steps
+        if (pending) {
+            commit();
+            fill += 16;
         }
-        uint32_t sl3 = st3 & mask, sl2 = st2 & mask, sl1 = st1 & mask, sl0 = st0 & mask;
-        uint32_t w3 = sl3 / 24, w2 = sl2 / 24, w1 = sl1 / 24, w0 = sl0 / 24;
-        uint32_t b3 = bm[w3 * 32], b2 = bm[w2 * 32], b1 = bm[w1 * 32], b0 = bm[w0 * 32];
-        uint32_t i3 = ((b3 >> 24) + __popc(b3 & ((2u << (sl3 - 24 * w3)) - 1u) & 0xFFFFFFu)) & 0xFF;
-        uint32_t i2 = ((b2 >> 24) + __popc(b2 & ((2u << (sl2 - 24 * w2)) - 1u) & 0xFFFFFFu)) & 0xFF;
-        uint32_t i1 = ((b1 >> 24) + __popc(b1 & ((2u << (sl1 - 24 * w1)) - 1u) & 0xFFFFFFu)) & 0xFF;
-        uint32_t i0 = ((b0 >> 24) + __popc(b0 & ((2u << (sl0 - 24 * w0)) - 1u) & 0xFFFFFFu)) & 0xFF;
-        uint32_t e3 = symtab[i3 * 32], e2 = symtab[i2 * 32], e1 = symtab[i1 * 32], e0 = symtab[i0 * 32];
-        // D(x) = (s, freq * (x >> lr) + (x & mask) - cum)   (:849)
-        st3 = ((e3 >> 8) & 0xFFF) * (st3 >> lr) + sl3 - (e3 >> 20);
-        st2 = ((e2 >> 8) & 0xFFF) * (st2 >> lr) + sl2 - (e2 >> 20);
-        st1 = ((e1 >> 8) & 0xFFF) * (st1 >> lr) + sl1 - (e1 >> 20);
-        st0 = ((e0 >> 8) & 0xFFF) * (st0 >> lr) + sl0 - (e0 >> 20);
-        // renormalisation: states below ANS_TOP pull 16 bits each from the shared cursor, in the order 3,2,1,0
-        const uint32_t n3 = st3 < (uint32_t)ANS_TOP, n2 = st2 < (uint32_t)ANS_TOP, n1 = st1 < (uint32_t)ANS_TOP, n0 = st0 < (uint32_t)ANS_TOP;
-        const uint32_t p2 = n3, p1 = n3 + n2, p0 = p1 + n1, tot = p0 + n0;
-        const uint32_t qlo = (uint32_t)q0, qhi = (uint32_t)(q0 >> 32);
-        if (n3) st3 = (st3 << 16) | (qhi >> 16);
-        if (n2) st2 = (st2 << 16) | (__byte_perm(qlo, qhi, 0x7676 - 0x2222 * p2) & 0xFFFF);
-        if (n1) st1 = (st1 << 16) | (__byte_perm(qlo, qhi, 0x7676 - 0x2222 * p1) & 0xFFFF);
-        if (n0) st0 = (st0 << 16) | (__byte_perm(qlo, qhi, 0x7676 - 0x2222 * p0) & 0xFFFF);
-        const uint32_t sh = 16 * tot;
-        if (sh == 64) {
-            q0 = q1;
-            q1 = 0;
-        } else if (sh) {
-            q0 = (q0 << sh) | (q1 >> (64 - sh));
-            q1 <<= sh;
-        }
-        cnt -= sh;
-        return (e3 & 0xFF) | ((e2 & 0xFF) << 8) | ((e1 & 0xFF) << 16) | (e0 << 24);
+        __syncwarp();
+        // refill when at most 40 words are buffered ahead of the cursor: the new round then only overwrites consumed words
+        pending = mode && (int32_t)(fill - (L.cur2 >> 2)) <= (RING_WORDS - 16 - 8);
+        issue(pending);
     };
 
-    uint32_t i = 0;
-    for (; i + 16 <= end4; i += 16) {
-        uint4 o;
-        o.x = step();
-        o.y = step();
-        o.z = step();
-        o.w = step();
-        *reinterpret_cast<uint4*>(dst + i) = o;
+    const uint32_t fast_iters = min_steps >> 2;  // iterations in which every group of the warp is active
+    uint32_t it = 0;
+    uint8_t* dptr = dst + 4 * k;
+    for (; it < fast_iters; it++) {
+        dec_step<true>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, true);
+        dec_step<true>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, true);
+        dec_step<true>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, true);
+        dec_step<true>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, true);
+        *reinterpret_cast<uint32_t*>(dptr + (size_t)it * 16) = transpose(L.acc);
+        maintain();
     }
-    for (; i < end4; i += 4) *reinterpret_cast<uint32_t*>(dst + i) = step();
-    // tail bytes follow the consumed words (:951-954); cursor = pe - cnt-adjusted position
-    {
-        // bits consumed so far = (bits loaded into the window) - cnt; recompute the cursor from what is left:
-        // window holds cnt bits, c-halves hold (2 - pfh) * 64 bits, nxt block and beyond start at 128 * (jn - 1)
-        const uint64_t loaded_end = (jn - 1) << 7;  // first bit of `nxt`
-        uint64_t cursor = loaded_end - (uint64_t)(2 - pfh) * 64 - cnt;
-        for (uint32_t k = end4; k < ck.out_len; k++, cursor += 8) dst[k] = cursor + 8 <= pe ? (uint8_t)bits_at(words, cursor, 8) : 0;
+    const uint32_t all_iters = max_steps >> 2;
+    for (; it < all_iters; it++) {  // groups with fewer steps idle here
+        const bool active = (it * 4 + 3) < nsteps;
+        dec_step<false>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, active);
+        dec_step<false>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, active);
+        dec_step<false>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, active);
+        dec_step<false>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, active);
+        const uint32_t w = transpose(L.acc);
+        if (active) *reinterpret_cast<uint32_t*>(dptr + (size_t)it * 16) = w;
+        maintain();
+    }
+    {  // remaining 0..3 steps of a group (only the last chunk of a block can have nsteps % 4 != 0)
+        if (pending) {
+            commit();
+            fill += 16;
+            pending = false;
+        }
+        __syncwarp();
+        const uint32_t done = nsteps & ~3u;
+        uint32_t rem_max = nsteps - done;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) rem_max = max(rem_max, __shfl_xor_sync(0xFFFFFFFFu, rem_max, d));
+        for (uint32_t r = 0; r < rem_max; r++) {
+            const bool active = done + r < nsteps;
+            dec_step<false>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, active);
+            if (active) dst[(size_t)(done + r) * 4 + (3 - k)] = (uint8_t)(L.acc >> 24);
+        }
+    }
+    // tail bytes follow the consumed words (:951-954)
+    if (mode && k == 0 && tail) {
+        const uint64_t consumed16 = (uint64_t)(L.cur2 >> 1) - 2ull * ((pb >> 5) - base_w);
+        uint64_t pos = pb + 16 * consumed16;
+        for (uint32_t j = 0; j < tail; j++, pos += 8) dst[(size_t)nsteps * 4 + j] = pos + 8 <= pe ? (uint8_t)bits_at(words, pos, 8) : 0;
     }
 }
 

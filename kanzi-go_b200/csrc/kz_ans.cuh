@@ -31,9 +31,12 @@ static const int STATS_WARPS = 4;
 static const int HDR_STRIDE = 512;             // bytes reserved per chunk header (max 3453 header bits + 19 bytes)
 static const int PAY_STRIDE = 32768 + 64;      // per chunk rANS byte scratch: 2 bytes/symbol worst case + tail + alignment
 static const int PAY_WORDS_END = 32768 + 32;   // 16-byte aligned end of the 16-bit word region; tail bytes follow
-static const int DEC_BM_WORDS = 171;           // ceil(4096 / 24)
 static const size_t ENC_SMEM = 256 * 32 * sizeof(uint2);
-static const size_t DEC_SMEM = (DEC_BM_WORDS + 256) * 32 * sizeof(uint32_t);
+// decode: per warp (8 chunks): 171x8 bitmap buckets (24 slots each) + 256x8 symbol entries + 8 rings of 64 words; 2 warps per CTA
+static const int DEC_BM_WORDS = 171;
+static const int DEC_WARP_WORDS = (DEC_BM_WORDS + 256) * 8 + 8 * 64;
+static const int DEC_CTA_CHUNKS = 16;
+static const size_t DEC_SMEM = 2 * DEC_WARP_WORDS * sizeof(uint32_t);
 
 __global__ void ans0_stats_kernel(const uint8_t* in, const ChunkIn* chunks, int nchunks, uint2* enc_tab, uint8_t* hdr, uint32_t* hdr_bits,
                                   uint32_t* asz_out);
@@ -42,6 +45,8 @@ __global__ void ans0_encode_kernel(const uint8_t* in, const ChunkIn* chunks, int
                                    const uint32_t* seg_index);
 __global__ void ans_walk_kernel(const uint32_t* words, const DecBlock* blocks, int nblocks, int order, uint64_t* chunk_hdr_bit, uint64_t* blk_end,
                                 int32_t* status);
+__global__ void ans0_walk_kernel(const uint32_t* words, uint64_t words_len, const DecBlock* blocks, int nblocks, uint64_t* chunk_hdr_bit,
+                                 uint64_t* blk_end, int32_t* status);
 __global__ void ans0_decode_kernel(const uint32_t* words, uint64_t words_len, const DecChunk* chunks, int nchunks, const uint64_t* chunk_hdr_bit,
                                    uint8_t* out, int32_t* status);
 
