@@ -617,13 +617,15 @@ KZ_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_share
 
 struct DecLane {
     uint32_t st;      // rANS state of this lane
-    uint32_t cur2;    // 2 * cursor (16-bit units, relative to the ring origin)
+    uint32_t cur2;    // byte offset of the cursor inside the (unwrapped) ring coordinate system, always even
     uint32_t acc;     // last 4 decoded symbols of this state
 };
 
+// The ring holds RAW stream bytes (filled with cp.async, no register staging); the payload starts s16 bits into the
+// 16-bit unit at ring byte 0 + cur2, so a renormalisation word is the 16 bits at bit offset s16 of the 4 bytes at cur2.
 template <bool ALL_ACTIVE>
-KZ_D void dec_step(DecLane& L, const uint32_t* bm, const uint32_t* symtab, uint32_t ring_base, uint32_t mask, uint32_t lr, uint32_t hi_mask,
-                   uint32_t grp_mask, bool active) {
+KZ_D void dec_step(DecLane& L, const uint32_t* bm, const uint32_t* symtab, uint32_t ring_base, uint32_t mask, uint32_t lr, uint32_t rsh,
+                   uint32_t hi_mask, uint32_t grp_mask, bool active) {
     const uint32_t slot = L.st & mask;
     const uint32_t w = (slot * 2731u) >> 16;  // slot / 24 (exact for slot < 4096)
     const uint32_t b = bm[w * 8];
@@ -635,9 +637,11 @@ KZ_D void dec_step(DecLane& L, const uint32_t* bm, const uint32_t* symtab, uint3
     if (!ALL_ACTIVE) need = need && active;
     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, need);
     const uint32_t t2 = L.cur2 + 2u * __popc(bal & hi_mask);
-    uint32_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(ring_base + ((t2 & (4 * RING_WORDS - 2)) ^ 2u)));
-    const uint32_t nst2 = (nst << 16) | v;
+    uint32_t va, vb;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(va) : "r"(ring_base + (t2 & (4 * RING_WORDS - 2))));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(vb) : "r"(ring_base + ((t2 + 2) & (4 * RING_WORDS - 2))));
+    const uint32_t x = __byte_perm(va, vb, 0x0145) >> rsh;  // big-endian 32 bits at t2, shifted so that the word sits in the low 16 bits
+    const uint32_t nst2 = __byte_perm(x, nst, 0x5410);      // (nst << 16) | (x & 0xFFFF)
     if (ALL_ACTIVE || active) {
         L.st = need ? nst2 : nst;
         L.cur2 += 2u * __popc(bal & grp_mask);
@@ -775,44 +779,37 @@ __global__ void __launch_bounds__(64, 7) ans0_decode_kernel(const uint32_t* __re
     }
     if (max_steps == 0) return;
 
-    // ---- payload ring. Ring coordinates are relative to the 16-byte aligned source block holding the first payload
-    // bit: relative word r <-> source word base_w + r, re-aligned by s = pb & 31 bits; 16-bit unit t <-> word t >> 1.
-    const uint32_t s = (uint32_t)(pb & 31);
-    const uint64_t base_w = (pb >> 5) & ~3ull;
-    const uint64_t last_w = pe ? ((pe - 1) >> 5) : 0;  // last source word holding payload bits
-    uint32_t fill = 0;                                   // relative word index of the next refill round (multiple of 16)
-    L.cur2 = 4u * (uint32_t)((pb >> 5) - base_w);        // 2 * (16-bit units)
-    uint4 ld = make_uint4(0, 0, 0, 0);
-    uint32_t ld_next = 0;
-    bool ld_valid = false, pending = false;
-    const uint4* src128 = reinterpret_cast<const uint4*>(words);
-    auto issue = [&](bool want) {  // lane k loads relative words [fill + 4k, fill + 4k + 4]; always executes the loads
-        const uint64_t w0 = base_w + fill + 4u * k;
-        ld_valid = want && w0 <= last_w && w0 + 4 < words_len;
-        const uint64_t wa = ld_valid ? w0 : 0;
-        ld = __ldg(src128 + (wa >> 2));
-        ld_next = __ldg(words + wa + 4);
-    };
-    auto commit = [&]() {  // re-align to 16-bit units and store into the ring; zero guard past the payload (:888-893)
-        const uint32_t a0 = bswap32(ld.x), a1 = bswap32(ld.y), a2 = bswap32(ld.z), a3 = bswap32(ld.w), a4 = bswap32(ld_next);
-        uint4 r;
-        r.x = ld_valid ? __funnelshift_l(a1, a0, s) : 0u;
-        r.y = ld_valid ? __funnelshift_l(a2, a1, s) : 0u;
-        r.z = ld_valid ? __funnelshift_l(a3, a2, s) : 0u;
-        r.w = ld_valid ? __funnelshift_l(a4, a3, s) : 0u;
-        *reinterpret_cast<uint4*>(ring + ((fill + 4u * k) & (RING_WORDS - 1))) = r;
+    // ---- payload ring: raw copy of the stream starting at the 16-byte aligned block that holds the first payload bit.
+    // Ring byte r <-> source byte base_b + r. The 4 lanes of a group fetch 4 x 16 bytes per refill round with cp.async
+    // (no register destination: nothing in the decode loop waits on a global load it issued itself).
+    const uint64_t base_b = (pb >> 3) & ~15ull;            // source byte of ring byte 0
+    const uint32_t rel = (uint32_t)(pb - 8 * base_b);      // payload bit offset inside the ring, 0..134
+    const uint32_t rsh = 16u - (rel & 15u);                // see dec_step
+    const uint64_t end_b = (pe + 7) >> 3;                  // first source byte past the payload
+    const uint64_t lim_b = words_len * 4;
+    uint32_t fill = 0;                                     // ring byte offset (unwrapped, multiple of 64) of the next refill round
+    L.cur2 = 2u * (rel >> 4);
+    const uint32_t ring_base = smem_u32(ring);
+    auto issue = [&](bool want) {  // lane k copies source bytes [base_b + fill + 16k, +16) into the ring
+        const uint64_t sb = base_b + fill + 16u * k;
+        const bool ok = want && sb < end_b && sb + 16 <= lim_b;
+        const uint32_t dst_addr = ring_base + ((fill + 16u * k) & (4 * RING_WORDS - 1));
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(words) + (ok ? sb : 0);
+        const uint32_t src_size = ok ? 16u : 0u;  // src-size 0 zero-fills: the guard past the payload (:888-893)
+        if (want) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_addr), "l"(src), "r"(src_size) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {  // initial fill: the whole ring
         issue(mode != 0);
-        commit();
-        fill += 16;
+        fill += 64;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
+    bool pending = false;
     const uint32_t mask = (1u << lr) - 1u;
-    const uint32_t ring_base = smem_u32(ring);
 
-    // 4x4 byte transpose inside the group: after 4 steps lane k holds [a_k0 a_k1 a_k2 a_k3] (a_kj = symbol of state k in
+    // 4x4 byte transpose    // 4x4 byte transpose inside the group: after 4 steps lane k holds [a_k0 a_k1 a_k2 a_k3] (a_kj = symbol of state k in
     // step j, output position 4j + 3 - k); lane j stores the word of step j: [a_3j a_2j a_1j a_0j].
     auto transpose = [&](uint32_t acc) -> uint32_t {
         const uint32_t o2 = __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
@@ -820,14 +817,13 @@ __global__ void __launch_bounds__(64, 7) ans0_decode_kernel(const uint32_t* __re
         const uint32_t o1 = __shfl_xor_sync(0xFFFFFFFFu, t1, 1);
         return (k & 1) ? __byte_perm(t1, o1, 0x5173) : __byte_perm(t1, o1, 0x0426);
     };
-    auto maintain = [&]() {  // uniform for the warp, every 4 steps
-        if (pending) {
-            commit();
-            fill += 16;
-        }
+    auto maintain = [&]() {  // every 4 steps, uniform for the warp
+        asm volatile("cp.async.wait_group 0;" ::: "memory");  // the round issued one iteration ago has landed
+        fill += pending ? 64u : 0u;
         __syncwarp();
-        // refill when at most 40 words are buffered ahead of the cursor: the new round then only overwrites consumed words
-        pending = mode && (int32_t)(fill - (L.cur2 >> 2)) <= (RING_WORDS - 16 - 8);
+        // refill when at most 160 bytes are buffered ahead of the cursor: the new 64-byte round then only overwrites
+        // consumed bytes, and 4 steps consume at most 32 bytes
+        pending = mode && (int32_t)(fill - L.cur2) <= (4 * RING_WORDS - 64 - 32);
         issue(pending);
     };
 
@@ -835,30 +831,26 @@ __global__ void __launch_bounds__(64, 7) ans0_decode_kernel(const uint32_t* __re
     uint32_t it = 0;
     uint8_t* dptr = dst + 4 * k;
     for (; it < fast_iters; it++) {
-        dec_step<true>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, true);
-        dec_step<true>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, true);
-        dec_step<true>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, true);
-        dec_step<true>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, true);
+        dec_step<true>(L, bm, symtab, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        dec_step<true>(L, bm, symtab, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        dec_step<true>(L, bm, symtab, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        dec_step<true>(L, bm, symtab, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
         *reinterpret_cast<uint32_t*>(dptr + (size_t)it * 16) = transpose(L.acc);
         maintain();
     }
     const uint32_t all_iters = max_steps >> 2;
     for (; it < all_iters; it++) {  // groups with fewer steps idle here
         const bool active = (it * 4 + 3) < nsteps;
-        dec_step<false>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, active);
-        dec_step<false>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, active);
-        dec_step<false>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, active);
-        dec_step<false>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, active);
+        dec_step<false>(L, bm, symtab, ring_base, mask, lr, rsh, hi_mask, grp_mask, active);
+        dec_step<false>(L, bm, symtab, ring_base, mask, lr, rsh, hi_mask, grp_mask, active);
+        dec_step<false>(L, bm, symtab, ring_base, mask, lr, rsh, hi_mask, grp_mask, active);
+        dec_step<false>(L, bm, symtab, ring_base, mask, lr, rsh, hi_mask, grp_mask, active);
         const uint32_t w = transpose(L.acc);
         if (active) *reinterpret_cast<uint32_t*>(dptr + (size_t)it * 16) = w;
         maintain();
     }
     {  // remaining 0..3 steps of a group (only the last chunk of a block can have nsteps % 4 != 0)
-        if (pending) {
-            commit();
-            fill += 16;
-            pending = false;
-        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         const uint32_t done = nsteps & ~3u;
         uint32_t rem_max = nsteps - done;
@@ -866,14 +858,13 @@ __global__ void __launch_bounds__(64, 7) ans0_decode_kernel(const uint32_t* __re
         for (int d = 16; d > 0; d >>= 1) rem_max = max(rem_max, __shfl_xor_sync(0xFFFFFFFFu, rem_max, d));
         for (uint32_t r = 0; r < rem_max; r++) {
             const bool active = done + r < nsteps;
-            dec_step<false>(L, bm, symtab, ring_base, mask, lr, hi_mask, grp_mask, active);
+            dec_step<false>(L, bm, symtab, ring_base, mask, lr, rsh, hi_mask, grp_mask, active);
             if (active) dst[(size_t)(done + r) * 4 + (3 - k)] = (uint8_t)(L.acc >> 24);
         }
     }
     // tail bytes follow the consumed words (:951-954)
     if (mode && k == 0 && tail) {
-        const uint64_t consumed16 = (uint64_t)(L.cur2 >> 1) - 2ull * ((pb >> 5) - base_w);
-        uint64_t pos = pb + 16 * consumed16;
+        uint64_t pos = 8 * (base_b + L.cur2) + (rel & 15u);  // bit position of the cursor in the stream
         for (uint32_t j = 0; j < tail; j++, pos += 8) dst[(size_t)nsteps * 4 + j] = pos + 8 <= pe ? (uint8_t)bits_at(words, pos, 8) : 0;
     }
 }
