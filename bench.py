@@ -262,7 +262,7 @@ def main():
         line["roofline"] = roof
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = cpu_reference(2, 1, sample_blocks=16)
+            r = cpu_reference(2, 1, sample_blocks=NBLOCKS)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:  # the checker is absent: report, never substitute
             line["cpu_baseline"] = {"value": None, "unit": "MB/s", "cores": 0, "kind": "port", "sample": "unavailable: %s" % e}

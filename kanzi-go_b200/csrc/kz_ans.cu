@@ -25,6 +25,8 @@ namespace kz {
 // ------------------------------------------------------------------------------------------------------------
 namespace {
 
+KZ_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 KZ_D void smem_put_bits(uint32_t* words, uint32_t bitpos, uint32_t value, uint32_t n) {  // n in 1..32, MSB-first words
     if (n < 32) value &= (1u << n) - 1u;
     uint32_t w = bitpos >> 5, o = bitpos & 31;
@@ -157,27 +159,31 @@ static __device__ int warp_normalize(uint32_t (&f)[8], uint32_t total, uint32_t 
     return asz;
 }
 
-// encSymbol.reset (ANSRangeCodec.go:446-468) packed into 8 bytes:
-//   x = inv_freq (32 bit), y = freq(13) | bias(14) << 13 | (inv_shift-32)(4) << 27   [bias <= cum + 2^lr - 1 < 2^14 for lr <= 13]
-static __device__ __forceinline__ uint2 make_enc_entry(uint32_t cum, uint32_t freq, uint32_t lr) {
-    uint32_t fr = freq < (1u << lr) - 1u ? freq : (1u << lr) - 1u;
-    uint32_t inv, sh, bias;
-    if (fr < 2) {
-        inv = 0xFFFFFFFFu;
-        sh = 0;
-        bias = cum + (1u << lr) - 1u;
-    } else {
-        uint32_t shift = 32u - (uint32_t)__clz((int)(fr - 1));  // smallest shift with fr <= 1<<shift
-        inv = (uint32_t)((((uint64_t)1 << (shift + 31)) + (uint64_t)(fr - 1)) / (uint64_t)fr);
-        sh = shift - 1;
-        bias = cum;
+// encSymbol.reset (ANSRangeCodec.go:446-468). The per-symbol entry keeps only what depends on the chunk:
+//   freq (13 bits, clamped to 2^lr - 1) | bias << 13   (bias = cum, or cum + 2^lr - 1 when freq < 2)
+// The reciprocal (invFreq, invShift) depends on freq alone and comes from one table shared by all chunks
+// (rcp_table_kernel): invShift - 32 = ceil(log2 freq) - 1 is recomputed with a count-leading-zeros.
+static __device__ __forceinline__ uint32_t make_enc_entry(uint32_t cum, uint32_t freq, uint32_t lr) {
+    const uint32_t fr = freq < (1u << lr) - 1u ? freq : (1u << lr) - 1u;
+    const uint32_t bias = fr < 2 ? cum + (1u << lr) - 1u : cum;
+    return fr | (bias << 13);
+}
+
+// inv[f] for f in [0, 4096): the 32-bit fixed point reciprocal of :452-466 (Alverson)
+__global__ void rcp_table_kernel(uint32_t* __restrict__ inv) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= 4096) return;
+    uint32_t v = 0xFFFFFFFFu;
+    if (f >= 2) {
+        const uint32_t shift = 32u - (uint32_t)__clz((int)(f - 1));  // smallest shift with f <= 1 << shift
+        v = (uint32_t)((((uint64_t)1 << (shift + 31)) + (uint64_t)(f - 1)) / (uint64_t)f);
     }
-    return make_uint2(inv, fr | (bias << 13) | (sh << 27));
+    inv[f] = v;
 }
 
 // grid: ceil(nchunks / STATS_WARPS) CTAs of STATS_WARPS warps
 __global__ void __launch_bounds__(STATS_WARPS * 32) ans0_stats_kernel(const uint8_t* __restrict__ in, const ChunkIn* __restrict__ chunks, int nchunks,
-                                                                       uint2* __restrict__ enc_tab, uint8_t* __restrict__ hdr,
+                                                                       uint32_t* __restrict__ enc_tab, uint8_t* __restrict__ hdr,
                                                                        uint32_t* __restrict__ hdr_bits, uint32_t* __restrict__ asz_out) {
     __shared__ uint32_t s_hist[STATS_WARPS][8][256];  // 8 replicas per warp to spread same-address atomics
     __shared__ uint32_t s_hdr[STATS_WARPS][HDR_STRIDE / 4];
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(STATS_WARPS * 32) ans0_stats_kernel(const uint
     uint32_t carry = 0;
     int rank_base = 0;
     uint32_t last_sym = 0;
-    uint2* tab = enc_tab + (size_t)c * 256;
+    uint32_t* tab = enc_tab + (size_t)c * 256;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         uint32_t incl = warp_incl_scan(f[j], lane);
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(STATS_WARPS * 32) ans0_stats_kernel(const uint
             tab[lane + 32 * j] = make_enc_entry(cum, f[j], lr);
             s_rank[warp][rank] = (uint16_t)(f[j] - 1);
         } else {
-            tab[lane + 32 * j] = make_uint2(0, 0);
+            tab[lane + 32 * j] = 0;
         }
         if (b) last_sym = 32u * j + (31u - (uint32_t)__clz((int)b));
         carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
@@ -302,125 +308,203 @@ __global__ void __launch_bounds__(STATS_WARPS * 32) ans0_stats_kernel(const uint
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// encode: one thread per chunk, one warp (32 chunks) per CTA
+// encode (v2): FOUR lanes per chunk (lane k owns rANS state k), 8 chunks per warp, 64 chunks per 256-thread CTA.
+//
+// v1 (one thread per chunk) ran one warp per scheduler: 2.3 ms for 64 x 4 MiB (profiles/r01_ncu_v1_summary.json).
+// Reference loop (ANSRangeCodec.go:347-352): the chunk is walked backwards four bytes at a time, state k takes byte
+// 4g + 3 - k, a state that reaches xMax first emits its low 16 bits (low byte at buffer[n], high byte at buffer[n-1]);
+// the states emit in the order st0, st1, st2, st3 towards lower addresses. Here
+//   * the backward write cursor is resolved with one __ballot_sync per step (prefix count over the lower-numbered
+//     states); every lane stores its 16-bit word into a 256-byte per-chunk ring in shared memory and complete
+//     64-byte blocks are flushed to the chunk's scratch area with one 16-byte store per lane;
+//   * input bytes arrive through a 64-byte per-chunk ring filled with cp.async three iterations ahead;
+//   * per-chunk tables hold 4 bytes per symbol (freq, bias); the reciprocals come from one 16 KiB table per CTA.
+// 64 chunks x 1344 bytes + 16 KiB = 100 KiB per CTA -> 2 CTAs = 128 chunks per SM (one wave for 64 x 4 MiB).
 // ------------------------------------------------------------------------------------------------------------
-struct EncState {
-    uint32_t a0, a1, a2, a3;  // 16 bytes of pending output; a0 = lowest address
-    uint32_t cnt;             // pending 16-bit words (0..7)
-    uint8_t* ptr;             // next 16-byte store goes to ptr-16
+struct EncLane {
+    uint32_t st;
+    uint32_t emitted;  // 16-bit words emitted so far by the whole group
 };
 
-KZ_D void enc_symbol(uint32_t& st, uint2 e, uint32_t lr, EncState& o) {
-    const uint32_t freq = e.y & 0x1FFF;
-    const uint32_t bias = (e.y >> 13) & 0x3FFF;
-    const uint32_t sh = e.y >> 27;
-    const uint32_t x_max = freq << (31 - lr);  // ((ANS_TOP >> lr) << 16) * freq
-    if (st >= x_max) {
-        // emit st & 0xFFFF: low byte at buffer[n], high byte at buffer[n-1] (:322-326) -> ascending memory = [hi, lo]
-        o.a3 = __byte_perm(o.a2, o.a3, 0x5432);
-        o.a2 = __byte_perm(o.a1, o.a2, 0x5432);
-        o.a1 = __byte_perm(o.a0, o.a1, 0x5432);
-        o.a0 = __byte_perm(st, o.a0, 0x5401);
-        st >>= 16;
-        if (++o.cnt == 8) {
-            o.ptr -= 16;
-            *reinterpret_cast<uint4*>(o.ptr) = make_uint4(o.a0, o.a1, o.a2, o.a3);
-            o.cnt = 0;
-        }
+template <bool ALL_ACTIVE>
+KZ_D void enc_step(EncLane& L, uint32_t sym, const uint32_t* tab, const uint32_t* rcp, uint32_t out_ring, uint32_t lr, uint32_t lo_mask,
+                   uint32_t grp_mask, bool active) {
+    const uint32_t e = tab[sym * 8];
+    const uint32_t freq = e & 0x1FFFu;
+    const uint32_t inv = rcp[freq];
+    const uint32_t sh = 31u - (uint32_t)__clz((int)((freq - 1u) | 1u));  // invShift - 32
+    bool emit = L.st >= (freq << (31u - lr));                             // xMax = ((ANS_TOP >> lr) << 16) * freq
+    if (!ALL_ACTIVE) emit = emit && active;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, emit);
+    // word index counted from the end of the stream: states with a lower index emit first (higher addresses)
+    const uint32_t u = L.emitted + __popc(bal & lo_mask);
+    const uint32_t addr = out_ring + ((0u - 2u * (u + 1u)) & (4 * ENC_OUT_RING_WORDS - 1));
+    const uint32_t w16 = __byte_perm(L.st, 0, 0x4401);  // memory order [hi, lo] (:322-326)
+    if (emit) asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(w16) : "memory");
+    const uint32_t x = emit ? (L.st >> 16) : L.st;
+    const uint32_t q = __umulhi(x, inv) >> sh;  // (st * invFreq) >> invShift
+    const uint32_t nst = x + (e >> 13) + q * ((1u << lr) - freq);
+    if (ALL_ACTIVE || active) {
+        L.st = nst;
+        L.emitted += __popc(bal & grp_mask);
     }
-    const uint32_t q = __umulhi(st, e.x) >> sh;  // (st * invFreq) >> invShift, invShift = 32 + sh
-    st = st + bias + q * ((1u << lr) - freq);
 }
 
-__global__ void __launch_bounds__(32) ans0_encode_kernel(const uint8_t* __restrict__ in, const ChunkIn* __restrict__ chunks, int nchunks,
-                                                          const uint2* __restrict__ enc_tab, uint8_t* __restrict__ hdr,
-                                                          const uint32_t* __restrict__ hdr_bits, const uint32_t* __restrict__ asz_in,
-                                                          uint8_t* __restrict__ pay, uint64_t* __restrict__ seg_src, uint64_t* __restrict__ seg_bits,
-                                                          const uint32_t* __restrict__ seg_index) {
-    extern __shared__ uint2 s_tab[];  // [256][32] : entry of symbol s for lane l at s*32 + l
-    const int lane = threadIdx.x;
-    const int base = blockIdx.x * 32;
-    // cooperative, coalesced table load
-    for (int cc = 0; cc < 32; cc++) {
-        int c = base + cc;
-        if (c >= nchunks) break;
-        const uint2* t = enc_tab + (size_t)c * 256;
+__global__ void __launch_bounds__(256, 2) ans0_encode_kernel(const uint8_t* __restrict__ in, const ChunkIn* __restrict__ chunks, int nchunks,
+                                                             const uint32_t* __restrict__ enc_tab, const uint32_t* __restrict__ rcp_g,
+                                                             uint8_t* __restrict__ hdr, const uint32_t* __restrict__ hdr_bits,
+                                                             const uint32_t* __restrict__ asz_in, uint8_t* __restrict__ pay,
+                                                             uint64_t* __restrict__ seg_src, uint64_t* __restrict__ seg_bits,
+                                                             const uint32_t* __restrict__ seg_index) {
+    extern __shared__ uint32_t s_enc[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, k = lane & 3;
+    uint32_t* rcp = s_enc;                                  // 4096 words
+    uint32_t* wbase = s_enc + 4096 + warp * ENC_WARP_WORDS;
+    uint32_t* tab = wbase + g;                              // entry of symbol s at tab[s*8]
+    uint32_t* oring = wbase + 256 * 8 + g * ENC_OUT_RING_WORDS;
+    uint32_t* iring = wbase + 256 * 8 + 8 * ENC_OUT_RING_WORDS + g * 16;
+    for (int i = tid; i < 4096; i += 256) rcp[i] = __ldg(rcp_g + i);
+    const int cbase = blockIdx.x * ENC_CTA_CHUNKS + warp * 8;
+    for (int cc = 0; cc < 8; cc++) {  // cooperative, coalesced table load
+        const int c2 = cbase + cc;
+        if (c2 >= nchunks) break;
+        const uint32_t* t = enc_tab + (size_t)c2 * 256;
 #pragma unroll
-        for (int j = 0; j < 8; j++) s_tab[(lane + 32 * j) * 32 + cc] = __ldg(&t[lane + 32 * j]);
+        for (int j = 0; j < 8; j++) wbase[(lane + 32 * j) * 8 + cc] = __ldg(t + lane + 32 * j);
     }
-    __syncwarp();
-    const int c = base + lane;
-    if (c >= nchunks) return;
-    const ChunkIn ck = chunks[c];
-    const uint32_t asz = asz_in[c];
-    const uint32_t hb = hdr_bits[c];
-    const uint32_t si = seg_index[c];
-    uint8_t* my_hdr = hdr + (size_t)c * HDR_STRIDE;
-    seg_src[si] = (uint64_t)(uintptr_t)my_hdr;
-    if (asz <= 1) {  // Write :303: chunk not encoded, header only
-        seg_bits[si] = hb;
-        seg_src[si + 1] = 0;
-        seg_bits[si + 1] = 0;
-        return;
-    }
-    const uint8_t* src = in + ck.src_off;
-    const uint32_t len = ck.len;
-    const uint32_t end4 = len & ~3u;
+    __syncthreads();
+    const int c = cbase + g;
+    const uint32_t grp_mask = 0xFu << (lane & ~3);
+    const uint32_t lo_mask = grp_mask & ((1u << lane) - 1u);  // lanes of my group with a lower state index (they emit first)
     const uint32_t lr = 12;
-    uint8_t* e_words = pay + (size_t)c * PAY_STRIDE + PAY_WORDS_END;
-    // tail bytes go last in the stream (:339-342)
-    for (uint32_t i = end4; i < len; i++) e_words[i - end4] = src[i];
-    EncState o;
-    o.a0 = o.a1 = o.a2 = o.a3 = 0;
-    o.cnt = 0;
-    o.ptr = e_words;
-    uint32_t st0 = ANS_TOP, st1 = ANS_TOP, st2 = ANS_TOP, st3 = ANS_TOP;
-    const uint2* tab = s_tab + lane;
-    uint32_t g = end4 >> 2;  // groups of 4 bytes still to encode, processed from the last to the first
-    const uint32_t* src32 = reinterpret_cast<const uint32_t*>(src);
-    // :347-352: st0 <- block[i], st1 <- block[i-1], st2 <- block[i-2], st3 <- block[i-3] with i = 4g-1
-    while (g & 3) {
-        g--;
-        uint32_t v = __ldg(&src32[g]);
-        enc_symbol(st0, tab[(v >> 24) * 32], lr, o);
-        enc_symbol(st1, tab[((v >> 16) & 0xFF) * 32], lr, o);
-        enc_symbol(st2, tab[((v >> 8) & 0xFF) * 32], lr, o);
-        enc_symbol(st3, tab[(v & 0xFF) * 32], lr, o);
-    }
-    const uint4* src128 = reinterpret_cast<const uint4*>(src);
-    uint32_t q = g >> 2;
-    while (q) {
-        q--;
-        const uint4 v4 = __ldg(&src128[q]);
-        const uint32_t w[4] = {v4.w, v4.z, v4.y, v4.x};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t v = w[k];
-            enc_symbol(st0, tab[(v >> 24) * 32], lr, o);
-            enc_symbol(st1, tab[((v >> 16) & 0xFF) * 32], lr, o);
-            enc_symbol(st2, tab[((v >> 8) & 0xFF) * 32], lr, o);
-            enc_symbol(st3, tab[(v & 0xFF) * 32], lr, o);
+    // ---- per chunk set-up
+    uint32_t len = 0, end4 = 0, asz = 0, hb = 0, si = 0;
+    const uint8_t* src = in;
+    uint8_t* e_words = pay;
+    uint8_t* my_hdr = hdr;
+    bool mode = false;
+    if (c < nchunks) {
+        const ChunkIn ck = chunks[c];
+        src = in + ck.src_off;
+        len = ck.len;
+        end4 = len & ~3u;
+        asz = asz_in[c];
+        hb = hdr_bits[c];
+        si = seg_index[c];
+        my_hdr = hdr + (size_t)c * HDR_STRIDE;
+        e_words = pay + (size_t)c * PAY_STRIDE + PAY_WORDS_END;
+        mode = asz > 1;
+        if (k == 0) {
+            seg_src[si] = (uint64_t)(uintptr_t)my_hdr;
+            if (!mode) {  // Write :303: chunk not encoded, header only
+                seg_bits[si] = hb;
+                seg_src[si + 1] = 0;
+                seg_bits[si + 1] = 0;
+            } else {
+                for (uint32_t i = end4; i < len; i++) e_words[i - end4] = src[i];  // tail bytes go last in the stream (:339-342)
+            }
         }
     }
-    // flush the pending words: they occupy the low 2*cnt bytes of a0..a3 and belong right below o.ptr
+    EncLane L;
+    L.st = ANS_TOP;
+    L.emitted = 0;
+    uint32_t ngroups = mode ? (end4 >> 2) : 0;  // groups of 4 bytes, processed from the last to the first
+    const uint32_t oring_a = smem_u32(oring), iring_a = smem_u32(iring);
+    // ---- leading groups so that the rest is a whole number of 16-byte units (only tail chunks of a block)
     {
-        const uint32_t a[4] = {o.a0, o.a1, o.a2, o.a3};
-        const uint32_t nb = 2 * o.cnt;
-        uint8_t* p = o.ptr - nb;
-        for (uint32_t i = 0; i < nb; i++) p[i] = (uint8_t)(a[i >> 2] >> (8 * (i & 3)));
-        o.ptr = p;
+        uint32_t lead = ngroups & 3;
+        uint32_t lead_max = lead;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) lead_max = max(lead_max, __shfl_xor_sync(0xFFFFFFFFu, lead_max, d));
+        for (uint32_t r = 0; r < lead_max; r++) {
+            const bool active = r < lead;
+            uint32_t sym = 0;
+            if (active) sym = src[(size_t)(ngroups - 1 - r) * 4 + (3 - k)];
+            enc_step<false>(L, sym, tab, rcp, oring_a, lr, lo_mask, grp_mask, active);
+        }
+        ngroups -= lead;
     }
-    const uint32_t sz = (uint32_t)(e_words - o.ptr) + (len - end4);
-    // varint(sz) + 4 x 32-bit states appended to the chunk header (:392-399)
-    BitWriter bw(my_hdr, hb);
-    bw.write_varint(sz);
-    bw.write(st0, 32);
-    bw.write(st1, 32);
-    bw.write(st2, 32);
-    bw.write(st3, 32);
-    seg_bits[si] = bw.pos;
-    seg_src[si + 1] = (uint64_t)(uintptr_t)o.ptr;
-    seg_bits[si + 1] = 8ull * sz;
+    const uint32_t units = ngroups >> 2;  // 16-byte units still to encode: units-1 down to 0
+    uint32_t max_units = units, min_units = units;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        max_units = max(max_units, __shfl_xor_sync(0xFFFFFFFFu, max_units, d));
+        min_units = min(min_units, __shfl_xor_sync(0xFFFFFFFFu, min_units, d));
+    }
+    // input ring: unit q lives in slot q & 3; lane k copies 4 of its 16 bytes
+    auto fetch = [&](int64_t q) {
+        const bool ok = mode && q >= 0 && q < (int64_t)units;
+        const uint8_t* p = src + (ok ? (size_t)q * 16 + 4 * k : 0);
+        const uint32_t a = iring_a + (((uint32_t)q & 3u) << 4) + 4u * k;
+        if (ok) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(p) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint32_t flushed = 0;  // 64-byte blocks already written to the scratch area
+    auto flush = [&]() {   // every 4 steps (at most 32 new bytes): write out a completed 64-byte block of the ring
+        __syncwarp();
+        if (mode && 2u * L.emitted >= 64u * (flushed + 1u)) {
+            const uint32_t ro = (0u - 64u * (flushed + 1u)) & (4 * ENC_OUT_RING_WORDS - 1);
+            const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(oring) + ro + 16 * k);
+            *reinterpret_cast<uint4*>(e_words - 64 * (size_t)(flushed + 1) + 16 * k) = v;
+            flushed++;
+        }
+        __syncwarp();
+    };
+    fetch((int64_t)units - 1);
+    fetch((int64_t)units - 2);
+    fetch((int64_t)units - 3);
+    uint32_t it = 0;
+    for (; it < max_units; it++) {
+        const int64_t q = (int64_t)units - 1 - it;  // negative for groups that have finished
+        const bool active = q >= 0;
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        __syncwarp();
+        const uint32_t slot = iring_a + (((uint32_t)q & 3u) << 4) + (3u - k);
+        uint32_t s3, s2, s1, s0;
+        asm volatile("ld.shared.u8 %0, [%1+12];" : "=r"(s3) : "r"(slot));
+        asm volatile("ld.shared.u8 %0, [%1+8];" : "=r"(s2) : "r"(slot));
+        asm volatile("ld.shared.u8 %0, [%1+4];" : "=r"(s1) : "r"(slot));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(s0) : "r"(slot));
+        if (it < min_units) {
+            enc_step<true>(L, s3, tab, rcp, oring_a, lr, lo_mask, grp_mask, true);
+            enc_step<true>(L, s2, tab, rcp, oring_a, lr, lo_mask, grp_mask, true);
+            enc_step<true>(L, s1, tab, rcp, oring_a, lr, lo_mask, grp_mask, true);
+            enc_step<true>(L, s0, tab, rcp, oring_a, lr, lo_mask, grp_mask, true);
+        } else {
+            enc_step<false>(L, s3 & 0xFF, tab, rcp, oring_a, lr, lo_mask, grp_mask, active);
+            enc_step<false>(L, s2 & 0xFF, tab, rcp, oring_a, lr, lo_mask, grp_mask, active);
+            enc_step<false>(L, s1 & 0xFF, tab, rcp, oring_a, lr, lo_mask, grp_mask, active);
+            enc_step<false>(L, s0 & 0xFF, tab, rcp, oring_a, lr, lo_mask, grp_mask, active);
+        }
+        flush();
+        fetch(q - 3);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    // ---- epilogue: the bytes not yet flushed (< 64), chunk size, final states (:390-404)
+    const uint32_t total = 2u * L.emitted;  // bytes of 16-bit words
+    if (mode) {
+        const uint32_t done = 64u * flushed;
+        const uint8_t* rb = reinterpret_cast<const uint8_t*>(oring);
+        for (uint32_t o = done + k; o < total; o += 4) e_words[-(int64_t)o - 1] = rb[(0u - (o + 1u)) & (4 * ENC_OUT_RING_WORDS - 1)];
+    }
+    const uint32_t s0 = __shfl_sync(0xFFFFFFFFu, L.st, lane & ~3);
+    const uint32_t s1 = __shfl_sync(0xFFFFFFFFu, L.st, (lane & ~3) + 1);
+    const uint32_t s2 = __shfl_sync(0xFFFFFFFFu, L.st, (lane & ~3) + 2);
+    const uint32_t s3 = __shfl_sync(0xFFFFFFFFu, L.st, (lane & ~3) + 3);
+    if (mode && k == 0) {
+        const uint32_t sz = total + (len - end4);
+        BitWriter bw(my_hdr, hb);
+        bw.write_varint(sz);
+        bw.write(s0, 32);
+        bw.write(s1, 32);
+        bw.write(s2, 32);
+        bw.write(s3, 32);
+        seg_bits[si] = bw.pos;
+        seg_src[si + 1] = (uint64_t)(uintptr_t)(e_words - total);
+        seg_bits[si + 1] = 8ull * sz;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -612,8 +696,6 @@ __global__ void __launch_bounds__(32) ans0_walk_kernel(const uint32_t* __restric
 // Table word w of chunk g lives at (w * 8 + g): the 8 chunks of a warp own disjoint groups of 4 banks.
 // ------------------------------------------------------------------------------------------------------------
 static const int RING_WORDS = 64;  // 32-bit words per chunk ring (256 bytes)
-
-KZ_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 struct DecLane {
     uint32_t st;      // rANS state of this lane

@@ -31,16 +31,21 @@ static const int STATS_WARPS = 4;
 static const int HDR_STRIDE = 512;             // bytes reserved per chunk header (max 3453 header bits + 19 bytes)
 static const int PAY_STRIDE = 32768 + 64;      // per chunk rANS byte scratch: 2 bytes/symbol worst case + tail + alignment
 static const int PAY_WORDS_END = 32768 + 32;   // 16-byte aligned end of the 16-bit word region; tail bytes follow
-static const size_t ENC_SMEM = 256 * 32 * sizeof(uint2);
+// encode: per warp (8 chunks): 256x8 symbol entries + 8 output rings of 64 words + 8 input rings of 16 words; 8 warps per CTA + 4096 reciprocals
+static const int ENC_OUT_RING_WORDS = 64;
+static const int ENC_WARP_WORDS = 256 * 8 + 8 * ENC_OUT_RING_WORDS + 8 * 16;
+static const int ENC_CTA_CHUNKS = 64;
+static const size_t ENC_SMEM = (4096 + 8 * ENC_WARP_WORDS) * sizeof(uint32_t);
 // decode: per warp (8 chunks): 171x8 bitmap buckets (24 slots each) + 256x8 symbol entries + 8 rings of 64 words; 2 warps per CTA
 static const int DEC_BM_WORDS = 171;
 static const int DEC_WARP_WORDS = (DEC_BM_WORDS + 256) * 8 + 8 * 64;
 static const int DEC_CTA_CHUNKS = 16;
 static const size_t DEC_SMEM = 2 * DEC_WARP_WORDS * sizeof(uint32_t);
 
-__global__ void ans0_stats_kernel(const uint8_t* in, const ChunkIn* chunks, int nchunks, uint2* enc_tab, uint8_t* hdr, uint32_t* hdr_bits,
+__global__ void rcp_table_kernel(uint32_t* inv);
+__global__ void ans0_stats_kernel(const uint8_t* in, const ChunkIn* chunks, int nchunks, uint32_t* enc_tab, uint8_t* hdr, uint32_t* hdr_bits,
                                   uint32_t* asz_out);
-__global__ void ans0_encode_kernel(const uint8_t* in, const ChunkIn* chunks, int nchunks, const uint2* enc_tab, uint8_t* hdr,
+__global__ void ans0_encode_kernel(const uint8_t* in, const ChunkIn* chunks, int nchunks, const uint32_t* enc_tab, const uint32_t* rcp, uint8_t* hdr,
                                    const uint32_t* hdr_bits, const uint32_t* asz_in, uint8_t* pay, uint64_t* seg_src, uint64_t* seg_bits,
                                    const uint32_t* seg_index);
 __global__ void ans_walk_kernel(const uint32_t* words, const DecBlock* blocks, int nblocks, int order, uint64_t* chunk_hdr_bit, uint64_t* blk_end,
