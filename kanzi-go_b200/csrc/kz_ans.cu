@@ -17,38 +17,13 @@
 // Compressed bytes are read / written 16 bytes at a time per thread so that the L1 line throughput of the inherently
 // uncoalesced per-chunk streams stays below the dependent-chain latency.
 #include "kz_ans.cuh"
+#include "kz_warp.cuh"
 
 namespace kz {
 
 // ------------------------------------------------------------------------------------------------------------
 // statistics: one warp per chunk
 // ------------------------------------------------------------------------------------------------------------
-namespace {
-
-KZ_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-KZ_D void smem_put_bits(uint32_t* words, uint32_t bitpos, uint32_t value, uint32_t n) {  // n in 1..32, MSB-first words
-    if (n < 32) value &= (1u << n) - 1u;
-    uint32_t w = bitpos >> 5, o = bitpos & 31;
-    if (o + n <= 32) {
-        atomicOr(&words[w], value << (32 - o - n));
-    } else {
-        uint32_t r = o + n - 32;  // bits spilling into the next word
-        atomicOr(&words[w], value >> r);
-        atomicOr(&words[w + 1], value << (32 - r));
-    }
-}
-
-KZ_D uint32_t warp_incl_scan(uint32_t v, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d);
-        if (lane >= d) v += t;
-    }
-    return v;
-}
-
-}  // namespace
 
 // lr: log range (12 for ANS0). Shared by the order-1 path which calls it per context with lr = 11.
 // freq8[j] holds the raw count of symbol (lane + 32 j); on return the normalised frequency. Returns alphabet size.
@@ -194,35 +169,9 @@ __global__ void __launch_bounds__(STATS_WARPS * 32) ans0_stats_kernel(const uint
     const ChunkIn ck = chunks[c];
     const uint8_t* src = in + ck.src_off;
     const uint32_t len = ck.len;
-    uint32_t* hist = &s_hist[warp][0][0];
-    for (int i = lane; i < 8 * 256; i += 32) hist[i] = 0;
     for (int i = lane; i < HDR_STRIDE / 4; i += 32) s_hdr[warp][i] = 0;
-    __syncwarp();
-    // histogram (internal/Global.go:220-251); chunk starts are 16-byte aligned
-    uint32_t* my = &s_hist[warp][lane & 7][0];
-    const uint32_t n16 = len >> 4;
-    const uint4* src4 = reinterpret_cast<const uint4*>(src);
-    for (uint32_t i = lane; i < n16; i += 32) {
-        uint4 v = __ldg(&src4[i]);
-        uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            atomicAdd(&my[w[k] & 0xFF], 1u);
-            atomicAdd(&my[(w[k] >> 8) & 0xFF], 1u);
-            atomicAdd(&my[(w[k] >> 16) & 0xFF], 1u);
-            atomicAdd(&my[w[k] >> 24], 1u);
-        }
-    }
-    for (uint32_t i = (n16 << 4) + lane; i < len; i += 32) atomicAdd(&my[src[i]], 1u);
-    __syncwarp();
     uint32_t f[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        uint32_t s = 0;
-#pragma unroll
-        for (int r = 0; r < 8; r++) s += s_hist[warp][r][lane + 32 * j];
-        f[j] = s;
-    }
+    warp_histogram(src, len, &s_hist[warp][0][0], lane, f);  // chunk starts are 16-byte aligned
     const uint32_t lr = 12;
     const int asz = warp_normalize(f, len, lr, lane);
     // cumulative frequencies in symbol order + table entries (updateFrequencies :187-203)

@@ -1,4 +1,4 @@
-"""GPU parity tests for the order-0 rANS path: the CUDA encoder must emit the oracle's bits exactly, the CUDA decoder
+"""GPU parity tests for the entropy codecs (order-0 rANS, Huffman): the CUDA encoder must emit the oracle's bits exactly, the CUDA decoder
 must invert the oracle's streams, through every level of the C ABI (single block codec, block batch, whole stream)."""
 import numpy as np
 import pytest
@@ -26,31 +26,48 @@ def shapes(synth, n, seed):
     yield "two", (synth.uniform_bytes(n, seed=seed + 4) & 1).astype(np.uint8) * 255
     yield "small_alpha", (synth.zipf_bytes(n, 1.2, seed=seed + 5, alphabet=40) + 50).astype(np.uint8)
     yield "ramp", (np.arange(n) % 256).astype(np.uint8)
+    # Fibonacci-like counts force Huffman codes longer than 12 bits (limitCodeLengths path)
+    fib = [1, 1]
+    while sum(fib) < 14000:
+        fib.append(fib[-1] + fib[-2])
+    pat = np.repeat(np.arange(len(fib), dtype=np.uint8) * 7 + 3, fib)
+    rng = np.random.default_rng(seed + 9)
+    rng.shuffle(pat)
+    yield "fib", np.resize(pat, n)
+    geo = np.minimum(rng.geometric(0.35, n), 40).astype(np.uint8)
+    yield "geometric", geo
 
 
 SIZES = [1, 31, 32, 33, 36, 37, 38, 39, 100, 4095, 4096, 4097, 16383, 16384, 16385, 16386, 16387, 16388, 50000, 65536 + 19, 262144, 1 << 20]
 
 
+CODECS = ["ANS0", "HUFFMAN"]
+
+
+@pytest.mark.parametrize("codec", CODECS)
 @pytest.mark.parametrize("n", SIZES)
-def test_entropy_codec_parity(gpu, oracle, synth, kz, n):
+def test_entropy_codec_parity(gpu, oracle, synth, kz, n, codec):
+    et = oracle.parse_entropy(codec)
     for name, x in shapes(synth, n, seed=n):
-        want, want_bits = oracle.entropy_encode(oracle.E_ANS0, x)
-        got, got_bits = gpu.entropy_encode(kz.E_ANS0, x)
-        assert got_bits == want_bits, (name, n, got_bits, want_bits, first_diff(got, want))
-        assert np.array_equal(got, want), (name, n, first_diff(got, want))
-        y, used = gpu.entropy_decode(kz.E_ANS0, want, n)
-        assert np.array_equal(y, x), (name, n, first_diff(y, x))
-        assert used == want_bits, (name, n, used, want_bits)
+        want, want_bits = oracle.entropy_encode(et, x)
+        got, got_bits = gpu.entropy_encode(et, x)
+        assert got_bits == want_bits, (codec, name, n, got_bits, want_bits, first_diff(got, want))
+        assert np.array_equal(got, want), (codec, name, n, first_diff(got, want))
+        y, used = gpu.entropy_decode(et, want, n)
+        assert np.array_equal(y, x), (codec, name, n, first_diff(y, x))
+        assert used == want_bits, (codec, name, n, used, want_bits)
 
 
-def test_reference_test_inputs(gpu, oracle, synth, kz):
+@pytest.mark.parametrize("codec", CODECS)
+def test_reference_test_inputs(gpu, oracle, synth, kz, codec):
+    et = oracle.parse_entropy(codec)
     for x in synth.reference_test_inputs():
         if len(x) == 0:
             continue
-        want, want_bits = oracle.entropy_encode(oracle.E_ANS0, x)
-        got, got_bits = gpu.entropy_encode(kz.E_ANS0, x)
+        want, want_bits = oracle.entropy_encode(et, x)
+        got, got_bits = gpu.entropy_encode(et, x)
         assert got_bits == want_bits and np.array_equal(got, want), first_diff(got, want)
-        y, _ = gpu.entropy_decode(kz.E_ANS0, want, len(x))
+        y, _ = gpu.entropy_decode(et, want, len(x))
         assert np.array_equal(y, x)
 
 
@@ -69,7 +86,7 @@ def test_mirror_interfaces(gpu, oracle, synth, kz):
     assert ed.consumed == want_bits
 
 
-@pytest.mark.parametrize("entropy", ["ANS0", "NONE"])
+@pytest.mark.parametrize("entropy", ["ANS0", "NONE", "HUFFMAN"])
 def test_block_batch_parity(gpu, oracle, synth, kz, entropy):
     """kz_encode_blocks / kz_decode_blocks against encodingTask.encode / decodingTask.decode restated in the oracle."""
     lens = [1, 15, 16, 33, 255, 256, 1000, 65535, 65536, 65537, 100000, 16384 * 3, 5, 70000]
@@ -87,7 +104,7 @@ def test_block_batch_parity(gpu, oracle, synth, kz, entropy):
 
 
 @pytest.mark.parametrize("n,bs", [(0, 1024), (5, 1024), (1024, 1024), (4096 + 7, 1024), (1 << 20, 65536), (3 * (1 << 20) + 12345, 1 << 20), (40 << 20, 4 << 20)])
-@pytest.mark.parametrize("entropy", ["ANS0", "NONE"])
+@pytest.mark.parametrize("entropy", ["ANS0", "NONE", "HUFFMAN"])
 def test_stream_parity(gpu, oracle, synth, kz, n, bs, entropy):
     """Whole CompressedOutputStream / CompressedInputStream byte parity (header, block prefixes, end marker)."""
     x = synth.zipf_bytes(n, 1.0, seed=n + 17) if n else np.zeros(0, np.uint8)
@@ -116,9 +133,19 @@ def test_config2_full_size(gpu, oracle, synth, kz):
     assert len(got) == len(want) and np.array_equal(got, want), first_diff(got, want)
 
 
-def test_corrupt_streams_do_not_crash(gpu, oracle, synth, kz):
+def test_config1_huffman_4mb(gpu, oracle, synth, kz):
+    """BASELINE config 1: -e HUFFMAN -t NONE, 4 MiB Zipf(1.0) bytes, 1 block."""
+    x = synth.zipf_bytes(4 << 20, 1.0, seed=synth.SEED)
+    want = oracle.compress(x, "NONE", "HUFFMAN", block_size=4 << 20, input_size=len(x))
+    got = gpu.compress(x, "NONE", "HUFFMAN", block_size=4 << 20, input_size=len(x))
+    assert np.array_equal(got, want), first_diff(got, want)
+    assert np.array_equal(gpu.decompress(want, len(x) + 64), x)
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_corrupt_streams_do_not_crash(gpu, oracle, synth, kz, codec):
     x = synth.zipf_bytes(200000, 1.0, seed=5)
-    s = oracle.compress(x, "NONE", "ANS0", block_size=65536, jobs=2)
+    s = oracle.compress(x, "NONE", codec, block_size=65536, jobs=2)
     rng = np.random.default_rng(7)
     for trial in range(12):
         t = s.copy()
