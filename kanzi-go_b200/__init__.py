@@ -175,6 +175,25 @@ class Context:
         self._check(self.lib.kz_entropy_decode(self.h, etype, _p(s), s.size, out.ctypes.data, n, C.byref(used)))
         return out[:n], used.value
 
+    def transform_forward(self, ttype, block, data_type=0):
+        """ByteTransform.Forward for one transform id -> (bytes or None when the transform declines, data_type after)."""
+        a = _u8(block)
+        cap = max(int(self.lib.kz_transform_max_encoded_len(ttype, a.size)), a.size) + 64
+        out = np.empty(cap, np.uint8)
+        n = C.c_size_t(0)
+        dt = C.c_int(data_type)
+        rc = self._check(self.lib.kz_transform_forward(self.h, ttype, C.byref(dt), _p(a), a.size, out.ctypes.data, cap, C.byref(n)))
+        if rc == 1:
+            return None, dt.value
+        return out[: n.value].copy(), dt.value
+
+    def transform_inverse(self, ttype, block, cap):
+        a = _u8(block)
+        out = np.empty(max(cap, 1), np.uint8)
+        n = C.c_size_t(0)
+        self._check(self.lib.kz_transform_inverse(self.h, ttype, _p(a), a.size, out.ctypes.data, cap, C.byref(n)))
+        return out[: n.value].copy()
+
     def encode_blocks(self, transform48, etype, blocks, checksum_bits=0):
         """blocks: list of byte arrays -> list of (bytes, nbits). One kz_encode_blocks call (Writer.processBlock batch)."""
         nb = len(blocks)
@@ -351,6 +370,26 @@ class EntropyDecoder:
 
     def dispose(self):
         pass
+
+
+class ByteTransform:
+    """kanzi.ByteTransform (v2/Definitions.go:78-91) for the GPU transforms: transform.New(ctx, type) of a single id."""
+
+    def __init__(self, name, ctx=None):
+        self.type = TRANSFORM_IDS[name.upper()]
+        self.ctx = ctx or default_context()
+        self.data_type = 0
+
+    def forward(self, src):
+        """-> transformed bytes, or None when the transform declines (the reference returns an error = "skip me")."""
+        out, self.data_type = self.ctx.transform_forward(self.type, src, self.data_type)
+        return out
+
+    def inverse(self, src, max_len):
+        return self.ctx.transform_inverse(self.type, src, max_len)
+
+    def max_encoded_len(self, n):
+        return int(self.ctx.lib.kz_transform_max_encoded_len(self.type, n))
 
 
 class Writer:

@@ -1,0 +1,14 @@
+// BWT entry points (kz_bwt.cu). All pointers are device pointers unless noted.
+#pragma once
+#include "kz_common.cuh"
+
+namespace kz {
+size_t bwt_forward_workspace(uint32_t n);
+size_t bwt_inverse_workspace(uint32_t n);
+// BWTBlockCodec.Forward of one block: d_dst receives header + BWT bytes (n + 1 + chunks * index size), *d_out_len its length
+cudaError_t bwt_forward_device(const uint8_t* d_src, uint32_t n, uint8_t* d_dst, uint32_t* d_out_len, uint8_t* ws, size_t ws_bytes, cudaStream_t stream,
+                               uint64_t* launches);
+// BWTBlockCodec.Inverse of one block; h_header = the first min(len, 33) bytes of d_src copied to the host
+cudaError_t bwt_inverse_device(const uint8_t* d_src, const uint8_t* h_header, uint32_t len, uint8_t* d_dst, uint32_t cap, uint32_t* out_len, uint8_t* ws,
+                               size_t ws_bytes, cudaStream_t stream, uint64_t* launches);
+}  // namespace kz
