@@ -87,10 +87,23 @@ public:
         if ((used & 7) == 0) {
             flush_whole_bytes();
             buf.insert(buf.end(), bits, bits + nbytes);
+        } else if (nbytes >= 8) {
+            // unaligned bulk path (DefaultOutputBitStream.go:144-185): shift whole 64-bit words through the accumulator
+            const unsigned u = used;  // 1..63 pending bits, unchanged by whole words
+            const uint64_t nwords = nbytes >> 3;
+            size_t n = buf.size();
+            buf.resize(n + size_t(nwords) * 8);
+            uint8_t* out = buf.data() + n;
+            uint64_t a = acc;
+            for (uint64_t i = 0; i < nwords; i++) {
+                const uint64_t v = load_be64(bits + 8 * i);
+                store_be64(out + 8 * i, a | (v >> u));
+                a = v << (64 - u);
+            }
+            acc = a;
+            for (uint64_t i = nwords * 8; i < nbytes; i++) write_bits(bits[i], 8);
         } else {
-            uint64_t i = 0;
-            for (; i + 8 <= nbytes; i += 8) write_bits(load_be64(bits + i), 64);
-            for (; i < nbytes; i++) write_bits(bits[i], 8);
+            for (uint64_t i = 0; i < nbytes; i++) write_bits(bits[i], 8);
         }
         if (tail) write_bits(uint64_t(bits[nbytes]) >> (8 - tail), tail);
     }
@@ -164,8 +177,17 @@ public:
             std::memcpy(bits, data + (pos >> 3), size_t(nbytes));
             pos += nbytes << 3;
         } else {
+            const unsigned off = unsigned(pos & 7);
+            const uint8_t* p = data + (pos >> 3);
+            const uint64_t total_bytes = (nbits + 7) >> 3;
             uint64_t i = 0;
-            for (; i + 8 <= nbytes; i += 8) store_be64(bits + i, read_bits(64));
+            // bulk: needs 9 readable bytes per word
+            const uint64_t avail = total_bytes - (pos >> 3);
+            for (; i + 8 <= nbytes && i + 9 <= avail; i += 8) {
+                const uint64_t hi = load_be64(p + i);
+                store_be64(bits + i, (hi << off) | (uint64_t(p[i + 8]) >> (8 - off)));
+            }
+            pos += i << 3;
             for (; i < nbytes; i++) bits[i] = uint8_t(read_bits(8));
         }
         if (tail) bits[nbytes] = uint8_t(read_bits(tail) << (8 - tail));
