@@ -101,6 +101,16 @@ def cpu_reference(steps, warmup, sample_blocks=None):
             "ms_per_step": t * 1e3}
 
 
+def emit(line):
+    """Writes the one JSON line to the real stdout (fd 1 is pointed at stderr during the run so that library chatter such
+    as "NCCL version ..." cannot end up in front of it)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -125,7 +135,7 @@ def main():
                 "config": {"workload": "ANS0/NONE 64x4MiB Zipf(1.0) (BASELINE.json configs[1]), CPU path", "block_size": BLOCK, "blocks": NBLOCKS},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -266,7 +276,7 @@ def main():
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:  # the checker is absent: report, never substitute
             line["cpu_baseline"] = {"value": None, "unit": "MB/s", "cores": 0, "kind": "port", "sample": "unavailable: %s" % e}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
