@@ -1,0 +1,35 @@
+// LZ / LZX kernels (kz_lz.cu)
+#pragma once
+#include "kz_common.cuh"
+
+namespace kz {
+
+struct LzBlock {
+    uint64_t src_off;      // input offset (forward: block data, inverse: LZ stream), 16-byte aligned
+    uint64_t dst_off;      // output offset, 16-byte aligned
+    uint64_t scratch_off;  // forward only
+    uint32_t len;          // input length
+    uint32_t cap;          // inverse only: size of the destination (len(dst) of the reference call)
+    int32_t data_type;     // ctx["dataType"] (internal/Global.go DataType)
+    uint32_t pad;
+};
+struct LzRun {
+    uint32_t src, dst, len;
+};
+struct LzResult {
+    int32_t status;  // 0 = transformed, 1 = skip (the reference returns an error: block too small / no compression / small alphabet)
+    uint32_t out_len, n_runs, lit_end, tk_n, m_n, mlen_n;
+};
+
+static inline size_t lz_scratch_bytes(size_t count) {
+    size_t s = (count / 4 + 64) + (3 * (count / 4) + 64) + (count + 64);
+    s = (s + 15) & ~size_t(15);
+    return s + (count / 4 + 8) * sizeof(LzRun) + 256;
+}
+
+__global__ void lz_parse_kernel(const uint8_t* in, const LzBlock* blocks, int nblocks, int extra, int32_t* hashes_all, uint8_t* scratch_all, uint8_t* out,
+                                LzResult* res);
+__global__ void lz_gather_kernel(const uint8_t* in, const LzBlock* blocks, int nblocks, const uint8_t* scratch_all, const LzResult* res, uint8_t* out);
+__global__ void lz_inverse_kernel(const uint8_t* in, const LzBlock* blocks, int nblocks, uint8_t* out, uint32_t* out_len, int32_t* status);
+
+}  // namespace kz
