@@ -80,7 +80,7 @@ def _ptr(a):
 def entropy_encode(etype, data):
     """-> (bytes, nbits)"""
     a = _arr(data)
-    cap = a.size + a.size // 4 + 70000
+    cap = a.size + a.size // 4 + 70000 + 110000 * (a.size // (4 << 20) + 1)
     out = np.empty(cap, np.uint8)
     bits = C.c_uint64(0)
     rc = lib().kzo_entropy_encode(etype, _ptr(a), a.size, out.ctypes.data, cap, C.byref(bits))
@@ -145,7 +145,7 @@ def bwt_inverse_raw(data, prim):
 
 def encode_block(data, transform48, entropy, checksum_bits=0, skip_blocks=False):
     a = _arr(data)
-    cap = a.size + a.size // 4 + 70000
+    cap = a.size + a.size // 4 + 70000 + 110000 * (a.size // (4 << 20) + 1)
     out = np.empty(cap, np.uint8)
     bits = C.c_uint64(0)
     rc = lib().kzo_encode_block(_ptr(a), a.size, transform48, entropy, checksum_bits, int(skip_blocks), out.ctypes.data, cap, C.byref(bits))
@@ -169,7 +169,7 @@ def compress(data, transform="NONE", entropy="NONE", block_size=4 << 20, checksu
     a = _arr(data)
     t48 = parse_transform(transform) if isinstance(transform, str) else transform
     et = parse_entropy(entropy) if isinstance(entropy, str) else entropy
-    cap = a.size + a.size // 4 + 70000 + 64 * (a.size // max(block_size, 1) + 1)
+    cap = a.size + a.size // 4 + 70000 + (64 + 110000) * (a.size // max(block_size, 1) + 1)
     out = np.empty(cap, np.uint8)
     n = C.c_size_t(0)
     secs = C.c_double(0)
