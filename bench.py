@@ -203,7 +203,8 @@ def main():
     dev_ms = e0.elapsed_time(e1)
     launches = ctx.launch_count(reset=True)
     kern = {}
-    for name in ("ans0_decode", "ans0_encode", "ans0_stats", "ans_walk", "concat", "concat_zero", "scan", "stream_walk", "block_header", "block_prefix", "extract"):
+    for name in ("ans0_decode", "ans0_encode", "ans0_stats", "ans_walk", "concat", "concat_zero", "scan", "stream_walk", "block_header", "block_prefix", "extract",
+                 "host:encode_batch", "host:enc_tables", "host:enc_sync"):
         cnt, ms = ctx.kernel_time(name)
         if cnt:
             kern[name] = {"launches": cnt, "ms_avg": ms / cnt}

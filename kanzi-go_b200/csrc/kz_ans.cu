@@ -414,103 +414,158 @@ __global__ void ans_walk_kernel(const uint32_t* __restrict__ words, const DecBlo
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// header walk v2 (order 0): one WARP per block. The chunk headers of a block form a serial chain (chunk k+1 starts
-// where chunk k's payload ends, at an arbitrary bit), so the walk is latency bound: 256 links per 4 MiB block. Per
-// link the warp stages a 512-byte window of the stream in shared memory with one coalesced load, counts the alphabet
-// with one popc per lane, and only the <= 32 frequency-group length nibbles are chased serially from shared memory.
+// header walk v3 (order 0): one WARP per block. The chunk headers of a block form a serial chain (chunk k+1 starts
+// where chunk k's payload ends, at an arbitrary bit), so the walk is latency bound: 256 links per 4 MiB block.
+//   v2 staged a 512-byte window per link with a register load + byte swap (29 % of the samples waited on that load)
+//   and chased the <= 32 frequency-group length fields with ~20 instructions and two data-dependent branches each.
+//   v3 * keeps two 2 KiB windows of RAW stream bytes in shared memory, filled by cp.async (no register staging): while
+//        link k is parsed, the window around the PREDICTED start of link k+1 (start of k + length of k-1) is already
+//        in flight; only a misprediction (> ~700 bytes off) pays a synchronous load;
+//      * chases the group lengths branch free (error flags accumulate, trip count known up front, unrolled);
+//      * counts the alphabet with one popc per lane + redux.
+// A header is at most 3+6+256 + 32*(4+8*15) = 4233 bits (lr <= 15 on corrupt input) + 5 varint bytes: a link that
+// starts no later than WALK_WIN - WALK_NEED bytes into a window never reads outside it.
 // ------------------------------------------------------------------------------------------------------------
-static const int WALK_WORDS = 128;
+static const int WALK_WIN = 2048;   // bytes per window
+static const int WALK_NEED = 560;   // bytes a header can span (incl. read slack)
+static const int WALK_BACK = 736;   // bytes kept before the predicted position
+
+KZ_D void walk_fetch(uint32_t smem_base, const uint8_t* bytes, uint64_t nbytes, uint64_t base, int lane) {
+    const uint32_t o = (uint32_t)lane * 16u;
+    const uint8_t* src = bytes + base + o;
+    if (base + WALK_WIN <= nbytes) {  // uniform: whole window readable
+#pragma unroll
+        for (int j = 0; j < WALK_WIN / 512; j++)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_base + o + 512u * j), "l"(src + 512 * j) : "memory");
+    } else {  // end of the stream: 16-byte units that are not entirely readable are zero filled
+#pragma unroll
+        for (int j = 0; j < WALK_WIN / 512; j++) {
+            const bool ok = base + o + 512u * j + 16u <= nbytes;
+            const uint32_t sz = ok ? 16u : 0u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_base + o + 512u * j), "l"(ok ? src + 512 * j : bytes), "r"(sz)
+                         : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
 __global__ void __launch_bounds__(32) ans0_walk_kernel(const uint32_t* __restrict__ words, uint64_t words_len, const DecBlock* __restrict__ blocks,
                                                         int nblocks, uint64_t* __restrict__ chunk_hdr_bit, uint64_t* __restrict__ blk_end,
                                                         int32_t* __restrict__ status) {
-    __shared__ uint32_t s_stage[WALK_WORDS + 4];
+    __shared__ __align__(16) uint32_t s_win[2][WALK_WIN / 4 + 4];
     const int b = blockIdx.x, lane = threadIdx.x;
     if (b >= nblocks) return;
     const DecBlock blk = blocks[b];
     if (blk.nchunks == 0) return;
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(words);
+    const uint64_t nbytes = words_len * 4;
+    if (lane < 8) s_win[lane >> 2][WALK_WIN / 4 + (lane & 3)] = 0;
     uint64_t pos = blk.data_bit;
     uint32_t remaining = blk.pre_len;
     int32_t st = 0;
     uint64_t prev_bits = 0;
+    // window `c` is the candidate for the current link, window `o` receives the prefetch for the next one
+    uint32_t* win = s_win[0];
+    uint32_t* win_o = s_win[1];
+    uint64_t base_c = (pos >> 3) & ~15ull, base_o = ~0ull >> 1;  // byte offset of each window (multiple of 16)
+    walk_fetch(smem_u32(win), bytes, nbytes, base_c, lane);
     for (uint32_t k = 0; k < blk.nchunks; k++) {
         if (lane == 0) chunk_hdr_bit[blk.chunk_base + k] = pos;
         if (st) continue;
         const uint32_t clen = remaining < (uint32_t)ANS0_CHUNK ? remaining : (uint32_t)ANS0_CHUNK;
         remaining -= clen;
-        const uint64_t w0 = pos >> 5;
-        // warm L2 around the predicted start of the next chunk while this header is parsed
-        if (prev_bits && lane < 8) {
-            const uint64_t pw = ((pos + prev_bits) >> 5) + (uint64_t)lane * 32 - 64;
-            if (pw < words_len) asm volatile("prefetch.global.L2 [%0];" ::"l"(words + pw));
-        }
-        for (int i = lane; i < WALK_WORDS + 2; i += 32) s_stage[i] = (w0 + i < words_len) ? bswap32(__ldg(words + w0 + i)) : 0u;
+        // ---- make sure a window covers this link
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
-        uint32_t q = (uint32_t)(pos & 31);
+        const uint64_t pbyte = pos >> 3;
+        if (!(pbyte >= base_c && pbyte - base_c <= (uint64_t)(WALK_WIN - WALK_NEED))) {
+            base_c = pbyte & ~15ull;
+            walk_fetch(smem_u32(win), bytes, nbytes, base_c, lane);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+        }
+        // ---- start fetching the window of the next link at its predicted position
+        if (prev_bits && k + 1 < blk.nchunks) {
+            const uint64_t pred = (pos + prev_bits) >> 3;
+            base_o = (pred > (uint64_t)WALK_BACK ? pred - WALK_BACK : 0) & ~15ull;
+            walk_fetch(smem_u32(win_o), bytes, nbytes, base_o, lane);
+        }
+        uint32_t q = (uint32_t)(pos - (base_c << 3));
         auto sbits = [&](uint32_t at, uint32_t n) -> uint32_t {  // n in 1..32, window relative bit position
             const uint32_t w = at >> 5, o = at & 31;
-            return __funnelshift_l(s_stage[w + 1], s_stage[w], o) >> (32 - n);
+            return __funnelshift_l(bswap32(win[w + 1]), bswap32(win[w]), o) >> (32 - n);
         };
-        const uint32_t lr = 8 + sbits(q, 3);
+        const uint32_t h = sbits(q, 10);
+        const uint32_t lr = 8 + (h >> 7);
+        const uint32_t llr = 32u - (uint32_t)__clz((int)lr);  // smallest llr >= 3 with (1 << llr) > lr, lr in 8..15
         q += 3;
-        uint32_t llr = 3;
-        while ((1u << llr) <= lr) llr++;
         int asz;
-        if (sbits(q, 1) == 0) {
-            asz = sbits(q + 1, 1) ? 0 : 256;
+        if (((h >> 6) & 1) == 0) {
+            asz = ((h >> 5) & 1) ? 0 : 256;
             q += 2;
         } else {
-            const uint32_t last = sbits(q + 1, 5);
+            const uint32_t last = (h >> 1) & 31;
             q += 6;
-            uint32_t cnt = (uint32_t)lane <= last ? (uint32_t)__popc(sbits(q + 8 * lane, 8)) : 0u;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
-            asz = (int)cnt;
+            const uint32_t cnt = (uint32_t)lane <= last ? (uint32_t)__popc(sbits(q + 8 * lane, 8)) : 0u;
+            asz = (int)__reduce_add_sync(0xFFFFFFFFu, cnt);
             q += 8 * (last + 1);
         }
         if (asz == 0) st = -KZ_E_PROCESS_BLOCK;
         if (st == 0 && lr > 12) st = -KZ_E_INVALID_CODEC;  // decode tables are sized for the encoder's fixed range (<= 12)
         if (st == 0 && asz > 1) {
-            const int gs = asz < 64 ? 6 : 8;
-            for (int i = 1; i < asz; i += gs) {
+            const uint32_t gs = asz < 64 ? 6 : 8;
+            const uint32_t ngroups = ((uint32_t)asz - 2u + gs) / gs;  // >= 1
+            const uint32_t last_n = (uint32_t)asz - 1u - (ngroups - 1u) * gs;
+            uint32_t max_log = 0;
+#pragma unroll 4
+            for (uint32_t i = 0; i + 1 < ngroups; i++) {
                 const uint32_t log_max = sbits(q, llr);
-                if (log_max > lr) st = -KZ_E_PROCESS_BLOCK;
-                const int n = asz - i < gs ? asz - i : gs;
-                q += llr + (uint32_t)n * log_max;
-                if (q > 32u * (WALK_WORDS - 3)) {  // cannot happen for lr <= 12 (max 3453 header bits); guards corrupt input
-                    st = -KZ_E_PROCESS_BLOCK;
-                    break;
+                max_log = max(max_log, log_max);
+                q += llr + gs * log_max;
+            }
+            {
+                const uint32_t log_max = sbits(q, llr);
+                max_log = max(max_log, log_max);
+                q += llr + last_n * log_max;
+            }
+            if (max_log > lr) st = -KZ_E_PROCESS_BLOCK;
+            // varint (EntropyUtils.go:278-296): at most 5 bytes
+            const uint32_t v4 = sbits(q, 32), v1 = sbits(q + 32, 8);
+            uint32_t sz = (v4 >> 24) & 0x7F, nb = 1;
+            if (v4 & 0x80000000u) {
+                sz |= ((v4 >> 16) & 0x7F) << 7, nb = 2;
+                if (v4 & 0x00800000u) {
+                    sz |= ((v4 >> 8) & 0x7F) << 14, nb = 3;
+                    if (v4 & 0x00008000u) {
+                        sz |= (v4 & 0x7F) << 21, nb = 4;
+                        if (v4 & 0x00000080u) sz |= (v1 & 0x0F) << 28, nb = 5;
+                    }
                 }
             }
+            q += 8 * nb;
             if (st == 0) {
-                // varint (EntropyUtils.go:278-296)
-                uint32_t sz = 0, shift = 0;
-                bool more = true;
-                for (int i = 0; i < 4 && more; i++) {
-                    const uint32_t v = sbits(q, 8);
-                    q += 8;
-                    sz |= (v & 0x7F) << shift;
-                    more = v >= 128;
-                    shift += 7;
-                }
-                if (more) {
-                    const uint32_t v = sbits(q, 8);
-                    q += 8;
-                    sz |= (v & 0x0F) << 28;
-                }
                 if (sz >= (uint32_t)ANS_MAX_CHUNK) st = -KZ_E_PROCESS_BLOCK;
-                const uint64_t next = (w0 << 5) + q + 128 + 8ull * sz;
+                const uint64_t next = (base_c << 3) + q + 128 + 8ull * sz;
                 prev_bits = next - pos;
                 pos = next;
             }
         } else if (st == 0) {
-            const uint64_t next = (w0 << 5) + q;
+            const uint64_t next = (base_c << 3) + q;
             prev_bits = next - pos;
             pos = next;
         }
         if (st == 0 && pos > blk.end_bit) st = -KZ_E_PROCESS_BLOCK;
+        {  // the prefetched window (if any) is the candidate for the next link
+            uint32_t* t = win;
+            win = win_o;
+            win_o = t;
+            const uint64_t tb = base_c;
+            base_c = base_o;
+            base_o = tb;
+        }
         __syncwarp();
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (lane == 0) {
         blk_end[b] = pos;
         if (st) status[b] = st;
