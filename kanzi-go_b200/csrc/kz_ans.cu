@@ -846,4 +846,283 @@ __global__ void __launch_bounds__(64, 7) ans0_decode_kernel(const uint32_t* __re
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// decode (v4): same decomposition as v3 (4 lanes per chunk, 8 chunks per warp, 16 chunks per 64-thread CTA, one wave
+// for 64 x 4 MiB), shorter per-step dependent chain. ncu of v3 (profiles/r01_ncu_v4_summary.json): 58.6 instructions
+// per warp per step, almost all of them on one serial chain ("wait" 2.2 + "short_scoreboard" 1.8 cycles per issue,
+// issue slots 52 % used) -> the step time is (instructions on the chain) x (dependent-issue latency). v4
+//   * bucket word = start flags of 24 slots in bits 0..23 | (symbols started before the bucket - 1) << 24, bucket 0
+//     stores its flags without slot 0: symbol index = (b >> 24) + popc(b & ((2 << r) - 1)) needs no masking and the
+//     byte address of the symbol entry is one IMAD after the POPC;
+//   * bucket index with one IMAD.HI (slot / 24 = umulhi(slot, ceil(2^32 / 24)));
+//   * symbol entry = freq << 20 | cum << 8 | sym: the frequency is one shift away from the multiply;
+//   * every chunk's 256-byte ring is 256-byte aligned in the shared window: ring addresses are one LOP3
+//     ((pos & 0xFE) | base);
+//   * the refill bookkeeping is a per-lane countdown of valid 16-byte units and a running source pointer instead of
+//     64-bit range checks per round.
+// Warp region (bytes): 8 rings x 256 | 171 x 8 bucket words | 256 x 8 symbol words | pad to a multiple of 256.
+// ------------------------------------------------------------------------------------------------------------
+template <bool ALL_ACTIVE>
+KZ_D void dec4_step(DecLane& L, uint32_t bm_base, uint32_t sym_base, uint32_t ring_base, uint32_t mask, uint32_t lr, uint32_t rsh, uint32_t hi_mask,
+                    uint32_t grp_mask, bool active) {
+    const uint32_t st = L.st;
+    const uint32_t slot = st & mask;
+    const uint32_t w = __umulhi(slot, 178956971u);  // slot / 24, exact for slot < 2^16
+    uint32_t b, e;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(b) : "r"(bm_base + w * 32u));
+    const uint32_t r = slot - 24u * w;
+    const uint32_t p = (uint32_t)__popc(b & ((2u << r) - 1u));
+    const uint32_t ea = (b >> 24) * 32u + sym_base;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(ea + p * 32u));
+    const uint32_t nst = (e >> 20) * (st >> lr) + (slot - ((e >> 8) & 0xFFFu));  // D(x) (ANSRangeCodec.go:849)
+    bool need = nst < (uint32_t)ANS_TOP;
+    if (!ALL_ACTIVE) need = need && active;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, need);
+    const uint32_t t2 = L.cur2 + 2u * (uint32_t)__popc(bal & hi_mask);
+    uint32_t va, vb;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(va) : "r"((t2 & 0xFEu) | ring_base));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(vb) : "r"(((t2 + 2u) & 0xFEu) | ring_base));
+    const uint32_t x = __byte_perm(va, vb, 0x0145) >> rsh;  // big-endian 32 bits at t2, renormalisation word in the low 16 bits
+    const uint32_t nst2 = __byte_perm(x, nst, 0x5410);      // (nst << 16) | (x & 0xFFFF)
+    if (ALL_ACTIVE || active) {
+        L.st = need ? nst2 : nst;
+        L.cur2 += 2u * (uint32_t)__popc(bal & grp_mask);
+    }
+    L.acc = __byte_perm(L.acc, e, 0x4321);  // acc = (acc >> 8) | (sym << 24)
+}
+
+__global__ void __launch_bounds__(64, 7) ans0_decode4_kernel(const uint32_t* __restrict__ words, uint64_t words_len /*in 32-bit words*/,
+                                                             const DecChunk* __restrict__ chunks, int nchunks,
+                                                             const uint64_t* __restrict__ chunk_hdr_bit, uint8_t* __restrict__ out,
+                                                             int32_t* __restrict__ status) {
+    extern __shared__ __align__(256) uint32_t s_dec4[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, k = lane & 3;  // chunk slot inside the warp, state index
+    // the rings must be 256-byte aligned in the shared window (DEC4_SMEM carries 256 bytes of slack for this)
+    uint32_t* s_al = s_dec4 + (((0u - smem_u32(s_dec4)) & 255u) >> 2);
+    uint32_t* wbase = s_al + warp * DEC4_WARP_WORDS;
+    uint32_t* ring = wbase + g * RING_WORDS;
+    uint32_t* bm = wbase + 8 * RING_WORDS + g;                       // bucket w at bm[w*8]
+    uint32_t* symtab = wbase + 8 * RING_WORDS + DEC_BM_WORDS * 8 + g;  // entry i at symtab[i*8]
+    const int c = blockIdx.x * DEC_CTA_CHUNKS + warp * 8 + g;
+    const uint32_t grp_mask = 0xFu << (lane & ~3);
+    const uint32_t hi_mask = grp_mask & ~((2u << lane) - 1u);  // lanes of my group with a higher state index (they read first)
+
+    // ---- per-chunk set-up by the group leader (k == 0): header parse, tables, chunk prologue (decodeHeader :605-710)
+    uint32_t lr = 12, nsteps = 0, tail = 0;
+    uint64_t pb = 0, pe = 0;
+    uint8_t* dst = nullptr;
+    int mode = 0;  // 0 = nothing to do, 1 = rANS decode
+    if (k == 0 && c < nchunks) {
+        const DecChunk ck = chunks[c];
+        dst = out + ck.out_off;
+        if (status[ck.block] == 0) {
+            BitReader br(words, chunk_hdr_bit[c], ck.end_bit);
+            lr = 8 + br.read(3);
+            const uint32_t scale = 1u << lr;
+            uint32_t llr = 3;
+            while ((1u << llr) <= lr) llr++;
+            int asz = 0;
+            if (br.read(1) == 0) {
+                if (br.read(1) == 0) {
+                    asz = 256;
+                    for (int i = 0; i < 256; i++) symtab[i * 8] = (uint32_t)i;
+                }
+            } else {
+                uint32_t last = br.read(5);
+                for (uint32_t i = 0; i <= last; i++) {
+                    uint32_t m = br.read(8);
+                    while (m) {
+                        int j = __ffs((int)m) - 1;
+                        m &= m - 1;
+                        symtab[asz * 8] = 8 * i + (uint32_t)j;
+                        asz++;
+                    }
+                }
+            }
+            if (asz == 0 || lr > 12) {
+                atomicCAS(&status[ck.block], 0, asz == 0 ? -KZ_E_PROCESS_BLOCK : -KZ_E_INVALID_CODEC);
+            } else if (asz == 1) {  // Read :737-741
+                const uint8_t v = (uint8_t)symtab[0];
+                for (uint32_t i = 0; i < ck.out_len; i++) dst[i] = v;
+            } else {
+                const int gs = asz < 64 ? 6 : 8;
+                uint32_t sum = 0;
+                bool bad = false;
+                for (int i = 1; i < asz; i += gs) {
+                    uint32_t log_max = br.read(llr);
+                    if ((1u << log_max) > scale) bad = true;
+                    int endj = i + gs < asz ? i + gs : asz;
+                    for (int j = i; j < endj; j++) {
+                        uint32_t freq = 1;
+                        if (log_max > 0) {
+                            freq = 1 + br.read(log_max);
+                            if (freq >= scale) bad = true;
+                        }
+                        symtab[j * 8] |= freq << 20;
+                        sum += freq;
+                    }
+                }
+                if (scale <= sum) bad = true;
+                if (!bad) {
+                    symtab[0] |= (scale - sum) << 20;
+                    const uint32_t nb = (scale + 23) / 24;
+                    for (uint32_t w = 0; w < nb; w++) bm[w * 8] = 0;
+                    uint32_t cum = 0;
+                    for (int i = 0; i < asz; i++) {
+                        const uint32_t e = symtab[i * 8];
+                        const uint32_t f = e >> 20;  // every frequency is <= scale - 1 <= 4095 when asz >= 2 (decSymbol.reset :973-978)
+                        const uint32_t w = cum / 24;
+                        if (cum) bm[w * 8] |= 1u << (cum - 24 * w);  // slot 0 always starts symbol 0: its flag is implied
+                        symtab[i * 8] = e | (cum << 8);
+                        cum += f;
+                    }
+                    uint32_t running = 0;  // symbols started before the bucket, minus 1 (bucket 0: the implied start)
+                    for (uint32_t w = 0; w < nb; w++) {
+                        const uint32_t b = bm[w * 8];
+                        bm[w * 8] = b | (running << 24);
+                        running += __popc(b);
+                    }
+                    const uint32_t sz = br.read_varint();
+                    const uint32_t s0 = br.read(32), s1 = br.read(32), s2 = br.read(32), s3 = br.read(32);
+                    if (sz >= (uint32_t)ANS_MAX_CHUNK || br.overrun || br.pos + 8ull * sz > ck.end_bit) bad = true;
+                    if (!bad) {
+                        pb = br.pos;
+                        pe = pb + 8ull * sz;
+                        nsteps = ck.out_len >> 2;
+                        tail = ck.out_len & 3;
+                        mode = 1;
+                        ring[0] = s0;  // park the initial states where the other lanes can fetch them
+                        ring[1] = s1;
+                        ring[2] = s2;
+                        ring[3] = s3;
+                    }
+                }
+                if (bad || br.overrun) atomicCAS(&status[ck.block], 0, -KZ_E_PROCESS_BLOCK);
+            }
+        }
+    }
+    __syncwarp();
+    const int leader = lane & ~3;
+    mode = __shfl_sync(0xFFFFFFFFu, mode, leader);
+    lr = __shfl_sync(0xFFFFFFFFu, lr, leader);
+    nsteps = __shfl_sync(0xFFFFFFFFu, nsteps, leader);
+    pb = __shfl_sync(0xFFFFFFFFu, pb, leader);
+    pe = __shfl_sync(0xFFFFFFFFu, pe, leader);
+    dst = (uint8_t*)(uintptr_t)__shfl_sync(0xFFFFFFFFu, (uint64_t)(uintptr_t)dst, leader);
+    DecLane L;
+    L.st = mode ? ring[k] : 0u;
+    L.acc = 0;
+    if (!mode) nsteps = 0;
+    __syncwarp();
+    uint32_t max_steps = nsteps, min_steps = nsteps;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        max_steps = max(max_steps, __shfl_xor_sync(0xFFFFFFFFu, max_steps, d));
+        min_steps = min(min_steps, __shfl_xor_sync(0xFFFFFFFFu, min_steps, d));
+    }
+    if (max_steps == 0) return;
+
+    // ---- payload ring: raw copy of the stream starting at the 16-byte aligned block that holds the first payload bit.
+    // Ring byte r <-> source byte base_b + r. Round n copies source bytes [base_b + 64 n, +64): lane k its 16-byte unit.
+    // A unit is copied when it starts before the end of the payload and lies inside the stream buffer, otherwise it is
+    // zero filled (the guard past the payload, :888-893): the first `left` rounds of this lane copy, the others fill.
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(words);
+    const uint64_t base_b = (pb >> 3) & ~15ull;            // source byte of ring byte 0
+    const uint32_t rel = (uint32_t)(pb - 8 * base_b);      // payload bit offset inside the ring, 0..134
+    const uint32_t rsh = 16u - (rel & 15u);                // see dec4_step
+    const uint64_t end_b = (pe + 7) >> 3;                  // first source byte past the payload
+    const uint64_t lim_b = words_len * 4;
+    const uint64_t lim_u = lim_b >= 15 ? lim_b - 15 : 0;   // units must start below this to be entirely readable
+    const uint64_t stop_b = end_b < lim_u ? end_b : lim_u;
+    const uint64_t first_u = base_b + 16u * k;
+    int32_t left = (mode && stop_b > first_u) ? (int32_t)((stop_b - first_u + 63) >> 6) : 0;
+    const uint8_t* src = bytes + first_u;
+    const uint32_t ring_base = smem_u32(ring);
+    const uint32_t unit_base = ring_base | (16u * k);
+    uint32_t fill = 0;  // ring byte offset (unwrapped, multiple of 64) of the next refill round
+    L.cur2 = 2u * (rel >> 4);
+    auto issue = [&]() {
+        const bool ok = left > 0;
+        const uint8_t* s = ok ? src : bytes;
+        const uint32_t src_size = ok ? 16u : 0u;  // src-size 0 zero-fills
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(unit_base | (fill & 0xC0u)), "l"(s), "r"(src_size) : "memory");
+        src += 64;
+        fill += 64;
+        left--;
+    };
+    if (mode) {
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) issue();  // initial fill: the whole ring
+    } else {
+        fill = 0x40000000u;  // never refills
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const uint32_t mask = (1u << lr) - 1u;
+    const uint32_t bm_base = smem_u32(bm), sym_base = smem_u32(symtab);
+
+    // 4x4 byte transpose inside the group: after 4 steps lane k holds [a_k0 a_k1 a_k2 a_k3] (a_kj = symbol of state k in
+    // step j, output position 4j + 3 - k); lane j stores the word of step j: [a_3j a_2j a_1j a_0j].
+    auto transpose = [&](uint32_t acc) -> uint32_t {
+        const uint32_t o2 = __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+        const uint32_t t1 = (k & 2) ? __byte_perm(acc, o2, 0x3276) : __byte_perm(acc, o2, 0x5410);
+        const uint32_t o1 = __shfl_xor_sync(0xFFFFFFFFu, t1, 1);
+        return (k & 1) ? __byte_perm(t1, o1, 0x5173) : __byte_perm(t1, o1, 0x0426);
+    };
+    auto maintain = [&]() {  // every 4 steps, uniform for the warp
+        asm volatile("cp.async.wait_group 0;" ::: "memory");  // the round issued one iteration ago has landed
+        __syncwarp();
+        // refill when at most 160 bytes are buffered ahead of the cursor: the new 64-byte round then only overwrites
+        // consumed bytes (4 steps consume at most 32 bytes) and at least 128 buffered bytes remain while it is in flight
+        if ((int32_t)(fill - L.cur2) <= (4 * RING_WORDS - 64 - 32)) issue();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const uint32_t fast_iters = min_steps >> 2;  // iterations in which every group of the warp is active
+    uint32_t it = 0;
+    uint8_t* dptr = dst + 4 * k;
+    for (; it < fast_iters; it++) {
+        dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        *reinterpret_cast<uint32_t*>(dptr) = transpose(L.acc);
+        dptr += 16;
+        maintain();
+    }
+    const uint32_t all_iters = max_steps >> 2;
+    for (; it < all_iters; it++) {  // groups with fewer steps idle here
+        const bool active = (it * 4 + 3) < nsteps;
+        dec4_step<false>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, active);
+        dec4_step<false>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, active);
+        dec4_step<false>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, active);
+        dec4_step<false>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, active);
+        const uint32_t w = transpose(L.acc);
+        if (active) *reinterpret_cast<uint32_t*>(dptr) = w;
+        dptr += 16;
+        maintain();
+    }
+    {  // remaining 0..3 steps of a group (only the last chunk of a block can have nsteps % 4 != 0)
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        const uint32_t done = nsteps & ~3u;
+        uint32_t rem_max = nsteps - done;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) rem_max = max(rem_max, __shfl_xor_sync(0xFFFFFFFFu, rem_max, d));
+        for (uint32_t r = 0; r < rem_max; r++) {
+            const bool active = done + r < nsteps;
+            dec4_step<false>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, active);
+            if (active) dst[(size_t)(done + r) * 4 + (3 - k)] = (uint8_t)(L.acc >> 24);
+        }
+    }
+    // tail bytes follow the consumed words (:951-954)
+    if (mode && k == 0 && tail) {
+        uint64_t pos = 8 * (base_b + L.cur2) + (rel & 15u);  // bit position of the cursor in the stream
+        for (uint32_t j = 0; j < tail; j++, pos += 8) dst[(size_t)nsteps * 4 + j] = pos + 8 <= pe ? (uint8_t)bits_at(words, pos, 8) : 0;
+    }
+}
+
 }  // namespace kz

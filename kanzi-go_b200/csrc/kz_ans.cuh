@@ -41,6 +41,9 @@ static const int DEC_BM_WORDS = 171;
 static const int DEC_WARP_WORDS = (DEC_BM_WORDS + 256) * 8 + 8 * 64;
 static const int DEC_CTA_CHUNKS = 16;
 static const size_t DEC_SMEM = 2 * DEC_WARP_WORDS * sizeof(uint32_t);
+// decode v4: per warp 8 rings of 64 words (each 256-byte aligned) + 171x8 bucket words + 256x8 symbol words, padded to 256 bytes
+static const int DEC4_WARP_WORDS = ((8 * 64 + (DEC_BM_WORDS + 256) * 8) + 63) & ~63;
+static const size_t DEC4_SMEM = 2 * DEC4_WARP_WORDS * sizeof(uint32_t) + 256;
 
 __global__ void rcp_table_kernel(uint32_t* inv);
 __global__ void ans0_stats_kernel(const uint8_t* in, const ChunkIn* chunks, int nchunks, uint32_t* enc_tab, uint8_t* hdr, uint32_t* hdr_bits,
@@ -54,6 +57,8 @@ __global__ void ans0_walk_kernel(const uint32_t* words, uint64_t words_len, cons
                                  uint64_t* blk_end, int32_t* status);
 __global__ void ans0_decode_kernel(const uint32_t* words, uint64_t words_len, const DecChunk* chunks, int nchunks, const uint64_t* chunk_hdr_bit,
                                    uint8_t* out, int32_t* status);
+__global__ void ans0_decode4_kernel(const uint32_t* words, uint64_t words_len, const DecChunk* chunks, int nchunks, const uint64_t* chunk_hdr_bit,
+                                    uint8_t* out, int32_t* status);
 
 // ---- bit-granular concatenation (kz_concat.cu)
 // seg_dst[i] = absolute destination bit of segment i; copies seg_bits[i] bits from seg_src[i] (byte address, any alignment)

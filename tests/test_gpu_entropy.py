@@ -41,7 +41,7 @@ def shapes(synth, n, seed):
 SIZES = [1, 31, 32, 33, 36, 37, 38, 39, 100, 4095, 4096, 4097, 16383, 16384, 16385, 16386, 16387, 16388, 50000, 65536 + 19, 262144, 1 << 20]
 
 
-CODECS = ["ANS0", "HUFFMAN", "ANS1"]
+CODECS = ["ANS0", "HUFFMAN", "ANS1", "RANGE"]
 
 
 @pytest.mark.parametrize("codec", CODECS)
@@ -86,7 +86,7 @@ def test_mirror_interfaces(gpu, oracle, synth, kz):
     assert ed.consumed == want_bits
 
 
-@pytest.mark.parametrize("entropy", ["ANS0", "NONE", "HUFFMAN", "ANS1"])
+@pytest.mark.parametrize("entropy", ["ANS0", "NONE", "HUFFMAN", "ANS1", "RANGE"])
 def test_block_batch_parity(gpu, oracle, synth, kz, entropy):
     """kz_encode_blocks / kz_decode_blocks against encodingTask.encode / decodingTask.decode restated in the oracle."""
     lens = [1, 15, 16, 33, 255, 256, 1000, 65535, 65536, 65537, 100000, 16384 * 3, 5, 70000]
@@ -104,7 +104,7 @@ def test_block_batch_parity(gpu, oracle, synth, kz, entropy):
 
 
 @pytest.mark.parametrize("n,bs", [(0, 1024), (5, 1024), (1024, 1024), (4096 + 7, 1024), (1 << 20, 65536), (3 * (1 << 20) + 12345, 1 << 20), (40 << 20, 4 << 20)])
-@pytest.mark.parametrize("entropy", ["ANS0", "NONE", "HUFFMAN", "ANS1"])
+@pytest.mark.parametrize("entropy", ["ANS0", "NONE", "HUFFMAN", "ANS1", "RANGE"])
 def test_stream_parity(gpu, oracle, synth, kz, n, bs, entropy):
     """Whole CompressedOutputStream / CompressedInputStream byte parity (header, block prefixes, end marker)."""
     x = synth.zipf_bytes(n, 1.0, seed=n + 17) if n else np.zeros(0, np.uint8)
