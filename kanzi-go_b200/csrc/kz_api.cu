@@ -14,6 +14,7 @@
 #include "kz_huffman.cuh"
 #include "kz_lz.cuh"
 #include "kz_range.cuh"
+#include "kz_hash.cuh"
 
 #include <memory>
 
@@ -99,6 +100,52 @@ int upload(kz_ctx* ctx, Packer& pk) {
     CK(ctx->d_tables.ensure(pk.bytes.size() + 256));
     memcpy(ctx->h_stage.p, pk.bytes.data(), pk.bytes.size());
     CK(cudaMemcpyAsync(ctx->d_tables.p, ctx->h_stage.p, pk.bytes.size(), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+// XXHash32/64 of a set of blocks (hash/XXHash32.go, XXHash64.go; seed "KANZ", io/CompressedStream.go:354-356). Synchronous.
+int hash_blocks(kz_ctx* ctx, const uint8_t* d_base, const std::vector<uint64_t>& off, const std::vector<uint32_t>& len, uint32_t bits,
+                std::vector<uint64_t>& out) {
+    const size_t nb = off.size();
+    out.assign(nb, 0);
+    if (nb == 0) return 0;
+    std::vector<HashJob> hj(nb);
+    for (size_t b = 0; b < nb; b++) {
+        hj[b].off = off[b];
+        hj[b].len = len[b];
+        hj[b].pad = 0;
+    }
+    Packer pk;
+    const size_t o_j = pk.add(hj.data(), hj.size() * sizeof(HashJob));
+    const size_t o_h = pk.reserve(nb * 8);
+    int rc = upload(ctx, pk);
+    if (rc) return rc;
+    uint8_t* T = ctx->d_tables.as<uint8_t>();
+    {
+        LaunchScope ls(ctx, "xxhash");
+        xxhash_blocks_kernel<<<(int)nb, 32, 0, ctx->stream>>>(d_base, (const HashJob*)(T + o_j), (int)nb, (int)bits, (uint64_t*)(T + o_h));
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out.data(), T + o_h, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (bits == 32)
+        for (auto& h : out) h &= 0xFFFFFFFFull;
+    return 0;
+}
+
+// decodingTask.decode :1990-2006: hash of the decoded block against the transmitted checksum
+int verify_checksums(kz_ctx* ctx, const uint8_t* d_base, const std::vector<uint64_t>& off, const std::vector<uint32_t>& len, uint32_t bits,
+                     std::vector<DecJob>& jobs) {
+    std::vector<uint64_t> hv;
+    int rc = hash_blocks(ctx, d_base, off, len, bits, hv);
+    if (rc) return rc;
+    for (size_t b = 0; b < jobs.size(); b++) {
+        const uint64_t want = bits == 32 ? (jobs[b].checksum & 0xFFFFFFFFull) : jobs[b].checksum;
+        if (hv[b] != want) {
+            jobs[b].status = -KZ_ERR_CRC_CHECK;
+            return ctx->fail(KZ_ERR_CRC_CHECK, "Corrupted bitstream: block checksum mismatch");
+        }
+    }
     return 0;
 }
 
@@ -1040,7 +1087,7 @@ int kz_compress_stream_device(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_
     if (!ctx || !out_n) return -KZ_ERR_INVALID_PARAM;
     CK(cudaSetDevice(ctx->device));
     if (block_size < 1024 || block_size > (1u << 30) || (block_size & 15)) return ctx->fail(KZ_ERR_INVALID_PARAM, "Invalid block size");
-    if (checksum_bits != 0) return ctx->fail(KZ_ERR_INVALID_PARAM, "block checksums are not available on the GPU path yet");
+    if (checksum_bits != 0 && checksum_bits != 32 && checksum_bits != 64) return ctx->fail(KZ_ERR_INVALID_PARAM, "checksum must be 0, 32 or 64 bits");
     if (((uintptr_t)d_src & 15) || ((uintptr_t)d_dst & 15)) return ctx->fail(KZ_ERR_INVALID_PARAM, "device buffers must be 16-byte aligned");
     const uint32_t nblocks = (uint32_t)((n + block_size - 1) / block_size);
     std::vector<EncJob> jobs;
@@ -1050,6 +1097,17 @@ int kz_compress_stream_device(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_
     const uint8_t* d_data = nullptr;
     rc = forward_stage(ctx, plan, (const uint8_t*)d_src, n, block_size, block_size, nullptr, nblocks, &d_data, jobs);
     if (rc) return rc;
+    if (checksum_bits && nblocks) {  // encodingTask.encode :753-763: hash of the original block
+        std::vector<uint64_t> hoff(nblocks), hv;
+        std::vector<uint32_t> hlen(nblocks);
+        for (uint32_t b = 0; b < nblocks; b++) {
+            hoff[b] = (uint64_t)b * block_size;
+            hlen[b] = (uint32_t)std::min<uint64_t>(block_size, n - (uint64_t)b * block_size);
+        }
+        rc = hash_blocks(ctx, (const uint8_t*)d_src, hoff, hlen, checksum_bits, hv);
+        if (rc) return rc;
+        for (uint32_t b = 0; b < nblocks; b++) jobs[b].checksum = hv[b];
+    }
     std::vector<uint8_t> hdr;
     uint32_t hdr_bits = build_stream_header(hdr, t48, etype, block_size, checksum_bits, input_size);
     EncResult res;
@@ -1074,7 +1132,6 @@ int kz_decompress_stream_device(kz_ctx* ctx, const void* d_src, size_t n, void* 
     TransformPlan plan;
     rc = plan_transforms(ctx, sh.t48, plan, KZ_ERR_INVALID_CODEC);
     if (rc) return rc;
-    if (sh.checksum_bits) return ctx->fail(KZ_ERR_INVALID_CODEC, "block checksums are not available on the GPU path yet");
     const uint32_t* d_words = (const uint32_t*)d_src;
     const uint64_t words_len = (n + 3) / 4 + 16;  // callers guarantee >= 64 readable bytes past n
     // block prefixes
@@ -1119,6 +1176,16 @@ int kz_decompress_stream_device(kz_ctx* ctx, const void* d_src, size_t n, void* 
         if (rc) return rc;
         for (uint32_t b = 0; b < nblocks; b++)
             if (jobs[b].status) return ctx->fail(-jobs[b].status, "Invalid bitstream: block decoding failed");
+        if (sh.checksum_bits) {
+            std::vector<uint64_t> hoff(nblocks);
+            std::vector<uint32_t> hlen(nblocks);
+            for (uint32_t b = 0; b < nblocks; b++) {
+                hoff[b] = jobs[b].out_off;
+                hlen[b] = jobs[b].pre_len;
+            }
+            rc = verify_checksums(ctx, (const uint8_t*)d_dst, hoff, hlen, sh.checksum_bits, jobs);
+            if (rc) return rc;
+        }
         *out_n = (size_t)out_off;
         return 0;
     }
@@ -1139,6 +1206,16 @@ int kz_decompress_stream_device(kz_ctx* ctx, const void* d_src, size_t n, void* 
     rc = inverse_stage(ctx, plan, jobs, ctx->d_tmp.as<uint8_t>(), pstride, (uint8_t*)d_dst, cap, olen, &out_off, sh.block_size, true);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
+    if (sh.checksum_bits) {  // decoded blocks lie back to back (every block but the last is block_size long)
+        std::vector<uint64_t> hoff(nblocks);
+        uint64_t o = 0;
+        for (uint32_t b = 0; b < nblocks; b++) {
+            hoff[b] = o;
+            o += olen[b];
+        }
+        rc = verify_checksums(ctx, (const uint8_t*)d_dst, hoff, olen, sh.checksum_bits, jobs);
+        if (rc) return rc;
+    }
     *out_n = (size_t)out_off;
     return 0;
 }
@@ -1183,7 +1260,7 @@ int kz_encode_blocks(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_t checksu
                      const uint32_t* block_len, uint32_t nblocks, uint8_t* out, uint64_t out_stride, uint64_t* out_bits, int32_t* status) {
     if (!ctx || !slab || !block_len || !out || !out_bits) return -KZ_ERR_INVALID_PARAM;
     CK(cudaSetDevice(ctx->device));
-    if (checksum_bits != 0) return ctx->fail(KZ_ERR_INVALID_PARAM, "block checksums are not available on the GPU path yet");
+    if (checksum_bits != 0 && checksum_bits != 32 && checksum_bits != 64) return ctx->fail(KZ_ERR_INVALID_PARAM, "checksum must be 0, 32 or 64 bits");
     if (nblocks == 0) return 0;
     // device layout: block b at b * dstride (16-byte aligned)
     uint32_t max_len = 0;
@@ -1203,6 +1280,14 @@ int kz_encode_blocks(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_t checksu
     const uint8_t* d_data = nullptr;
     rc = forward_stage(ctx, plan, ctx->d_in.as<uint8_t>(), 0, 0, dstride, block_len, nblocks, &d_data, jobs);
     if (rc) return rc;
+    if (checksum_bits) {  // encodingTask.encode :753-763: hash of the original block
+        std::vector<uint64_t> hoff(nblocks), hv;
+        std::vector<uint32_t> hlen(block_len, block_len + nblocks);
+        for (uint32_t b = 0; b < nblocks; b++) hoff[b] = (uint64_t)b * dstride;
+        rc = hash_blocks(ctx, ctx->d_in.as<uint8_t>(), hoff, hlen, checksum_bits, hv);
+        if (rc) return rc;
+        for (uint32_t b = 0; b < nblocks; b++) jobs[b].checksum = hv[b];
+    }
     std::vector<uint64_t> base(nblocks);
     for (uint32_t b = 0; b < nblocks; b++) base[b] = 8 * (uint64_t)b * ostride;
     EncResult res;
@@ -1223,7 +1308,7 @@ int kz_decode_blocks(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_t checksu
                      int32_t* status) {
     if (!ctx || !in || !in_off || !in_bits || !out || !out_len) return -KZ_ERR_INVALID_PARAM;
     CK(cudaSetDevice(ctx->device));
-    if (checksum_bits != 0) return ctx->fail(KZ_ERR_INVALID_PARAM, "block checksums are not available on the GPU path yet");
+    if (checksum_bits != 0 && checksum_bits != 32 && checksum_bits != 64) return ctx->fail(KZ_ERR_INVALID_PARAM, "checksum must be 0, 32 or 64 bits");
     TransformPlan plan;
     {
         int prc = plan_transforms(ctx, t48, plan, KZ_ERR_INVALID_CODEC);
@@ -1258,6 +1343,16 @@ int kz_decode_blocks(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_t checksu
     int worst = 0;
     for (uint32_t b = 0; b < nblocks; b++)
         if (jobs[b].status && !worst) worst = jobs[b].status;
+    if (checksum_bits && plan.none() && !worst) {
+        std::vector<uint64_t> hoff(nblocks);
+        std::vector<uint32_t> hlen(nblocks);
+        for (uint32_t b = 0; b < nblocks; b++) {
+            hoff[b] = b * ostride;
+            hlen[b] = jobs[b].pre_len;
+        }
+        int vrc = verify_checksums(ctx, ctx->d_out.as<uint8_t>(), hoff, hlen, checksum_bits, jobs);
+        if (vrc) return vrc;
+    }
     if (plan.none() || worst) {
         for (uint32_t b = 0; b < nblocks; b++) {
             if (status) status[b] = jobs[b].status;
@@ -1278,6 +1373,16 @@ int kz_decode_blocks(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_t checksu
     uint64_t total = 0;
     rc = inverse_stage(ctx, plan, jobs, ctx->d_out.as<uint8_t>(), ostride, ctx->d_tmp.as<uint8_t>(), ostride * nblocks, olen, &total, ostride, false);
     if (rc) return rc;
+    if (checksum_bits) {
+        std::vector<uint64_t> hoff(nblocks);
+        uint64_t o = 0;
+        for (uint32_t b = 0; b < nblocks; b++) {
+            hoff[b] = plan.lz() ? (uint64_t)b * ostride : o;
+            o += olen[b];
+        }
+        int vrc = verify_checksums(ctx, ctx->d_tmp.as<uint8_t>(), hoff, olen, checksum_bits, jobs);
+        if (vrc) return vrc;
+    }
     uint64_t off = 0;
     for (uint32_t b = 0; b < nblocks; b++) {
         if (status) status[b] = 0;

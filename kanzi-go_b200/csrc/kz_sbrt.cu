@@ -1,0 +1,219 @@
+// Sort-by-rank transforms (kanzi RANK and MTFT) on sm_100a.
+//
+// Reference: transform/SBRT.go:127-172 (Forward), :177-226 (Inverse); modes :30-38, :93-111:
+//   MTFT  qc = i                 (mask1 = -1, mask2 = 0,  shift 0)
+//   RANK  qc = (i + p[c]) >> 1   (mask1 = -1, mask2 = -1, shift 1)        p[c] = previous position of c (0 before any)
+// The reference keeps a list of the 256 symbols; coding symbol c at position i outputs c's index r in the list, sets
+// q[c] = qc and moves c up past every symbol d with q[d] <= qc.
+//
+// Forward, restated for a GPU. qc never decreases for a given symbol (i grows, p[c] grows), so the list is always
+// sorted by (q descending, time of the last update descending) and symbols never updated keep their initial order
+// (by symbol value) behind every updated symbol of equal q. Hence
+//     r(i) = #{ d != c : key(d) > key(c) },  key(d) = (q[d], t[d]),  t[d] = last position of d, or -1-d if none so far,
+// which depends only on, per symbol, its last TWO positions before i. That makes the block cuttable: SBRT_SEG-byte
+// segments are processed concurrently, each starting from the per-symbol (last, second last) positions before it:
+//   1. sbrt_last2_kernel   per segment: last two positions of every symbol inside the segment (shared-memory atomics);
+//   2. sbrt_carry_kernel   per block: running (last, second last) over the segments, one thread per symbol;
+//   3. sbrt_rank_kernel    per segment, one warp: lane l owns the keys of symbols l, l+32, ...; per byte the owner of c
+//                          broadcasts key(c), every lane counts its larger keys, one REDUX gives r.
+// Inverse: the list itself is the decoder state (r -> c needs the list, which needs all earlier symbols), so a block is
+// one serial chain: one thread per block walks it with the list in shared memory (blocks run concurrently).
+#include "kz_sbrt.cuh"
+
+namespace kz {
+
+static const int SBRT_SEG = 4096;
+
+// ---- 1. last two positions of every symbol inside each segment
+// grid: (segments of the block, blocks). table[(seg_base + s) * 512 + 2*sym + {0,1}] = (last, second last) block-relative, -1 = none
+__global__ void __launch_bounds__(256) sbrt_last2_kernel(const uint8_t* __restrict__ data, const SbrtBlock* __restrict__ blocks,
+                                                         int32_t* __restrict__ table) {
+    __shared__ int s_l1[256], s_l2[256];
+    const SbrtBlock blk = blocks[blockIdx.y];
+    const uint32_t nseg = (blk.len + SBRT_SEG - 1) / SBRT_SEG;
+    if (blockIdx.x >= nseg || !blk.active) return;
+    const uint32_t s0 = blockIdx.x * SBRT_SEG;
+    const uint32_t s1 = min(s0 + (uint32_t)SBRT_SEG, blk.len);
+    const uint8_t* src = data + blk.src_off;
+    s_l1[threadIdx.x] = -1;
+    s_l2[threadIdx.x] = -1;
+    __syncthreads();
+    for (uint32_t i = s0 + threadIdx.x; i < s1; i += 256) atomicMax(&s_l1[src[i]], (int)i);
+    __syncthreads();
+    for (uint32_t i = s0 + threadIdx.x; i < s1; i += 256) {
+        const uint8_t c = src[i];
+        if ((int)i != s_l1[c]) atomicMax(&s_l2[c], (int)i);
+    }
+    __syncthreads();
+    int32_t* t = table + ((size_t)blk.seg_base + blockIdx.x) * 512;
+    t[2 * threadIdx.x] = s_l1[threadIdx.x];
+    t[2 * threadIdx.x + 1] = s_l2[threadIdx.x];
+}
+
+// ---- 2. exclusive running (last, second last) over the segments of a block; in place. grid: blocks, 256 threads (symbols)
+__global__ void __launch_bounds__(256) sbrt_carry_kernel(const SbrtBlock* __restrict__ blocks, int32_t* __restrict__ table) {
+    const SbrtBlock blk = blocks[blockIdx.x];
+    if (!blk.active) return;
+    const uint32_t nseg = (blk.len + SBRT_SEG - 1) / SBRT_SEG;
+    int32_t l1 = -1, l2 = -1;
+    int32_t* t = table + (size_t)blk.seg_base * 512 + 2 * threadIdx.x;
+    for (uint32_t s = 0; s < nseg; s++, t += 512) {
+        const int32_t a = t[0], b = t[1];
+        t[0] = l1;
+        t[1] = l2;
+        if (a >= 0) {
+            l2 = b >= 0 ? b : l1;
+            l1 = a;
+        }
+    }
+}
+
+// ---- 3. ranks of one segment by one warp. mode: 1 = MTFT, 2 = RANK
+// key = q << 32 | (t + 2^31): unsigned 64-bit order = (q, t) order; t = -1-d for a symbol never seen
+KZ_D uint64_t sbrt_key(int32_t q, int32_t t) { return ((uint64_t)(uint32_t)q << 32) | (uint32_t)(t ^ 0x80000000); }
+
+__global__ void __launch_bounds__(128) sbrt_rank_kernel(const uint8_t* __restrict__ data, const SbrtBlock* __restrict__ blocks, int nblocks, int mode,
+                                                        const uint32_t* __restrict__ seg_block, uint32_t nsegs_total,
+                                                        const int32_t* __restrict__ table, uint8_t* __restrict__ out) {
+    __shared__ uint8_t s_in[4][SBRT_SEG];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.x * 4 + warp;  // global segment id
+    if (g >= nsegs_total) return;
+    const uint32_t b = seg_block[g];
+    const SbrtBlock blk = blocks[b];
+    if (!blk.active) return;
+    const uint32_t s = g - blk.seg_base;
+    const uint32_t s0 = s * SBRT_SEG;
+    const uint32_t cnt = min((uint32_t)SBRT_SEG, blk.len - s0);
+    const uint8_t* src = data + blk.src_off + s0;
+    uint8_t* dst = out + blk.dst_off + s0;
+    // stage the segment (block offsets are 16-byte aligned, segments are multiples of 16)
+    {
+        const uint32_t n16 = cnt >> 4;
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(s_in[warp]);
+        for (uint32_t i = lane; i < n16; i += 32) d4[i] = __ldg(&s4[i]);
+        for (uint32_t i = (n16 << 4) + lane; i < cnt; i += 32) s_in[warp][i] = src[i];
+    }
+    // keys of my 8 symbols (symbol = lane + 32 k) and their last positions
+    const int32_t* t0 = table + (size_t)g * 512;
+    uint64_t key[8];
+    int32_t last[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int sym = lane + 32 * k;
+        const int32_t l1 = t0[2 * sym], l2 = t0[2 * sym + 1];
+        int32_t q = 0, t = -1 - sym;
+        if (l1 >= 0) {
+            t = l1;
+            q = mode == 1 ? l1 : (l1 + (l2 >= 0 ? l2 : 0)) >> 1;
+        }
+        key[k] = sbrt_key(q, t);
+        last[k] = l1 >= 0 ? l1 : 0;  // p[c] (0 before the first occurrence)
+    }
+    __syncwarp();
+    uint32_t pack = 0;  // ranks of 4 consecutive positions handled by this lane
+    for (uint32_t i0 = 0; i0 < cnt; i0 += 128) {  // 128 positions per outer round: lane l keeps positions i0 + 4 l .. + 3
+#pragma unroll 4
+        for (uint32_t j = 0; j < 128; j++) {
+            const uint32_t i = i0 + j;
+            if (i >= cnt) break;
+            const uint32_t c = s_in[warp][i];
+            const int owner = (int)(c & 31), slot = (int)(c >> 5);
+            // the owner picks key(c) and p[c]
+            uint64_t kc = key[0];
+            int32_t pc = last[0];
+#pragma unroll
+            for (int k = 1; k < 8; k++) {
+                if (slot == k) {
+                    kc = key[k];
+                    pc = last[k];
+                }
+            }
+            kc = __shfl_sync(0xFFFFFFFFu, kc, owner);
+            pc = __shfl_sync(0xFFFFFFFFu, pc, owner);
+            uint32_t larger = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) larger += key[k] > kc ? 1u : 0u;
+            const uint32_t r = __reduce_add_sync(0xFFFFFFFFu, larger);
+            if ((j >> 2) == (uint32_t)lane) pack |= r << (8 * (j & 3));
+            // update (SBRT.go:150-153)
+            const int32_t pos = (int32_t)(s0 + i);
+            const int32_t qc = mode == 1 ? pos : (pos + pc) >> 1;
+            if (lane == owner) {
+                const uint64_t nk = sbrt_key(qc, pos);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (slot == k) {
+                        key[k] = nk;
+                        last[k] = pos;
+                    }
+                }
+            }
+        }
+        // store the 128 ranks (4 per lane)
+        const uint32_t base = i0 + 4 * lane;
+        if (base + 4 <= cnt) {
+            *reinterpret_cast<uint32_t*>(dst + base) = pack;
+        } else {
+            for (uint32_t q = 0; q < 4 && base + q < cnt; q++) dst[base + q] = (uint8_t)(pack >> (8 * q));
+        }
+        pack = 0;
+    }
+}
+
+// ---- inverse: one warp per block, lane 0 walks the chain (SBRT.go:177-226)
+__global__ void __launch_bounds__(32) sbrt_inverse_kernel(const uint8_t* __restrict__ data, const SbrtBlock* __restrict__ blocks, int nblocks, int mode,
+                                                          uint8_t* __restrict__ out) {
+    __shared__ uint8_t s_r2s[256];
+    __shared__ int32_t s_q[256], s_p[256];
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (b >= nblocks) return;
+    const SbrtBlock blk = blocks[b];
+    if (!blk.active) return;
+    for (int i = lane; i < 256; i += 32) {
+        s_r2s[i] = (uint8_t)i;
+        s_q[i] = 0;
+        s_p[i] = 0;
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    const uint8_t* src = data + blk.src_off;
+    uint8_t* dst = out + blk.dst_off;
+    const uint32_t n = blk.len;
+    auto step = [&](uint32_t i, uint32_t r) -> uint32_t {
+        const uint32_t c = s_r2s[r];
+        const int32_t qc = mode == 1 ? (int32_t)i : ((int32_t)i + s_p[c]) >> 1;
+        s_p[c] = (int32_t)i;
+        s_q[c] = qc;
+        while (r > 0) {
+            const uint32_t d = s_r2s[r - 1];
+            if (s_q[d] > qc) break;
+            s_r2s[r] = (uint8_t)d;
+            r--;
+        }
+        s_r2s[r] = (uint8_t)c;
+        return c;
+    };
+    const uint32_t n16 = n >> 4;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (uint32_t v = 0; v < n16; v++) {
+        const uint4 x = __ldg(&s4[v]);
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t i = 16 * v + 4 * k;
+            uint32_t y = step(i, w[k] & 0xFF);
+            y |= step(i + 1, (w[k] >> 8) & 0xFF) << 8;
+            y |= step(i + 2, (w[k] >> 16) & 0xFF) << 16;
+            y |= step(i + 3, w[k] >> 24) << 24;
+            o[k] = y;
+        }
+        d4[v] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    for (uint32_t i = n16 << 4; i < n; i++) dst[i] = (uint8_t)step(i, src[i]);
+}
+
+}  // namespace kz

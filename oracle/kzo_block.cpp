@@ -276,7 +276,8 @@ size_t decode_block(const uint8_t* payload, uint64_t bits, uint64_t t48, uint32_
     ctx.entropy_type = etype;
     ctx.block_size = pre;
     std::vector<uint64_t> seq = sequence_of(t48);
-    size_t cap = std::max(r, block_size);
+    // Reader.processBlock :1649-1653: the task buffers hold blockSize + max(EXTRA_BUFFER_SIZE = 512, blockSize >> 4) bytes
+    size_t cap = std::max(r, block_size + std::max<size_t>(512, block_size >> 4));
     size_t decoded = seq_inverse(seq, ctx, skip_flags, buffer.data(), pre, out, cap);
     if (checksum_bits == 32) {
         if (xxhash32(out.data(), decoded, BS_TYPE) != uint32_t(checksum1)) throw Error(ERR_CRC_CHECK, "Corrupted bitstream: checksum mismatch");

@@ -8,4 +8,8 @@ bool bwt_block_inverse(Ctx& ctx, const uint8_t* src, size_t n, uint8_t* dst, siz
 size_t lz_max_encoded_len(size_t n);
 bool lz_forward(Ctx& ctx, bool extra, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
 bool lz_inverse(Ctx& ctx, bool extra, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
+bool sbrt_forward(int mode, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
+bool sbrt_inverse(int mode, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
+bool zrlt_forward(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
+bool zrlt_inverse(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
 }  // namespace kzo
