@@ -12,7 +12,7 @@
  *   - no entry point aborts or throws; kz_last_error() gives the message of the last failure on that context;
  *   - there is NO CPU fallback: if no CUDA device is usable kz_init fails with -ERR_CREATE_COMPRESSOR.
  *   - entropy type ids (entropy/EntropyCodecFactory.go:26-35): NONE 0, HUFFMAN 1, RANGE 4, ANS0 5, ANS1 8.
- *   - transform ids (transform/Factory.go:31-50): NONE 0, BWT 1, BWTS 2, LZ 3, ROLZ 11, LZX 16; a "transform48"
+ *   - transform ids (transform/Factory.go:31-50): NONE 0, BWT 1, BWTS 2, LZ 3, ZRLT 6, MTFT 7, RANK 8, ROLZ 11, LZX 16; a "transform48"
  *     word packs up to 8 six-bit ids, first transform in the top 6 bits (Factory.go:26-54).
  */
 #ifndef KANZI_B200_H
@@ -36,7 +36,7 @@ enum {
 };
 
 enum { KZ_E_NONE = 0, KZ_E_HUFFMAN = 1, KZ_E_RANGE = 4, KZ_E_ANS0 = 5, KZ_E_ANS1 = 8 };
-enum { KZ_T_NONE = 0, KZ_T_BWT = 1, KZ_T_BWTS = 2, KZ_T_LZ = 3, KZ_T_ROLZ = 11, KZ_T_LZX = 16 };
+enum { KZ_T_NONE = 0, KZ_T_BWT = 1, KZ_T_BWTS = 2, KZ_T_LZ = 3, KZ_T_ZRLT = 6, KZ_T_MTFT = 7, KZ_T_RANK = 8, KZ_T_ROLZ = 11, KZ_T_LZX = 16 };
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
 int kz_device_count(void);

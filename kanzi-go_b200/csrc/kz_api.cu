@@ -15,6 +15,8 @@
 #include "kz_lz.cuh"
 #include "kz_range.cuh"
 #include "kz_hash.cuh"
+#include "kz_sbrt.cuh"
+#include "kz_zrlt.cuh"
 
 #include <memory>
 
@@ -757,11 +759,314 @@ struct TransformPlan {
     bool bwt() const { return nt == 1 && ids[0] == KZ_T_BWT; }
     bool lz() const { return nt == 1 && (ids[0] == KZ_T_LZ || ids[0] == KZ_T_LZX); }
     bool lzx() const { return nt == 1 && ids[0] == KZ_T_LZX; }
+    static bool seq_id(uint64_t t) { return t == KZ_T_BWT || t == KZ_T_BWTS || t == KZ_T_RANK || t == KZ_T_MTFT || t == KZ_T_ZRLT; }
+    // any sequence of BWT / BWTS / RANK / MTFT / ZRLT stages (e.g. "BWT+RANK+ZRLT", the transform chain of kanzi -l 5)
+    bool generic() const {
+        if (bwt()) return false;
+        for (int i = 0; i < nt; i++)
+            if (!seq_id(ids[i])) return false;
+        return true;
+    }
 };
 
 int plan_transforms(kz_ctx* ctx, uint64_t t48, TransformPlan& p, int err_code) {
     p.nt = count_transforms(t48, p.ids);
-    if (!(p.none() || p.bwt() || p.lz())) return ctx->fail(err_code, "transform sequence not available on the GPU path (NONE, BWT, LZ, LZX are)");
+    if (!(p.none() || p.bwt() || p.lz() || p.generic()))
+        return ctx->fail(err_code, "transform sequence not available on the GPU path (NONE, LZ, LZX, and sequences of BWT / BWTS / RANK / MTFT / ZRLT are)");
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Generic transform sequences (ByteTransformSequence, transform/Sequence.go:64-186) over the stages that exist as
+// kernels: BWT, RANK, MTFT, ZRLT. Every stage processes all blocks of the batch; a stage that declines a block
+// ("skip", Sequence.go:100-105) leaves its skip bit set and the block moves on unchanged.
+// ------------------------------------------------------------------------------------------------------------
+// One forward stage. Block b: d_in + b*istride (len[b] bytes) -> d_out + b*ostride. applied[b] = 1 and len[b] updated on success.
+int apply_forward(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint64_t istride, uint8_t* d_out, uint64_t ostride, std::vector<uint32_t>& len,
+                  const std::vector<uint8_t>& active, std::vector<uint8_t>& applied) {
+    const uint32_t nblocks = (uint32_t)len.size();
+    applied.assign(nblocks, 0);
+    if (t == KZ_T_BWT) {
+        uint32_t max_len = 0;
+        for (uint32_t b = 0; b < nblocks; b++) max_len = std::max(max_len, len[b]);
+        CK(ctx->d_ws.ensure(bwt_forward_workspace(max_len)));
+        CK(ctx->d_lens.ensure((size_t)nblocks * 4 + 64));
+        uint32_t* d_post = ctx->d_lens.as<uint32_t>();
+        for (uint32_t b = 0; b < nblocks; b++) {
+            if (!active[b] || len[b] < 2) continue;
+            LaunchScope ls(ctx, "bwt_forward");
+            cudaError_t e = bwt_forward_device(d_in + b * istride, len[b], d_out + b * ostride, d_post + b, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap, ctx->stream,
+                                               &ctx->launches);
+            if (e == cudaSuccess) applied[b] = 1;
+            else if (e != cudaErrorInvalidValue) return ctx->cuda_fail(e, "bwt_forward");
+        }
+        std::vector<uint32_t> post(nblocks);
+        CK(cudaMemcpyAsync(post.data(), d_post, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t b = 0; b < nblocks; b++)
+            if (applied[b]) len[b] = post[b];
+    } else if (t == KZ_T_BWTS) {  // BWTS.Forward: n bytes -> n bytes, never declines
+        uint32_t max_len = 0;
+        for (uint32_t b = 0; b < nblocks; b++) max_len = std::max(max_len, len[b]);
+        CK(ctx->d_ws.ensure(bwts_forward_workspace(max_len)));
+        for (uint32_t b = 0; b < nblocks; b++) {
+            if (!active[b] || len[b] == 0) continue;
+            LaunchScope ls(ctx, "bwts_forward");
+            cudaError_t e = bwts_forward_device(d_in + b * istride, len[b], d_out + b * ostride, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap, ctx->stream,
+                                                &ctx->launches);
+            if (e != cudaSuccess) return ctx->cuda_fail(e, "bwts_forward");
+            applied[b] = 1;
+        }
+    } else if (t == KZ_T_RANK || t == KZ_T_MTFT) {  // SBRT.Forward never declines (buffers are sized for MaxEncodedLen)
+        std::vector<SbrtBlock> sb(nblocks);
+        std::vector<uint32_t> seg_block;
+        uint32_t max_segs = 0;
+        for (uint32_t b = 0; b < nblocks; b++) {
+            sb[b].src_off = b * istride;
+            sb[b].dst_off = b * ostride;
+            sb[b].len = len[b];
+            sb[b].seg_base = (uint32_t)seg_block.size();
+            sb[b].active = active[b] && len[b] > 0;
+            sb[b].pad = 0;
+            const uint32_t nseg = sb[b].active ? (len[b] + SBRT_SEG_BYTES - 1) / SBRT_SEG_BYTES : 0;
+            max_segs = std::max(max_segs, nseg);
+            for (uint32_t s = 0; s < nseg; s++) seg_block.push_back(b);
+            applied[b] = sb[b].active ? 1 : 0;
+        }
+        const uint32_t nsegs = (uint32_t)seg_block.size();
+        if (nsegs) {
+            Packer pk;
+            const size_t o_sb = pk.add(sb.data(), sb.size() * sizeof(SbrtBlock));
+            const size_t o_map = pk.add(seg_block.data(), seg_block.size() * 4);
+            int rc = upload(ctx, pk);
+            if (rc) return rc;
+            CK(ctx->d_seg.ensure((size_t)nsegs * 512 * 4 + 64));
+            uint8_t* T = ctx->d_tables.as<uint8_t>();
+            const SbrtBlock* d_sb = (const SbrtBlock*)(T + o_sb);
+            const int mode = t == KZ_T_MTFT ? 1 : 2;
+            {
+                LaunchScope ls(ctx, "sbrt_last2");
+                sbrt_last2_kernel<<<dim3(max_segs, nblocks), 256, 0, ctx->stream>>>(d_in, d_sb, ctx->d_seg.as<int32_t>());
+            }
+            {
+                LaunchScope ls(ctx, "sbrt_carry");
+                sbrt_carry_kernel<<<nblocks, 256, 0, ctx->stream>>>(d_sb, ctx->d_seg.as<int32_t>());
+            }
+            {
+                LaunchScope ls(ctx, "sbrt_rank");
+                sbrt_rank_kernel<<<(nsegs + 3) / 4, 128, 0, ctx->stream>>>(d_in, d_sb, (int)nblocks, mode, (const uint32_t*)(T + o_map), nsegs,
+                                                                          ctx->d_seg.as<int32_t>(), d_out);
+            }
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(ctx->stream));  // the tables live in d_tables, which the next stage reuses
+        }
+    } else if (t == KZ_T_ZRLT) {
+        std::vector<ZrltBlock> zb(nblocks);
+        for (uint32_t b = 0; b < nblocks; b++) {
+            zb[b].src_off = b * istride;
+            zb[b].dst_off = b * ostride;
+            zb[b].len = len[b];
+            zb[b].cap = len[b];
+            zb[b].active = active[b] && len[b] > 0;
+            zb[b].pad = 0;
+        }
+        Packer pk;
+        const size_t o_zb = pk.add(zb.data(), zb.size() * sizeof(ZrltBlock));
+        const size_t o_len = pk.reserve((size_t)nblocks * 4);
+        const size_t o_st = pk.reserve((size_t)nblocks * 4);
+        int rc = upload(ctx, pk);
+        if (rc) return rc;
+        uint8_t* T = ctx->d_tables.as<uint8_t>();
+        {
+            LaunchScope ls(ctx, "zrlt_forward");
+            zrlt_forward_kernel<<<nblocks, 512, 0, ctx->stream>>>(d_in, (const ZrltBlock*)(T + o_zb), (int)nblocks, d_out, (uint32_t*)(T + o_len),
+                                                                  (int32_t*)(T + o_st));
+        }
+        CK(cudaGetLastError());
+        std::vector<uint32_t> hl(nblocks);
+        std::vector<int32_t> hs(nblocks);
+        CK(cudaMemcpyAsync(hl.data(), T + o_len, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(hs.data(), T + o_st, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t b = 0; b < nblocks; b++) {
+            if (zb[b].active && hs[b] == 0) {
+                applied[b] = 1;
+                len[b] = hl[b];
+            }
+        }
+    } else {
+        return ctx->fail(KZ_ERR_CREATE_CODEC, "transform not available on the GPU path");
+    }
+    return 0;
+}
+
+// ByteTransformSequence.Forward for every block of a batch. jobs[] must be initialised (copy flags, lengths).
+int forward_generic(kz_ctx* ctx, const TransformPlan& plan, const uint8_t* d_src, uint64_t stride, const std::vector<uint32_t>& blen, const uint8_t** d_data,
+                    std::vector<EncJob>& jobs) {
+    const uint32_t nblocks = (uint32_t)blen.size();
+    uint32_t max_len = 0;
+    for (uint32_t b = 0; b < nblocks; b++) max_len = std::max(max_len, blen[b]);
+    const uint64_t gstride = ((uint64_t)max_len + 33ull * plan.nt + 64 + 15) & ~15ull;
+    CK(ctx->d_tmp.ensure(gstride * nblocks + 64));
+    CK(ctx->d_tmp2.ensure(gstride * nblocks + 64));
+    std::vector<uint32_t> len(blen);
+    std::vector<uint8_t> active(nblocks), applied;
+    std::vector<uint8_t> flags(nblocks, 0xFF);
+    for (uint32_t b = 0; b < nblocks; b++) active[b] = !jobs[b].copy && blen[b] > 0;
+    const uint8_t* cur = d_src;
+    uint64_t cur_stride = stride;
+    for (int i = 0; i < plan.nt; i++) {
+        uint8_t* outb = (i & 1) ? ctx->d_tmp2.as<uint8_t>() : ctx->d_tmp.as<uint8_t>();
+        int rc = apply_forward(ctx, plan.ids[i], cur, cur_stride, outb, gstride, len, active, applied);
+        if (rc) return rc;
+        for (uint32_t b = 0; b < nblocks; b++) {
+            if (applied[b]) flags[b] &= (uint8_t)~(1u << (7 - i));
+            else if (len[b]) CK(cudaMemcpyAsync(outb + b * gstride, cur + b * cur_stride, len[b], cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        cur = outb;
+        cur_stride = gstride;
+    }
+    for (uint32_t b = 0; b < nblocks; b++) {
+        EncJob& j = jobs[b];
+        j.data_off = b * gstride;
+        j.post_len = len[b];
+        if (!j.copy) j.skip_flags = flags[b];
+    }
+    *d_data = cur;
+    return 0;
+}
+
+// One inverse stage, mirror of apply_forward. cap = capacity of a destination block.
+int apply_inverse(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint8_t* d_out, uint64_t stride, uint32_t cap, std::vector<uint32_t>& len,
+                  const std::vector<uint8_t>& active) {
+    const uint32_t nblocks = (uint32_t)len.size();
+    if (t == KZ_T_BWT) {
+        std::vector<uint8_t> heads((size_t)nblocks * 64, 0);
+        CK(cudaMemcpy2DAsync(heads.data(), 64, d_in, stride, 33, nblocks, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        uint32_t max_len = 0;
+        for (uint32_t b = 0; b < nblocks; b++) max_len = std::max(max_len, len[b]);
+        CK(ctx->d_ws.ensure(bwt_inverse_workspace(max_len)));
+        for (uint32_t b = 0; b < nblocks; b++) {
+            if (!active[b]) continue;
+            uint32_t produced = 0;
+            LaunchScope ls(ctx, "bwt_inverse");
+            cudaError_t e = bwt_inverse_device(d_in + b * stride, &heads[(size_t)b * 64], len[b], d_out + b * stride, cap, &produced, ctx->d_ws.as<uint8_t>(),
+                                               ctx->d_ws.cap, ctx->stream, &ctx->launches);
+            if (e == cudaErrorInvalidValue) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "BWT inverse transform failed: invalid header");
+            if (e != cudaSuccess) return ctx->cuda_fail(e, "bwt_inverse");
+            len[b] = produced;
+        }
+    } else if (t == KZ_T_BWTS) {
+        uint32_t max_len = 0;
+        for (uint32_t b = 0; b < nblocks; b++) max_len = std::max(max_len, len[b]);
+        CK(ctx->d_ws.ensure(bwts_inverse_workspace(max_len)));
+        for (uint32_t b = 0; b < nblocks; b++) {
+            if (!active[b] || len[b] == 0) continue;
+            if (len[b] > cap) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "BWTS inverse transform failed: output buffer too small");
+            LaunchScope ls(ctx, "bwts_inverse");
+            cudaError_t e = bwts_inverse_device(d_in + b * stride, len[b], d_out + b * stride, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap, ctx->stream, &ctx->launches);
+            if (e != cudaSuccess) return ctx->cuda_fail(e, "bwts_inverse");
+        }
+    } else if (t == KZ_T_RANK || t == KZ_T_MTFT) {
+        std::vector<SbrtBlock> sb(nblocks);
+        for (uint32_t b = 0; b < nblocks; b++) {
+            sb[b].src_off = b * stride;
+            sb[b].dst_off = b * stride;
+            sb[b].len = len[b];
+            sb[b].seg_base = 0;
+            sb[b].active = active[b] && len[b] > 0;
+            sb[b].pad = 0;
+            if (sb[b].active && len[b] > cap) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "SBRT inverse transform failed: output buffer too small");
+        }
+        Packer pk;
+        const size_t o_sb = pk.add(sb.data(), sb.size() * sizeof(SbrtBlock));
+        int rc = upload(ctx, pk);
+        if (rc) return rc;
+        {
+            LaunchScope ls(ctx, "sbrt_inverse");
+            sbrt_inverse_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_in, (const SbrtBlock*)(ctx->d_tables.as<uint8_t>() + o_sb), (int)nblocks,
+                                                                 t == KZ_T_MTFT ? 1 : 2, d_out);
+        }
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else if (t == KZ_T_ZRLT) {
+        std::vector<ZrltBlock> zb(nblocks);
+        for (uint32_t b = 0; b < nblocks; b++) {
+            zb[b].src_off = b * stride;
+            zb[b].dst_off = b * stride;
+            zb[b].len = len[b];
+            zb[b].cap = cap;
+            zb[b].active = active[b] && len[b] > 0;
+            zb[b].pad = 0;
+        }
+        Packer pk;
+        const size_t o_zb = pk.add(zb.data(), zb.size() * sizeof(ZrltBlock));
+        const size_t o_len = pk.reserve((size_t)nblocks * 4);
+        const size_t o_st = pk.reserve((size_t)nblocks * 4);
+        int rc = upload(ctx, pk);
+        if (rc) return rc;
+        uint8_t* T = ctx->d_tables.as<uint8_t>();
+        CK(cudaMemsetAsync(d_out, 0, stride * nblocks, ctx->stream));  // runs of zeros are never written, only skipped
+        {
+            LaunchScope ls(ctx, "zrlt_inverse");
+            zrlt_inverse_kernel<<<nblocks, 512, 0, ctx->stream>>>(d_in, (const ZrltBlock*)(T + o_zb), (int)nblocks, d_out, (uint32_t*)(T + o_len),
+                                                                  (int32_t*)(T + o_st));
+        }
+        CK(cudaGetLastError());
+        std::vector<uint32_t> hl(nblocks);
+        std::vector<int32_t> hs(nblocks);
+        CK(cudaMemcpyAsync(hl.data(), T + o_len, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(hs.data(), T + o_st, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t b = 0; b < nblocks; b++) {
+            if (!zb[b].active) continue;
+            if (hs[b]) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "ZRLT inverse transform failed: output buffer is too small");
+            len[b] = hl[b];
+        }
+    } else {
+        return ctx->fail(KZ_ERR_INVALID_CODEC, "transform not available on the GPU path");
+    }
+    return 0;
+}
+
+// ByteTransformSequence.Inverse for every block of a batch. Block b's pre_len bytes are at d_pre + b*pstride (a scratch
+// buffer of this context with room for blk_cap bytes per block); decoded blocks go to d_dst back to back (compact) or at
+// b * slot.
+int inverse_generic(kz_ctx* ctx, const TransformPlan& plan, std::vector<DecJob>& jobs, uint8_t* d_pre, uint64_t pstride, uint32_t blk_cap, uint8_t* d_dst,
+                    size_t cap, std::vector<uint32_t>& out_len, uint64_t* total, uint64_t slot, bool compact) {
+    const uint32_t nblocks = (uint32_t)jobs.size();
+    std::vector<uint32_t> len(nblocks);
+    for (uint32_t b = 0; b < nblocks; b++) len[b] = jobs[b].pre_len;
+    CK(ctx->d_tmp2.ensure(pstride * nblocks + 64));
+    uint8_t* cur = d_pre;
+    uint8_t* other = ctx->d_tmp2.as<uint8_t>();
+    if (other == cur) return ctx->fail(KZ_ERR_UNKNOWN, "internal: scratch buffers alias");
+    std::vector<uint8_t> active(nblocks);
+    for (int i = plan.nt - 1; i >= 0; i--) {
+        bool any = false;
+        for (uint32_t b = 0; b < nblocks; b++) {
+            active[b] = !jobs[b].copy && !(jobs[b].skip_flags & (1u << (7 - i))) && len[b] > 0;
+            any = any || active[b];
+        }
+        if (!any) continue;
+        int rc = apply_inverse(ctx, plan.ids[i], cur, other, pstride, blk_cap, len, active);
+        if (rc) return rc;
+        for (uint32_t b = 0; b < nblocks; b++)
+            if (!active[b] && len[b]) CK(cudaMemcpyAsync(other + b * pstride, cur + b * pstride, len[b], cudaMemcpyDeviceToDevice, ctx->stream));
+        std::swap(cur, other);
+    }
+    uint64_t off = 0;
+    for (uint32_t b = 0; b < nblocks; b++) {
+        const uint64_t at = compact ? off : (uint64_t)b * slot;
+        if (at + len[b] > cap) return ctx->fail(KZ_ERR_WRITE_FILE, "output buffer too small");
+        if (len[b]) CK(cudaMemcpyAsync(d_dst + at, cur + b * pstride, len[b], cudaMemcpyDeviceToDevice, ctx->stream));
+        out_len[b] = len[b];
+        off += len[b];
+    }
+    *total = off;
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -788,6 +1093,7 @@ int forward_stage(kz_ctx* ctx, const TransformPlan& plan, const uint8_t* d_src, 
         j.checksum = 0;
     }
     if (plan.none() || nblocks == 0) return 0;
+    if (plan.generic()) return forward_generic(ctx, plan, d_src, stride, blen, d_data, jobs);
     if (plan.lz()) {
         // ---- LZ / LZX (LZXCodec.Forward): one serial parse per block, all blocks of the batch in parallel
         const bool extra = plan.lzx();
@@ -891,6 +1197,9 @@ int inverse_stage(kz_ctx* ctx, const TransformPlan& plan, std::vector<DecJob>& j
     out_len.assign(nblocks, 0);
     *total = 0;
     if (nblocks == 0) return 0;
+    if (plan.generic())
+        return inverse_generic(ctx, plan, jobs, const_cast<uint8_t*>(d_pre), pstride, (uint32_t)std::min<uint64_t>(pstride - 64, 0xFFFFFFF0u), d_dst, cap, out_len,
+                               total, lz_slot, compact);
     if (plan.lz()) {
         // every block decodes into its own slot (valid streams: all blocks but the last are block_size long)
         uint32_t max_pre = 0;
@@ -1018,7 +1327,7 @@ void kz_destroy(kz_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     drain_profile(ctx);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
-    DevBuf* bufs[] = {&ctx->d_in, &ctx->d_out, &ctx->d_tmp, &ctx->d_tables, &ctx->d_enc_tab, &ctx->d_hdr, &ctx->d_pay, &ctx->d_small, &ctx->d_dl, &ctx->d_rcp, &ctx->d_ws, &ctx->d_lens, &ctx->d_hist};
+    DevBuf* bufs[] = {&ctx->d_in, &ctx->d_out, &ctx->d_tmp, &ctx->d_tmp2, &ctx->d_seg, &ctx->d_tables, &ctx->d_enc_tab, &ctx->d_hdr, &ctx->d_pay, &ctx->d_small, &ctx->d_dl, &ctx->d_rcp, &ctx->d_ws, &ctx->d_lens, &ctx->d_hist};
     for (auto b : bufs) b->release();
     ctx->h_stage.release();
     ctx->h_dl.release();
@@ -1075,6 +1384,10 @@ size_t kz_transform_max_encoded_len(uint64_t type, size_t n) {
     switch (type) {
         case KZ_T_NONE: return n;
         case KZ_T_BWT: return n + 33;  // transform/BWTBlockCodec.go:228
+        case KZ_T_RANK:
+        case KZ_T_MTFT: return n + 33;  // transform/SBRT.go:229-231
+        case KZ_T_ZRLT: return n;       // transform/ZRLT.go:228-230
+        case KZ_T_BWTS: return n;       // transform/BWTS.go:291-293
         case KZ_T_LZ:
         case KZ_T_LZX: return n <= 1024 ? n + 16 : n + n / 64;  // transform/LZCodec.go:935-941
         default: return 0;
@@ -1195,7 +1508,10 @@ int kz_decompress_stream_device(kz_ctx* ctx, const void* d_src, size_t n, void* 
         if (jobs[b].status) return ctx->fail(-jobs[b].status, "Invalid compressed block header");
         max_pre = std::max(max_pre, jobs[b].pre_len);
     }
-    const uint64_t pstride = ((uint64_t)max_pre + 64 + 15) & ~15ull;
+    uint64_t blk_room = max_pre;
+    if (plan.generic())  // Reader.processBlock :1649-1653: the task buffers hold blockSize + max(512, blockSize >> 4) bytes
+        blk_room = std::max<uint64_t>(blk_room, (uint64_t)sh.block_size + std::max<uint64_t>(512, sh.block_size >> 4));
+    const uint64_t pstride = (blk_room + 64 + 15) & ~15ull;
     CK(ctx->d_tmp.ensure(pstride * nblocks + 64));
     for (uint32_t b = 0; b < nblocks; b++) jobs[b].out_off = (uint64_t)b * pstride;
     rc = decode_batch(ctx, sh.etype, d_words, words_len, jobs, ctx->d_tmp.as<uint8_t>());
@@ -1377,7 +1693,7 @@ int kz_decode_blocks(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_t checksu
         std::vector<uint64_t> hoff(nblocks);
         uint64_t o = 0;
         for (uint32_t b = 0; b < nblocks; b++) {
-            hoff[b] = plan.lz() ? (uint64_t)b * ostride : o;
+            hoff[b] = (plan.lz() || plan.generic()) ? (uint64_t)b * ostride : o;
             o += olen[b];
         }
         int vrc = verify_checksums(ctx, ctx->d_tmp.as<uint8_t>(), hoff, olen, checksum_bits, jobs);
@@ -1388,7 +1704,7 @@ int kz_decode_blocks(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_t checksu
         if (status) status[b] = 0;
         out_len[b] = olen[b];
         if (olen[b] > out_stride) return ctx->fail(KZ_ERR_WRITE_FILE, "output buffer too small");
-        const uint64_t from = plan.lz() ? (uint64_t)b * ostride : off;
+        const uint64_t from = (plan.lz() || plan.generic()) ? (uint64_t)b * ostride : off;
         CK(cudaMemcpyAsync(out + b * out_stride, ctx->d_tmp.as<uint8_t>() + from, olen[b], cudaMemcpyDeviceToHost, ctx->stream));
         off += olen[b];
     }
@@ -1477,7 +1793,25 @@ int kz_transform_forward(kz_ctx* ctx, uint64_t type, int* data_type, const uint8
         *out_n = jobs[0].post_len;
         return 0;
     }
-    if (type != KZ_T_BWT) return ctx->fail(KZ_ERR_CREATE_CODEC, "transform not available on the GPU path (BWT, LZ, LZX are)");
+    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS) {  // SBRT.Forward / ZRLT.Forward / BWTS.Forward
+        if (n == 0) return 0;
+        if (n > (1u << 30)) return ctx->fail(KZ_ERR_BLOCK_SIZE, "block too large");
+        if (cap < kz_transform_max_encoded_len(type, n)) return 1;  // Forward returns an error: the sequence skips the transform
+        const uint64_t stride = ((uint64_t)n + 33 + 64 + 15) & ~15ull;
+        CK(ctx->d_in.ensure(stride));
+        CK(ctx->d_out.ensure(stride));
+        CK(cudaMemcpyAsync(ctx->d_in.p, src, n, cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<uint32_t> len(1, (uint32_t)n);
+        std::vector<uint8_t> active(1, 1), applied;
+        int rc = apply_forward(ctx, type, ctx->d_in.as<uint8_t>(), stride, ctx->d_out.as<uint8_t>(), stride, len, active, applied);
+        if (rc) return rc;
+        if (!applied[0]) return 1;
+        CK(cudaMemcpyAsync(dst, ctx->d_out.p, len[0], cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        *out_n = len[0];
+        return 0;
+    }
+    if (type != KZ_T_BWT) return ctx->fail(KZ_ERR_CREATE_CODEC, "transform not available on the GPU path (BWT, LZ, LZX, RANK, MTFT, ZRLT are)");
     if (n == 0) return 0;
     if (n > (1u << 30)) return ctx->fail(KZ_ERR_BLOCK_SIZE, "The max BWT block size is 1 GiB");
     if (cap < n + 33) return ctx->fail(KZ_ERR_INVALID_PARAM, "Output buffer is too small");
@@ -1529,7 +1863,23 @@ int kz_transform_inverse(kz_ctx* ctx, uint64_t type, const uint8_t* src, size_t 
         *out_n = olen[0];
         return 0;
     }
-    if (type != KZ_T_BWT) return ctx->fail(KZ_ERR_CREATE_CODEC, "transform not available on the GPU path (BWT, LZ, LZX are)");
+    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS) {  // SBRT / ZRLT / BWTS Inverse; cap = len(dst) of the reference call
+        if (n == 0 || cap == 0) return 0;
+        if (n > (1u << 30) || cap > (1u << 30) + 4096) return ctx->fail(KZ_ERR_BLOCK_SIZE, "block too large");
+        const uint64_t stride = ((uint64_t)std::max(n, cap) + 64 + 15) & ~15ull;
+        CK(ctx->d_in.ensure(stride));
+        CK(ctx->d_out.ensure(stride));
+        CK(cudaMemcpyAsync(ctx->d_in.p, src, n, cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<uint32_t> len(1, (uint32_t)n);
+        std::vector<uint8_t> active(1, 1);
+        int rc = apply_inverse(ctx, type, ctx->d_in.as<uint8_t>(), ctx->d_out.as<uint8_t>(), stride, (uint32_t)cap, len, active);
+        if (rc) return rc;
+        if (len[0]) CK(cudaMemcpyAsync(dst, ctx->d_out.p, len[0], cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        *out_n = len[0];
+        return 0;
+    }
+    if (type != KZ_T_BWT) return ctx->fail(KZ_ERR_CREATE_CODEC, "transform not available on the GPU path (BWT, LZ, LZX, RANK, MTFT, ZRLT are)");
     if (n == 0) return 0;
     if (n == 1) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "BWT inverse transform failed: invalid size");
     if (n > (1u << 30) + 33) return ctx->fail(KZ_ERR_BLOCK_SIZE, "The max BWT block size is 1 GiB");

@@ -452,4 +452,398 @@ cudaError_t bwt_inverse_device(const uint8_t* d_src, const uint8_t* h_header /*f
     return cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// BWTS (bijective BWT, transform/BWTS.go:58-170 Forward, :211-288 Inverse).
+//
+// Forward. The reference builds the suffix array, finds the Lyndon factors (a factor starts where the rank of the
+// suffix is smaller than every earlier one, :120-125) and repairs the order of the rotations factor by factor. The
+// result is canonical: all rotations of all Lyndon factors sorted by their infinite periodic repetition, output byte =
+// cyclic predecessor inside the factor (equal rotations of repeated factors carry equal bytes, so their mutual order
+// does not matter). On the GPU: (1) suffix ranks by the same prefix doubling as the BWT, (2) factor starts by a
+// prefix-minimum over the ranks, (3) a second prefix doubling in which "the position h bytes further" follows the
+// cyclic successor inside the factor (succ_2h = succ_h o succ_h) until no group splits any more, (4) scatter.
+// Inverse. The reference builds the LF mapping and walks its cycles, smallest unvisited index first, filling the output
+// from the end. On the GPU: LF by one stable radix sort, cycle leaders (minimum index of a cycle) by pointer doubling of
+// minima, distance from the leader by list ranking of the cycles cut at their leader, cycle offsets by a prefix sum.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void bwts_negrank_kernel(const uint32_t* __restrict__ rank, uint32_t n, uint32_t* __restrict__ v) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = n - rank[i];  // >= 1; larger = smaller rank
+}
+// in: v (n - rank), m = inclusive prefix maximum of v (finished with block_max). out: head position for the next scan
+__global__ void bwts_heads_kernel(const uint32_t* __restrict__ v, const uint32_t* __restrict__ m, const uint32_t* __restrict__ block_max, uint32_t n,
+                                  uint32_t* __restrict__ hpos) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool head = i == 0;
+    if (i > 0) {
+        const uint32_t j = i - 1;
+        const uint32_t blk = j / 2048;
+        uint32_t before = m[j];
+        if (blk > 0) before = max(before, block_max[blk - 1]);
+        head = v[i] > before;  // rank[i] smaller than every earlier rank
+    }
+    hpos[i] = head ? i : 0u;
+}
+// fstart = inclusive prefix maximum of hpos (local part in fs, block part in block_max): succ1 / pred inside the factor
+__global__ void bwts_succ_kernel(const uint32_t* __restrict__ hpos, const uint32_t* __restrict__ fs, const uint32_t* __restrict__ block_max, uint32_t n,
+                                 uint32_t* __restrict__ succ, uint32_t* __restrict__ pred) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t blk = i / 2048;
+    uint32_t start = fs[i];
+    if (blk > 0) start = max(start, block_max[blk - 1]);
+    const bool last = i + 1 == n || hpos[i + 1] == i + 1;
+    const uint32_t sx = last ? start : i + 1;
+    succ[i] = sx;
+    pred[sx] = i;
+}
+// first key: 7 bytes along the cyclic successor (8 bits each are enough: every rotation has all 7), succ7 for the doubling
+__global__ void bwts_init_keys_kernel(const uint8_t* __restrict__ src, const uint32_t* __restrict__ succ1, uint32_t n, uint64_t* __restrict__ keys,
+                                      uint32_t* __restrict__ idx, uint32_t* __restrict__ succ7) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = 0;
+    uint32_t p = i;
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+        k = (k << 9) | ((uint64_t)src[p] + 1);
+        p = succ1[p];
+    }
+    keys[i] = k;
+    idx[i] = i;
+    succ7[i] = p;
+}
+__global__ void bwts_double_keys_kernel(const uint32_t* __restrict__ rank, const uint32_t* __restrict__ succ_h, uint32_t n, uint32_t log_n,
+                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ succ_2h) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = succ_h[i];
+    keys[i] = ((uint64_t)rank[i] << log_n) | (uint64_t)rank[s];
+    idx[i] = i;
+    succ_2h[i] = succ_h[s];
+}
+// counts the groups (positions that head their group) of the current order
+__global__ void bwts_count_groups_kernel(const uint32_t* __restrict__ head, uint32_t n, uint32_t* __restrict__ count) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool is_head = j < n && head[j] == j;
+    const uint32_t b = __ballot_sync(0xFFFFFFFFu, is_head);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, (uint32_t)__popc(b));
+}
+__global__ void bwts_emit_kernel(const uint8_t* __restrict__ src, const uint32_t* __restrict__ sa, const uint32_t* __restrict__ pred, uint32_t n,
+                                 uint8_t* __restrict__ dst) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) dst[j] = src[pred[sa[j]]];
+}
+
+// ---- inverse
+__global__ void ibwts_init_kernel(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        keys[i] = src[i];
+        vals[i] = i;
+    }
+}
+// sorted position s holds original index v[s]  ->  lf[v[s]] = s ; min/jump initialisation
+__global__ void ibwts_lf_kernel(const uint32_t* __restrict__ v, uint32_t n, uint32_t* __restrict__ lf) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) lf[v[s]] = s;
+}
+__global__ void ibwts_min_init_kernel(const uint32_t* __restrict__ lf, uint32_t n, uint32_t* __restrict__ mn, uint32_t* __restrict__ jp) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint32_t t = lf[i];
+        mn[i] = min(i, t);
+        jp[i] = t;
+    }
+}
+__global__ void ibwts_min_jump_kernel(const uint32_t* __restrict__ mn_in, const uint32_t* __restrict__ jp_in, uint32_t n, uint32_t* __restrict__ mn_out,
+                                      uint32_t* __restrict__ jp_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint32_t j = jp_in[i];
+        mn_out[i] = min(mn_in[i], mn_in[j]);
+        jp_out[i] = jp_in[j];
+    }
+}
+// lists = cycles cut in front of their leader: nx[p] = lf[p], END when lf[p] leads its cycle; cnt[p] = 1
+__global__ void ibwts_rank_init_kernel(const uint32_t* __restrict__ lf, const uint32_t* __restrict__ mn, uint32_t n, uint32_t* __restrict__ nx,
+                                       uint32_t* __restrict__ cnt) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint32_t t = lf[i];
+        nx[i] = mn[t] == t ? 0xFFFFFFFFu : t;
+        cnt[i] = 1;
+    }
+}
+__global__ void ibwts_rank_jump_kernel(const uint32_t* __restrict__ nx_in, const uint32_t* __restrict__ cnt_in, uint32_t n, uint32_t* __restrict__ nx_out,
+                                       uint32_t* __restrict__ cnt_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint32_t j = nx_in[i];
+        uint32_t c = cnt_in[i];
+        uint32_t j2 = j;
+        if (j != 0xFFFFFFFFu) {
+            c += cnt_in[j];
+            j2 = nx_in[j];
+        }
+        nx_out[i] = j2;
+        cnt_out[i] = c;
+    }
+}
+// cnt[p] = nodes from p to the end of its list; a leader's cnt is the cycle length
+__global__ void ibwts_len_kernel(const uint32_t* __restrict__ mn, const uint32_t* __restrict__ cnt, uint32_t n, uint32_t* __restrict__ len_at) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) len_at[i] = mn[i] == i ? cnt[i] : 0u;
+}
+// exclusive sum over len_at: three-phase like scan_max (values fit 32 bits: total = n)
+__global__ void scan_add_local_kernel(uint32_t* __restrict__ v, uint32_t n, uint32_t* __restrict__ block_sum) {
+    __shared__ uint32_t s_warp[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t base = blockIdx.x * (blockDim.x * 8);
+    uint32_t x[8];
+    uint32_t run = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const uint32_t j = base + tid * 8 + q;
+        const uint32_t a = j < n ? v[j] : 0u;
+        x[q] = run;  // exclusive inside the thread
+        run += a;
+    }
+    uint32_t incl = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < (blockDim.x >> 5) ? s_warp[lane] : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, w, d);
+            if (lane >= d) w += t;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    uint32_t prev = incl - run;
+    if (warp > 0) prev += s_warp[warp - 1];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const uint32_t j = base + tid * 8 + q;
+        if (j < n) v[j] = x[q] + prev;
+    }
+    if (tid == blockDim.x - 1) block_sum[blockIdx.x] = prev + run;
+}
+__global__ void scan_add_blocks_kernel(uint32_t* __restrict__ block_sum, uint32_t nblocks) {  // one thread: nblocks = n / 2048 is small
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t acc = 0;
+    for (uint32_t i = 0; i < nblocks; i++) {
+        const uint32_t t = block_sum[i];
+        block_sum[i] = acc;
+        acc += t;
+    }
+}
+// dst[n - 1 - (offset of the cycle + steps from the leader)] = src[p]
+__global__ void ibwts_write_kernel(const uint8_t* __restrict__ src, const uint32_t* __restrict__ mn, const uint32_t* __restrict__ cnt,
+                                   const uint32_t* __restrict__ excl, const uint32_t* __restrict__ block_sum, uint32_t n, uint8_t* __restrict__ dst) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t leader = mn[p];
+    const uint32_t len = cnt[leader];
+    const uint32_t d = len - cnt[p];
+    const uint32_t off = excl[leader] + block_sum[leader / 2048];
+    const uint64_t pos = (uint64_t)off + d;
+    if (pos < n) dst[n - 1 - (uint32_t)pos] = src[p];
+}
+
+}  // namespace
+
+size_t bwts_forward_workspace(uint32_t n) { return bwt_forward_workspace(n) + (size_t)n * 4 * 4 + 4096; }
+size_t bwts_inverse_workspace(uint32_t n) {
+    size_t temp = 0;
+    cub::DoubleBuffer<uint8_t> k(nullptr, nullptr);
+    cub::DoubleBuffer<uint32_t> v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, k, v, (int)n, 0, 8);
+    return (size_t)n * (1 * 2 + 4 * 7) + 4 * ((size_t)n / 2048 + 16) + 4096 + temp + 4096;
+}
+
+// sorts keys_a/idx_a (n pairs), ranks the groups; returns the sorted order in *sa_out, group ranks in `rank`; flags[0] = 1 when some
+// group has several members, flags[1] = number of groups
+static cudaError_t bwt_sort_round(uint64_t* keys_a, uint64_t* keys_b, uint32_t* idx_a, uint32_t* idx_b, uint32_t n, int end_bit, void* temp,
+                                  size_t temp_bytes, uint32_t* head, uint32_t* block_max, uint32_t nscan, uint32_t* rank, uint32_t* flags,
+                                  const uint32_t** sa_out, bool count_groups, cudaStream_t stream, uint64_t* launches) {
+    const uint32_t T = 256, G = (n + T - 1) / T;
+    cub::DoubleBuffer<uint64_t> k(keys_a, keys_b);
+    cub::DoubleBuffer<uint32_t> v(idx_a, idx_b);
+    size_t tb = temp_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, tb, k, v, (int)n, 0, end_bit, stream);
+    if (e != cudaSuccess) return e;
+    (*launches) += 8;
+    const uint64_t* sk = k.Current();
+    const uint32_t* sa = v.Current();
+    cudaMemsetAsync(flags, 0, 8, stream);
+    bwt_flag_kernel<<<G, T, 0, stream>>>(sk, n, head);
+    scan_max_local_kernel<<<nscan, 256, 0, stream>>>(head, n, block_max);
+    scan_max_blocks_kernel<<<1, 1024, 0, stream>>>(block_max, nscan);
+    bwt_apply_rank_kernel<<<G, T, 0, stream>>>(head, block_max, sa, n, rank, flags);
+    (*launches) += 4;
+    if (count_groups) {
+        bwts_count_groups_kernel<<<G, T, 0, stream>>>(head, n, flags + 1);
+        (*launches)++;
+    }
+    *sa_out = sa;
+    return cudaGetLastError();
+}
+
+// BWTS.Forward of one block: d_dst receives n bytes
+cudaError_t bwts_forward_device(const uint8_t* d_src, uint32_t n, uint8_t* d_dst, uint8_t* ws, size_t ws_bytes, cudaStream_t stream, uint64_t* launches) {
+    if (n < 2) return n == 1 ? cudaMemcpyAsync(d_dst, d_src, 1, cudaMemcpyDeviceToDevice, stream) : cudaSuccess;
+    auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
+    size_t off = 0;
+    uint64_t* keys_a = (uint64_t*)(ws + off); off = align(off + (size_t)n * 8);
+    uint64_t* keys_b = (uint64_t*)(ws + off); off = align(off + (size_t)n * 8);
+    uint32_t* idx_a = (uint32_t*)(ws + off); off = align(off + (size_t)n * 4);
+    uint32_t* idx_b = (uint32_t*)(ws + off); off = align(off + (size_t)n * 4);
+    uint32_t* rank = (uint32_t*)(ws + off); off = align(off + (size_t)n * 4);
+    uint32_t* head = (uint32_t*)(ws + off); off = align(off + (size_t)n * 4);
+    uint32_t* succ_a = (uint32_t*)(ws + off); off = align(off + (size_t)n * 4);
+    uint32_t* succ_b = (uint32_t*)(ws + off); off = align(off + (size_t)n * 4);
+    uint32_t* pred = (uint32_t*)(ws + off); off = align(off + (size_t)n * 4);
+    uint32_t* aux = (uint32_t*)(ws + off); off = align(off + (size_t)n * 4);
+    const uint32_t nscan = (n + 2047) / 2048;
+    uint32_t* block_max = (uint32_t*)(ws + off); off = align(off + (size_t)nscan * 4);
+    uint32_t* flags = (uint32_t*)(ws + off); off = align(off + 64);
+    void* temp = ws + off;
+    const size_t temp_bytes = ws_bytes > off ? ws_bytes - off : 0;
+    const uint32_t T = 256, G = (n + T - 1) / T;
+    uint32_t log_n = 1;
+    while ((1ull << log_n) <= n) log_n++;
+    // ---- (1) suffix ranks
+    bwt_init_keys_kernel<<<G, T, 0, stream>>>(d_src, n, keys_a, idx_a);
+    (*launches)++;
+    uint32_t h = 7;
+    int end_bit = 63;
+    const uint32_t* sa = nullptr;
+    bool done = false;
+    for (int round = 0; round < 40 && !done; round++) {
+        cudaError_t e = bwt_sort_round(keys_a, keys_b, idx_a, idx_b, n, end_bit, temp, temp_bytes, head, block_max, nscan, rank, flags, &sa, false, stream, launches);
+        if (e != cudaSuccess) return e;
+        uint32_t unsorted = 0;
+        e = cudaMemcpyAsync(&unsorted, flags, 4, cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return e;
+        if (!unsorted || h >= n) {
+            done = true;
+            break;
+        }
+        bwt_double_keys_kernel<<<G, T, 0, stream>>>(rank, n, h, log_n, keys_a, idx_a);
+        (*launches)++;
+        h *= 2;
+        end_bit = 2 * (int)log_n;
+    }
+    if (!done) return cudaErrorUnknown;
+    // ---- (2) Lyndon factor starts: rank smaller than every earlier rank; cyclic successor / predecessor inside the factor
+    bwts_negrank_kernel<<<G, T, 0, stream>>>(rank, n, aux);
+    cudaMemcpyAsync(head, aux, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream);
+    scan_max_local_kernel<<<nscan, 256, 0, stream>>>(head, n, block_max);
+    scan_max_blocks_kernel<<<1, 1024, 0, stream>>>(block_max, nscan);
+    bwts_heads_kernel<<<G, T, 0, stream>>>(aux, head, block_max, n, succ_b /*hpos*/);
+    cudaMemcpyAsync(head, succ_b, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream);
+    scan_max_local_kernel<<<nscan, 256, 0, stream>>>(head, n, block_max);
+    scan_max_blocks_kernel<<<1, 1024, 0, stream>>>(block_max, nscan);
+    bwts_succ_kernel<<<G, T, 0, stream>>>(succ_b /*hpos*/, head, block_max, n, aux /*succ1*/, pred);
+    (*launches) += 7;
+    // ---- (3) order of the rotations: doubling along the cyclic successor until no group splits
+    bwts_init_keys_kernel<<<G, T, 0, stream>>>(d_src, aux, n, keys_a, idx_a, succ_a);
+    (*launches)++;
+    end_bit = 63;
+    uint32_t prev_groups = 0;
+    for (int round = 0; round < 64; round++) {
+        cudaError_t e = bwt_sort_round(keys_a, keys_b, idx_a, idx_b, n, end_bit, temp, temp_bytes, head, block_max, nscan, rank, flags, &sa, true, stream, launches);
+        if (e != cudaSuccess) return e;
+        uint32_t fl[2] = {0, 0};
+        e = cudaMemcpyAsync(fl, flags, 8, cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return e;
+        if (!fl[0] || fl[1] == prev_groups) {  // all distinct, or only equal rotations of repeated factors are left
+            bwts_emit_kernel<<<G, T, 0, stream>>>(d_src, sa, pred, n, d_dst);
+            (*launches)++;
+            return cudaGetLastError();
+        }
+        prev_groups = fl[1];
+        bwts_double_keys_kernel<<<G, T, 0, stream>>>(rank, succ_a, n, log_n, keys_a, idx_a, succ_b);
+        (*launches)++;
+        std::swap(succ_a, succ_b);
+        end_bit = 2 * (int)log_n;
+    }
+    return cudaErrorUnknown;
+}
+
+// BWTS.Inverse of one block
+cudaError_t bwts_inverse_device(const uint8_t* d_src, uint32_t n, uint8_t* d_dst, uint8_t* ws, size_t ws_bytes, cudaStream_t stream, uint64_t* launches) {
+    if (n < 2) return n == 1 ? cudaMemcpyAsync(d_dst, d_src, 1, cudaMemcpyDeviceToDevice, stream) : cudaSuccess;
+    auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
+    size_t off = 0;
+    uint8_t* keys_a = ws + off; off = align(off + n);
+    uint8_t* keys_b = ws + off; off = align(off + n);
+    uint32_t* val_a = (uint32_t*)(ws + off); off = align(off + (size_t)n * 4);
+    uint32_t* val_b = (uint32_t*)(ws + off); off = align(off + (size_t)n * 4);
+    uint32_t* lf = (uint32_t*)(ws + off); off = align(off + (size_t)n * 4);
+    uint32_t* a0 = (uint32_t*)(ws + off); off = align(off + (size_t)n * 4);
+    uint32_t* a1 = (uint32_t*)(ws + off); off = align(off + (size_t)n * 4);
+    uint32_t* b0 = (uint32_t*)(ws + off); off = align(off + (size_t)n * 4);
+    uint32_t* b1 = (uint32_t*)(ws + off); off = align(off + (size_t)n * 4);
+    const uint32_t nscan = (n + 2047) / 2048;
+    uint32_t* block_sum = (uint32_t*)(ws + off); off = align(off + (size_t)nscan * 4);
+    void* temp = ws + off;
+    const size_t temp_bytes = ws_bytes > off ? ws_bytes - off : 0;
+    const uint32_t T = 256, G = (n + T - 1) / T;
+    ibwts_init_kernel<<<G, T, 0, stream>>>(d_src, n, keys_a, val_a);
+    cub::DoubleBuffer<uint8_t> k(keys_a, keys_b);
+    cub::DoubleBuffer<uint32_t> v(val_a, val_b);
+    size_t tb = temp_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, tb, k, v, (int)n, 0, 8, stream);  // stable: rank of i among equal bytes keeps the order
+    if (e != cudaSuccess) return e;
+    ibwts_lf_kernel<<<G, T, 0, stream>>>(v.Current(), n, lf);
+    (*launches) += 10;
+    uint32_t rounds = 1;
+    while ((1ull << rounds) < n) rounds++;
+    // cycle leaders: minimum index over the whole cycle. val_a / val_b are free again after the scatter
+    uint32_t *mn = a0, *jp = a1, *mn2 = b0, *jp2 = b1;
+    ibwts_min_init_kernel<<<G, T, 0, stream>>>(lf, n, mn, jp);
+    for (uint32_t r = 0; r < rounds; r++) {
+        ibwts_min_jump_kernel<<<G, T, 0, stream>>>(mn, jp, n, mn2, jp2);
+        std::swap(mn, mn2);
+        std::swap(jp, jp2);
+    }
+    (*launches) += rounds + 1;
+    // distance to the end of the cut cycle: mn must stay intact -> use val_a/val_b and the free pair
+    uint32_t* nx = jp;       // jump pointers are no longer needed
+    uint32_t* cnt = mn2;
+    uint32_t* nx2 = jp2;
+    uint32_t* cnt2 = val_a;
+    ibwts_rank_init_kernel<<<G, T, 0, stream>>>(lf, mn, n, nx, cnt);
+    for (uint32_t r = 0; r < rounds; r++) {
+        ibwts_rank_jump_kernel<<<G, T, 0, stream>>>(nx, cnt, n, nx2, cnt2);
+        std::swap(nx, nx2);
+        std::swap(cnt, cnt2);
+    }
+    (*launches) += rounds + 1;
+    uint32_t* len_at = val_b;
+    ibwts_len_kernel<<<G, T, 0, stream>>>(mn, cnt, n, len_at);
+    scan_add_local_kernel<<<nscan, 256, 0, stream>>>(len_at, n, block_sum);
+    scan_add_blocks_kernel<<<1, 32, 0, stream>>>(block_sum, nscan);
+    ibwts_write_kernel<<<G, T, 0, stream>>>(d_src, mn, cnt, len_at, block_sum, n, d_dst);
+    (*launches) += 4;
+    return cudaGetLastError();
+}
+
 }  // namespace kz

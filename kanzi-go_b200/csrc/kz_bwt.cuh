@@ -11,4 +11,9 @@ cudaError_t bwt_forward_device(const uint8_t* d_src, uint32_t n, uint8_t* d_dst,
 // BWTBlockCodec.Inverse of one block; h_header = the first min(len, 33) bytes of d_src copied to the host
 cudaError_t bwt_inverse_device(const uint8_t* d_src, const uint8_t* h_header, uint32_t len, uint8_t* d_dst, uint32_t cap, uint32_t* out_len, uint8_t* ws,
                                size_t ws_bytes, cudaStream_t stream, uint64_t* launches);
+// BWTS.Forward / BWTS.Inverse of one block (n bytes in, n bytes out)
+size_t bwts_forward_workspace(uint32_t n);
+size_t bwts_inverse_workspace(uint32_t n);
+cudaError_t bwts_forward_device(const uint8_t* d_src, uint32_t n, uint8_t* d_dst, uint8_t* ws, size_t ws_bytes, cudaStream_t stream, uint64_t* launches);
+cudaError_t bwts_inverse_device(const uint8_t* d_src, uint32_t n, uint8_t* d_dst, uint8_t* ws, size_t ws_bytes, cudaStream_t stream, uint64_t* launches);
 }  // namespace kz

@@ -244,4 +244,120 @@ bool bwt_block_inverse(Ctx&, const uint8_t* src, size_t n, uint8_t* dst, size_t 
     return true;
 }
 
+
+// ---- BWTS (bijective BWT, transform/BWTS.go). ComputeSuffixArray (DivSufSort.go:161-177) is any correct suffix sort.
+namespace {
+// BWTS.go:172-209 moveLyndonWordHead
+int32_t move_lyndon_word_head(std::vector<int32_t>& sa, std::vector<int32_t>& isa, const uint8_t* data, int32_t count, int32_t start, int32_t size,
+                              int32_t rank) {
+    const int32_t end = start + size;
+    while (rank + 1 < count) {
+        const int32_t next_start0 = sa[size_t(rank) + 1];
+        if (next_start0 <= end) break;
+        int32_t next_start = next_start0;
+        int32_t k = 0;
+        while (k < size && next_start < count && data[start + k] == data[next_start]) {
+            k++;
+            next_start++;
+        }
+        if (k == size && rank < isa[size_t(next_start)]) break;
+        if (k < size && next_start < count && data[start + k] < data[next_start]) break;
+        sa[size_t(rank)] = next_start0;
+        isa[size_t(next_start0)] = rank;
+        rank++;
+    }
+    sa[size_t(rank)] = start;
+    isa[size_t(start)] = rank;
+    return rank;
+}
+}  // namespace
+
+// BWTS.Forward :58-170
+bool bwts_forward(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n) {
+    *out_n = 0;
+    if (n == 0) return true;
+    if (cap < n) return false;
+    if (n > (size_t(1) << 30)) return false;
+    if (n < 2) {
+        dst[0] = src[0];
+        *out_n = n;
+        return true;
+    }
+    const int32_t count = int32_t(n);
+    std::vector<int32_t> sa, isa(n);
+    suffix_array(src, count, sa);
+    for (int32_t i = 0; i < count; i++) isa[size_t(sa[size_t(i)])] = i;
+    int32_t mn = isa[0];
+    int32_t idx_min = 0;
+    for (int32_t i = 1; i < count && mn > 0; i++) {
+        if (isa[size_t(i)] >= mn) continue;
+        int32_t ref_rank = move_lyndon_word_head(sa, isa, src, count, idx_min, i - idx_min, mn);
+        for (int32_t j = i - 1; j > idx_min; j--) {  // iterate through the new lyndon word from end to start
+            int32_t test_rank = isa[size_t(j)];
+            const int32_t start_rank = test_rank;
+            while (test_rank < count - 1) {
+                const int32_t next_rank_start = sa[size_t(test_rank) + 1];
+                if (j > next_rank_start || src[j] != src[next_rank_start] || ref_rank < isa[size_t(next_rank_start) + 1]) break;
+                sa[size_t(test_rank)] = next_rank_start;
+                isa[size_t(next_rank_start)] = test_rank;
+                test_rank++;
+            }
+            sa[size_t(test_rank)] = j;
+            isa[size_t(j)] = test_rank;
+            ref_rank = test_rank;
+            if (start_rank == test_rank) break;
+        }
+        mn = isa[size_t(i)];
+        idx_min = i;
+    }
+    mn = count;
+    for (int32_t i = 0; i < count; i++) {
+        if (isa[size_t(i)] >= mn) {
+            dst[isa[size_t(i)]] = src[i - 1];
+            continue;
+        }
+        if (mn < count) dst[mn] = src[i - 1];
+        mn = isa[size_t(i)];
+    }
+    dst[0] = src[count - 1];
+    *out_n = n;
+    return true;
+}
+
+// BWTS.Inverse :211-288
+bool bwts_inverse(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n) {
+    *out_n = 0;
+    if (n == 0) return true;
+    if (n > (size_t(1) << 30) || n > cap) return false;
+    if (n < 2) {
+        dst[0] = src[0];
+        *out_n = n;
+        return true;
+    }
+    const int32_t count = int32_t(n);
+    std::vector<int32_t> lf(n);
+    int32_t buckets[256] = {0};
+    for (int32_t i = 0; i < count; i++) buckets[src[i]]++;
+    int32_t sum = 0;
+    for (int i = 0; i < 256; i++) {
+        sum += buckets[i];
+        buckets[i] = sum - buckets[i];
+    }
+    for (int32_t i = 0; i < count; i++) lf[size_t(i)] = buckets[src[i]]++;
+    for (int32_t i = 0, j = count - 1; j >= 0; i++) {
+        if (lf[size_t(i)] < 0) continue;
+        int32_t p = i;
+        for (;;) {
+            dst[j] = src[p];
+            j--;
+            const int32_t t = lf[size_t(p)];
+            lf[size_t(p)] = -1;
+            p = t;
+            if (lf[size_t(p)] < 0) break;
+        }
+    }
+    *out_n = n;
+    return true;
+}
+
 }  // namespace kzo

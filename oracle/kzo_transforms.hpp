@@ -12,4 +12,6 @@ bool sbrt_forward(int mode, const uint8_t* src, size_t n, uint8_t* dst, size_t c
 bool sbrt_inverse(int mode, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
 bool zrlt_forward(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
 bool zrlt_inverse(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
+bool bwts_forward(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
+bool bwts_inverse(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
 }  // namespace kzo

@@ -14,6 +14,7 @@ _SO = os.path.join(_HERE, "_build", "libkanzi_oracle.so")
 
 E_NONE, E_HUFFMAN, E_RANGE, E_ANS0, E_ANS1 = 0, 1, 4, 5, 8
 T_NONE, T_BWT, T_BWTS, T_LZ, T_ROLZ, T_LZX = 0, 1, 2, 3, 11, 16
+T_ZRLT, T_MTFT, T_RANK = 6, 7, 8
 
 
 def build(force=False):
