@@ -32,6 +32,47 @@ BLOCK = 4 << 20
 NBLOCKS = 64
 METRIC = "encode+decode MB/s (ANS0/NONE, 64x4MiB Zipf(1.0) blocks per GPU)"
 
+# The default workload is BASELINE.json configs[1] (the configuration the roofline target is quoted on). The others are
+# the GPU-covered parts of the remaining configs, run by hand with --workload and recorded under profiles/ (they are
+# parity-test cases first; the driver's bench line is always the default).
+#   name: (transform, entropy, block size, blocks per GPU, data generator, dominant kernel for the roofline, metric label)
+WORKLOADS = {
+    "ans0": ("NONE", "ANS0", 4 << 20, 64, "zipf1", "ans0_decode", METRIC),
+    "huffman": ("NONE", "HUFFMAN", 4 << 20, 64, "zipf1", "huf_decode", "encode+decode MB/s (HUFFMAN/NONE, 64x4MiB Zipf(1.0) blocks per GPU)"),
+    "ans1": ("NONE", "ANS1", 4 << 20, 64, "text", "ans1_decode", "encode+decode MB/s (ANS1/NONE, 64x4MiB order-1 text blocks per GPU; configs[4] at 4 MiB)"),
+    "l3core": ("LZX", "HUFFMAN", 4 << 20, 48, "text", "lz_parse",
+               "encode+decode MB/s (-t LZX -e HUFFMAN, 48x4MiB text blocks: the GPU covered part of kanzi -l 3, configs[2] shape)"),
+    "l5core": ("BWT+RANK+ZRLT", "ANS0", 32 << 20, 4, "text", "bwt_forward",
+               "encode+decode MB/s (-t BWT+RANK+ZRLT -e ANS0, 4x32MiB text blocks: the GPU covered part of kanzi -l 5, configs[3] shape)"),
+    "l5core4m": ("BWT+RANK+ZRLT", "ANS0", 4 << 20, 16, "text", "bwt_forward",
+                 "encode+decode MB/s (-t BWT+RANK+ZRLT -e ANS0, 16x4MiB text blocks)"),
+}
+
+
+def make_data(kind, n, seed):
+    synth = importlib.import_module("kanzi-go_b200.synth")
+    if kind == "zipf1":
+        return synth.zipf_bytes(n, 1.0, seed=seed)
+    if kind == "text":
+        return synth.markov_text(n, seed=seed)
+    raise ValueError(kind)
+
+
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` from the newest committed `ncu --set full` summary
+    (profiles/*ncu*summary.json, written by tools/ncu_summary.py): per launch of the default workload, or None."""
+    import glob
+
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu*summary*.json"))):
+        try:
+            for k in json.load(open(f)).get("kernels", []):
+                if kernel in k.get("kernel", "") and k.get("dram_traffic_bytes"):
+                    best = (float(k["dram_traffic_bytes"]), os.path.basename(f))
+        except Exception:
+            pass
+    return best
+
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -74,21 +115,22 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def cpu_reference(steps, warmup, sample_blocks=None):
+def cpu_reference(steps, warmup, sample_blocks=None, workload="ans0"):
     """Times the CPU restatement of the reference path (oracle) with one worker per block on all host cores."""
     from oracle import pyoracle
 
     synth = importlib.import_module("kanzi-go_b200.synth")
+    transform, entropy, BLOCK, NBLOCKS, kind = WORKLOADS[workload][:5]
     cores = os.cpu_count() or 1
     jobs = min(64, cores)
     if sample_blocks is None:
         sample_blocks = NBLOCKS  # the full batch is ~1-3 s of CPU work per step on a multi-core host
     n = sample_blocks * BLOCK
-    x = synth.zipf_bytes(n, 1.0, seed=synth.SEED + 1)
+    x = make_data(kind, n, synth.SEED + 1)
     times = []
     for it in range(warmup + steps):
         te, td = [], []
-        s = pyoracle.compress(x, "NONE", "ANS0", block_size=BLOCK, jobs=jobs, input_size=n, timing=te)
+        s = pyoracle.compress(x, transform, entropy, block_size=BLOCK, jobs=jobs, input_size=n, timing=te)
         y = pyoracle.decompress(s, n + 64, jobs=jobs, timing=td)
         if it == 0:
             assert np.array_equal(y, x)
@@ -96,9 +138,15 @@ def cpu_reference(steps, warmup, sample_blocks=None):
             times.append(te[0] + td[0])
     t = float(np.mean(times))
     return {"value": 2 * n / t / 1e6, "unit": "MB/s", "cores": jobs, "kind": "port",
-            "sample": "%d x 4 MiB Zipf(1.0) blocks (%d MiB), compress+decompress in memory, %d worker threads, C++ restatement of kanzi-go (no Go toolchain)"
-                      % (sample_blocks, n >> 20, jobs),
+            "sample": "%d x %d MiB %s blocks (%d MiB), -t %s -e %s, compress+decompress in memory, %d worker threads, C++ restatement of kanzi-go (no Go toolchain)"
+                      % (sample_blocks, BLOCK >> 20, kind, n >> 20, transform, entropy, jobs),
             "ms_per_step": t * 1e3}
+
+
+def workload_label(name):
+    transform, entropy, block, nblocks, kind = WORKLOADS[name][:5]
+    label = "%s/%s %dx%dMiB %s" % (entropy, transform, nblocks, block >> 20, {"zipf1": "Zipf(1.0)", "text": "order-1 text"}[kind])
+    return label + (" (BASELINE.json configs[1])" if name == "ans0" else "")
 
 
 def emit(line):
@@ -118,7 +166,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="ans0", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    transform, entropy, BLOCK, NBLOCKS, kind, roof_kernel, METRIC = WORKLOADS[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -129,10 +179,10 @@ def main():
         if rank != 0:
             return 0
         steps = min(args.steps, 5)
-        r = cpu_reference(steps, min(args.warmup, 1))
+        r = cpu_reference(steps, min(args.warmup, 1), workload=args.workload)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "MB/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "ANS0/NONE 64x4MiB Zipf(1.0) (BASELINE.json configs[1]), CPU path", "block_size": BLOCK, "blocks": NBLOCKS},
+                "config": {"workload": "%s, CPU path" % workload_label(args.workload), "block_size": BLOCK, "blocks": NBLOCKS},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         emit(line)
@@ -151,8 +201,8 @@ def main():
     torch.cuda.set_device(local_rank)
     ctx = kz.Context(local_rank)
     n = NBLOCKS * BLOCK
-    x = synth.zipf_bytes(n, 1.0, seed=synth.SEED + 1 + rank)
-    t48, et = 0, kz.E_ANS0
+    x = make_data(kind, n, synth.SEED + 1 + rank)
+    t48, et = kz.transform_type(transform), kz.entropy_type(entropy)
     cap = int(ctx.lib.kz_max_stream_output(n, BLOCK))
 
     # ---------------- device-resident pass (value) ----------------
@@ -204,7 +254,9 @@ def main():
     launches = ctx.launch_count(reset=True)
     kern = {}
     for name in ("ans0_decode", "ans0_encode", "ans0_stats", "ans_walk", "concat", "concat_zero", "scan", "stream_walk", "block_header", "block_prefix", "extract",
-                 "host:encode_batch", "host:enc_tables", "host:enc_sync"):
+                 "huf_stats", "huf_encode", "huf_walk", "huf_decode", "ans1_hist", "ans1_stats", "ans1_encode", "ans1_decode", "range_encode", "range_decode",
+                 "bwt_forward", "bwt_inverse", "bwts_forward", "bwts_inverse", "lz_parse", "lz_gather", "lz_inverse", "sbrt_last2", "sbrt_carry", "sbrt_rank",
+                 "sbrt_inverse", "zrlt_forward", "zrlt_inverse", "xxhash", "host:encode_batch", "host:enc_tables", "host:enc_sync"):
         cnt, ms = ctx.kernel_time(name)
         if cnt:
             kern[name] = {"launches": cnt, "ms_avg": ms / cnt}
@@ -251,18 +303,28 @@ def main():
     e2e_value = total_bytes * e2e_steps / (e2e_ms / 1e3) / 1e6
     peak, peak_src = peaks()
     roof = None
-    if "ans0_decode" in kern:
-        alg = float(n + m)  # compressed bytes read + decoded bytes written per launch
-        ach = alg / (kern["ans0_decode"]["ms_avg"] / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": "ans0_decode_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": kern["ans0_decode"]["ms_avg"]}
+    if roof_kernel in kern:
+        # algorithmic bytes per launch: entropy stage = compressed + uncompressed bytes of the batch; a transform
+        # launched per block (BWT) = 2 x block bytes; the serial LZ parse = block bytes in + out of the batch
+        per_block = roof_kernel in ("bwt_forward", "bwt_inverse")
+        alg = float(2 * BLOCK) if per_block else float(n + m)
+        ach = alg / (kern[roof_kernel]["ms_avg"] / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": roof_kernel + ("_device (all kernels of one block)" if per_block else "_kernel"), "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                "ms_per_launch": kern[roof_kernel]["ms_avg"]}
+        if args.workload == "ans0":
+            t = measured_traffic("ans0_decode")
+            if t:
+                roof["traffic"] = t[0]
+                roof["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/" + t[1]
     line = {
         "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "ANS0/NONE 64x4MiB Zipf(1.0) (BASELINE.json configs[1])", "block_size": BLOCK, "blocks_per_gpu": NBLOCKS,
-                   "uncompressed_bytes_per_gpu": n, "compressed_bytes_per_gpu": int(m), "l2": "inputs (256 MiB in, %d MiB compressed) larger than the 126 MB L2" % (m >> 20),
+        "config": {"workload": workload_label(args.workload), "block_size": BLOCK, "blocks_per_gpu": NBLOCKS,
+                   "uncompressed_bytes_per_gpu": n, "compressed_bytes_per_gpu": int(m),
+                   "l2": "inputs (%d MiB in, %d MiB compressed) larger than the 126 MB L2" % (n >> 20, m >> 20),
                    "encode_MBps": n * world * args.steps / (enc_ms / 1e3) / 1e6, "decode_MBps": n * world * args.steps / (dec_ms / 1e3) / 1e6,
-                   "parallelism": "1 process per GPU, 64 blocks per GPU, no data-path collective"},
+                   "parallelism": "1 process per GPU, %d blocks per GPU, no data-path collective" % NBLOCKS},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": int(n + m), "d2h_bytes_per_step": int(m + n), "steps": e2e_steps,
                 "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": e2e_wall_ms / e2e_steps, "api": "kz_compress_stream + kz_decompress_stream, pinned host buffers"},
@@ -273,7 +335,7 @@ def main():
         line["roofline"] = roof
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = cpu_reference(2, 1, sample_blocks=NBLOCKS)
+            r = cpu_reference(2, 1, sample_blocks=NBLOCKS, workload=args.workload)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:  # the checker is absent: report, never substitute
             line["cpu_baseline"] = {"value": None, "unit": "MB/s", "cores": 0, "kind": "port", "sample": "unavailable: %s" % e}

@@ -1125,4 +1125,379 @@ __global__ void __launch_bounds__(64, 7) ans0_decode4_kernel(const uint32_t* __r
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// decode tables (v5): the header parse and table construction of decode v3/v4 ran on ONE lane per chunk (a serial
+// walk of ~300 bit-field reads through global memory, ~7 % of the kernel) while the other 31 lanes waited. Here one WARP
+// per chunk parses the header from a shared-memory window (alphabet by popc/prefix sums, group lengths chased by lane 0,
+// frequencies extracted group-parallel, cumulative frequencies by a warp scan, start flags by shared-memory atomics) and
+// writes a DEC_TAB_WORDS record per chunk: 171 bucket words | 256 symbol entries | lr, mode, steps, tail, payload begin /
+// end bit, 4 states. ans0_decode5_kernel only copies the records (cp.async) into its interleaved layout.
+// Chunks whose alphabet has a single symbol are filled here (Read :737-741) and need no decode.
+// ------------------------------------------------------------------------------------------------------------
+static const int TAB_WIN_WORDS = 160;  // 3 + 6 + 256 + 32 x 124 bits of header + 40 bits varint + 128 bits states + slack
+
+__global__ void __launch_bounds__(128) ans0_tables_kernel(const uint32_t* __restrict__ words, uint64_t words_len, const DecChunk* __restrict__ chunks,
+                                                          int nchunks, const uint64_t* __restrict__ chunk_hdr_bit, uint32_t* __restrict__ tabs,
+                                                          uint8_t* __restrict__ out, int32_t* __restrict__ status) {
+    __shared__ uint32_t s_win[4][TAB_WIN_WORDS + 2];
+    __shared__ uint32_t s_bm[4][192];
+    __shared__ uint16_t s_freq[4][256];
+    __shared__ uint8_t s_sym[4][256];
+    __shared__ uint16_t s_goff[4][32];
+    __shared__ uint8_t s_glog[4][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 4 + warp;
+    if (c >= nchunks) return;
+    uint32_t* rec = tabs + (size_t)c * DEC_TAB_WORDS;
+    uint32_t* meta = rec + DEC_BM_WORDS + 256;
+    const DecChunk ck = chunks[c];
+    if (lane == 0) meta[1] = 0;  // mode: nothing to decode unless everything below checks out
+    if (status[ck.block] != 0) return;
+    const uint64_t hbit = chunk_hdr_bit[c];
+    const uint64_t w0 = hbit >> 5;
+    uint32_t* win = s_win[warp];
+    for (int i = lane; i < TAB_WIN_WORDS + 2; i += 32) win[i] = w0 + i < words_len ? bswap32(__ldg(words + w0 + i)) : 0u;
+    for (int i = lane; i < 192; i += 32) s_bm[warp][i] = 0;
+    __syncwarp();
+    auto rd = [&](uint32_t at, uint32_t n) -> uint32_t {  // n in 1..32 bits at window relative position `at`
+        const uint32_t w = at >> 5, o = at & 31;
+        return __funnelshift_l(win[w + 1], win[w], o) >> (32 - n);
+    };
+    const uint64_t room = ck.end_bit > hbit ? ck.end_bit - hbit : 0;  // bits of the block that follow the header start
+    uint32_t q = (uint32_t)(hbit & 31);
+    const uint32_t q0 = q;
+    const uint32_t lr = 8 + rd(q, 3);
+    q += 3;
+    const uint32_t scale = 1u << lr;
+    const uint32_t llr = 32u - (uint32_t)__clz((int)lr);  // smallest llr >= 3 with (1 << llr) > lr, lr in 8..15
+    int asz = 0;
+    if (rd(q, 1) == 0) {
+        asz = rd(q + 1, 1) ? 0 : 256;
+        q += 2;
+        for (int i = lane; i < 256; i += 32) s_sym[warp][i] = (uint8_t)i;
+    } else {
+        const uint32_t last = rd(q + 1, 5);
+        q += 6;
+        const uint32_t m = (uint32_t)lane <= last ? rd(q + 8 * lane, 8) : 0u;
+        const uint32_t pc = (uint32_t)__popc(m);
+        uint32_t incl = pc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        uint32_t r = incl - pc, mm = m;
+        while (mm) {
+            const int j = __ffs((int)mm) - 1;
+            mm &= mm - 1;
+            s_sym[warp][r++] = (uint8_t)(8 * lane + j);
+        }
+        asz = (int)__shfl_sync(0xFFFFFFFFu, incl, 31);
+        q += 8 * (last + 1);
+    }
+    __syncwarp();
+    if (asz == 0 || lr > 12) {
+        if (lane == 0) atomicCAS(&status[ck.block], 0, asz == 0 ? -KZ_E_PROCESS_BLOCK : -KZ_E_INVALID_CODEC);
+        return;
+    }
+    if (asz == 1) {  // Read :737-741: the chunk is one repeated symbol, nothing else is read
+        if ((uint64_t)(q - q0) > room) {
+            if (lane == 0) atomicCAS(&status[ck.block], 0, -KZ_E_PROCESS_BLOCK);
+            return;
+        }
+        const uint32_t v = s_sym[warp][0] * 0x01010101u;
+        uint8_t* dst = out + ck.out_off;  // 16-byte aligned
+        const uint32_t n16 = ck.out_len >> 4;
+        for (uint32_t i = lane; i < n16; i += 32) reinterpret_cast<uint4*>(dst)[i] = make_uint4(v, v, v, v);
+        for (uint32_t i = (n16 << 4) + lane; i < ck.out_len; i += 32) dst[i] = (uint8_t)v;
+        return;
+    }
+    // ---- frequency groups: lane 0 chases the group offsets (serial by format), every lane extracts one group
+    const uint32_t gs = asz < 64 ? 6 : 8;
+    const uint32_t ngroups = ((uint32_t)asz - 2u + gs) / gs;  // 1..32
+    uint32_t bad = 0;
+    if (lane == 0) {
+        uint32_t p = q;
+        for (uint32_t g = 0; g < ngroups; g++) {
+            const uint32_t log_max = rd(p, llr);
+            const uint32_t cnt = min(gs, (uint32_t)asz - 1u - g * gs);
+            s_goff[warp][g] = (uint16_t)(p + llr);
+            s_glog[warp][g] = (uint8_t)log_max;
+            if ((1u << log_max) > scale) bad = 1;
+            p += llr + cnt * log_max;
+        }
+        q = p;
+    }
+    q = __shfl_sync(0xFFFFFFFFu, q, 0);
+    __syncwarp();
+    uint32_t part = 0;
+    if ((uint32_t)lane < ngroups) {
+        const uint32_t log_max = s_glog[warp][lane];
+        const uint32_t first = 1 + lane * gs;
+        const uint32_t cnt = min(gs, (uint32_t)asz - first);
+        uint32_t p = s_goff[warp][lane];
+        for (uint32_t k2 = 0; k2 < cnt; k2++, p += log_max) {
+            uint32_t f = 1;
+            if (log_max > 0 && log_max <= 15) {
+                f = 1 + rd(p, log_max);
+                if (f >= scale) bad = 1;
+            }
+            s_freq[warp][first + k2] = (uint16_t)f;
+            part += f;
+        }
+    }
+    const uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, part);
+    if (scale <= sum) bad = 1;
+    // size of the payload and the four states (ANSRangeCodec.go:726-733, :866-886)
+    uint32_t sz = 0, nb = 0;
+    {
+        const uint32_t v4 = rd(q, 32), v1 = rd(q + 32, 8);
+        sz = (v4 >> 24) & 0x7F, nb = 1;
+        if (v4 & 0x80000000u) {
+            sz |= ((v4 >> 16) & 0x7F) << 7, nb = 2;
+            if (v4 & 0x00800000u) {
+                sz |= ((v4 >> 8) & 0x7F) << 14, nb = 3;
+                if (v4 & 0x00008000u) {
+                    sz |= (v4 & 0x7F) << 21, nb = 4;
+                    if (v4 & 0x00000080u) sz |= (v1 & 0x0F) << 28, nb = 5;
+                }
+            }
+        }
+    }
+    q += 8 * nb;
+    const uint32_t st_k = rd(q + 32 * (lane & 3), 32);
+    q += 128;
+    if (sz >= (uint32_t)ANS_MAX_CHUNK || (uint64_t)(q - q0) + 8ull * sz > room) bad = 1;
+    bad = __ballot_sync(0xFFFFFFFFu, bad != 0) ? 1u : 0u;
+    if (bad) {
+        if (lane == 0) atomicCAS(&status[ck.block], 0, -KZ_E_PROCESS_BLOCK);
+        return;
+    }
+    if (lane == 0) s_freq[warp][0] = (uint16_t)(scale - sum);
+    __syncwarp();
+    // ---- cumulative frequencies (lane l owns ranks 8 l .. 8 l + 7), symbol entries, start flags
+    uint32_t f8[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int r = lane * 8 + j;
+        f8[j] = r < asz ? s_freq[warp][r] : 0u;
+        tot += f8[j];
+    }
+    uint32_t incl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    uint32_t cum = incl - tot;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int r = lane * 8 + j;
+        uint32_t e = 0;
+        if (r < asz) {
+            e = (f8[j] << 20) | (cum << 8) | s_sym[warp][r];
+            if (cum) atomicOr(&s_bm[warp][cum / 24], 1u << (cum % 24));  // slot 0 always starts symbol 0: its flag is implied
+        }
+        rec[DEC_BM_WORDS + r] = e;
+        cum += f8[j];
+    }
+    __syncwarp();
+    // symbols started before each bucket, minus one (6 buckets per lane)
+    uint32_t b6[6], pc6 = 0;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        b6[j] = s_bm[warp][lane * 6 + j];
+        pc6 += (uint32_t)__popc(b6[j]);
+    }
+    uint32_t inc2 = pc6;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc2, d);
+        if (lane >= d) inc2 += t;
+    }
+    uint32_t running = inc2 - pc6;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        const int w = lane * 6 + j;
+        if (w < DEC_BM_WORDS) rec[w] = b6[j] | (running << 24);
+        running += (uint32_t)__popc(b6[j]);
+    }
+    // ---- meta
+    const uint64_t pb = hbit + (q - q0);
+    const uint64_t pe = pb + 8ull * sz;
+    if (lane < 4) meta[8 + lane] = st_k;
+    if (lane == 0) {
+        meta[0] = lr;
+        meta[2] = ck.out_len >> 2;
+        meta[3] = ck.out_len & 3;
+        meta[4] = (uint32_t)pb;
+        meta[5] = (uint32_t)(pb >> 32);
+        meta[6] = (uint32_t)pe;
+        meta[7] = (uint32_t)(pe >> 32);
+        __threadfence_block();
+        meta[1] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(64, 7) ans0_decode5_kernel(const uint32_t* __restrict__ words, uint64_t words_len /*in 32-bit words*/, const uint32_t* __restrict__ tabs,
+                                                             const DecChunk* __restrict__ chunks, int nchunks,
+                                                             const uint64_t* __restrict__ chunk_hdr_bit, uint8_t* __restrict__ out,
+                                                             int32_t* __restrict__ status) {
+    extern __shared__ __align__(256) uint32_t s_dec5[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, k = lane & 3;  // chunk slot inside the warp, state index
+    // the rings must be 256-byte aligned in the shared window (DEC4_SMEM carries 256 bytes of slack for this)
+    uint32_t* s_al = s_dec5 + (((0u - smem_u32(s_dec5)) & 255u) >> 2);
+    uint32_t* wbase = s_al + warp * DEC4_WARP_WORDS;
+    uint32_t* ring = wbase + g * RING_WORDS;
+    uint32_t* bm = wbase + 8 * RING_WORDS + g;                       // bucket w at bm[w*8]
+    uint32_t* symtab = wbase + 8 * RING_WORDS + DEC_BM_WORDS * 8 + g;  // entry i at symtab[i*8]
+    const int c = blockIdx.x * DEC_CTA_CHUNKS + warp * 8 + g;
+    const uint32_t grp_mask = 0xFu << (lane & ~3);
+    const uint32_t hi_mask = grp_mask & ~((2u << lane) - 1u);  // lanes of my group with a higher state index (they read first)
+
+    // ---- per-chunk set-up: the tables were built by ans0_tables_kernel; the warp copies its 8 records into the
+    // interleaved shared-memory layout (lane l moves word (l >> 3) + 4 j of chunk l & 7: conflict-free stores)
+    {
+        const int cg = blockIdx.x * DEC_CTA_CHUNKS + warp * 8 + (lane & 7);
+        if (cg < nchunks) {
+            const uint32_t* rec = tabs + (size_t)cg * DEC_TAB_WORDS;
+            const uint32_t dst0 = smem_u32(wbase + 8 * RING_WORDS) + 4u * (uint32_t)(lane & 7);
+            for (int i = lane >> 3; i < DEC_BM_WORDS + 256; i += 4)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst0 + 32u * (uint32_t)i), "l"(rec + i) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    uint32_t lr = 12, nsteps = 0, tail = 0;
+    uint64_t pb = 0, pe = 0;
+    uint8_t* dst = nullptr;
+    int mode = 0;  // 0 = nothing to do, 1 = rANS decode
+    DecLane L;
+    L.st = 0;
+    L.acc = 0;
+    if (c < nchunks) {
+        const uint32_t* meta = tabs + (size_t)c * DEC_TAB_WORDS + DEC_BM_WORDS + 256;
+        mode = (int)__ldg(meta + 1);
+        if (mode) {
+            lr = __ldg(meta);
+            nsteps = __ldg(meta + 2);
+            tail = __ldg(meta + 3);
+            pb = (uint64_t)__ldg(meta + 4) | ((uint64_t)__ldg(meta + 5) << 32);
+            pe = (uint64_t)__ldg(meta + 6) | ((uint64_t)__ldg(meta + 7) << 32);
+            L.st = __ldg(meta + 8 + k);
+            dst = out + chunks[c].out_off;
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    uint32_t max_steps = nsteps, min_steps = nsteps;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        max_steps = max(max_steps, __shfl_xor_sync(0xFFFFFFFFu, max_steps, d));
+        min_steps = min(min_steps, __shfl_xor_sync(0xFFFFFFFFu, min_steps, d));
+    }
+    if (max_steps == 0) return;
+
+    // ---- payload ring: raw copy of the stream starting at the 16-byte aligned block that holds the first payload bit.
+    // Ring byte r <-> source byte base_b + r. Round n copies source bytes [base_b + 64 n, +64): lane k its 16-byte unit.
+    // A unit is copied when it starts before the end of the payload and lies inside the stream buffer, otherwise it is
+    // zero filled (the guard past the payload, :888-893): the first `left` rounds of this lane copy, the others fill.
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(words);
+    const uint64_t base_b = (pb >> 3) & ~15ull;            // source byte of ring byte 0
+    const uint32_t rel = (uint32_t)(pb - 8 * base_b);      // payload bit offset inside the ring, 0..134
+    const uint32_t rsh = 16u - (rel & 15u);                // see dec4_step
+    const uint64_t end_b = (pe + 7) >> 3;                  // first source byte past the payload
+    const uint64_t lim_b = words_len * 4;
+    const uint64_t lim_u = lim_b >= 15 ? lim_b - 15 : 0;   // units must start below this to be entirely readable
+    const uint64_t stop_b = end_b < lim_u ? end_b : lim_u;
+    const uint64_t first_u = base_b + 16u * k;
+    int32_t left = (mode && stop_b > first_u) ? (int32_t)((stop_b - first_u + 63) >> 6) : 0;
+    const uint8_t* src = bytes + first_u;
+    const uint32_t ring_base = smem_u32(ring);
+    const uint32_t unit_base = ring_base | (16u * k);
+    uint32_t fill = 0;  // ring byte offset (unwrapped, multiple of 64) of the next refill round
+    L.cur2 = 2u * (rel >> 4);
+    auto issue = [&]() {
+        const bool ok = left > 0;
+        const uint8_t* s = ok ? src : bytes;
+        const uint32_t src_size = ok ? 16u : 0u;  // src-size 0 zero-fills
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(unit_base | (fill & 0xC0u)), "l"(s), "r"(src_size) : "memory");
+        src += 64;
+        fill += 64;
+        left--;
+    };
+    if (mode) {
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) issue();  // initial fill: the whole ring
+    } else {
+        fill = 0x40000000u;  // never refills
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const uint32_t mask = (1u << lr) - 1u;
+    const uint32_t bm_base = smem_u32(bm), sym_base = smem_u32(symtab);
+
+    // 4x4 byte transpose inside the group: after 4 steps lane k holds [a_k0 a_k1 a_k2 a_k3] (a_kj = symbol of state k in
+    // step j, output position 4j + 3 - k); lane j stores the word of step j: [a_3j a_2j a_1j a_0j].
+    auto transpose = [&](uint32_t acc) -> uint32_t {
+        const uint32_t o2 = __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+        const uint32_t t1 = (k & 2) ? __byte_perm(acc, o2, 0x3276) : __byte_perm(acc, o2, 0x5410);
+        const uint32_t o1 = __shfl_xor_sync(0xFFFFFFFFu, t1, 1);
+        return (k & 1) ? __byte_perm(t1, o1, 0x5173) : __byte_perm(t1, o1, 0x0426);
+    };
+    auto maintain = [&]() {  // every 4 steps, uniform for the warp
+        asm volatile("cp.async.wait_group 0;" ::: "memory");  // the round issued one iteration ago has landed
+        __syncwarp();
+        // refill when at most 160 bytes are buffered ahead of the cursor: the new 64-byte round then only overwrites
+        // consumed bytes (4 steps consume at most 32 bytes) and at least 128 buffered bytes remain while it is in flight
+        if ((int32_t)(fill - L.cur2) <= (4 * RING_WORDS - 64 - 32)) issue();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const uint32_t fast_iters = min_steps >> 2;  // iterations in which every group of the warp is active
+    uint32_t it = 0;
+    uint8_t* dptr = dst + 4 * k;
+    for (; it < fast_iters; it++) {
+        dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        *reinterpret_cast<uint32_t*>(dptr) = transpose(L.acc);
+        dptr += 16;
+        maintain();
+    }
+    const uint32_t all_iters = max_steps >> 2;
+    for (; it < all_iters; it++) {  // groups with fewer steps idle here
+        const bool active = (it * 4 + 3) < nsteps;
+        dec4_step<false>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, active);
+        dec4_step<false>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, active);
+        dec4_step<false>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, active);
+        dec4_step<false>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, active);
+        const uint32_t w = transpose(L.acc);
+        if (active) *reinterpret_cast<uint32_t*>(dptr) = w;
+        dptr += 16;
+        maintain();
+    }
+    {  // remaining 0..3 steps of a group (only the last chunk of a block can have nsteps % 4 != 0)
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        const uint32_t done = nsteps & ~3u;
+        uint32_t rem_max = nsteps - done;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) rem_max = max(rem_max, __shfl_xor_sync(0xFFFFFFFFu, rem_max, d));
+        for (uint32_t r = 0; r < rem_max; r++) {
+            const bool active = done + r < nsteps;
+            dec4_step<false>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, active);
+            if (active) dst[(size_t)(done + r) * 4 + (3 - k)] = (uint8_t)(L.acc >> 24);
+        }
+    }
+    // tail bytes follow the consumed words (:951-954)
+    if (mode && k == 0 && tail) {
+        uint64_t pos = 8 * (base_b + L.cur2) + (rel & 15u);  // bit position of the cursor in the stream
+        for (uint32_t j = 0; j < tail; j++, pos += 8) dst[(size_t)nsteps * 4 + j] = pos + 8 <= pe ? (uint8_t)bits_at(words, pos, 8) : 0;
+    }
+}
+
 }  // namespace kz

@@ -57,6 +57,12 @@ __global__ void ans0_walk_kernel(const uint32_t* words, uint64_t words_len, cons
                                  uint64_t* blk_end, int32_t* status);
 __global__ void ans0_decode_kernel(const uint32_t* words, uint64_t words_len, const DecChunk* chunks, int nchunks, const uint64_t* chunk_hdr_bit,
                                    uint8_t* out, int32_t* status);
+// decode v5: per chunk record written by ans0_tables_kernel: 171 bucket words | 256 symbol entries | 12 words of chunk state
+static const int DEC_TAB_WORDS = 440;
+__global__ void ans0_tables_kernel(const uint32_t* words, uint64_t words_len, const DecChunk* chunks, int nchunks, const uint64_t* chunk_hdr_bit,
+                                   uint32_t* tabs, uint8_t* out, int32_t* status);
+__global__ void ans0_decode5_kernel(const uint32_t* words, uint64_t words_len, const uint32_t* tabs, const DecChunk* chunks, int nchunks,
+                                    const uint64_t* chunk_hdr_bit, uint8_t* out, int32_t* status);
 __global__ void ans0_decode4_kernel(const uint32_t* words, uint64_t words_len, const DecChunk* chunks, int nchunks, const uint64_t* chunk_hdr_bit,
                                     uint8_t* out, int32_t* status);
 

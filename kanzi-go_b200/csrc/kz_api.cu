@@ -636,8 +636,17 @@ int decode_batch(kz_ctx* ctx, uint32_t etype, const uint32_t* d_words, uint64_t 
             ans0_walk_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_words, words_len, (DecBlock*)(T + o_blocks), nblocks, (uint64_t*)(T + o_hbit),
                                                               (uint64_t*)(T + o_end), d_status);
         }
+        if (ctx->ans0_dec_version >= 5) {
+            CK(ctx->d_enc_tab.ensure((size_t)nchunks * DEC_TAB_WORDS * sizeof(uint32_t) + 256));
+            LaunchScope ls(ctx, "ans0_tables");
+            ans0_tables_kernel<<<(nchunks + 3) / 4, 128, 0, ctx->stream>>>(d_words, words_len, (DecChunk*)(T + o_chunks), nchunks, (uint64_t*)(T + o_hbit),
+                                                                        ctx->d_enc_tab.as<uint32_t>(), d_out, d_status);
+        }
         LaunchScope ls(ctx, "ans0_decode");
-        if (ctx->ans0_dec_version == 3)
+        if (ctx->ans0_dec_version >= 5)
+            ans0_decode5_kernel<<<(nchunks + DEC_CTA_CHUNKS - 1) / DEC_CTA_CHUNKS, 64, DEC4_SMEM, ctx->stream>>>(
+                d_words, words_len, ctx->d_enc_tab.as<uint32_t>(), (DecChunk*)(T + o_chunks), nchunks, (uint64_t*)(T + o_hbit), d_out, d_status);
+        else if (ctx->ans0_dec_version == 3)
             ans0_decode_kernel<<<(nchunks + DEC_CTA_CHUNKS - 1) / DEC_CTA_CHUNKS, 64, DEC_SMEM, ctx->stream>>>(d_words, words_len, (DecChunk*)(T + o_chunks),
                                                                                                    nchunks, (uint64_t*)(T + o_hbit), d_out, d_status);
         else
@@ -1315,6 +1324,7 @@ int kz_init(int device, kz_ctx** out) {
     cudaFuncSetAttribute(ans0_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM);
     cudaFuncSetAttribute(ans0_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM);
     cudaFuncSetAttribute(ans0_decode4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC4_SMEM);
+    cudaFuncSetAttribute(ans0_decode5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC4_SMEM);
     if (const char* v = getenv("KZ_ANS0_DEC")) ctx->ans0_dec_version = atoi(v);  // 3 = previous kernel generation (A/B measurements)
     cudaFuncSetAttribute(huf_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HUF_DEC_SMEM);
     *out = ctx;

@@ -109,7 +109,7 @@ struct kz_ctx {
     std::string err;
     uint64_t launches = 0;
     bool profile = false;
-    int ans0_dec_version = 4;
+    int ans0_dec_version = 5;
     std::map<std::string, kz::ProfEntry> prof;
     struct Pending {
         std::string name;

@@ -47,6 +47,22 @@ def test_single_transform_parity(gpu, oracle, synth, kz, name, n):
         assert np.array_equal(back, x), (name, cname, n)
 
 
+BWTS_SIZES = [1, 2, 3, 7, 16, 100, 255, 256, 257, 1000, 4096, 65536, 100003, 1 << 20]
+
+
+@pytest.mark.parametrize("n", BWTS_SIZES)
+def test_bwts_parity(gpu, oracle, synth, kz, n):
+    """BWTS.Forward / BWTS.Inverse (transform/BWTS.go): rotations of the Lyndon factors in infinite-periodic order"""
+    extra = [("abab", np.resize(np.array([1, 2], np.uint8), n)), ("descending", (255 - (np.arange(n) * 255 // max(n, 1))).astype(np.uint8)),
+             ("repeat7", np.resize(synth.markov_text(max(n // 7, 1), seed=n + 3), n)), ("aab", np.resize(np.array([1, 1, 2], np.uint8), n))]
+    for cname, x in list(cases(synth, n, seed=n)) + extra:
+        want, _ = oracle.transform_forward(kz.T_BWTS, x)
+        got, _ = gpu.transform_forward(kz.T_BWTS, x)
+        assert want is not None and got is not None, (cname, n)
+        assert np.array_equal(got, want), (cname, n, int(np.argmax(got != want)))
+        assert np.array_equal(gpu.transform_inverse(kz.T_BWTS, want, n + 64), x), (cname, n)
+
+
 def test_zrlt_long_runs(gpu, oracle, synth, kz):
     """runs that cross many tiles, a block that is one run, a run at the very end"""
     for n, pat in [(1 << 20, "all"), (1 << 20, "tail"), (300000, "mid")]:
@@ -63,7 +79,7 @@ def test_zrlt_long_runs(gpu, oracle, synth, kz):
 
 
 @pytest.mark.parametrize("seq,entropy", [("BWT+RANK+ZRLT", "ANS0"), ("BWT+MTFT+ZRLT", "HUFFMAN"), ("RANK", "ANS0"), ("ZRLT", "NONE"), ("RANK+ZRLT", "ANS1"),
-                                         ("BWT+ZRLT", "RANGE")])
+                                         ("BWT+ZRLT", "RANGE"), ("BWTS", "ANS0"), ("BWTS+MTFT+ZRLT", "HUFFMAN")])
 @pytest.mark.parametrize("n,bs", [(10, 1024), (5000, 1024), (70000, 65536), (3 * (1 << 20) + 777, 1 << 20)])
 def test_stream_parity_sequences(gpu, oracle, synth, kz, seq, entropy, n, bs):
     for kind in ("text", "uniform"):
