@@ -13,6 +13,7 @@ size_t transform_max_encoded_len(uint64_t type, size_t n) {
         case T_BWT: return n + 33;                               // BWTBlockCodec.go:228-230 (_BWT_MAX_HEADER_SIZE = 8*4+1)
         case T_LZ: case T_LZX: return lz_max_encoded_len(n);     // LZCodec.go:935-941
         case T_BWTS: return n;                                   // BWTS.go:291-293
+        case T_ROLZ: return rolz_max_encoded_len(n);             // ROLZCodec.go:916-918
         case T_RANK: case T_MTFT: return n + 33;                 // SBRT.go:229-231
         case T_ZRLT: return n;                                   // ZRLT.go:228-230
         default: throw Error(ERR_CREATE_CODEC, "transform not restated in the oracle");
@@ -30,6 +31,7 @@ bool transform_forward(uint64_t type, Ctx& ctx, const uint8_t* src, size_t n, ui
         case T_LZ: return lz_forward(ctx, false, src, n, dst, cap, out_n);
         case T_LZX: return lz_forward(ctx, true, src, n, dst, cap, out_n);
         case T_BWTS: return bwts_forward(src, n, dst, cap, out_n);
+        case T_ROLZ: return rolz_forward(ctx, src, n, dst, cap, out_n);
         case T_RANK: return sbrt_forward(2, src, n, dst, cap, out_n);  // Factory.go: RANK -> SBRT_MODE_RANK
         case T_MTFT: return sbrt_forward(1, src, n, dst, cap, out_n);  // MTFT -> SBRT_MODE_MTF
         case T_ZRLT: return zrlt_forward(src, n, dst, cap, out_n);
@@ -48,6 +50,7 @@ bool transform_inverse(uint64_t type, Ctx& ctx, const uint8_t* src, size_t n, ui
         case T_LZ: return lz_inverse(ctx, false, src, n, dst, cap, out_n);
         case T_LZX: return lz_inverse(ctx, true, src, n, dst, cap, out_n);
         case T_BWTS: return bwts_inverse(src, n, dst, cap, out_n);
+        case T_ROLZ: return rolz_inverse(ctx, src, n, dst, cap, out_n);
         case T_RANK: return sbrt_inverse(2, src, n, dst, cap, out_n);
         case T_MTFT: return sbrt_inverse(1, src, n, dst, cap, out_n);
         case T_ZRLT: return zrlt_inverse(src, n, dst, cap, out_n);

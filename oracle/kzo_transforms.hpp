@@ -14,4 +14,8 @@ bool zrlt_forward(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t
 bool zrlt_inverse(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
 bool bwts_forward(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
 bool bwts_inverse(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
+size_t rolz_max_encoded_len(size_t n);
+bool rolz_forward(Ctx& ctx, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
+bool rolz_inverse(Ctx& ctx, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
+int detect_simple_type(size_t count, const int* freqs0);
 }  // namespace kzo
