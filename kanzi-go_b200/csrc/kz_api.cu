@@ -169,9 +169,10 @@ int encode_batch(kz_ctx* ctx, EncLayout layout, uint32_t etype, uint32_t checksu
     if (!etype_supported(etype)) return ctx->fail(KZ_ERR_CREATE_CODEC, "entropy codec not available on the GPU path");
     HostScope hs_all(ctx, "encode_batch");
     std::unique_ptr<HostScope> hs_tab(new HostScope(ctx, "enc_tables"));
-    // ---- host: segment and chunk tables
-    // small host-generated byte strings live in one device buffer (d_small): stream header | 16 bytes per block header |
-    // 8 bytes per block prefix | 8 zero bytes (end marker)
+    // ---- host: segment and chunk tables. They are a pure function of the batch description (layout, codec, block
+    // lengths and flags, buffer addresses), and a stream of equal-sized blocks repeats the same description batch after
+    // batch (Writer.processBlock is called once per `jobs` blocks): the packed tables of the last batch are kept and
+    // reused when the description is byte-identical (0.6 ms of host work per 64 x 4 MiB batch otherwise).
     const size_t small_hdr_off = 0;
     const size_t small_blk_off = 64;
     const size_t small_prefix_off = small_blk_off + 16 * (size_t)nblocks;
@@ -180,114 +181,145 @@ int encode_batch(kz_ctx* ctx, EncLayout layout, uint32_t etype, uint32_t checksu
     const size_t small_size = small_zero_off + 16;
     CK(ctx->d_small.ensure(small_size));
     uint8_t* d_small = ctx->d_small.as<uint8_t>();
-    std::vector<uint8_t> small(small_size, 0);
-    if (!stream_hdr.empty()) memcpy(&small[small_hdr_off], stream_hdr.data(), stream_hdr.size());
-    small[small_lr1_off] = 0x60;
-
-    std::vector<uint64_t> seg_src, seg_bits;
-    std::vector<uint32_t> blk_first(nblocks + 1);
-    std::vector<ChunkIn> chunks;
-    std::vector<uint32_t> chunk_seg;
-    auto add_seg = [&](uint64_t src, uint64_t bits) {
-        seg_src.push_back(src);
-        seg_bits.push_back(bits);
-    };
-    auto add_raw = [&](const uint8_t* p, uint64_t nbytes) {
-        for (uint64_t o = 0; o < nbytes; o += RAW_PIECE) add_seg((uint64_t)(uintptr_t)(p + o), 8 * std::min<uint64_t>(RAW_PIECE, nbytes - o));
-    };
-    if (layout == LAYOUT_STREAM) add_seg((uint64_t)(uintptr_t)(d_small + small_hdr_off), stream_hdr_bits);
-    for (int b = 0; b < nblocks; b++) {
-        const EncJob& j = jobs[b];
-        if (layout == LAYOUT_STREAM) add_seg(0, 0);  // block prefix, filled by block_prefix_kernel
-        blk_first[b] = (uint32_t)seg_src.size();
-        const uint32_t et = j.copy ? (uint32_t)KZ_E_NONE : etype;
-        if (layout != LAYOUT_RAW) {
-            uint8_t* hb = &small[small_blk_off + 16 * (size_t)b];
-            uint32_t hbits = make_block_header(hb, j.copy, j.ntransforms, j.skip_flags, j.post_len, checksum_bits, j.checksum);
-            add_seg((uint64_t)(uintptr_t)(d_small + small_blk_off + 16 * (size_t)b), hbits);
+    std::vector<uint8_t> key;
+    {
+        auto put = [&](const void* p, size_t n) {
+            const uint8_t* q = (const uint8_t*)p;
+            key.insert(key.end(), q, q + n);
+        };
+        const uint64_t scal[8] = {(uint64_t)layout, etype, checksum_bits, (uint64_t)(uintptr_t)d_data, (uint64_t)(uintptr_t)d_small, (uint64_t)nblocks,
+                                  stream_hdr_bits, (uint64_t)stream_hdr.size()};
+        key.reserve(sizeof(scal) + stream_hdr.size() + jobs.size() * 40 + blk_base_bits.size() * 8);
+        put(scal, sizeof(scal));
+        put(stream_hdr.data(), stream_hdr.size());
+        for (const EncJob& j : jobs) {
+            const uint64_t f[4] = {j.data_off, ((uint64_t)j.post_len << 32) | j.ntransforms, ((uint64_t)j.skip_flags << 8) | (j.copy ? 1u : 0u), j.checksum};
+            put(f, sizeof(f));
         }
-        const uint8_t* data = d_data + j.data_off;
-        if (et == KZ_E_NONE || ((et == KZ_E_ANS0 || et == KZ_E_ANS1) && j.post_len <= 32)) {  // NullEntropyCodec.go:43-61 / ANSRangeCodec.go:279-282
-            add_raw(data, j.post_len);
-        } else if (et == KZ_E_ANS1) {
-            for (uint32_t o = 0; o < j.post_len; o += ANS1_CHUNK) {
-                ChunkIn c;
-                c.src_off = j.data_off + o;
-                c.len = std::min<uint32_t>(ANS1_CHUNK, j.post_len - o);
-                c.block = (uint32_t)b;
-                chunks.push_back(c);
-                add_seg((uint64_t)(uintptr_t)(d_small + small_lr1_off), 3);  // lr - 8 (updateFrequencies :174)
-                chunk_seg.push_back((uint32_t)seg_src.size());
-                for (int q = 0; q < ANS1_SEGS - 1; q++) add_seg(0, 0);  // 256 context tables, size + states, payload
-            }
-        } else if (et == KZ_E_ANS0) {
-            for (uint32_t o = 0; o < j.post_len; o += ANS0_CHUNK) {
-                ChunkIn c;
-                c.src_off = j.data_off + o;
-                c.len = std::min<uint32_t>(ANS0_CHUNK, j.post_len - o);
-                c.block = (uint32_t)b;
-                chunks.push_back(c);
-                chunk_seg.push_back((uint32_t)seg_src.size());
-                add_seg(0, 0);  // A: chunk header + varint + states
-                add_seg(0, 0);  // B: rANS bytes
-            }
-        } else if (et == KZ_E_RANGE) {  // RangeCodec.go:233-272: one bit string per 32 KiB chunk
-            for (uint32_t o = 0; o < j.post_len; o += RANGE_CHUNK) {
-                ChunkIn c;
-                c.src_off = j.data_off + o;
-                c.len = std::min<uint32_t>(RANGE_CHUNK, j.post_len - o);
-                c.block = (uint32_t)b;
-                chunks.push_back(c);
-                chunk_seg.push_back((uint32_t)seg_src.size());
-                add_seg(0, 0);
-            }
-        } else if (et == KZ_E_HUFFMAN) {  // HuffmanCodec.go:408-430
-            for (uint32_t o = 0; o < j.post_len; o += HUF_CHUNK) {
-                const uint32_t clen = std::min<uint32_t>(HUF_CHUNK, j.post_len - o);
-                if (clen < 32) {
-                    add_raw(data + o, clen);
-                    continue;
+        put(blk_base_bits.data(), blk_base_bits.size() * 8);
+    }
+    EncPlan& plan = ctx->enc_plan;
+    if (!(plan.valid && plan.key == key)) {
+        plan.valid = false;
+        plan.build(key, [&](EncPlan& P) {
+            std::vector<uint8_t> small(small_size, 0);
+            if (!stream_hdr.empty()) memcpy(&small[small_hdr_off], stream_hdr.data(), stream_hdr.size());
+            small[small_lr1_off] = 0x60;
+
+            std::vector<uint64_t> seg_src, seg_bits;
+            std::vector<uint32_t> blk_first(nblocks + 1);
+            std::vector<ChunkIn> chunks;
+            std::vector<uint32_t> chunk_seg;
+            auto add_seg = [&](uint64_t src, uint64_t bits) {
+                seg_src.push_back(src);
+                seg_bits.push_back(bits);
+            };
+            auto add_raw = [&](const uint8_t* p, uint64_t nbytes) {
+                for (uint64_t o = 0; o < nbytes; o += RAW_PIECE) add_seg((uint64_t)(uintptr_t)(p + o), 8 * std::min<uint64_t>(RAW_PIECE, nbytes - o));
+            };
+            if (layout == LAYOUT_STREAM) add_seg((uint64_t)(uintptr_t)(d_small + small_hdr_off), stream_hdr_bits);
+            for (int b = 0; b < nblocks; b++) {
+                const EncJob& j = jobs[b];
+                if (layout == LAYOUT_STREAM) add_seg(0, 0);  // block prefix, filled by block_prefix_kernel
+                blk_first[b] = (uint32_t)seg_src.size();
+                const uint32_t et = j.copy ? (uint32_t)KZ_E_NONE : etype;
+                if (layout != LAYOUT_RAW) {
+                    uint8_t* hb = &small[small_blk_off + 16 * (size_t)b];
+                    uint32_t hbits = make_block_header(hb, j.copy, j.ntransforms, j.skip_flags, j.post_len, checksum_bits, j.checksum);
+                    add_seg((uint64_t)(uintptr_t)(d_small + small_blk_off + 16 * (size_t)b), hbits);
                 }
-                ChunkIn c;
-                c.src_off = j.data_off + o;
-                c.len = clen;
-                c.block = (uint32_t)b;
-                chunks.push_back(c);
-                chunk_seg.push_back((uint32_t)seg_src.size());
-                for (int q = 0; q < 6; q++) add_seg(0, 0);  // header+sizes, 4 fragments, chunk last bytes
+                const uint8_t* data = d_data + j.data_off;
+                if (et == KZ_E_NONE || ((et == KZ_E_ANS0 || et == KZ_E_ANS1) && j.post_len <= 32)) {  // NullEntropyCodec.go:43-61 / ANSRangeCodec.go:279-282
+                    add_raw(data, j.post_len);
+                } else if (et == KZ_E_ANS1) {
+                    for (uint32_t o = 0; o < j.post_len; o += ANS1_CHUNK) {
+                        ChunkIn c;
+                        c.src_off = j.data_off + o;
+                        c.len = std::min<uint32_t>(ANS1_CHUNK, j.post_len - o);
+                        c.block = (uint32_t)b;
+                        chunks.push_back(c);
+                        add_seg((uint64_t)(uintptr_t)(d_small + small_lr1_off), 3);  // lr - 8 (updateFrequencies :174)
+                        chunk_seg.push_back((uint32_t)seg_src.size());
+                        for (int q = 0; q < ANS1_SEGS - 1; q++) add_seg(0, 0);  // 256 context tables, size + states, payload
+                    }
+                } else if (et == KZ_E_ANS0) {
+                    for (uint32_t o = 0; o < j.post_len; o += ANS0_CHUNK) {
+                        ChunkIn c;
+                        c.src_off = j.data_off + o;
+                        c.len = std::min<uint32_t>(ANS0_CHUNK, j.post_len - o);
+                        c.block = (uint32_t)b;
+                        chunks.push_back(c);
+                        chunk_seg.push_back((uint32_t)seg_src.size());
+                        add_seg(0, 0);  // A: chunk header + varint + states
+                        add_seg(0, 0);  // B: rANS bytes
+                    }
+                } else if (et == KZ_E_RANGE) {  // RangeCodec.go:233-272: one bit string per 32 KiB chunk
+                    for (uint32_t o = 0; o < j.post_len; o += RANGE_CHUNK) {
+                        ChunkIn c;
+                        c.src_off = j.data_off + o;
+                        c.len = std::min<uint32_t>(RANGE_CHUNK, j.post_len - o);
+                        c.block = (uint32_t)b;
+                        chunks.push_back(c);
+                        chunk_seg.push_back((uint32_t)seg_src.size());
+                        add_seg(0, 0);
+                    }
+                } else if (et == KZ_E_HUFFMAN) {  // HuffmanCodec.go:408-430
+                    for (uint32_t o = 0; o < j.post_len; o += HUF_CHUNK) {
+                        const uint32_t clen = std::min<uint32_t>(HUF_CHUNK, j.post_len - o);
+                        if (clen < 32) {
+                            add_raw(data + o, clen);
+                            continue;
+                        }
+                        ChunkIn c;
+                        c.src_off = j.data_off + o;
+                        c.len = clen;
+                        c.block = (uint32_t)b;
+                        chunks.push_back(c);
+                        chunk_seg.push_back((uint32_t)seg_src.size());
+                        for (int q = 0; q < 6; q++) add_seg(0, 0);  // header+sizes, 4 fragments, chunk last bytes
+                    }
+                }
             }
-        }
-    }
-    if (layout == LAYOUT_STREAM) {
-        add_seg((uint64_t)(uintptr_t)(d_small + small_zero_off), 8);  // end marker: 5+3 zero bits (Close :593-594)
-        blk_first[nblocks] = (uint32_t)seg_src.size();
-    } else {
-        blk_first[nblocks] = (uint32_t)seg_src.size();
-    }
-    const int nsegs = (int)seg_src.size();
-    add_seg(0, 0);  // sentinel for the scan
-    const int nchunks = (int)chunks.size();
+            if (layout == LAYOUT_STREAM) {
+                add_seg((uint64_t)(uintptr_t)(d_small + small_zero_off), 8);  // end marker: 5+3 zero bits (Close :593-594)
+                blk_first[nblocks] = (uint32_t)seg_src.size();
+            } else {
+                blk_first[nblocks] = (uint32_t)seg_src.size();
+            }
+            P.nsegs = (int)seg_src.size();
+            add_seg(0, 0);  // sentinel for the scan
+            P.nchunks = (int)chunks.size();
+            P.max_chunk = 0;
+            for (auto& c : chunks) P.max_chunk = std::max(P.max_chunk, c.len);
 
-    Packer pk;
-    const size_t o_small = pk.add(small.data(), small.size());
-    const size_t o_src = pk.add(seg_src.data(), seg_src.size() * 8);
-    const size_t o_bits = pk.add(seg_bits.data(), seg_bits.size() * 8);
-    const size_t o_first = pk.add(blk_first.data(), blk_first.size() * 4);
-    const size_t o_chunks = pk.add(chunks.data(), chunks.size() * sizeof(ChunkIn));
-    const size_t o_cseg = pk.add(chunk_seg.data(), chunk_seg.size() * 4);
-    const size_t o_base = pk.add(blk_base_bits.data(), blk_base_bits.size() * 8);
-    const size_t o_off = pk.reserve(seg_src.size() * 8);
-    const size_t o_dst = pk.reserve(seg_src.size() * 8);
-    const size_t o_blkbits = pk.reserve((size_t)(nblocks + 1) * 8);
-    const size_t o_total = pk.reserve(16);
-    const size_t o_hbits = pk.reserve((size_t)nchunks * 4 + 4);
-    const size_t o_asz = pk.reserve((size_t)nchunks * 4 + 4);
-    const size_t o_estatus = pk.reserve((size_t)nblocks * 4 + 4);
+            Packer& pk = P.pk;
+            pk.bytes.clear();
+            P.o_small = pk.add(small.data(), small.size());
+            P.o_src = pk.add(seg_src.data(), seg_src.size() * 8);
+            P.o_bits = pk.add(seg_bits.data(), seg_bits.size() * 8);
+            P.o_first = pk.add(blk_first.data(), blk_first.size() * 4);
+            P.o_chunks = pk.add(chunks.data(), chunks.size() * sizeof(ChunkIn));
+            P.o_cseg = pk.add(chunk_seg.data(), chunk_seg.size() * 4);
+            P.o_base = pk.add(blk_base_bits.data(), blk_base_bits.size() * 8);
+            P.o_off = pk.reserve(seg_src.size() * 8);
+            P.o_dst = pk.reserve(seg_src.size() * 8);
+            P.o_blkbits = pk.reserve((size_t)(nblocks + 1) * 8);
+            P.o_total = pk.reserve(16);
+            P.o_hbits = pk.reserve((size_t)P.nchunks * 4 + 4);
+            P.o_asz = pk.reserve((size_t)P.nchunks * 4 + 4);
+            P.o_estatus = pk.reserve((size_t)nblocks * 4 + 4);
+        });
+    }
+    Packer& pk = plan.pk;
+    const int nsegs = plan.nsegs, nchunks = plan.nchunks;
+    const size_t o_small = plan.o_small, o_src = plan.o_src, o_bits = plan.o_bits, o_first = plan.o_first, o_chunks = plan.o_chunks, o_cseg = plan.o_cseg,
+                 o_base = plan.o_base, o_off = plan.o_off, o_dst = plan.o_dst, o_blkbits = plan.o_blkbits, o_total = plan.o_total, o_hbits = plan.o_hbits,
+                 o_asz = plan.o_asz, o_estatus = plan.o_estatus;
     int rc = upload(ctx, pk);
     if (rc) return rc;
     uint8_t* T = ctx->d_tables.as<uint8_t>();
     // the small byte strings must live at the addresses baked into the segment table
-    CK(cudaMemcpyAsync(d_small, T + o_small, small.size(), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_small, T + o_small, small_size, cudaMemcpyDeviceToDevice, ctx->stream));
     uint64_t* d_seg_src = (uint64_t*)(T + o_src);
     uint64_t* d_seg_bits = (uint64_t*)(T + o_bits);
     uint32_t* d_blk_first = (uint32_t*)(T + o_first);
@@ -305,8 +337,7 @@ int encode_batch(kz_ctx* ctx, EncLayout layout, uint32_t etype, uint32_t checksu
 
     // ---- entropy kernels
     if (nchunks > 0 && etype == KZ_E_ANS1) {
-        uint32_t max_chunk = 0;
-        for (auto& c : chunks) max_chunk = std::max(max_chunk, c.len);
+        const uint32_t max_chunk = plan.max_chunk;
         const uint64_t pay_stride = (2ull * max_chunk + 96 + 15) & ~15ull;
         CK(ctx->d_enc_tab.ensure((size_t)nchunks * 65536 * sizeof(uint32_t)));
         CK(ctx->d_hdr.ensure((size_t)nchunks * 256 * ANS1_CTX_HDR_STRIDE + (size_t)nchunks * 32 + 256));
@@ -1467,13 +1498,23 @@ int kz_decompress_stream_device(kz_ctx* ctx, const void* d_src, size_t n, void* 
         LaunchScope ls(ctx, "stream_walk");
         stream_walk_kernel<<<1, 32, 0, ctx->stream>>>(d_words, sh.bits, 8ull * n, max_blocks, d_boff, d_bbits, d_cnt);
     }
-    uint32_t cs[2];
+    // count + the first SPEC block descriptors in one round trip (streams with more blocks pay a second copy)
+    const uint32_t SPEC = std::min<uint32_t>(max_blocks, 1024);
+    CK(ctx->h_dl.ensure((size_t)SPEC * 16 + 64));
+    uint32_t* cs = (uint32_t*)ctx->h_dl.p;
+    uint64_t* h_boff = (uint64_t*)((uint8_t*)ctx->h_dl.p + 64);
+    uint64_t* h_bbits = h_boff + SPEC;
     CK(cudaMemcpyAsync(cs, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_boff, d_boff, (size_t)SPEC * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_bbits, d_bbits, (size_t)SPEC * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if ((int32_t)cs[1] != 0) return ctx->fail(-(int32_t)cs[1], "Invalid bitstream: corrupted block length");
     const uint32_t nblocks = cs[0];
     std::vector<uint64_t> boff(nblocks), bbits(nblocks);
-    if (nblocks) {
+    if (nblocks && nblocks <= SPEC) {
+        memcpy(boff.data(), h_boff, (size_t)nblocks * 8);
+        memcpy(bbits.data(), h_bbits, (size_t)nblocks * 8);
+    } else if (nblocks) {
         CK(cudaMemcpyAsync(boff.data(), d_boff, (size_t)nblocks * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(bbits.data(), d_bbits, (size_t)nblocks * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));

@@ -72,6 +72,23 @@ struct Packer {
     }
 };
 
+// packed host tables of one encode batch (see encode_batch), kept for the next batch with an identical description
+struct EncPlan {
+    bool valid = false;
+    std::vector<uint8_t> key;
+    Packer pk;
+    size_t o_small = 0, o_src = 0, o_bits = 0, o_first = 0, o_chunks = 0, o_cseg = 0, o_base = 0, o_off = 0, o_dst = 0, o_blkbits = 0, o_total = 0,
+           o_hbits = 0, o_asz = 0, o_estatus = 0;
+    int nsegs = 0, nchunks = 0;
+    uint32_t max_chunk = 0;
+    template <class F>
+    void build(const std::vector<uint8_t>& k, F&& fill) {
+        fill(*this);
+        key = k;
+        valid = true;
+    }
+};
+
 struct ProfEntry {
     double ms = 0;
     uint32_t launches = 0;
@@ -110,6 +127,7 @@ struct kz_ctx {
     uint64_t launches = 0;
     bool profile = false;
     int ans0_dec_version = 5;
+    kz::EncPlan enc_plan;
     std::map<std::string, kz::ProfEntry> prof;
     struct Pending {
         std::string name;
