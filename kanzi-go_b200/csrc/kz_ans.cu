@@ -1500,4 +1500,164 @@ __global__ void __launch_bounds__(64, 7) ans0_decode5_kernel(const uint32_t* __r
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// decode (v6): ONE THREAD per chunk. v3..v5 put the four states of a chunk on four lanes: every warp instruction then
+// sits on one serial chain (ncu: 47 instructions per step at ~7 cycles each, issue slots half empty) and the shared
+// cursor costs a ballot + popc + two ring loads per symbol. Here a thread owns all four states of its chunk:
+//   * the four table look-ups of a step are independent -> the in-order issue of the warp always has other work while a
+//     shared-memory load or a dependent ALU result is in flight (4-way ILP instead of none);
+//   * the byte cursor is a private 64-bit shift register refilled 32 bits at a time from the thread's ring: a
+//     renormalisation is "take the top 16 bits, shift" (no ballot, no popc, no address arithmetic), and the arbitrary bit
+//     alignment of the payload is absorbed once per refill by a funnel shift;
+//   * tables are lane-private columns (word i of thread t at i * 112 + t): at most 2-way bank conflicts (t vs t + 16);
+//   * a step yields one complete output word [s3 s2 s1 s0]; four steps are stored with one 16-byte store.
+// 112 chunk slots per CTA, one CTA per SM (219,968 bytes of shared memory), 147 CTAs for 64 x 4 MiB: still one wave.
+// No barrier of any kind is needed: a thread only touches its own column, its own ring and its own cp.async groups.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) ans0_decode6_kernel(const uint32_t* __restrict__ words, uint64_t words_len /*in 32-bit words*/,
+                                                              const uint32_t* __restrict__ tabs, const DecChunk* __restrict__ chunks, int nchunks,
+                                                              uint8_t* __restrict__ out) {
+    extern __shared__ __align__(16) uint32_t s_dec6[];
+    const int t = threadIdx.x;
+    const int c = blockIdx.x * DEC6_CHUNKS + t;
+    if (t >= DEC6_CHUNKS || c >= nchunks) return;
+    const uint32_t* rec = tabs + (size_t)c * DEC_TAB_WORDS;
+    const uint32_t* meta = rec + DEC_BM_WORDS + 256;
+    if (__ldg(meta + 1) == 0) return;  // nothing to decode (single symbol chunk, or the block failed)
+    constexpr int NT = DEC_BM_WORDS + 256;
+    constexpr uint32_t COL = 4u * DEC6_CHUNKS;  // byte stride between two words of a column
+    uint32_t* col = s_dec6 + t;
+    {  // my column: 427 words of the record
+        const uint4* r4 = reinterpret_cast<const uint4*>(rec);
+#pragma unroll 4
+        for (int i = 0; i < NT / 4; i++) {
+            const uint4 v = __ldg(r4 + i);
+            col[(4 * i) * DEC6_CHUNKS] = v.x;
+            col[(4 * i + 1) * DEC6_CHUNKS] = v.y;
+            col[(4 * i + 2) * DEC6_CHUNKS] = v.z;
+            col[(4 * i + 3) * DEC6_CHUNKS] = v.w;
+        }
+        for (int i = NT & ~3; i < NT; i++) col[i * DEC6_CHUNKS] = __ldg(rec + i);
+    }
+    const uint32_t lr = __ldg(meta);
+    const uint32_t nsteps = __ldg(meta + 2), tail = __ldg(meta + 3);
+    const uint64_t pb = (uint64_t)__ldg(meta + 4) | ((uint64_t)__ldg(meta + 5) << 32);
+    const uint64_t pe = (uint64_t)__ldg(meta + 6) | ((uint64_t)__ldg(meta + 7) << 32);
+    uint32_t st0 = __ldg(meta + 8), st1 = __ldg(meta + 9), st2 = __ldg(meta + 10), st3 = __ldg(meta + 11);
+    uint8_t* dst = out + chunks[c].out_off;
+
+    // ---- payload ring (256 bytes, private): raw copy of the stream from the 16-byte aligned unit that holds the first
+    // payload bit; units that start at or after the end of the payload (or would leave the buffer) are zero filled
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(words);
+    const uint64_t base_b = (pb >> 3) & ~15ull;
+    const uint32_t rel = (uint32_t)(pb - 8 * base_b);  // 0..135
+    const uint64_t end_b = (pe + 7) >> 3;
+    const uint64_t lim_b = words_len * 4;
+    const uint64_t lim_u = lim_b >= 15 ? lim_b - 15 : 0;
+    const uint64_t stop_b = end_b < lim_u ? end_b : lim_u;
+    int32_t left = stop_b > base_b ? (int32_t)((stop_b - base_b + 15) >> 4) : 0;  // valid 16-byte units still to copy
+    const uint8_t* src = bytes + base_b;
+    const uint32_t ring_base = smem_u32(s_dec6 + NT * DEC6_CHUNKS + t * 64);
+    uint32_t fill = 0;  // bytes copied into the ring so far (unwrapped, multiple of 64)
+    auto issue_round = [&]() {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const bool ok = left > 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ring_base + ((fill + 16u * u) & 255u)), "l"(ok ? src : bytes),
+                         "r"(ok ? 16u : 0u)
+                         : "memory");
+            src += 16;
+            left--;
+        }
+        fill += 64;
+    };
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) issue_round();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+    // ---- bit reader: `head` holds the next nbits (multiple of 16) bits of the payload, most significant first
+    const uint32_t sh = rel & 31u;
+    uint32_t rp = (rel >> 5) * 4u;  // ring byte offset (unwrapped) of the next word to pull
+    auto ring_be32 = [&](uint32_t off) -> uint32_t {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring_base + (off & 252u)));
+        return bswap32(v);
+    };
+    uint64_t head;
+    uint32_t prev;
+    {
+        const uint32_t w0 = ring_be32(rp), w1 = ring_be32(rp + 4), w2 = ring_be32(rp + 8);
+        head = ((uint64_t)__funnelshift_l(w1, w0, sh) << 32) | __funnelshift_l(w2, w1, sh);
+        prev = w2;
+        rp += 12;
+    }
+    const uint32_t rp0 = rp;
+    uint32_t nbits = 64;
+    auto refill = [&]() {  // nbits in {0, 16, 32} here
+        const uint32_t w = ring_be32(rp);
+        const uint32_t x = __funnelshift_l(w, prev, sh);
+        prev = w;
+        rp += 4;
+        head |= (uint64_t)x << (32u - nbits);
+        nbits += 32;
+    };
+    const uint32_t mask = (1u << lr) - 1u;
+    const uint32_t bm_base = smem_u32(col), sym_base = smem_u32(col + DEC_BM_WORDS * DEC6_CHUNKS);
+    uint32_t acc = 0;
+    auto decode = [&](uint32_t& st) {
+        const uint32_t slot = st & mask;
+        const uint32_t w = __umulhi(slot, 178956971u);  // slot / 24
+        uint32_t b, e;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(b) : "r"(bm_base + w * COL));
+        const uint32_t r = slot - 24u * w;
+        const uint32_t p = (uint32_t)__popc(b & ((2u << r) - 1u));
+        asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(sym_base + (b >> 24) * COL + p * COL));
+        uint32_t nst = (e >> 20) * (st >> lr) + (slot - ((e >> 8) & 0xFFFu));  // D(x) (ANSRangeCodec.go:849)
+        if (nst < (uint32_t)ANS_TOP) {  // renormalise: 16 bits, big endian (:851-856)
+            nst = (nst << 16) | (uint32_t)(head >> 48);
+            head <<= 16;
+            nbits -= 16;
+        }
+        st = nst;
+        acc = __byte_perm(acc, e, 0x4321);  // acc = (acc >> 8) | (sym << 24)
+    };
+    auto step = [&]() -> uint32_t {  // one symbol per state in the order st3, st2, st1, st0 (:904-917); returns [s3 s2 s1 s0]
+        if (nbits <= 32) refill();
+        decode(st3);
+        decode(st2);
+        if (nbits <= 32) refill();
+        decode(st1);
+        decode(st0);
+        return acc;
+    };
+    const uint32_t iters = nsteps >> 2;
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (uint32_t it = 0; it < iters; it++) {
+        uint4 o;
+        o.x = step();
+        o.y = step();
+        o.z = step();
+        o.w = step();
+        d4[it] = o;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");  // the round issued one iteration ago has landed
+        // refill when at most 160 bytes are buffered ahead of the reader: the new round only overwrites consumed bytes
+        if ((int32_t)(fill - rp) <= 160) issue_round();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    for (uint32_t s = iters << 2; s < nsteps; s++) {  // only the last chunk of a block has nsteps % 4 != 0
+        const uint32_t w = step();
+        dst[4 * s] = (uint8_t)w;
+        dst[4 * s + 1] = (uint8_t)(w >> 8);
+        dst[4 * s + 2] = (uint8_t)(w >> 16);
+        dst[4 * s + 3] = (uint8_t)(w >> 24);
+    }
+    if (tail) {  // the tail bytes follow the consumed words (:951-954)
+        uint64_t pos = pb + 64ull + 8ull * (rp - rp0) - nbits;
+        for (uint32_t j = 0; j < tail; j++, pos += 8) dst[(size_t)nsteps * 4 + j] = pos + 8 <= pe ? (uint8_t)bits_at(words, pos, 8) : 0;
+    }
+}
+
 }  // namespace kz

@@ -63,6 +63,10 @@ __global__ void ans0_tables_kernel(const uint32_t* words, uint64_t words_len, co
                                    uint32_t* tabs, uint8_t* out, int32_t* status);
 __global__ void ans0_decode5_kernel(const uint32_t* words, uint64_t words_len, const uint32_t* tabs, const DecChunk* chunks, int nchunks,
                                     const uint64_t* chunk_hdr_bit, uint8_t* out, int32_t* status);
+// decode v6: one thread per chunk, 112 chunks per CTA: 427 table words + 64 ring words per chunk
+static const int DEC6_CHUNKS = 112;
+static const size_t DEC6_SMEM = (size_t)DEC6_CHUNKS * (DEC_BM_WORDS + 256 + 64) * sizeof(uint32_t);
+__global__ void ans0_decode6_kernel(const uint32_t* words, uint64_t words_len, const uint32_t* tabs, const DecChunk* chunks, int nchunks, uint8_t* out);
 __global__ void ans0_decode4_kernel(const uint32_t* words, uint64_t words_len, const DecChunk* chunks, int nchunks, const uint64_t* chunk_hdr_bit,
                                     uint8_t* out, int32_t* status);
 

@@ -674,7 +674,10 @@ int decode_batch(kz_ctx* ctx, uint32_t etype, const uint32_t* d_words, uint64_t 
                                                                         ctx->d_enc_tab.as<uint32_t>(), d_out, d_status);
         }
         LaunchScope ls(ctx, "ans0_decode");
-        if (ctx->ans0_dec_version >= 5)
+        if (ctx->ans0_dec_version >= 6)
+            ans0_decode6_kernel<<<(nchunks + DEC6_CHUNKS - 1) / DEC6_CHUNKS, 128, DEC6_SMEM, ctx->stream>>>(
+                d_words, words_len, ctx->d_enc_tab.as<uint32_t>(), (DecChunk*)(T + o_chunks), nchunks, d_out);
+        else if (ctx->ans0_dec_version >= 5)
             ans0_decode5_kernel<<<(nchunks + DEC_CTA_CHUNKS - 1) / DEC_CTA_CHUNKS, 64, DEC4_SMEM, ctx->stream>>>(
                 d_words, words_len, ctx->d_enc_tab.as<uint32_t>(), (DecChunk*)(T + o_chunks), nchunks, (uint64_t*)(T + o_hbit), d_out, d_status);
         else if (ctx->ans0_dec_version == 3)
@@ -1356,6 +1359,7 @@ int kz_init(int device, kz_ctx** out) {
     cudaFuncSetAttribute(ans0_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM);
     cudaFuncSetAttribute(ans0_decode4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC4_SMEM);
     cudaFuncSetAttribute(ans0_decode5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC4_SMEM);
+    cudaFuncSetAttribute(ans0_decode6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC6_SMEM);
     if (const char* v = getenv("KZ_ANS0_DEC")) ctx->ans0_dec_version = atoi(v);  // 3 = previous kernel generation (A/B measurements)
     cudaFuncSetAttribute(huf_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HUF_DEC_SMEM);
     *out = ctx;

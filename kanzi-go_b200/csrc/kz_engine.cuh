@@ -126,7 +126,7 @@ struct kz_ctx {
     std::string err;
     uint64_t launches = 0;
     bool profile = false;
-    int ans0_dec_version = 5;
+    int ans0_dec_version = 6;
     kz::EncPlan enc_plan;
     std::map<std::string, kz::ProfEntry> prof;
     struct Pending {
