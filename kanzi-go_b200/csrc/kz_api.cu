@@ -655,8 +655,8 @@ int decode_batch(kz_ctx* ctx, uint32_t etype, const uint32_t* d_words, uint64_t 
     } else if (nchunks > 0 && etype == KZ_E_HUFFMAN) {
         {
             LaunchScope ls(ctx, "huf_walk");
-            huf_walk_kernel<<<(nblocks + 31) / 32, 32, 0, ctx->stream>>>(d_words, (DecBlock*)(T + o_blocks), nblocks, (uint64_t*)(T + o_hbit),
-                                                                         (uint64_t*)(T + o_end), d_status);
+            huf_walk_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_words, words_len, (DecBlock*)(T + o_blocks), nblocks, (uint64_t*)(T + o_hbit),
+                                                             (uint64_t*)(T + o_end), d_status);
         }
         LaunchScope ls(ctx, "huf_decode");
         huf_decode_kernel<<<(nchunks + HUF_DEC_CTA_CHUNKS - 1) / HUF_DEC_CTA_CHUNKS, HUF_DEC_CTA_CHUNKS * 4, HUF_DEC_SMEM, ctx->stream>>>(

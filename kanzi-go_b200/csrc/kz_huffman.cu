@@ -508,58 +508,110 @@ KZ_D int read_lengths(BitReader& br, uint8_t* alphabet /*smem, count entries*/, 
 
 }  // namespace
 
-// one thread per block: skims the chunk headers to find where every chunk starts (serial by format)
-__global__ void huf_walk_kernel(const uint32_t* __restrict__ words, const DecBlock* __restrict__ blocks, int nblocks,
-                                uint64_t* __restrict__ chunk_hdr_bit, uint64_t* __restrict__ blk_end, int32_t* __restrict__ status) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per block: skims the chunk headers to find where every chunk starts (serial by format: a chunk's position is
+// known only after the previous header and its four fragment sizes are parsed). v1 walked the <= 256 Exp-Golomb codes of
+// every header with two dependent global loads per bit field (18.9 ms per 64 x 4 MiB); here the header window
+// (<= 545 + 20 bytes) is staged in shared memory with one coalesced load, the alphabet is counted by popc + REDUX and the
+// code lengths are skimmed with one count-leading-zeros per code (ExpGolombCodec.go:159-187: '1' = 0, otherwise z zeros,
+// a one, (z & 7) + 1 bits), several codes per 32-bit window.
+static const int HUF_WIN_WORDS = 176;
+
+__global__ void __launch_bounds__(32) huf_walk_kernel(const uint32_t* __restrict__ words, uint64_t words_len, const DecBlock* __restrict__ blocks,
+                                                      int nblocks, uint64_t* __restrict__ chunk_hdr_bit, uint64_t* __restrict__ blk_end,
+                                                      int32_t* __restrict__ status) {
+    __shared__ uint32_t s_win[HUF_WIN_WORDS + 2];
+    const int b = blockIdx.x, lane = threadIdx.x;
     if (b >= nblocks) return;
     const DecBlock blk = blocks[b];
     if (blk.nchunks == 0) return;
-    BitReader br(words, blk.data_bit, blk.end_bit);
+    uint64_t pos = blk.data_bit;
     uint32_t remaining = blk.pre_len;
     int32_t st = 0;
+    auto rd = [&](uint64_t at, uint32_t n) -> uint32_t {  // n in 1..32 bits at window relative bit `at`; zeros past the window
+        const uint64_t w = at >> 5;
+        if (w >= (uint64_t)HUF_WIN_WORDS) return 0u;
+        return __funnelshift_l(s_win[w + 1], s_win[w], (uint32_t)at & 31u) >> (32 - n);
+    };
     for (uint32_t k = 0; k < blk.nchunks; k++) {
-        chunk_hdr_bit[blk.chunk_base + k] = br.pos;
-        if (st) continue;
+        if (lane == 0) chunk_hdr_bit[blk.chunk_base + k] = pos;
+        if (st) continue;  // descriptors of the remaining chunks point at the failure position; decode is skipped
         const uint32_t clen = remaining < (uint32_t)HUF_CHUNK ? remaining : (uint32_t)HUF_CHUNK;
         remaining -= clen;
         if (clen < 32) {  // :768-770 raw
-            br.skip(8ull * clen);
+            pos += 8ull * clen;
         } else {
-            // alphabet
+            const uint64_t w0 = pos >> 5;
+            __syncwarp();
+            for (int i = lane; i < HUF_WIN_WORDS + 2; i += 32) s_win[i] = w0 + i < words_len ? bswap32(__ldg(words + w0 + i)) : 0u;
+            __syncwarp();
+            uint64_t q = pos & 31;
             int count = 0;
-            if (br.read(1) == 0) {
-                count = br.read(1) ? 0 : 256;
+            if (rd(q, 1) == 0) {
+                count = rd(q + 1, 1) ? 0 : 256;
+                q += 2;
             } else {
-                const uint32_t last = br.read(5);
-                for (uint32_t i = 0; i <= last; i++) count += __popc(br.read(8));
+                const uint32_t last = rd(q + 1, 5);
+                q += 6;
+                const uint32_t cnt = (uint32_t)lane <= last ? (uint32_t)__popc(rd(q + 8 * lane, 8)) : 0u;
+                count = (int)__reduce_add_sync(0xFFFFFFFFu, cnt);
+                q += 8 * (last + 1);
             }
             if (count == 0) {
                 st = -KZ_E_PROCESS_BLOCK;
             } else {
-                for (int i = 0; i < count && !br.overrun; i++) {  // skip the Exp-Golomb coded size deltas
-                    if (br.read(1) == 0) {
-                        uint32_t lg = 1;
-                        while (br.read(1) != 1 && !br.overrun) lg++;
-                        lg &= 7;
-                        br.skip(lg + 1);
-                    }
+                int i = 0;
+                while (i < count) {  // skim the Exp-Golomb coded size deltas
+                    uint32_t win = rd(q, 32);
+                    uint32_t used = 0;
+                    do {
+                        uint32_t len = 1;
+                        if ((int32_t)win >= 0) {  // leading bit 0
+                            const uint32_t z = (uint32_t)__clz((int)win);  // 1..32
+                            len = z + 1 + (z & 7) + 1;
+                        }
+                        if (len > 32 - used) {
+                            if (used == 0) {  // longer than a window (corrupt input): advance and fetch again
+                                used = len;
+                                i++;
+                            }
+                            break;
+                        }
+                        used += len;
+                        win = len < 32 ? win << len : 0u;
+                        i++;
+                    } while (i < count && used <= 14);
+                    q += used;
                 }
                 if (count > 1) {
                     uint64_t total = 0;
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t v = br.read_varint();
+                    for (int j = 0; j < 4; j++) {  // ReadVarInt (EntropyUtils.go:278-296)
+                        uint32_t v = 0, shift = 0;
+                        int n = 0;
+                        for (; n < 4; n++) {
+                            const uint32_t by = rd(q, 8);
+                            q += 8;
+                            v |= (by & 0x7F) << shift;
+                            shift += 7;
+                            if (by < 128) break;
+                        }
+                        if (n == 4) {
+                            v |= (rd(q, 8) & 0x0F) << 28;
+                            q += 8;
+                        }
                         if ((int32_t)v < 0) st = -KZ_E_PROCESS_BLOCK;
                         total += v;
                     }
-                    br.skip(total + 8ull * (clen - 4 * (clen / 4)));
+                    q += total + 8ull * (clen - 4 * (clen / 4));
                 }
             }
+            pos = (w0 << 5) + q;
         }
-        if (br.overrun && st == 0) st = -KZ_E_PROCESS_BLOCK;
+        if (pos > blk.end_bit && st == 0) st = -KZ_E_PROCESS_BLOCK;
     }
-    blk_end[b] = br.pos;
-    if (st) status[b] = st;
+    if (lane == 0) {
+        blk_end[b] = pos;
+        if (st) status[b] = st;
+    }
 }
 
 // Four lanes per chunk (lane j decodes fragment j), 8 chunks per warp, HUF_DEC_CTA_CHUNKS chunks per CTA.

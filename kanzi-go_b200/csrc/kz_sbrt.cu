@@ -163,6 +163,10 @@ __global__ void __launch_bounds__(128) sbrt_rank_kernel(const uint8_t* __restric
 }
 
 // ---- inverse: one warp per block, lane 0 walks the chain (SBRT.go:177-226)
+// The list is the decoder state, so the chain is serial. v1 kept it in shared memory: ~5 dependent shared-memory loads
+// per byte (280 cycles per byte measured). After a BWT nearly all ranks are 0..3, so the first four list entries
+// (symbol, q, p) live in registers and such a byte costs a handful of compares; shared memory holds ranks >= 4 and the
+// q / p of the symbols that are not in registers.
 __global__ void __launch_bounds__(32) sbrt_inverse_kernel(const uint8_t* __restrict__ data, const SbrtBlock* __restrict__ blocks, int nblocks, int mode,
                                                           uint8_t* __restrict__ out) {
     __shared__ uint8_t s_r2s[256];
@@ -181,26 +185,87 @@ __global__ void __launch_bounds__(32) sbrt_inverse_kernel(const uint8_t* __restr
     const uint8_t* src = data + blk.src_off;
     uint8_t* dst = out + blk.dst_off;
     const uint32_t n = blk.len;
+    // register copies of list ranks 0..3
+    uint32_t y0 = 0, y1 = 1, y2 = 2, y3 = 3;  // symbols
+    int32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;   // their q
+    int32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;   // their last positions
     auto step = [&](uint32_t i, uint32_t r) -> uint32_t {
-        const uint32_t c = s_r2s[r];
-        const int32_t qc = mode == 1 ? (int32_t)i : ((int32_t)i + s_p[c]) >> 1;
-        s_p[c] = (int32_t)i;
-        s_q[c] = qc;
-        while (r > 0) {
-            const uint32_t d = s_r2s[r - 1];
-            if (s_q[d] > qc) break;
-            s_r2s[r] = (uint8_t)d;
-            r--;
+        uint32_t c;
+        int32_t pc;
+        if (r < 4) {  // take entry r out of the registers, close the gap from below
+            if (r == 0) {
+                c = y0, pc = p0;
+            } else if (r == 1) {
+                c = y1, pc = p1;
+            } else if (r == 2) {
+                c = y2, pc = p2;
+            } else {
+                c = y3, pc = p3;
+            }
+        } else {
+            c = s_r2s[r];
+            pc = s_p[c];
         }
-        s_r2s[r] = (uint8_t)c;
+        const int32_t qc = mode == 1 ? (int32_t)i : ((int32_t)i + pc) >> 1;
+        if (r >= 4) {  // bubble up inside shared memory down to rank 4 (SBRT.go:214-220)
+            while (r > 4) {
+                const uint32_t d = s_r2s[r - 1];
+                if (s_q[d] > qc) break;
+                s_r2s[r] = (uint8_t)d;
+                r--;
+            }
+            if (r > 4 || q3 > qc) {  // stays behind the register entries
+                s_r2s[r] = (uint8_t)c;
+                s_q[c] = qc;
+                s_p[c] = (int32_t)i;
+                return c;
+            }
+            // entry 3 drops to rank 4, c enters the registers at rank 3
+            s_r2s[4] = (uint8_t)y3;
+            s_q[y3] = q3;
+            s_p[y3] = p3;
+            r = 3;
+        } else {
+            // entries below rank r keep their place: the slot r is free; the moves below only touch ranks < r
+        }
+        // now c belongs at some rank <= r <= 3: shift the entries with q <= qc down by one (they are ranks r-1, r-2, ...)
+        if (r == 3) {
+            if (q2 <= qc) {
+                y3 = y2, q3 = q2, p3 = p2;
+                r = 2;
+            } else {
+                y3 = c, q3 = qc, p3 = (int32_t)i;
+                return c;
+            }
+        }
+        if (r == 2) {
+            if (q1 <= qc) {
+                y2 = y1, q2 = q1, p2 = p1;
+                r = 1;
+            } else {
+                y2 = c, q2 = qc, p2 = (int32_t)i;
+                return c;
+            }
+        }
+        if (r == 1) {
+            if (q0 <= qc) {
+                y1 = y0, q1 = q0, p1 = p0;
+                r = 0;
+            } else {
+                y1 = c, q1 = qc, p1 = (int32_t)i;
+                return c;
+            }
+        }
+        y0 = c, q0 = qc, p0 = (int32_t)i;
         return c;
     };
     const uint32_t n16 = n >> 4;
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     uint4* d4 = reinterpret_cast<uint4*>(dst);
+    uint4 x = n16 ? __ldg(&s4[0]) : make_uint4(0, 0, 0, 0);
     for (uint32_t v = 0; v < n16; v++) {
-        const uint4 x = __ldg(&s4[v]);
         const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+        if (v + 1 < n16) x = __ldg(&s4[v + 1]);  // next 16 ranks in flight while these are decoded
         uint32_t o[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
