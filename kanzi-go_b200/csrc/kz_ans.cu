@@ -1459,6 +1459,26 @@ __global__ void __launch_bounds__(64, 7) ans0_decode5_kernel(const uint32_t* __r
     const uint32_t fast_iters = min_steps >> 2;  // iterations in which every group of the warp is active
     uint32_t it = 0;
     uint8_t* dptr = dst + 4 * k;
+    // 8 steps per ring check while every group is active. A check sees a gap (buffered bytes ahead of the cursor) g >= 66:
+    // it starts at >= 240, drops by at most 64 per check while above 128, and never drops once it is refilled every time.
+    // 8 steps consume at most 64 bytes and a consuming lane reads at most 4 bytes past its word: always inside landed data.
+    for (; it + 2 <= fast_iters; it += 2) {
+        dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        *reinterpret_cast<uint32_t*>(dptr) = transpose(L.acc);
+        dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
+        *reinterpret_cast<uint32_t*>(dptr + 16) = transpose(L.acc);
+        dptr += 32;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if ((int32_t)(fill - L.cur2) <= 128) issue();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     for (; it < fast_iters; it++) {
         dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);
         dec4_step<true>(L, bm_base, sym_base, ring_base, mask, lr, rsh, hi_mask, grp_mask, true);

@@ -17,6 +17,7 @@
 #include "kz_hash.cuh"
 #include "kz_sbrt.cuh"
 #include "kz_zrlt.cuh"
+#include "kz_rolz.cuh"
 
 #include <memory>
 
@@ -802,8 +803,8 @@ struct TransformPlan {
     bool bwt() const { return nt == 1 && ids[0] == KZ_T_BWT; }
     bool lz() const { return nt == 1 && (ids[0] == KZ_T_LZ || ids[0] == KZ_T_LZX); }
     bool lzx() const { return nt == 1 && ids[0] == KZ_T_LZX; }
-    static bool seq_id(uint64_t t) { return t == KZ_T_BWT || t == KZ_T_BWTS || t == KZ_T_RANK || t == KZ_T_MTFT || t == KZ_T_ZRLT; }
-    // any sequence of BWT / BWTS / RANK / MTFT / ZRLT stages (e.g. "BWT+RANK+ZRLT", the transform chain of kanzi -l 5)
+    static bool seq_id(uint64_t t) { return t == KZ_T_BWT || t == KZ_T_BWTS || t == KZ_T_RANK || t == KZ_T_MTFT || t == KZ_T_ZRLT || t == KZ_T_ROLZ; }
+    // any sequence of BWT / BWTS / RANK / MTFT / ZRLT / ROLZ stages (e.g. "BWT+RANK+ZRLT", the transform chain of kanzi -l 5)
     bool generic() const {
         if (bwt()) return false;
         for (int i = 0; i < nt; i++)
@@ -815,7 +816,7 @@ struct TransformPlan {
 int plan_transforms(kz_ctx* ctx, uint64_t t48, TransformPlan& p, int err_code) {
     p.nt = count_transforms(t48, p.ids);
     if (!(p.none() || p.bwt() || p.lz() || p.generic()))
-        return ctx->fail(err_code, "transform sequence not available on the GPU path (NONE, LZ, LZX, and sequences of BWT / BWTS / RANK / MTFT / ZRLT are)");
+        return ctx->fail(err_code, "transform sequence not available on the GPU path (NONE, LZ, LZX, and sequences of BWT / BWTS / RANK / MTFT / ZRLT / ROLZ are)");
     return 0;
 }
 
@@ -827,7 +828,7 @@ int plan_transforms(kz_ctx* ctx, uint64_t t48, TransformPlan& p, int err_code) {
 // ------------------------------------------------------------------------------------------------------------
 // One forward stage. Block b: d_in + b*istride (len[b] bytes) -> d_out + b*ostride. applied[b] = 1 and len[b] updated on success.
 int apply_forward(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint64_t istride, uint8_t* d_out, uint64_t ostride, std::vector<uint32_t>& len,
-                  const std::vector<uint8_t>& active, std::vector<uint8_t>& applied) {
+                  const std::vector<uint8_t>& active, std::vector<uint8_t>& applied, int* data_type = nullptr) {
     const uint32_t nblocks = (uint32_t)len.size();
     applied.assign(nblocks, 0);
     if (t == KZ_T_BWT) {
@@ -860,6 +861,43 @@ int apply_forward(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint64_t istride
                                                 &ctx->launches);
             if (e != cudaSuccess) return ctx->cuda_fail(e, "bwts_forward");
             applied[b] = 1;
+        }
+    } else if (t == KZ_T_ROLZ) {  // ROLZCodec.Forward: declines small blocks and blocks it cannot shrink
+        uint32_t max_len = 0;
+        for (uint32_t b = 0; b < nblocks; b++) max_len = std::max(max_len, len[b]);
+        const size_t sstride = rolz_scratch_bytes(max_len);
+        CK(ctx->d_ws.ensure(sstride * nblocks + 256));
+        std::vector<RolzBlock> rb(nblocks);
+        for (uint32_t b = 0; b < nblocks; b++) {
+            rb[b].src_off = b * istride;
+            rb[b].dst_off = b * ostride;
+            rb[b].scratch_off = b * sstride;
+            rb[b].len = active[b] ? len[b] : 0;
+            rb[b].cap = (uint32_t)std::min<uint64_t>(ostride, 0xFFFFFFF0u);
+            rb[b].data_type = data_type ? *data_type : 0;
+            rb[b].pad = 0;
+        }
+        Packer pk;
+        const size_t o_rb = pk.add(rb.data(), rb.size() * sizeof(RolzBlock));
+        const size_t o_res = pk.reserve((size_t)nblocks * sizeof(RolzResult));
+        int rc = upload(ctx, pk);
+        if (rc) return rc;
+        uint8_t* T = ctx->d_tables.as<uint8_t>();
+        {
+            LaunchScope ls(ctx, "rolz_forward");
+            rolz_forward_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_in, (const RolzBlock*)(T + o_rb), (int)nblocks, ctx->d_ws.as<uint8_t>(), d_out,
+                                                                (RolzResult*)(T + o_res));
+        }
+        CK(cudaGetLastError());
+        std::vector<RolzResult> hr(nblocks);
+        CK(cudaMemcpyAsync(hr.data(), T + o_res, (size_t)nblocks * sizeof(RolzResult), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t b = 0; b < nblocks; b++) {
+            if (active[b] && len[b] && hr[b].status == 0) {
+                applied[b] = 1;
+                len[b] = hr[b].out_len;
+            }
+            if (data_type && nblocks == 1) *data_type = hr[b].data_type;
         }
     } else if (t == KZ_T_RANK || t == KZ_T_MTFT) {  // SBRT.Forward never declines (buffers are sized for MaxEncodedLen)
         std::vector<SbrtBlock> sb(nblocks);
@@ -1011,6 +1049,39 @@ int apply_inverse(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint8_t* d_out, 
             LaunchScope ls(ctx, "bwts_inverse");
             cudaError_t e = bwts_inverse_device(d_in + b * stride, len[b], d_out + b * stride, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap, ctx->stream, &ctx->launches);
             if (e != cudaSuccess) return ctx->cuda_fail(e, "bwts_inverse");
+        }
+    } else if (t == KZ_T_ROLZ) {
+        const size_t sstride = rolz_scratch_bytes(cap);
+        CK(ctx->d_ws.ensure(sstride * nblocks + 256));
+        std::vector<RolzBlock> rb(nblocks);
+        for (uint32_t b = 0; b < nblocks; b++) {
+            rb[b].src_off = b * stride;
+            rb[b].dst_off = b * stride;
+            rb[b].scratch_off = b * sstride;
+            rb[b].len = active[b] ? len[b] : 0;
+            rb[b].cap = cap;
+            rb[b].data_type = 0;
+            rb[b].pad = 0;
+        }
+        Packer pk;
+        const size_t o_rb = pk.add(rb.data(), rb.size() * sizeof(RolzBlock));
+        const size_t o_res = pk.reserve((size_t)nblocks * sizeof(RolzResult));
+        int rc = upload(ctx, pk);
+        if (rc) return rc;
+        uint8_t* T = ctx->d_tables.as<uint8_t>();
+        {
+            LaunchScope ls(ctx, "rolz_inverse");
+            rolz_inverse_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_in, (const RolzBlock*)(T + o_rb), (int)nblocks, ctx->d_ws.as<uint8_t>(), d_out,
+                                                                (RolzResult*)(T + o_res));
+        }
+        CK(cudaGetLastError());
+        std::vector<RolzResult> hr(nblocks);
+        CK(cudaMemcpyAsync(hr.data(), T + o_res, (size_t)nblocks * sizeof(RolzResult), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t b = 0; b < nblocks; b++) {
+            if (!active[b] || len[b] == 0) continue;
+            if (hr[b].status) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "ROLZ codec inverse transform failed: invalid data");
+            len[b] = hr[b].out_len;
         }
     } else if (t == KZ_T_RANK || t == KZ_T_MTFT) {
         std::vector<SbrtBlock> sb(nblocks);
@@ -1433,6 +1504,7 @@ size_t kz_transform_max_encoded_len(uint64_t type, size_t n) {
         case KZ_T_MTFT: return n + 33;  // transform/SBRT.go:229-231
         case KZ_T_ZRLT: return n;       // transform/ZRLT.go:228-230
         case KZ_T_BWTS: return n;       // transform/BWTS.go:291-293
+        case KZ_T_ROLZ: return n <= 512 ? n + 64 : n;  // transform/ROLZCodec.go:916-918
         case KZ_T_LZ:
         case KZ_T_LZX: return n <= 1024 ? n + 16 : n + n / 64;  // transform/LZCodec.go:935-941
         default: return 0;
@@ -1848,17 +1920,17 @@ int kz_transform_forward(kz_ctx* ctx, uint64_t type, int* data_type, const uint8
         *out_n = jobs[0].post_len;
         return 0;
     }
-    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS) {  // SBRT.Forward / ZRLT.Forward / BWTS.Forward
+    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS || type == KZ_T_ROLZ) {  // SBRT / ZRLT / BWTS / ROLZ Forward
         if (n == 0) return 0;
         if (n > (1u << 30)) return ctx->fail(KZ_ERR_BLOCK_SIZE, "block too large");
         if (cap < kz_transform_max_encoded_len(type, n)) return 1;  // Forward returns an error: the sequence skips the transform
-        const uint64_t stride = ((uint64_t)n + 33 + 64 + 15) & ~15ull;
+        const uint64_t stride = ((uint64_t)n + 33 + 64 + 64 + 15) & ~15ull;
         CK(ctx->d_in.ensure(stride));
         CK(ctx->d_out.ensure(stride));
         CK(cudaMemcpyAsync(ctx->d_in.p, src, n, cudaMemcpyHostToDevice, ctx->stream));
         std::vector<uint32_t> len(1, (uint32_t)n);
         std::vector<uint8_t> active(1, 1), applied;
-        int rc = apply_forward(ctx, type, ctx->d_in.as<uint8_t>(), stride, ctx->d_out.as<uint8_t>(), stride, len, active, applied);
+        int rc = apply_forward(ctx, type, ctx->d_in.as<uint8_t>(), stride, ctx->d_out.as<uint8_t>(), stride, len, active, applied, data_type);
         if (rc) return rc;
         if (!applied[0]) return 1;
         CK(cudaMemcpyAsync(dst, ctx->d_out.p, len[0], cudaMemcpyDeviceToHost, ctx->stream));
@@ -1918,7 +1990,7 @@ int kz_transform_inverse(kz_ctx* ctx, uint64_t type, const uint8_t* src, size_t 
         *out_n = olen[0];
         return 0;
     }
-    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS) {  // SBRT / ZRLT / BWTS Inverse; cap = len(dst) of the reference call
+    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS || type == KZ_T_ROLZ) {  // SBRT / ZRLT / BWTS / ROLZ Inverse; cap = len(dst)
         if (n == 0 || cap == 0) return 0;
         if (n > (1u << 30) || cap > (1u << 30) + 4096) return ctx->fail(KZ_ERR_BLOCK_SIZE, "block too large");
         const uint64_t stride = ((uint64_t)std::max(n, cap) + 64 + 15) & ~15ull;

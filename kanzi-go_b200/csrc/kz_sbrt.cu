@@ -163,36 +163,40 @@ __global__ void __launch_bounds__(128) sbrt_rank_kernel(const uint8_t* __restric
 }
 
 // ---- inverse: one warp per block, lane 0 walks the chain (SBRT.go:177-226)
-// The list is the decoder state, so the chain is serial. v1 kept it in shared memory: ~5 dependent shared-memory loads
-// per byte (280 cycles per byte measured). After a BWT nearly all ranks are 0..3, so the first four list entries
-// (symbol, q, p) live in registers and such a byte costs a handful of compares; shared memory holds ranks >= 4 and the
-// q / p of the symbols that are not in registers.
+// The list is the decoder state, so the chain is serial. v1 kept symbol -> q and rank -> symbol in shared memory: two
+// dependent loads per bubble step (280 cycles per byte measured). Now
+//   * the list is stored by RANK as 64-bit entries (q << 32 | symbol): moving an entry is one load + one store and the next
+//     four entries are loaded together before they are compared (their addresses do not depend on the comparisons);
+//   * the first four entries (symbol, q, p) live in registers: after a BWT most ranks are 0..3 and cost a few compares;
+//   * p (last position) stays a table by symbol for the entries that are not in registers.
 __global__ void __launch_bounds__(32) sbrt_inverse_kernel(const uint8_t* __restrict__ data, const SbrtBlock* __restrict__ blocks, int nblocks, int mode,
                                                           uint8_t* __restrict__ out) {
-    __shared__ uint8_t s_r2s[256];
-    __shared__ int32_t s_q[256], s_p[256];
+    __shared__ uint64_t s_ent[256 + 8];  // entry of rank r at s_ent[r + 4]; four sentinels (q = "infinite") below rank 0
+    __shared__ int32_t s_p[256];
     const int b = blockIdx.x, lane = threadIdx.x;
     if (b >= nblocks) return;
     const SbrtBlock blk = blocks[b];
     if (!blk.active) return;
     for (int i = lane; i < 256; i += 32) {
-        s_r2s[i] = (uint8_t)i;
-        s_q[i] = 0;
+        s_ent[i + 4] = (uint64_t)i;  // q = 0, symbol i
         s_p[i] = 0;
     }
+    if (lane < 4) s_ent[lane] = ~0ull >> 1;
+    if (lane < 4) s_ent[260 + lane] = 0;
     __syncwarp();
     if (lane != 0) return;
     const uint8_t* src = data + blk.src_off;
     uint8_t* dst = out + blk.dst_off;
     const uint32_t n = blk.len;
-    // register copies of list ranks 0..3
-    uint32_t y0 = 0, y1 = 1, y2 = 2, y3 = 3;  // symbols
-    int32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;   // their q
-    int32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;   // their last positions
+    uint64_t* ent = s_ent + 4;
+    // register copies of list ranks 0..3 (the shared entries of these ranks are stale and never read)
+    uint32_t y0 = 0, y1 = 1, y2 = 2, y3 = 3;
+    int32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+    int32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
     auto step = [&](uint32_t i, uint32_t r) -> uint32_t {
         uint32_t c;
         int32_t pc;
-        if (r < 4) {  // take entry r out of the registers, close the gap from below
+        if (r < 4) {
             if (r == 0) {
                 c = y0, pc = p0;
             } else if (r == 1) {
@@ -203,32 +207,38 @@ __global__ void __launch_bounds__(32) sbrt_inverse_kernel(const uint8_t* __restr
                 c = y3, pc = p3;
             }
         } else {
-            c = s_r2s[r];
+            c = (uint32_t)ent[r] & 0xFF;
             pc = s_p[c];
         }
         const int32_t qc = mode == 1 ? (int32_t)i : ((int32_t)i + pc) >> 1;
-        if (r >= 4) {  // bubble up inside shared memory down to rank 4 (SBRT.go:214-220)
+        if (r >= 4) {  // bubble up inside shared memory down to rank 4 (SBRT.go:214-220), four entries per round
+            const uint64_t lim = ((uint64_t)(uint32_t)qc << 32) | 0xFFFFFFFFull;  // entry <= lim  <=>  q <= qc
             while (r > 4) {
-                const uint32_t d = s_r2s[r - 1];
-                if (s_q[d] > qc) break;
-                s_r2s[r] = (uint8_t)d;
+                const uint64_t e1 = ent[r - 1], e2 = ent[(int)r - 2], e3 = ent[(int)r - 3], e4 = ent[(int)r - 4];  // ranks < 4 are stale: guarded by r > 4
+                if (e1 > lim) break;
+                ent[r] = e1;
+                r--;
+                if (r <= 4 || e2 > lim) break;
+                ent[r] = e2;
+                r--;
+                if (r <= 4 || e3 > lim) break;
+                ent[r] = e3;
+                r--;
+                if (r <= 4 || e4 > lim) break;
+                ent[r] = e4;
                 r--;
             }
-            if (r > 4 || q3 > qc) {  // stays behind the register entries
-                s_r2s[r] = (uint8_t)c;
-                s_q[c] = qc;
+            if (r > 4 || q3 > qc) {  // stays behind the register entries (r == 4: the entry of rank 3 is in a register)
+                ent[r] = ((uint64_t)(uint32_t)qc << 32) | c;
                 s_p[c] = (int32_t)i;
                 return c;
             }
             // entry 3 drops to rank 4, c enters the registers at rank 3
-            s_r2s[4] = (uint8_t)y3;
-            s_q[y3] = q3;
+            ent[4] = ((uint64_t)(uint32_t)q3 << 32) | y3;
             s_p[y3] = p3;
             r = 3;
-        } else {
-            // entries below rank r keep their place: the slot r is free; the moves below only touch ranks < r
         }
-        // now c belongs at some rank <= r <= 3: shift the entries with q <= qc down by one (they are ranks r-1, r-2, ...)
+        // c belongs at some rank <= r <= 3: the entries with q <= qc right above it move down by one
         if (r == 3) {
             if (q2 <= qc) {
                 y3 = y2, q3 = q2, p3 = p2;
