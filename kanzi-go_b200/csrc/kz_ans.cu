@@ -35,6 +35,22 @@ static __device__ __forceinline__ uint32_t make_enc_entry(uint32_t cum, uint32_t
     return fr | (bias << 13);
 }
 
+__global__ void expand_chunks_kernel(const DecBlock* __restrict__ blocks, int nblocks, DecChunk* __restrict__ chunks) {
+    const int b = blockIdx.y;
+    if (b >= nblocks) return;
+    const DecBlock blk = blocks[b];
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk.chunk_size == 0 || k >= blk.nchunks) return;
+    DecChunk c;
+    const uint64_t o = (uint64_t)k * blk.chunk_size;
+    c.out_off = blk.out_off + o;
+    c.end_bit = blk.end_bit;
+    const uint64_t left = (uint64_t)blk.pre_len - o;
+    c.out_len = left < blk.chunk_size ? (uint32_t)left : blk.chunk_size;
+    c.block = (uint32_t)b;
+    chunks[blk.chunk_base + k] = c;
+}
+
 // inv[f] for f in [0, 4096): the 32-bit fixed point reciprocal of :452-466 (Alverson)
 __global__ void rcp_table_kernel(uint32_t* __restrict__ inv) {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;

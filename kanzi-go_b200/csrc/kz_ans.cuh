@@ -18,7 +18,8 @@ struct DecBlock {
     uint32_t pre_len;    // number of bytes to decode
     uint32_t nchunks;
     uint32_t chunk_base; // index of the block's first chunk
-    uint32_t pad;
+    uint32_t chunk_size; // bytes per chunk (0: the block has no chunk table entries to expand)
+    uint64_t out_off;    // byte offset of the block's decoded bytes inside the output buffer (16-byte aligned)
 };
 struct DecChunk {
     uint64_t out_off;  // byte offset inside the output buffer (16-byte aligned)
@@ -45,6 +46,8 @@ static const size_t DEC_SMEM = 2 * DEC_WARP_WORDS * sizeof(uint32_t);
 static const int DEC4_WARP_WORDS = ((8 * 64 + (DEC_BM_WORDS + 256) * 8) + 63) & ~63;
 static const size_t DEC4_SMEM = 2 * DEC4_WARP_WORDS * sizeof(uint32_t) + 256;
 
+// expands the per-block descriptors into per-chunk ones on the device (grid: (ceil(max chunks per block / 256), blocks))
+__global__ void expand_chunks_kernel(const DecBlock* blocks, int nblocks, DecChunk* chunks);
 __global__ void rcp_table_kernel(uint32_t* inv);
 __global__ void ans0_stats_kernel(const uint8_t* in, const ChunkIn* chunks, int nchunks, uint32_t* enc_tab, uint8_t* hdr, uint32_t* hdr_bits,
                                   uint32_t* asz_out);

@@ -557,9 +557,9 @@ int decode_batch(kz_ctx* ctx, uint32_t etype, const uint32_t* d_words, uint64_t 
     if (nblocks == 0) return 0;
     if (!etype_supported(etype)) return ctx->fail(KZ_ERR_INVALID_CODEC, "entropy codec not available on the GPU path");
     std::vector<DecBlock> dblocks(nblocks);
-    std::vector<DecChunk> dchunks;
     std::vector<ExtractJob> xjobs;
     std::vector<int32_t> status(nblocks, 0);
+    uint32_t nchunks_total = 0, max_chunks = 0;
     for (int b = 0; b < nblocks; b++) {
         DecJob& j = jobs[b];
         DecBlock& db = dblocks[b];
@@ -567,8 +567,9 @@ int decode_batch(kz_ctx* ctx, uint32_t etype, const uint32_t* d_words, uint64_t 
         db.end_bit = j.bit_off + j.bits;
         db.pre_len = j.pre_len;
         db.nchunks = 0;
-        db.chunk_base = (uint32_t)dchunks.size();
-        db.pad = 0;
+        db.chunk_base = nchunks_total;
+        db.chunk_size = 0;
+        db.out_off = j.out_off;
         status[b] = j.status;
         if (j.status) continue;
         const uint32_t et = j.copy ? (uint32_t)KZ_E_NONE : etype;
@@ -586,50 +587,19 @@ int decode_batch(kz_ctx* ctx, uint32_t etype, const uint32_t* d_words, uint64_t 
                 xjobs.push_back(x);
             }
             j.end_pos = j.data_bit + 8ull * j.pre_len;
-        } else if (et == KZ_E_ANS0) {
-            for (uint32_t o = 0; o < j.pre_len; o += ANS0_CHUNK) {
-                DecChunk c;
-                c.out_off = j.out_off + o;
-                c.end_bit = db.end_bit;
-                c.out_len = std::min<uint32_t>(ANS0_CHUNK, j.pre_len - o);
-                c.block = (uint32_t)b;
-                dchunks.push_back(c);
-                db.nchunks++;
-            }
-        } else if (et == KZ_E_ANS1) {
-            for (uint32_t o = 0; o < j.pre_len; o += ANS1_CHUNK) {
-                DecChunk c;
-                c.out_off = j.out_off + o;
-                c.end_bit = db.end_bit;
-                c.out_len = std::min<uint32_t>(ANS1_CHUNK, j.pre_len - o);
-                c.block = (uint32_t)b;
-                dchunks.push_back(c);
-                db.nchunks++;
-            }
-        } else if (et == KZ_E_RANGE) {  // chunks carry no length: the block is one serial chain, described by one entry
-            DecChunk c;
-            c.out_off = j.out_off;
-            c.end_bit = db.end_bit;
-            c.out_len = j.pre_len;
-            c.block = (uint32_t)b;
-            dchunks.push_back(c);
-            db.nchunks = 1;
-        } else if (et == KZ_E_HUFFMAN) {
-            for (uint32_t o = 0; o < j.pre_len; o += HUF_CHUNK) {
-                DecChunk c;
-                c.out_off = j.out_off + o;
-                c.end_bit = db.end_bit;
-                c.out_len = std::min<uint32_t>(HUF_CHUNK, j.pre_len - o);
-                c.block = (uint32_t)b;
-                dchunks.push_back(c);
-                db.nchunks++;
-            }
+        } else {
+            // the chunk descriptors are expanded on the device (expand_chunks_kernel); Range blocks are one serial chain: one entry
+            const uint32_t cs = et == KZ_E_ANS0 ? (uint32_t)ANS0_CHUNK : et == KZ_E_ANS1 ? (uint32_t)ANS1_CHUNK : et == KZ_E_HUFFMAN ? (uint32_t)HUF_CHUNK
+                                                                                                                                     : 0xFFFFFFFFu;
+            db.chunk_size = cs;
+            db.nchunks = cs == 0xFFFFFFFFu ? 1u : (uint32_t)(((uint64_t)j.pre_len + cs - 1) / cs);
+            nchunks_total += db.nchunks;
+            max_chunks = std::max(max_chunks, db.nchunks);
         }
     }
-    const int nchunks = (int)dchunks.size();
+    const int nchunks = (int)nchunks_total;
     Packer pk;
     const size_t o_blocks = pk.add(dblocks.data(), dblocks.size() * sizeof(DecBlock));
-    const size_t o_chunks = pk.add(dchunks.data(), dchunks.size() * sizeof(DecChunk));
     const size_t o_x = pk.add(xjobs.data(), xjobs.size() * sizeof(ExtractJob));
     const size_t o_status = pk.add(status.data(), status.size() * 4);
     const size_t o_hbit = pk.reserve((size_t)nchunks * 8 + 8);
@@ -638,6 +608,12 @@ int decode_batch(kz_ctx* ctx, uint32_t etype, const uint32_t* d_words, uint64_t 
     if (rc) return rc;
     uint8_t* T = ctx->d_tables.as<uint8_t>();
     int32_t* d_status = (int32_t*)(T + o_status);
+    CK(ctx->d_chunks.ensure((size_t)nchunks * sizeof(DecChunk) + 64));
+    DecChunk* d_dchunks = ctx->d_chunks.as<DecChunk>();
+    if (nchunks > 0) {
+        LaunchScope ls(ctx, "expand_chunks");
+        expand_chunks_kernel<<<dim3((max_chunks + 255) / 256, nblocks), 256, 0, ctx->stream>>>((DecBlock*)(T + o_blocks), nblocks, d_dchunks);
+    }
     if (nchunks > 0 && etype == KZ_E_ANS1) {
         CK(ctx->d_enc_tab.ensure((size_t)nchunks * 65536 * sizeof(uint32_t)));
         CK(ctx->d_hist.ensure((size_t)nchunks * 256 * 2048 + 256));
@@ -647,11 +623,11 @@ int decode_batch(kz_ctx* ctx, uint32_t etype, const uint32_t* d_words, uint64_t 
                                                                          (uint64_t*)(T + o_end), d_status);
         }
         LaunchScope ls(ctx, "ans1_decode");
-        ans1_decode_kernel<<<nchunks, 32, 0, ctx->stream>>>(d_words, words_len, (DecChunk*)(T + o_chunks), nchunks, (uint64_t*)(T + o_hbit),
+        ans1_decode_kernel<<<nchunks, 32, 0, ctx->stream>>>(d_words, words_len, d_dchunks, nchunks, (uint64_t*)(T + o_hbit),
                                                             ctx->d_hist.as<uint8_t>(), ctx->d_enc_tab.as<uint32_t>(), d_out, d_status);
     } else if (nchunks > 0 && etype == KZ_E_RANGE) {
         LaunchScope ls(ctx, "range_decode");
-        range_decode_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_words, (DecBlock*)(T + o_blocks), (DecChunk*)(T + o_chunks), nblocks, d_out,
+        range_decode_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_words, (DecBlock*)(T + o_blocks), d_dchunks, nblocks, d_out,
                                                              (uint64_t*)(T + o_end), d_status);
     } else if (nchunks > 0 && etype == KZ_E_HUFFMAN) {
         {
@@ -661,7 +637,7 @@ int decode_batch(kz_ctx* ctx, uint32_t etype, const uint32_t* d_words, uint64_t 
         }
         LaunchScope ls(ctx, "huf_decode");
         huf_decode_kernel<<<(nchunks + HUF_DEC_CTA_CHUNKS - 1) / HUF_DEC_CTA_CHUNKS, HUF_DEC_CTA_CHUNKS * 4, HUF_DEC_SMEM, ctx->stream>>>(
-            d_words, (DecChunk*)(T + o_chunks), nchunks, (uint64_t*)(T + o_hbit), d_out, d_status);
+            d_words, d_dchunks, nchunks, (uint64_t*)(T + o_hbit), d_out, d_status);
     } else if (nchunks > 0) {
         {
             LaunchScope ls(ctx, "ans_walk");
@@ -671,21 +647,21 @@ int decode_batch(kz_ctx* ctx, uint32_t etype, const uint32_t* d_words, uint64_t 
         if (ctx->ans0_dec_version >= 5) {
             CK(ctx->d_enc_tab.ensure((size_t)nchunks * DEC_TAB_WORDS * sizeof(uint32_t) + 256));
             LaunchScope ls(ctx, "ans0_tables");
-            ans0_tables_kernel<<<(nchunks + 3) / 4, 128, 0, ctx->stream>>>(d_words, words_len, (DecChunk*)(T + o_chunks), nchunks, (uint64_t*)(T + o_hbit),
+            ans0_tables_kernel<<<(nchunks + 3) / 4, 128, 0, ctx->stream>>>(d_words, words_len, d_dchunks, nchunks, (uint64_t*)(T + o_hbit),
                                                                         ctx->d_enc_tab.as<uint32_t>(), d_out, d_status);
         }
         LaunchScope ls(ctx, "ans0_decode");
         if (ctx->ans0_dec_version >= 6)
             ans0_decode6_kernel<<<(nchunks + DEC6_CHUNKS - 1) / DEC6_CHUNKS, 128, DEC6_SMEM, ctx->stream>>>(
-                d_words, words_len, ctx->d_enc_tab.as<uint32_t>(), (DecChunk*)(T + o_chunks), nchunks, d_out);
+                d_words, words_len, ctx->d_enc_tab.as<uint32_t>(), d_dchunks, nchunks, d_out);
         else if (ctx->ans0_dec_version >= 5)
             ans0_decode5_kernel<<<(nchunks + DEC_CTA_CHUNKS - 1) / DEC_CTA_CHUNKS, 64, DEC4_SMEM, ctx->stream>>>(
-                d_words, words_len, ctx->d_enc_tab.as<uint32_t>(), (DecChunk*)(T + o_chunks), nchunks, (uint64_t*)(T + o_hbit), d_out, d_status);
+                d_words, words_len, ctx->d_enc_tab.as<uint32_t>(), d_dchunks, nchunks, (uint64_t*)(T + o_hbit), d_out, d_status);
         else if (ctx->ans0_dec_version == 3)
-            ans0_decode_kernel<<<(nchunks + DEC_CTA_CHUNKS - 1) / DEC_CTA_CHUNKS, 64, DEC_SMEM, ctx->stream>>>(d_words, words_len, (DecChunk*)(T + o_chunks),
+            ans0_decode_kernel<<<(nchunks + DEC_CTA_CHUNKS - 1) / DEC_CTA_CHUNKS, 64, DEC_SMEM, ctx->stream>>>(d_words, words_len, d_dchunks,
                                                                                                    nchunks, (uint64_t*)(T + o_hbit), d_out, d_status);
         else
-            ans0_decode4_kernel<<<(nchunks + DEC_CTA_CHUNKS - 1) / DEC_CTA_CHUNKS, 64, DEC4_SMEM, ctx->stream>>>(d_words, words_len, (DecChunk*)(T + o_chunks),
+            ans0_decode4_kernel<<<(nchunks + DEC_CTA_CHUNKS - 1) / DEC_CTA_CHUNKS, 64, DEC4_SMEM, ctx->stream>>>(d_words, words_len, d_dchunks,
                                                                                                      nchunks, (uint64_t*)(T + o_hbit), d_out, d_status);
     }
     if (!xjobs.empty()) {
@@ -1443,7 +1419,7 @@ void kz_destroy(kz_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     drain_profile(ctx);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
-    DevBuf* bufs[] = {&ctx->d_in, &ctx->d_out, &ctx->d_tmp, &ctx->d_tmp2, &ctx->d_seg, &ctx->d_tables, &ctx->d_enc_tab, &ctx->d_hdr, &ctx->d_pay, &ctx->d_small, &ctx->d_dl, &ctx->d_rcp, &ctx->d_ws, &ctx->d_lens, &ctx->d_hist};
+    DevBuf* bufs[] = {&ctx->d_in, &ctx->d_out, &ctx->d_tmp, &ctx->d_tmp2, &ctx->d_seg, &ctx->d_chunks, &ctx->d_tables, &ctx->d_enc_tab, &ctx->d_hdr, &ctx->d_pay, &ctx->d_small, &ctx->d_dl, &ctx->d_rcp, &ctx->d_ws, &ctx->d_lens, &ctx->d_hist};
     for (auto b : bufs) b->release();
     ctx->h_stage.release();
     ctx->h_dl.release();

@@ -137,7 +137,7 @@ struct kz_ctx {
     std::vector<cudaEvent_t> event_pool;
 
     // scratch
-    kz::DevBuf d_in, d_out, d_tmp, d_tmp2, d_seg, d_tables, d_enc_tab, d_hdr, d_pay, d_small, d_dl, d_rcp, d_ws, d_lens, d_hist;
+    kz::DevBuf d_in, d_out, d_tmp, d_tmp2, d_seg, d_chunks, d_tables, d_enc_tab, d_hdr, d_pay, d_small, d_dl, d_rcp, d_ws, d_lens, d_hist;
     kz::PinnedBuf h_stage, h_dl;
 
     int fail(int code, const std::string& msg) {
