@@ -63,3 +63,69 @@ def test_bwt_sizes(oracle, synth):
                 want = bytes([b[n - 1]] + [b[i - 1] for i in sa if i != 0])
                 assert bytes(out) == want
                 assert prim[0] == sa.index(0) + 1
+
+
+@pytest.mark.parametrize("seq,entropy", [("RANK", "ANS0"), ("MTFT", "HUFFMAN"), ("ZRLT", "NONE"), ("BWT+RANK+ZRLT", "ANS0"), ("BWTS", "ANS0"),
+                                         ("BWTS+MTFT+ZRLT", "RANGE"), ("ROLZ", "NONE"), ("ROLZ", "ANS0"), ("LZX", "HUFFMAN"), ("LZ", "NONE")])
+def test_sequence_stream_roundtrip(oracle, synth, seq, entropy):
+    """transform sequences of the restatement (Sequence.go skip flags included: uniform data makes ZRLT / LZ / ROLZ decline)"""
+    for n, bs in ((10, 1024), (5000, 1024), (70000, 65536), (300000, 65536)):
+        for x in (synth.markov_text(n, seed=n + 11), synth.uniform_bytes(n, seed=n + 12), np.zeros(n, np.uint8)):
+            s = oracle.compress(x, seq, entropy, block_size=bs, jobs=3, input_size=n)
+            assert np.array_equal(oracle.decompress(s, n + 16, jobs=2), x), (seq, entropy, n)
+
+
+def test_sbrt_and_zrlt_by_definition(oracle, synth):
+    """RANK / MTFT against a direct python transcription of the list update rule (SBRT.go:127-172), ZRLT against its definition
+    (ZRLT.go:58-141): zero runs -> binary digits of run + 1 without the leading one; other bytes + 1; 0xFE / 0xFF escaped."""
+    rng = np.random.default_rng(3)
+
+    def sbrt(x, mode):
+        s2r = list(range(256))
+        r2s = list(range(256))
+        p = [0] * 256
+        q = [0] * 256
+        out = []
+        for i, c in enumerate(x):
+            r = s2r[c]
+            out.append(r)
+            qc = i if mode == 1 else (i + p[c]) >> 1
+            p[c] = i
+            q[c] = qc
+            while r > 0 and q[r2s[r - 1]] <= qc:
+                t = r2s[r - 1]
+                r2s[r], s2r[t] = t, r
+                r -= 1
+            r2s[r] = c
+            s2r[c] = r
+        return bytes(out)
+
+    def zrlt(x):
+        out = bytearray()
+        i, n = 0, len(x)
+        while i < n:
+            if x[i] == 0:
+                j = i
+                while j < n and x[j] == 0:
+                    j += 1
+                run = j - i + 1
+                out += bytes(int(d) for d in bin(run)[3:])
+                i = j
+            elif x[i] >= 0xFE:
+                out += bytes([0xFF, x[i] - 0xFE])
+                i += 1
+            else:
+                out.append(x[i] + 1)
+                i += 1
+        return bytes(out) if len(out) <= n else None
+
+    for trial in range(40):
+        n = int(rng.integers(1, 400))
+        x = bytes((rng.geometric(0.3, n) - 1).astype(np.uint8)) if trial % 2 else bytes(rng.integers(0, 256, n).astype(np.uint8) * (rng.random(n) < 0.4))
+        for mode, tid in ((1, oracle.T_MTFT), (2, oracle.T_RANK)):
+            got, _ = oracle.transform_forward(tid, np.frombuffer(x, np.uint8))
+            assert bytes(got) == sbrt(x, mode)
+        want = zrlt(x)
+        got, _ = oracle.transform_forward(oracle.T_ZRLT, np.frombuffer(x, np.uint8))
+        if got is not None and want is not None:
+            assert bytes(got) == want
