@@ -637,7 +637,7 @@ int decode_batch(kz_ctx* ctx, uint32_t etype, const uint32_t* d_words, uint64_t 
         }
         LaunchScope ls(ctx, "huf_decode");
         huf_decode_kernel<<<(nchunks + HUF_DEC_CTA_CHUNKS - 1) / HUF_DEC_CTA_CHUNKS, HUF_DEC_CTA_CHUNKS * 4, HUF_DEC_SMEM, ctx->stream>>>(
-            d_words, d_dchunks, nchunks, (uint64_t*)(T + o_hbit), d_out, d_status);
+            d_words, words_len, d_dchunks, nchunks, (uint64_t*)(T + o_hbit), d_out, d_status);
     } else if (nchunks > 0) {
         {
             LaunchScope ls(ctx, "ans_walk");

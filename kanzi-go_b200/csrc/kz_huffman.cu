@@ -464,7 +464,43 @@ __global__ void __launch_bounds__(HUF_ENC_WARPS * 32) huf_encode_kernel(const ui
 namespace {
 
 // readLengths (:620-658) from a bit reader: alphabet + code lengths. sizes[] indexed by alphabet rank. Returns count or -1.
-KZ_D int read_lengths(BitReader& br, uint8_t* alphabet /*smem, count entries*/, uint8_t* sizes /*by rank*/) {
+// MSB-first reader over a window of the stream staged in shared memory (words already byte swapped): same interface as
+// BitReader, no global memory traffic. `base` = absolute bit position of win[0]; reads past the window return zeros.
+struct WinBitReader {
+    const uint32_t* win;
+    uint32_t nwords;
+    uint64_t base, pos, end;
+    bool overrun;
+    KZ_D WinBitReader(const uint32_t* w, uint32_t n, uint64_t b, uint64_t p, uint64_t e) : win(w), nwords(n), base(b), pos(p), end(e), overrun(false) {}
+    KZ_D uint32_t read(uint32_t n) {  // n in 1..32
+        if (pos + n > end) {
+            overrun = true;
+            pos += n;
+            return 0;
+        }
+        const uint64_t rel = pos - base;
+        const uint32_t w = (uint32_t)(rel >> 5), o = (uint32_t)rel & 31u;
+        pos += n;
+        if (w + 1 >= nwords) {
+            overrun = true;
+            return 0;
+        }
+        return __funnelshift_l(win[w + 1], win[w], o) >> (32 - n);
+    }
+    KZ_D uint32_t read_varint() {  // entropy/EntropyUtils.go:278-296
+        uint32_t res = 0, shift = 0;
+        for (int i = 0; i < 4; i++) {
+            const uint32_t v = read(8);
+            res |= (v & 0x7F) << shift;
+            if (v < 128) return res;
+            shift += 7;
+        }
+        return res | ((read(8) & 0x0F) << 28);
+    }
+};
+
+template <class Reader>
+KZ_D int read_lengths(Reader& br, uint8_t* alphabet /*smem, count entries*/, uint8_t* sizes /*by rank*/) {
     int count = 0;
     if (br.read(1) == 0) {
         if (br.read(1) == 0) {
@@ -520,10 +556,26 @@ __global__ void __launch_bounds__(32) huf_walk_kernel(const uint32_t* __restrict
                                                       int nblocks, uint64_t* __restrict__ chunk_hdr_bit, uint64_t* __restrict__ blk_end,
                                                       int32_t* __restrict__ status) {
     __shared__ uint32_t s_win[HUF_WIN_WORDS + 2];
+    __shared__ uint8_t s_lut[256];
     const int b = blockIdx.x, lane = threadIdx.x;
     if (b >= nblocks) return;
     const DecBlock blk = blocks[b];
     if (blk.nchunks == 0) return;
+    for (int v = lane; v < 256; v += 32) {  // whole 1-bit / 4-bit codes at the top of the byte v
+        uint32_t x = (uint32_t)v << 24, nb = 0, nc = 0;
+        for (;;) {
+            uint32_t len;
+            if (x & 0x80000000u) len = 1;
+            else if (x & 0x40000000u) len = 4;
+            else break;
+            if (nb + len > 8) break;
+            nb += len;
+            nc++;
+            x <<= len;
+        }
+        s_lut[v] = (uint8_t)((nc << 4) | nb);
+    }
+    __syncwarp();
     uint64_t pos = blk.data_bit;
     uint32_t remaining = blk.pre_len;
     int32_t st = 0;
@@ -559,11 +611,23 @@ __global__ void __launch_bounds__(32) huf_walk_kernel(const uint32_t* __restrict
             if (count == 0) {
                 st = -KZ_E_PROCESS_BLOCK;
             } else {
+                // skim the Exp-Golomb coded size deltas. Codes are 1 bit ('1'), 4 bits ('01vv'), 7 bits ('001vvvv') ... long:
+                // s_lut[byte] = (codes that end inside these 8 bits) << 4 | bits they occupy, so a typical header (mostly 1 and 4
+                // bit codes) advances several codes per look-up; longer codes take the count-leading-zeros path.
                 int i = 0;
-                while (i < count) {  // skim the Exp-Golomb coded size deltas
+                while (i < count) {
                     uint32_t win = rd(q, 32);
                     uint32_t used = 0;
                     do {
+                        const uint32_t e = s_lut[win >> 24];
+                        const uint32_t nc = e >> 4;
+                        if (nc != 0 && i + (int)nc <= count) {
+                            const uint32_t nb = e & 15u;
+                            used += nb;
+                            win <<= nb;
+                            i += (int)nc;
+                            continue;
+                        }
                         uint32_t len = 1;
                         if ((int32_t)win >= 0) {  // leading bit 0
                             const uint32_t z = (uint32_t)__clz((int)win);  // 1..32
@@ -617,9 +681,10 @@ __global__ void __launch_bounds__(32) huf_walk_kernel(const uint32_t* __restrict
 // Four lanes per chunk (lane j decodes fragment j), 8 chunks per warp, HUF_DEC_CTA_CHUNKS chunks per CTA.
 // Table per chunk: 1024 x u16 on the top 10 bits of the 12-bit window: (sym << 8) | len for codes of <= 10 bits,
 // 0xFFFF marks an 11/12-bit code which is resolved canonically (first code / count / symbol base per length).
-__global__ void __launch_bounds__(HUF_DEC_CTA_CHUNKS * 4) huf_decode_kernel(const uint32_t* __restrict__ words, const DecChunk* __restrict__ chunks,
-                                                                             int nchunks, const uint64_t* __restrict__ chunk_hdr_bit,
-                                                                             uint8_t* __restrict__ out, int32_t* __restrict__ status) {
+__global__ void __launch_bounds__(HUF_DEC_CTA_CHUNKS * 4) huf_decode_kernel(const uint32_t* __restrict__ words, uint64_t words_len,
+                                                                             const DecChunk* __restrict__ chunks, int nchunks,
+                                                                             const uint64_t* __restrict__ chunk_hdr_bit, uint8_t* __restrict__ out,
+                                                                             int32_t* __restrict__ status) {
     extern __shared__ uint8_t s_huf[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int slot = tid >> 2, k = tid & 3;
@@ -636,11 +701,22 @@ __global__ void __launch_bounds__(HUF_DEC_CTA_CHUNKS * 4) huf_decode_kernel(cons
     int mode = 0;
     // long codes: for len 11 and 12: first code (left aligned to 12 bits), count, base index into the sorted symbols
     uint32_t lim11 = 0, first11 = 0, base11 = 0, first12 = 0, base12 = 0;
+    // the chunk header (<= 545 + 20 bytes) is staged by the four lanes of the chunk in the (not yet built) table area: the
+    // serial parse below then runs on shared memory (v1 walked it with two dependent global loads per bit field)
+    constexpr uint32_t HWIN = 148;
+    uint32_t* hwin = reinterpret_cast<uint32_t*>(table);
+    uint64_t hbit = 0;
+    if (c < nchunks) {
+        hbit = chunk_hdr_bit[c];
+        const uint64_t w0 = hbit >> 5;
+        for (uint32_t j = (uint32_t)k; j < HWIN; j += 4) hwin[j] = w0 + j < words_len ? bswap32(__ldg(words + w0 + j)) : 0u;
+    }
+    __syncwarp();
     if (c < nchunks) {
         const DecChunk ck = chunks[c];
         dst = out + ck.out_off;
         if (k == 0 && status[ck.block] == 0) {
-            BitReader br(words, chunk_hdr_bit[c], ck.end_bit);
+            WinBitReader br(hwin, HWIN, (hbit >> 5) << 5, hbit, ck.end_bit);
             if (ck.out_len < 32) {  // raw chunk (:768-770)
                 for (uint32_t i = 0; i < ck.out_len; i++) dst[i] = (uint8_t)br.read(8);
                 if (br.overrun) atomicCAS(&status[ck.block], 0, -KZ_E_PROCESS_BLOCK);
@@ -674,6 +750,14 @@ __global__ void __launch_bounds__(HUF_DEC_CTA_CHUNKS * 4) huf_decode_kernel(cons
                         idx += cnt[l];
                         if (code > (1u << l)) bad = true;  // buildDecodingTable :683-685
                     }
+                    // the four fragment sizes follow the code lengths: read them before the table overwrites the staged header
+                    uint32_t szb[4];
+                    for (int j = 0; j < 4; j++) {
+                        szb[j] = br.read_varint();
+                        if ((int32_t)szb[j] < 0) bad = true;
+                    }
+                    const uint64_t fb = br.pos;
+                    if (br.overrun) bad = true;
                     if (bad) {
                         atomicCAS(&status[ck.block], 0, -KZ_E_PROCESS_BLOCK);
                     } else {
@@ -706,15 +790,8 @@ __global__ void __launch_bounds__(HUF_DEC_CTA_CHUNKS * 4) huf_decode_kernel(cons
                         info[7] = sbase[11];
                         info[8] = first[12];
                         info[9] = sbase[12];
-                        uint64_t fb = 0;
-                        uint32_t szb[4];
-                        for (int j = 0; j < 4; j++) {
-                            szb[j] = br.read_varint();
-                            if ((int32_t)szb[j] < 0) bad = true;
-                        }
-                        fb = br.pos;
                         uint64_t tot = (uint64_t)szb[0] + szb[1] + szb[2] + szb[3];
-                        if (bad || br.overrun || fb + tot + 8ull * (ck.out_len & 3) > ck.end_bit) {
+                        if (fb + tot + 8ull * (ck.out_len & 3) > ck.end_bit) {
                             atomicCAS(&status[ck.block], 0, -KZ_E_PROCESS_BLOCK);
                         } else {
                             info[0] = szb[0];

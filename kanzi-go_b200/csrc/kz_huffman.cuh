@@ -20,7 +20,7 @@ __global__ void huf_encode_kernel(const uint8_t* in, const ChunkIn* chunks, int 
                                   const uint32_t* seg_index);
 __global__ void huf_walk_kernel(const uint32_t* words, uint64_t words_len, const DecBlock* blocks, int nblocks, uint64_t* chunk_hdr_bit,
                                 uint64_t* blk_end, int32_t* status);
-__global__ void huf_decode_kernel(const uint32_t* words, const DecChunk* chunks, int nchunks, const uint64_t* chunk_hdr_bit, uint8_t* out,
-                                  int32_t* status);
+__global__ void huf_decode_kernel(const uint32_t* words, uint64_t words_len, const DecChunk* chunks, int nchunks, const uint64_t* chunk_hdr_bit,
+                                  uint8_t* out, int32_t* status);
 
 }  // namespace kz
