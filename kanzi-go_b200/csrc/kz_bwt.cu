@@ -10,7 +10,7 @@
 //     (cub::DeviceRadixSort for the sort itself; everything else is hand written).
 //   transform/BWT.go:178-358 Inverse (inverseMergeTPSI) / :361-628 (biPSIv2): both walk the permutation
 //     "rank of suffix i -> rank of suffix i+1" from primaryIndex(0)-1. The format only offers 8 independent walks,
-//     far too few for a GPU, so the permutation list is cut at every rank that is a multiple of 1024 (plus the 8 primary
+//     far too few for a GPU, so the permutation list is cut at every rank that is a multiple of 64 (plus the 8 primary
 //     ranks): all sub-lists are walked in parallel once to measure them, the few thousand sub-list heads are ranked with
 //     pointer doubling, and a second parallel walk writes the bytes at their final offsets.
 //   transform/BWTBlockCodec.go:78-136, :141-225: block header (mode byte + big-endian primaryIndex-1 per chunk).
@@ -190,7 +190,7 @@ __global__ void ibwt_init_kernel(const uint8_t* __restrict__ src, uint32_t n, ui
     vals[i] = i == 0 ? 0xFFFFFFFFu : (i < pidx ? i - 1 : i);
 }
 
-static const uint32_t IBWT_STRIDE = 1024;  // a sub-list starts at every rank that is a multiple of this
+static const uint32_t IBWT_STRIDE = 64;  // a sub-list starts at every rank that is a multiple of this (1024 left < 1 warp per SM for a 4 MiB block)
 
 KZ_D bool ibwt_is_head(uint32_t t, const uint32_t* prim, uint32_t nprim) {
     if ((t & (IBWT_STRIDE - 1)) == 0) return true;
