@@ -832,41 +832,32 @@ __global__ void __launch_bounds__(HUF_DEC_CTA_CHUNKS * 4) huf_decode_kernel(cons
     // ---- fragment decode: sequential table lookups on a zero-extended bit string (:872-959).
     // v1 fetched the 12-bit window of every symbol from global memory (two dependent loads per symbol, 4.2 ms per
     // 64 x 4 MiB). Now the lane keeps a 64-bit shift register of its fragment and pulls 32 bits at a time from a queue of
-    // four words loaded well ahead of their use (the addresses do not depend on the decoded symbols).
+    // four words loaded well ahead of their use (the addresses do not depend on the decoded symbols): 2.3 ms. A variant
+    // with two 16-byte quads in flight measured slower (4.0 ms) and was dropped.
     uint8_t* o = dst + (size_t)k * sz_frag;
-    // word queue: the current 16 bytes and the next 16 bytes of the stream (the load of the next quad is issued when the
-    // current one starts being consumed, ~20 symbols before it is needed: DRAM latency stays off the decode chain)
-    const uint64_t wi0 = frag_bit >> 5;
-    const uint4* q4 = reinterpret_cast<const uint4*>(words) + (wi0 >> 2);  // the stream buffer is 16-byte aligned
-    uint4 cur = __ldg(q4), nxt = __ldg(q4 + 1);
-    q4 += 2;
-    uint32_t qi = (uint32_t)wi0 & 3u;
+    const uint32_t* wp = words + (frag_bit >> 5);
     const uint32_t sh0 = (uint32_t)frag_bit & 31u;
+    uint32_t qa = __ldg(wp), qb = __ldg(wp + 1), qc = __ldg(wp + 2), qd = __ldg(wp + 3);
+    wp += 4;
     int64_t avail = (int64_t)frag_bits;  // fragment bits not yet moved into `head`
-    auto next_word = [&]() -> uint32_t {
-        const uint32_t w = qi == 0 ? cur.x : (qi == 1 ? cur.y : (qi == 2 ? cur.z : cur.w));
-        if (++qi == 4) {
-            cur = nxt;
-            nxt = avail > 0 ? __ldg(q4) : make_uint4(0, 0, 0, 0);  // quads past the fragment are never needed
-            q4++;
-            qi = 0;
-        }
-        return w;
-    };
     auto take = [&](uint32_t raw, uint32_t valid) -> uint32_t {  // the next `valid` (<= 32) stream bits, left aligned; zeros past the fragment
         uint32_t w = raw;
         if (avail < (int64_t)valid) w = avail <= 0 ? 0u : (w & ~(0xFFFFFFFFu >> (uint32_t)avail));
         avail -= valid;
         return w;
     };
-    uint64_t head = (uint64_t)take(bswap32(next_word()) << sh0, 32u - sh0) << 32;
+    uint64_t head = (uint64_t)take(bswap32(qa) << sh0, 32u - sh0) << 32;
     uint32_t nbits = 32u - sh0;
+    qa = qb, qb = qc, qc = qd, qd = __ldg(wp++);
     const bool al4 = ((uintptr_t)o & 3) == 0;
     uint32_t pack = 0;
     for (uint32_t i = 0; i < sz_frag; i++) {
         if (nbits <= 32) {
-            head |= (uint64_t)take(bswap32(next_word()), 32) << (32u - nbits);
+            head |= (uint64_t)take(bswap32(qa), 32) << (32u - nbits);
             nbits += 32;
+            qa = qb, qb = qc, qc = qd;
+            qd = avail > 96 ? __ldg(wp) : 0u;  // words past the fragment are never needed (and may lie past the buffer)
+            wp++;
         }
         const uint32_t w = (uint32_t)(head >> 52);
         const uint32_t e = table[w >> 2];

@@ -45,6 +45,18 @@ def main(rep, out):
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             k["dram_traffic_bytes"] = rd["value"] * scale.get(rd["unit"], 1) + wr["value"] * scale.get(wr["unit"], 1)
         res.append(k)
+    if len(sys.argv) > 3 and sys.argv[3] == "--longest":  # one entry per kernel name: its longest launch (+ launch count)
+        best = {}
+        for k in res:
+            t = k.get("gpu__time_duration.sum", {}).get("value", 0)
+            name = k["kernel"]
+            if name not in best or t > best[name]["gpu__time_duration.sum"]["value"]:
+                cnt = best[name]["launches_captured"] + 1 if name in best else 1
+                best[name] = k
+                best[name]["launches_captured"] = cnt
+            else:
+                best[name]["launches_captured"] += 1
+        res = list(best.values())
     json.dump({"source": rep, "kernels": res}, open(out, "w"), indent=1)
     print("wrote", out, len(res), "kernels")
 
