@@ -1076,8 +1076,9 @@ int apply_inverse(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint8_t* d_out, 
         if (rc) return rc;
         {
             LaunchScope ls(ctx, "sbrt_inverse");
-            sbrt_inverse_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_in, (const SbrtBlock*)(ctx->d_tables.as<uint8_t>() + o_sb), (int)nblocks,
-                                                                 t == KZ_T_MTFT ? 1 : 2, d_out);
+            bool packed = true;
+            for (uint32_t b = 0; b < nblocks; b++) packed = packed && len[b] < (1u << 27);
+            sbrt_inverse_launch(d_in, (const SbrtBlock*)(ctx->d_tables.as<uint8_t>() + o_sb), (int)nblocks, t == KZ_T_MTFT ? 1 : 2, d_out, packed, ctx->stream);
         }
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(ctx->stream));

@@ -169,8 +169,9 @@ __global__ void __launch_bounds__(128) sbrt_rank_kernel(const uint8_t* __restric
 //     four entries are loaded together before they are compared (their addresses do not depend on the comparisons);
 //   * the first four entries (symbol, q, p) live in registers: after a BWT most ranks are 0..3 and cost a few compares;
 //   * p (last position) stays a table by symbol for the entries that are not in registers.
-__global__ void __launch_bounds__(32) sbrt_inverse_kernel(const uint8_t* __restrict__ data, const SbrtBlock* __restrict__ blocks, int nblocks, int mode,
-                                                          uint8_t* __restrict__ out) {
+template <bool PACKED>
+__global__ void __launch_bounds__(32) sbrt_inverse_kernel_t(const uint8_t* __restrict__ data, const SbrtBlock* __restrict__ blocks, int nblocks, int mode,
+                                                            uint8_t* __restrict__ out) {
     __shared__ uint64_t s_ent[256 + 8];  // entry of rank r at s_ent[r + 4]; four sentinels (q = "infinite") below rank 0
     __shared__ int32_t s_p[256];
     const int b = blockIdx.x, lane = threadIdx.x;
@@ -206,13 +207,17 @@ __global__ void __launch_bounds__(32) sbrt_inverse_kernel(const uint8_t* __restr
             } else {
                 c = y3, pc = p3;
             }
+        } else if (PACKED) {  // blocks < 128 MiB: q (27 bits) | p (27 bits) | symbol in one entry, no second look-up
+            const uint64_t e = ent[r];
+            c = (uint32_t)e & 0xFF;
+            pc = (int32_t)((e >> 8) & 0x7FFFFFFu);
         } else {
             c = (uint32_t)ent[r] & 0xFF;
             pc = s_p[c];
         }
         const int32_t qc = mode == 1 ? (int32_t)i : ((int32_t)i + pc) >> 1;
         if (r >= 4) {  // bubble up inside shared memory down to rank 4 (SBRT.go:214-220), four entries per round
-            const uint64_t lim = ((uint64_t)(uint32_t)qc << 32) | 0xFFFFFFFFull;  // entry <= lim  <=>  q <= qc
+            const uint64_t lim = PACKED ? (((uint64_t)(uint32_t)qc << 35) | 0x7FFFFFFFFull) : (((uint64_t)(uint32_t)qc << 32) | 0xFFFFFFFFull);  // entry <= lim  <=>  q <= qc
             while (r > 4) {
                 const uint64_t e1 = ent[r - 1], e2 = ent[(int)r - 2], e3 = ent[(int)r - 3], e4 = ent[(int)r - 4];  // ranks < 4 are stale: guarded by r > 4
                 if (e1 > lim) break;
@@ -229,13 +234,21 @@ __global__ void __launch_bounds__(32) sbrt_inverse_kernel(const uint8_t* __restr
                 r--;
             }
             if (r > 4 || q3 > qc) {  // stays behind the register entries (r == 4: the entry of rank 3 is in a register)
-                ent[r] = ((uint64_t)(uint32_t)qc << 32) | c;
-                s_p[c] = (int32_t)i;
+                if (PACKED) {
+                    ent[r] = ((uint64_t)(uint32_t)qc << 35) | ((uint64_t)i << 8) | c;
+                } else {
+                    ent[r] = ((uint64_t)(uint32_t)qc << 32) | c;
+                    s_p[c] = (int32_t)i;
+                }
                 return c;
             }
             // entry 3 drops to rank 4, c enters the registers at rank 3
-            ent[4] = ((uint64_t)(uint32_t)q3 << 32) | y3;
-            s_p[y3] = p3;
+            if (PACKED) {
+                ent[4] = ((uint64_t)(uint32_t)q3 << 35) | ((uint64_t)(uint32_t)p3 << 8) | y3;
+            } else {
+                ent[4] = ((uint64_t)(uint32_t)q3 << 32) | y3;
+                s_p[y3] = p3;
+            }
             r = 3;
         }
         // c belongs at some rank <= r <= 3: the entries with q <= qc right above it move down by one
@@ -289,6 +302,12 @@ __global__ void __launch_bounds__(32) sbrt_inverse_kernel(const uint8_t* __restr
         d4[v] = make_uint4(o[0], o[1], o[2], o[3]);
     }
     for (uint32_t i = n16 << 4; i < n; i++) dst[i] = (uint8_t)step(i, src[i]);
+}
+
+// host entry: packed entries when every block is shorter than 128 MiB
+void sbrt_inverse_launch(const uint8_t* data, const SbrtBlock* d_blocks, int nblocks, int mode, uint8_t* out, bool packed, cudaStream_t stream) {
+    if (packed) sbrt_inverse_kernel_t<true><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, mode, out);
+    else sbrt_inverse_kernel_t<false><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, mode, out);
 }
 
 }  // namespace kz

@@ -1,4 +1,4 @@
-"""Driver for one ncu capture across the kernel families: small batches (8 blocks of 256 KiB) through every codec / transform
+"""Driver for one ncu capture across the kernel families: small batches (6 blocks of 128 KiB) through every codec / transform
 so that each hand-written kernel appears at least once. Used as: ncu --set full -k regex:... python tools/prof_all.py"""
 import importlib
 import os
@@ -10,8 +10,8 @@ import numpy as np
 kz = importlib.import_module("kanzi-go_b200")
 synth = importlib.import_module("kanzi-go_b200.synth")
 ctx = kz.Context(0)
-bs = 256 << 10
-n = 8 * bs
+bs = 128 << 10
+n = 6 * bs
 text = synth.markov_text(n, seed=3)
 zipf = synth.zipf_bytes(n, 1.0, seed=4)
 for transform, entropy, data, ck in (("NONE", "HUFFMAN", zipf, 0), ("NONE", "ANS1", text, 0), ("NONE", "RANGE", zipf, 0), ("NONE", "ANS0", zipf, 32),
