@@ -64,7 +64,8 @@ def measured_traffic(kernel):
     import glob
 
     best = None
-    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu*summary*.json"))):
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu*summary*.json")), key=lambda f: ("final" in os.path.basename(f), os.path.basename(f)))
+    for f in files:  # the capture named "final" wins, otherwise the highest generation
         try:
             for k in json.load(open(f)).get("kernels", []):
                 if kernel in k.get("kernel", "") and k.get("dram_traffic_bytes"):
