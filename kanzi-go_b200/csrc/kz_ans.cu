@@ -26,13 +26,15 @@ namespace kz {
 // ------------------------------------------------------------------------------------------------------------
 
 // encSymbol.reset (ANSRangeCodec.go:446-468). The per-symbol entry keeps only what depends on the chunk:
-//   freq (13 bits, clamped to 2^lr - 1) | bias << 13   (bias = cum, or cum + 2^lr - 1 when freq < 2)
-// The reciprocal (invFreq, invShift) depends on freq alone and comes from one table shared by all chunks
-// (rcp_table_kernel): invShift - 32 = ceil(log2 freq) - 1 is recomputed with a count-leading-zeros.
+//   freq (13 bits, clamped to 2^lr - 1) | (invShift - 32) << 13 | bias << 17
+//   (bias = cum, or cum + 2^lr - 1 when freq < 2; invShift - 32 = ceil(log2 freq) - 1, 0..11)
+// The reciprocal invFreq depends on freq alone and comes from one table shared by all chunks (rcp_table_kernel).
+// freq sits in the low bits so that e << (31 - lr + ...) style shifts drop the other fields for free.
 static __device__ __forceinline__ uint32_t make_enc_entry(uint32_t cum, uint32_t freq, uint32_t lr) {
     const uint32_t fr = freq < (1u << lr) - 1u ? freq : (1u << lr) - 1u;
     const uint32_t bias = fr < 2 ? cum + (1u << lr) - 1u : cum;
-    return fr | (bias << 13);
+    const uint32_t sh = 31u - (uint32_t)__clz((int)((fr - 1u) | 1u));
+    return fr | (sh << 13) | (bias << 17);
 }
 
 __global__ void expand_chunks_kernel(const DecBlock* __restrict__ blocks, int nblocks, DecChunk* __restrict__ chunks) {
@@ -182,13 +184,18 @@ struct EncLane {
     uint32_t emitted;  // 16-bit words emitted so far by the whole group
 };
 
+// The table entry and the reciprocal of a symbol do not depend on the rANS state: the caller loads them for the four
+// symbols of an iteration up front (enc_fetch), so that the state chain of a step is compare / select / multiply only and
+// never waits on shared memory (v2 loaded them inside the step, behind the ring store's compiler barrier).
+KZ_D void enc_fetch(uint32_t sym, const uint32_t* tab, const uint32_t* rcp, uint32_t& e, uint32_t& inv) {
+    e = tab[sym * 8];
+    inv = rcp[e & 0x1FFFu];
+}
+
 template <bool ALL_ACTIVE>
-KZ_D void enc_step(EncLane& L, uint32_t sym, const uint32_t* tab, const uint32_t* rcp, uint32_t out_ring, uint32_t lr, uint32_t lo_mask,
-                   uint32_t grp_mask, bool active) {
-    const uint32_t e = tab[sym * 8];
+KZ_D void enc_step(EncLane& L, uint32_t e, uint32_t inv, uint32_t out_ring, uint32_t lr, uint32_t lo_mask, uint32_t grp_mask, bool active) {
     const uint32_t freq = e & 0x1FFFu;
-    const uint32_t inv = rcp[freq];
-    const uint32_t sh = 31u - (uint32_t)__clz((int)((freq - 1u) | 1u));  // invShift - 32
+    const uint32_t sh = (e >> 13) & 15u;  // invShift - 32
     bool emit = L.st >= (freq << (31u - lr));                             // xMax = ((ANS_TOP >> lr) << 16) * freq
     if (!ALL_ACTIVE) emit = emit && active;
     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, emit);
@@ -196,10 +203,11 @@ KZ_D void enc_step(EncLane& L, uint32_t sym, const uint32_t* tab, const uint32_t
     const uint32_t u = L.emitted + __popc(bal & lo_mask);
     const uint32_t addr = out_ring + ((0u - 2u * (u + 1u)) & (4 * ENC_OUT_RING_WORDS - 1));
     const uint32_t w16 = __byte_perm(L.st, 0, 0x4401);  // memory order [hi, lo] (:322-326)
-    if (emit) asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(w16) : "memory");
+    // predicated store: no divergent branch inside the step, so the four states stay converged for the ballot
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.u16 [%0], %1; }" ::"r"(addr), "r"(w16), "r"((uint32_t)emit) : "memory");
     const uint32_t x = emit ? (L.st >> 16) : L.st;
     const uint32_t q = __umulhi(x, inv) >> sh;  // (st * invFreq) >> invShift
-    const uint32_t nst = x + (e >> 13) + q * ((1u << lr) - freq);
+    const uint32_t nst = x + (e >> 17) + q * ((1u << lr) - freq);
     if (ALL_ACTIVE || active) {
         L.st = nst;
         L.emitted += __popc(bal & grp_mask);
@@ -277,7 +285,9 @@ __global__ void __launch_bounds__(256, 2) ans0_encode_kernel(const uint8_t* __re
             const bool active = r < lead;
             uint32_t sym = 0;
             if (active) sym = src[(size_t)(ngroups - 1 - r) * 4 + (3 - k)];
-            enc_step<false>(L, sym, tab, rcp, oring_a, lr, lo_mask, grp_mask, active);
+            uint32_t e, inv;
+            enc_fetch(sym, tab, rcp, e, inv);
+            enc_step<false>(L, e, inv, oring_a, lr, lo_mask, grp_mask, active);
         }
         ngroups -= lead;
     }
@@ -322,16 +332,21 @@ __global__ void __launch_bounds__(256, 2) ans0_encode_kernel(const uint8_t* __re
         asm volatile("ld.shared.u8 %0, [%1+8];" : "=r"(s2) : "r"(slot));
         asm volatile("ld.shared.u8 %0, [%1+4];" : "=r"(s1) : "r"(slot));
         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(s0) : "r"(slot));
+        uint32_t e3, e2, e1, e0, i3, i2, i1, i0;
+        enc_fetch(s3 & 0xFF, tab, rcp, e3, i3);
+        enc_fetch(s2 & 0xFF, tab, rcp, e2, i2);
+        enc_fetch(s1 & 0xFF, tab, rcp, e1, i1);
+        enc_fetch(s0 & 0xFF, tab, rcp, e0, i0);
         if (it < min_units) {
-            enc_step<true>(L, s3, tab, rcp, oring_a, lr, lo_mask, grp_mask, true);
-            enc_step<true>(L, s2, tab, rcp, oring_a, lr, lo_mask, grp_mask, true);
-            enc_step<true>(L, s1, tab, rcp, oring_a, lr, lo_mask, grp_mask, true);
-            enc_step<true>(L, s0, tab, rcp, oring_a, lr, lo_mask, grp_mask, true);
+            enc_step<true>(L, e3, i3, oring_a, lr, lo_mask, grp_mask, true);
+            enc_step<true>(L, e2, i2, oring_a, lr, lo_mask, grp_mask, true);
+            enc_step<true>(L, e1, i1, oring_a, lr, lo_mask, grp_mask, true);
+            enc_step<true>(L, e0, i0, oring_a, lr, lo_mask, grp_mask, true);
         } else {
-            enc_step<false>(L, s3 & 0xFF, tab, rcp, oring_a, lr, lo_mask, grp_mask, active);
-            enc_step<false>(L, s2 & 0xFF, tab, rcp, oring_a, lr, lo_mask, grp_mask, active);
-            enc_step<false>(L, s1 & 0xFF, tab, rcp, oring_a, lr, lo_mask, grp_mask, active);
-            enc_step<false>(L, s0 & 0xFF, tab, rcp, oring_a, lr, lo_mask, grp_mask, active);
+            enc_step<false>(L, e3, i3, oring_a, lr, lo_mask, grp_mask, active);
+            enc_step<false>(L, e2, i2, oring_a, lr, lo_mask, grp_mask, active);
+            enc_step<false>(L, e1, i1, oring_a, lr, lo_mask, grp_mask, active);
+            enc_step<false>(L, e0, i0, oring_a, lr, lo_mask, grp_mask, active);
         }
         flush();
         fetch(q - 3);

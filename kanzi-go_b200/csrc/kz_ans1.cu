@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(128) ans1_stats_kernel(const uint32_t* __restr
         if (f[j] != 0) {
             const uint32_t fr = f[j] < (1u << LR1) - 1u ? f[j] : (1u << LR1) - 1u;  // encSymbol.reset :446-468
             const uint32_t bias = fr < 2 ? cum + (1u << LR1) - 1u : cum;
-            e = fr | (bias << 13);
+            const uint32_t sh = 31u - (uint32_t)__clz((int)((fr - 1u) | 1u));  // invShift - 32
+            e = fr | (sh << 13) | (bias << 17);
             s_rank[warp][rank] = (uint16_t)(f[j] - 1);
         }
         tab[lane + 32 * j] = e;
@@ -182,24 +183,28 @@ __global__ void __launch_bounds__(32) ans1_encode_kernel(const uint8_t* __restri
     uint32_t st = ANS_TOP, emitted = 0, flushed = 0;
     const uint8_t* q = src + (size_t)k * quarter;
     const uint32_t ring = smem_u32(s_ring);
-    auto step = [&](uint32_t e, bool active) {
+    // One rANS step of the four states. The table entry e (freq | (invShift-32) << 13 | bias << 17) and the reciprocal
+    // inv do not depend on the state, so the callers fetch them ahead of time: the dependent chain of a step is
+    // compare / select / multiply-high / multiply-add only.
+    auto core = [&](uint32_t e, uint32_t inv, bool active) {
         const uint32_t freq = e & 0x1FFFu;
-        const uint32_t inv = s_rcp[freq & 2047u];
-        const uint32_t sh = 31u - (uint32_t)__clz((int)((freq - 1u) | 1u));
+        const uint32_t sh = (e >> 13) & 15u;
         const bool emit = active && st >= (freq << (31u - LR1));
         const uint32_t bal = __ballot_sync(0xFFFFFFFFu, emit);
         const uint32_t u = emitted + __popc(bal & lo_mask);
-        if (emit) {
-            const uint32_t addr = ring + ((0u - 2u * (u + 1u)) & 255u);
-            const uint32_t w16 = __byte_perm(st, 0, 0x4401);
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(w16) : "memory");
-        }
+        const uint32_t addr = ring + ((0u - 2u * (u + 1u)) & 255u);
+        const uint32_t w16 = __byte_perm(st, 0, 0x4401);
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.u16 [%0], %1; }" ::"r"(addr), "r"(w16), "r"((uint32_t)emit) : "memory");
         const uint32_t x = emit ? (st >> 16) : st;
         const uint32_t qq = __umulhi(x, inv) >> sh;
-        if (active) st = x + (e >> 13) + qq * ((1u << LR1) - freq);
+        if (active) st = x + (e >> 17) + qq * ((1u << LR1) - freq);
         emitted += __popc(bal & grp_mask);
+    };
+    // write out every completed 64-byte block of the ring (uniform condition); a batch of ANS1_ENC_BATCH steps adds at
+    // most 8 bytes per step, so residual (< 64) + batch (<= 64) stays well inside the 256-byte ring
+    auto flush = [&]() {
         __syncwarp();
-        if (2u * emitted >= 64u * (flushed + 1u)) {  // uniform: flush a completed 64-byte block
+        while (2u * emitted >= 64u * (flushed + 1u)) {
             if (worker) {
                 const uint32_t ro = (0u - 64u * (flushed + 1u)) & 255u;
                 const uint4 v = *reinterpret_cast<const uint4*>(s_ring + ro + 16 * k);
@@ -209,17 +214,40 @@ __global__ void __launch_bounds__(32) ans1_encode_kernel(const uint8_t* __restri
         }
         __syncwarp();
     };
+    constexpr int B = 8;  // steps per batch
+    // table entries of steps i, i-1, .., i-B+1 (step j encodes with tab[(q[j] << 8) | q[j+1]]); needs i-B+1 >= 0
+    auto load_batch = [&](int64_t i, uint32_t (&E)[B]) {
+        uint32_t b[B + 1];
+#pragma unroll
+        for (int j = 0; j <= B; j++) b[j] = worker ? (uint32_t)q[i + 1 - j] : 0u;
+#pragma unroll
+        for (int j = 0; j < B; j++) E[j] = worker ? __ldg(tab + ((b[j + 1] << 8) | b[j])) : 0u;
+    };
     if (quarter > 0) {
         // positions quarter-1 .. 1 with their true context, then position 0 with context 0 (:364-387)
-        uint32_t prv = worker ? q[quarter - 1] : 0u;
-        for (int64_t i = (int64_t)quarter - 2; i >= 0; i--) {
-            const uint32_t cur = worker ? q[i] : 0u;
-            const uint32_t e = worker ? __ldg(tab + ((cur << 8) | prv)) : 0u;
-            step(e, worker);
-            prv = cur;
+        int64_t i = (int64_t)quarter - 2;
+        uint32_t En[B];
+        if (i >= B - 1) load_batch(i, En);
+        while (i >= B - 1) {
+            uint32_t E[B], I[B];
+#pragma unroll
+            for (int j = 0; j < B; j++) E[j] = En[j];
+            if (i - B >= B - 1) load_batch(i - B, En);  // next batch in flight (L2 / HBM latency) while this one is encoded
+#pragma unroll
+            for (int j = 0; j < B; j++) I[j] = s_rcp[E[j] & 2047u];
+#pragma unroll
+            for (int j = 0; j < B; j++) core(E[j], I[j], worker);
+            flush();
+            i -= B;
         }
-        const uint32_t e = worker ? __ldg(tab + prv) : 0u;
-        step(e, worker);
+        for (; i >= 0; i--) {
+            const uint32_t e = worker ? __ldg(tab + (((uint32_t)q[i] << 8) | (uint32_t)q[i + 1])) : 0u;
+            core(e, s_rcp[e & 2047u], worker);
+            flush();
+        }
+        const uint32_t e = worker ? __ldg(tab + (uint32_t)q[0]) : 0u;
+        core(e, s_rcp[e & 2047u], worker);
+        flush();
     }
     // epilogue
     const uint32_t total = 2u * emitted;

@@ -55,6 +55,7 @@ struct Ctx {
     uint32_t entropy_type = E_NONE;
     int jobs = 1;
     size_t block_size = 0;
+    size_t stream_block_size = 0;  // ctx["blockSize"] of the reference (CompressedStream.go:220,1406): TEXT sizes its hash map from it
 };
 size_t transform_max_encoded_len(uint64_t type, size_t n);
 bool transform_forward(uint64_t type, Ctx& ctx, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
@@ -71,7 +72,8 @@ struct BlockResult {
     uint64_t bits = 0;           // exact bit length ("written")
 };
 // transform48: 8 x 6-bit ids, first transform in the top 6 bits. checksum_bits: 0/32/64.
-void encode_block(const uint8_t* data, size_t n, uint64_t transform48, uint32_t entropy, int checksum_bits, bool skip_blocks, BlockResult& out);
+void encode_block(const uint8_t* data, size_t n, uint64_t transform48, uint32_t entropy, int checksum_bits, bool skip_blocks, BlockResult& out,
+                  size_t stream_block_size = 0 /* 0: the block's own length */);
 // returns decoded length. block_size = stream block size (sanity bound :1896)
 size_t decode_block(const uint8_t* payload, uint64_t bits, uint64_t transform48, uint32_t entropy, int checksum_bits, size_t block_size,
                     std::vector<uint8_t>& out);

@@ -119,6 +119,9 @@ bool magic_executable(uint32_t m) {
     }
 }
 
+}  // namespace
+uint32_t get_magic_type(const uint8_t* src, size_t n) { return magic_type(src, n); }
+namespace {
 // Factory.New (:58-95): the list of transforms of a 48-bit type word. All-NONE keeps a single NONE.
 std::vector<uint64_t> sequence_of(uint64_t t48) {
     std::vector<uint64_t> seq;
@@ -187,7 +190,8 @@ size_t seq_inverse(const std::vector<uint64_t>& seq, Ctx& ctx, uint8_t skip_flag
 }  // namespace
 
 // encodingTask.encode :729-933 (everything up to the ordered commit)
-void encode_block(const uint8_t* data, size_t n, uint64_t t48, uint32_t etype, int checksum_bits, bool skip_blocks, BlockResult& res) {
+void encode_block(const uint8_t* data, size_t n, uint64_t t48, uint32_t etype, int checksum_bits, bool skip_blocks, BlockResult& res,
+                  size_t stream_block_size) {
     uint8_t mode = 0;
     uint64_t checksum = 0;
     if (checksum_bits == 32) checksum = xxhash32(data, n, BS_TYPE);
@@ -215,6 +219,7 @@ void encode_block(const uint8_t* data, size_t n, uint64_t t48, uint32_t etype, i
     Ctx ctx;
     ctx.entropy_type = etype;
     ctx.block_size = n;
+    ctx.stream_block_size = stream_block_size ? stream_block_size : n;
     std::vector<uint64_t> seq = sequence_of(t48);
     uint32_t magic = magic_type(data, n);
     if (magic_compressed(magic)) ctx.data_type = DT_BIN;
@@ -275,6 +280,7 @@ size_t decode_block(const uint8_t* payload, uint64_t bits, uint64_t t48, uint32_
     Ctx ctx;
     ctx.entropy_type = etype;
     ctx.block_size = pre;
+    ctx.stream_block_size = block_size;
     std::vector<uint64_t> seq = sequence_of(t48);
     // Reader.processBlock :1649-1653: the task buffers hold blockSize + max(EXTRA_BUFFER_SIZE = 512, blockSize >> 4) bytes
     size_t cap = std::max(r, block_size + std::max<size_t>(512, block_size >> 4));
@@ -367,7 +373,7 @@ std::vector<uint8_t> compress_stream(const uint8_t* src, size_t n, const StreamP
     parallel_for(nblocks, p.jobs, [&](size_t b) {
         size_t off = b * size_t(p.block_size);
         size_t len = std::min<size_t>(p.block_size, n - off);
-        encode_block(src + off, len, p.transform48, p.entropy, p.checksum_bits, p.skip_blocks, results[b]);
+        encode_block(src + off, len, p.transform48, p.entropy, p.checksum_bits, p.skip_blocks, results[b], p.block_size);
     });
     for (size_t b = 0; b < nblocks; b++) {  // :951-976
         uint64_t written = results[b].bits;

@@ -49,11 +49,16 @@ int kzo_entropy_decode(uint32_t type, const uint8_t* src, size_t src_bytes, uint
     })
 }
 
+// ctx["blockSize"] for the single-transform calls below (0 = the call's own input length); thread local
+static thread_local size_t g_stream_block_size = 0;
+void kzo_set_stream_block_size(size_t n) { g_stream_block_size = n; }
+
 int kzo_transform_forward(uint64_t type, int data_type, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n, int* out_data_type) {
     try {
         Ctx ctx;
         ctx.data_type = data_type;
         ctx.block_size = n;
+        ctx.stream_block_size = g_stream_block_size;
         bool ok = transform_forward(type, ctx, src, n, dst, cap, out_n);
         if (out_data_type) *out_data_type = ctx.data_type;
         return ok ? 0 : 1;  // 1 = "skip me" (the reference returns a non-nil error)
@@ -71,6 +76,7 @@ int kzo_transform_inverse(uint64_t type, int data_type, const uint8_t* src, size
         Ctx ctx;
         ctx.data_type = data_type;
         ctx.block_size = n;
+        ctx.stream_block_size = g_stream_block_size;
         bool ok = transform_inverse(type, ctx, src, n, dst, cap, out_n);
         return ok ? 0 : -ERR_PROCESS_BLOCK;
     } catch (const Error& e) {

@@ -16,6 +16,10 @@ size_t transform_max_encoded_len(uint64_t type, size_t n) {
         case T_ROLZ: return rolz_max_encoded_len(n);             // ROLZCodec.go:916-918
         case T_RANK: case T_MTFT: return n + 33;                 // SBRT.go:229-231
         case T_ZRLT: return n;                                   // ZRLT.go:228-230
+        case T_PACK: case T_DNA: return alias_max_encoded_len(n);
+        case T_MM: return fsd_max_encoded_len(n);
+        case T_UTF: return utf_max_encoded_len(n);
+        case T_DICT: return text_max_encoded_len(n);
         default: throw Error(ERR_CREATE_CODEC, "transform not restated in the oracle");
     }
 }
@@ -35,6 +39,11 @@ bool transform_forward(uint64_t type, Ctx& ctx, const uint8_t* src, size_t n, ui
         case T_RANK: return sbrt_forward(2, src, n, dst, cap, out_n);  // Factory.go: RANK -> SBRT_MODE_RANK
         case T_MTFT: return sbrt_forward(1, src, n, dst, cap, out_n);  // MTFT -> SBRT_MODE_MTF
         case T_ZRLT: return zrlt_forward(src, n, dst, cap, out_n);
+        case T_PACK: return alias_forward(ctx, false, src, n, dst, cap, out_n);
+        case T_DNA: return alias_forward(ctx, true, src, n, dst, cap, out_n);  // Factory.go:151-153 packOnlyDNA
+        case T_MM: return fsd_forward(ctx, src, n, dst, cap, out_n);
+        case T_UTF: return utf_forward(ctx, src, n, dst, cap, out_n);
+        case T_DICT: return text_forward(ctx, src, n, dst, cap, out_n);
         default: throw Error(ERR_CREATE_CODEC, "transform not restated in the oracle");
     }
 }
@@ -54,6 +63,10 @@ bool transform_inverse(uint64_t type, Ctx& ctx, const uint8_t* src, size_t n, ui
         case T_RANK: return sbrt_inverse(2, src, n, dst, cap, out_n);
         case T_MTFT: return sbrt_inverse(1, src, n, dst, cap, out_n);
         case T_ZRLT: return zrlt_inverse(src, n, dst, cap, out_n);
+        case T_PACK: case T_DNA: return alias_inverse(src, n, dst, cap, out_n);
+        case T_MM: return fsd_inverse(src, n, dst, cap, out_n);
+        case T_UTF: return utf_inverse(src, n, dst, cap, out_n);
+        case T_DICT: return text_inverse(ctx, src, n, dst, cap, out_n);
         default: throw Error(ERR_INVALID_CODEC, "transform not restated in the oracle");
     }
 }

@@ -15,10 +15,16 @@ _SO = os.path.join(_HERE, "_build", "libkanzi_oracle.so")
 E_NONE, E_HUFFMAN, E_RANGE, E_ANS0, E_ANS1 = 0, 1, 4, 5, 8
 T_NONE, T_BWT, T_BWTS, T_LZ, T_ROLZ, T_LZX = 0, 1, 2, 3, 11, 16
 T_ZRLT, T_MTFT, T_RANK = 6, 7, 8
+T_TEXT, T_MM, T_UTF, T_PACK, T_DNA = 10, 15, 17, 18, 19  # oracle only so far
 
 
 def build(force=False):
+    # the TEXT codec's static dictionary is a format constant of the reference: extracted into oracle/_ref/ (not committed)
+    from . import gen_text_dict
+
+    gen_text_dict.main()
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp"))]
+    srcs.append(gen_text_dict.OUT)
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs if os.path.exists(s)):
         subprocess.check_call(["make", "-s", "-C", _HERE])
     return _SO
@@ -39,6 +45,8 @@ def lib():
         L.kzo_entropy_decode.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
         L.kzo_transform_forward.argtypes = [C.c_uint64, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
         L.kzo_transform_inverse.argtypes = [C.c_uint64, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.kzo_set_stream_block_size.argtypes = [C.c_size_t]
+        L.kzo_set_stream_block_size.restype = None
         L.kzo_transform_max_encoded_len.argtypes = [C.c_uint64, C.c_size_t]
         L.kzo_transform_max_encoded_len.restype = C.c_size_t
         L.kzo_bwt_forward_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -101,9 +109,11 @@ def entropy_decode(etype, stream, n):
     return out[:n], used.value
 
 
-def transform_forward(ttype, data, data_type=0):
-    """-> (out bytes or None when the transform asks to be skipped, data_type after)"""
+def transform_forward(ttype, data, data_type=0, block_size=0):
+    """-> (out bytes or None when the transform asks to be skipped, data_type after). block_size = the stream's block size
+    (ctx["blockSize"], only read by TEXT); 0 = len(data)."""
     a = _arr(data)
+    lib().kzo_set_stream_block_size(block_size)
     cap = max(lib().kzo_transform_max_encoded_len(ttype, a.size), a.size) + 64
     out = np.empty(cap, np.uint8)
     n = C.c_size_t(0)
@@ -116,8 +126,9 @@ def transform_forward(ttype, data, data_type=0):
     return out[: n.value].copy(), dt.value
 
 
-def transform_inverse(ttype, data, cap, data_type=0):
+def transform_inverse(ttype, data, cap, data_type=0, block_size=0):
     a = _arr(data)
+    lib().kzo_set_stream_block_size(block_size)
     out = np.empty(max(cap, 1), np.uint8)
     n = C.c_size_t(0)
     rc = lib().kzo_transform_inverse(ttype, data_type, _ptr(a), a.size, out.ctypes.data, cap, C.byref(n))
