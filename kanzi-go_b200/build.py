@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libkanzi_b200.so")
-SOURCES = ["kz_ans.cu", "kz_ans1.cu", "kz_huffman.cu", "kz_range.cu", "kz_hash.cu", "kz_sbrt.cu", "kz_zrlt.cu", "kz_rolz.cu", "kz_bwt.cu", "kz_lz.cu", "kz_concat.cu", "kz_api.cu"]
+SOURCES = ["kz_ans.cu", "kz_ans1.cu", "kz_huffman.cu", "kz_range.cu", "kz_hash.cu", "kz_sbrt.cu", "kz_zrlt.cu", "kz_rolz.cu", "kz_alias.cu", "kz_fsd.cu", "kz_bwt.cu", "kz_lz.cu", "kz_concat.cu", "kz_api.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
          "-Xptxas", "-v"]
 
@@ -26,12 +26,14 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = ["nvcc"] + FLAGS + srcs + ["-o", OUT]
+    tmp = OUT + ".tmp"  # link into a temporary name, then rename: the library never exists half written
+    cmd = ["nvcc"] + FLAGS + srcs + ["-o", tmp]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed")
+    os.replace(tmp, OUT)
     with open(os.path.join(HERE, "ptxas_info.txt"), "w") as f:
         f.write(r.stderr)
     return OUT

@@ -20,6 +20,7 @@ size_t transform_max_encoded_len(uint64_t type, size_t n) {
         case T_MM: return fsd_max_encoded_len(n);
         case T_UTF: return utf_max_encoded_len(n);
         case T_DICT: return text_max_encoded_len(n);
+        case T_EXE: return exe_max_encoded_len(n);
         default: throw Error(ERR_CREATE_CODEC, "transform not restated in the oracle");
     }
 }
@@ -44,6 +45,7 @@ bool transform_forward(uint64_t type, Ctx& ctx, const uint8_t* src, size_t n, ui
         case T_MM: return fsd_forward(ctx, src, n, dst, cap, out_n);
         case T_UTF: return utf_forward(ctx, src, n, dst, cap, out_n);
         case T_DICT: return text_forward(ctx, src, n, dst, cap, out_n);
+        case T_EXE: return exe_forward(ctx, src, n, dst, cap, out_n);
         default: throw Error(ERR_CREATE_CODEC, "transform not restated in the oracle");
     }
 }
@@ -67,6 +69,7 @@ bool transform_inverse(uint64_t type, Ctx& ctx, const uint8_t* src, size_t n, ui
         case T_MM: return fsd_inverse(src, n, dst, cap, out_n);
         case T_UTF: return utf_inverse(src, n, dst, cap, out_n);
         case T_DICT: return text_inverse(ctx, src, n, dst, cap, out_n);
+        case T_EXE: return exe_inverse(src, n, dst, cap, out_n);
         default: throw Error(ERR_INVALID_CODEC, "transform not restated in the oracle");
     }
 }

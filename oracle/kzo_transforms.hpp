@@ -29,6 +29,9 @@ bool fsd_inverse(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t*
 size_t utf_max_encoded_len(size_t n);
 bool utf_forward(Ctx& ctx, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
 bool utf_inverse(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
+size_t exe_max_encoded_len(size_t n);
+bool exe_forward(Ctx& ctx, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
+bool exe_inverse(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);
 bool text_available();  // false when the static dictionary could not be extracted (no reference tree at build time)
 size_t text_max_encoded_len(size_t n);
 bool text_forward(Ctx& ctx, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n);

@@ -238,3 +238,69 @@ def test_level_chains_roundtrip(chain, entropy):
 
 def po_dt(name):
     return ["UNDEFINED", "TEXT", "MULTIMEDIA", "EXE", "NUMERIC", "BASE64", "DNA", "BIN", "UTF8", "SMALL_ALPHABET"].index(name)
+
+
+# ---------------------------------------------------------------- EXE
+def _synth_x86(n, seed):
+    """random bytes shaped like machine code for detectExeType (all 256 values, >= 10 % zeros, >= 1 % 0xFF) with relative CALL / JMP
+    instructions (E8 / E9 + 32-bit offset whose top byte is 00 or FF) at more than 1 per 200 bytes"""
+    r = np.random.default_rng(seed)
+    x = r.integers(0, 256, n).astype(np.uint8)
+    x[r.random(n) < 0.15] = 0
+    x[r.random(n) < 0.03] = 255
+    for p in np.sort(r.choice(n - 16, n // 60, replace=False)):
+        x[p] = 0xE8 if r.random() < 0.7 else 0xE9
+        x[p + 1: p + 5] = np.frombuffer(np.int32(int(r.integers(-200000, 200000))).tobytes(), np.uint8)
+    return x
+
+
+def _synth_arm64(n, seed):
+    r = np.random.default_rng(seed)
+    n4 = n // 4
+    w = r.integers(0, 1 << 32, n4, dtype=np.uint64).astype(np.uint32)
+    w[r.random(n4) < 0.25] &= 0x00FF00FF  # zero bytes
+    w[r.random(n4) < 0.05] |= 0xFF00FF00
+    br = r.random(n4) < 0.03
+    off = r.integers(-50000, 50000, n4).astype(np.int64) & ((1 << 26) - 1)
+    w[br] = (np.where(r.random(n4) < 0.5, 0x94000000, 0x14000000)[br] | off[br]).astype(np.uint32)
+    x = np.frombuffer(w.tobytes(), np.uint8).copy()
+    x[:4] = [0x10, 0x20, 0x30, 0x40]  # no magic number
+    return np.concatenate([x, r.integers(0, 256, n - 4 * n4).astype(np.uint8)])
+
+
+@pytest.mark.parametrize("n", [4096, 100003, 1 << 20])
+def test_exe_roundtrip(n):
+    y, dt = _roundtrip(po.T_EXE, _synth_x86(n, n))
+    assert y[0] == 0x40 and dt == po_dt("EXE")
+    # header: mode, code start (0 without an executable header), end of the transformed code section
+    assert int.from_bytes(y[1:5].tobytes(), "little") == 0 and int.from_bytes(y[5:9].tobytes(), "little") <= len(y)
+    a = _synth_arm64(n, n + 1)
+    ya, dta = _fwd(po.T_EXE, a)
+    if ya is not None:  # the ARM64 heuristics may decline the synthetic sample
+        assert ya[0] == 0x20 and dta == po_dt("EXE")
+        z = _inv(po.T_EXE, ya, n + 64)
+        z = z[0] if isinstance(z, tuple) else z
+        assert np.array_equal(z, a)
+
+
+def test_exe_real_binary_and_skips():
+    import sys
+
+    exe = np.fromfile(sys.executable, dtype=np.uint8)[: 2 << 20]
+    if len(exe) >= 65536 and bytes(exe[:4]) == b"\x7fELF":  # the interpreter itself: an ELF header tells the code section
+        y, dt = _roundtrip(po.T_EXE, exe)
+        assert dt == po_dt("EXE") and y[0] in (0x40, 0x20)
+    rnd = np.random.default_rng(0).integers(0, 256, 1 << 16).astype(np.uint8)
+    y, dt = _fwd(po.T_EXE, rnd)
+    assert y is None and dt == po_dt("BIN")
+    y, dt = _fwd(po.T_EXE, synth.markov_text(1 << 16, seed=1))
+    assert y is None
+    assert _fwd(po.T_EXE, _synth_x86(1 << 16, 3), po_dt("TEXT"))[0] is None
+    assert _fwd(po.T_EXE, _synth_x86(4000, 3))[0] is None  # below _EXE_MIN_BLOCK_SIZE
+
+
+def test_level4_chain_roundtrip():
+    parts = [synth.markov_text(400000, seed=3), _synth_x86(300000, 5), np.random.default_rng(2).integers(0, 256, 100000).astype(np.uint8)]
+    for x in parts:
+        s = po.compress(x, "TEXT+UTF+EXE+PACK+MM+ROLZ", "NONE", block_size=1 << 18, jobs=4, input_size=len(x))
+        assert np.array_equal(po.decompress(s, len(x) + 64, jobs=4), x)
