@@ -36,7 +36,7 @@ enum {
 };
 
 enum { KZ_E_NONE = 0, KZ_E_HUFFMAN = 1, KZ_E_RANGE = 4, KZ_E_ANS0 = 5, KZ_E_ANS1 = 8 };
-enum { KZ_T_NONE = 0, KZ_T_BWT = 1, KZ_T_BWTS = 2, KZ_T_LZ = 3, KZ_T_ZRLT = 6, KZ_T_MTFT = 7, KZ_T_RANK = 8, KZ_T_ROLZ = 11, KZ_T_MM = 15, KZ_T_LZX = 16, KZ_T_PACK = 18, KZ_T_DNA = 19 };
+enum { KZ_T_NONE = 0, KZ_T_BWT = 1, KZ_T_BWTS = 2, KZ_T_LZ = 3, KZ_T_ZRLT = 6, KZ_T_MTFT = 7, KZ_T_RANK = 8, KZ_T_TEXT = 10, KZ_T_ROLZ = 11, KZ_T_MM = 15, KZ_T_LZX = 16, KZ_T_PACK = 18, KZ_T_DNA = 19 };
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
 int kz_device_count(void);
@@ -113,6 +113,11 @@ int kz_decompress_stream_device(kz_ctx* ctx, const void* d_src, size_t n, void* 
 void kz_profile(kz_ctx* ctx, int enable);
 uint32_t kz_kernel_time(kz_ctx* ctx, const char* name, double* total_ms);
 void kz_profile_reset(kz_ctx* ctx);
+
+/* ctx["blockSize"] of the stream the following kz_encode_blocks / kz_transform_forward / kz_transform_inverse calls belong to
+ * (io/CompressedStream.go:220,1406). Only TEXT reads it (it sizes its hash map from it, transform/TextCodec.go:1143-1156);
+ * 0 (default) = the longest block of the call. kz_decode_blocks and the stream entry points know the value themselves. */
+void kz_set_stream_block_size(kz_ctx* ctx, uint64_t block_size);
 
 #ifdef __cplusplus
 }

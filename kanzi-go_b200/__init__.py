@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(_HERE, "libkanzi_b200.so")
 E_NONE, E_HUFFMAN, E_RANGE, E_ANS0, E_ANS1 = 0, 1, 4, 5, 8
 T_NONE, T_BWT, T_BWTS, T_LZ, T_ROLZ, T_LZX = 0, 1, 2, 3, 11, 16
 T_ZRLT, T_MTFT, T_RANK = 6, 7, 8
-T_PACK, T_DNA, T_MM = 18, 19, 15
+T_PACK, T_DNA, T_MM, T_TEXT = 18, 19, 15, 10
 ENTROPY_IDS = {"NONE": 0, "HUFFMAN": 1, "FPAQ": 2, "RANGE": 4, "ANS0": 5, "CM": 6, "TPAQ": 7, "ANS1": 8, "TPAQX": 9}
 TRANSFORM_IDS = {"NONE": 0, "BWT": 1, "BWTS": 2, "LZ": 3, "RLT": 5, "ZRLT": 6, "MTFT": 7, "RANK": 8, "EXE": 9, "TEXT": 10, "ROLZ": 11,
                  "ROLZX": 12, "SRT": 13, "LZP": 14, "MM": 15, "LZX": 16, "UTF": 17, "PACK": 18, "DNA": 19}
@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "kz_device_count", "kz_init", "kz_destroy", "kz_last_error", "kz_alloc_pinned", "kz_free_pinned", "kz_cuda_stream", "kz_launch_count",
     "kz_entropy_encode", "kz_entropy_decode", "kz_transform_forward", "kz_transform_inverse", "kz_transform_max_encoded_len",
     "kz_encode_blocks", "kz_decode_blocks", "kz_max_block_output", "kz_compress_stream", "kz_decompress_stream", "kz_max_stream_output",
-    "kz_compress_stream_device", "kz_decompress_stream_device", "kz_profile", "kz_kernel_time", "kz_profile_reset",
+    "kz_compress_stream_device", "kz_decompress_stream_device", "kz_profile", "kz_kernel_time", "kz_profile_reset", "kz_set_stream_block_size",
 ]
 
 
@@ -119,6 +119,8 @@ def load_library(build_if_missing=True):
     L.kz_kernel_time.restype = u32
     L.kz_profile_reset.argtypes = [vp]
     L.kz_profile_reset.restype = None
+    L.kz_set_stream_block_size.argtypes = [vp, C.c_uint64]
+    L.kz_set_stream_block_size.restype = None
     _lib = L
     return L
 
@@ -176,6 +178,10 @@ class Context:
         used = C.c_uint64(0)
         self._check(self.lib.kz_entropy_decode(self.h, etype, _p(s), s.size, out.ctypes.data, n, C.byref(used)))
         return out[:n], used.value
+
+    def set_stream_block_size(self, block_size):
+        """ctx["blockSize"] for the following block / single-transform calls (only TEXT reads it); 0 = the longest block of the call"""
+        self.lib.kz_set_stream_block_size(self.h, block_size)
 
     def transform_forward(self, ttype, block, data_type=0):
         """ByteTransform.Forward for one transform id -> (bytes or None when the transform declines, data_type after)."""

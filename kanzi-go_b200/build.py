@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libkanzi_b200.so")
-SOURCES = ["kz_ans.cu", "kz_ans1.cu", "kz_huffman.cu", "kz_range.cu", "kz_hash.cu", "kz_sbrt.cu", "kz_zrlt.cu", "kz_rolz.cu", "kz_alias.cu", "kz_fsd.cu", "kz_bwt.cu", "kz_lz.cu", "kz_concat.cu", "kz_api.cu"]
+SOURCES = ["kz_ans.cu", "kz_ans1.cu", "kz_huffman.cu", "kz_range.cu", "kz_hash.cu", "kz_sbrt.cu", "kz_zrlt.cu", "kz_rolz.cu", "kz_alias.cu", "kz_fsd.cu", "kz_text.cu", "kz_bwt.cu", "kz_lz.cu", "kz_concat.cu", "kz_api.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
          "-Xptxas", "-v"]
 
@@ -23,6 +23,16 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    # TEXT's static dictionary is a constant of the kanzi format: generated from the reference tree when it is there (csrc/_gen/)
+    try:
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("kz_gen_text_dict", os.path.join(HERE, "gen_text_dict.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.main()
+    except Exception as e:  # the library then builds without the TEXT stage
+        sys.stderr.write("gen_text_dict: %s\n" % e)
     if not force and not needs_build():
         return OUT
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]

@@ -21,6 +21,7 @@
 #include "kz_rolz.cuh"
 #include "kz_alias.cuh"
 #include "kz_fsd.cuh"
+#include "kz_text.cuh"
 
 #include <memory>
 
@@ -814,13 +815,13 @@ struct TransformPlan {
     bool lzx() const { return nt == 1 && ids[0] == KZ_T_LZX; }
     static bool seq_id(uint64_t t) {
         return t == KZ_T_BWT || t == KZ_T_BWTS || t == KZ_T_RANK || t == KZ_T_MTFT || t == KZ_T_ZRLT || t == KZ_T_ROLZ || t == KZ_T_PACK || t == KZ_T_DNA || t == KZ_T_LZ ||
-               t == KZ_T_LZX || t == KZ_T_MM;
+               t == KZ_T_LZX || t == KZ_T_MM || t == KZ_T_TEXT;
     }
     // any sequence of BWT / BWTS / RANK / MTFT / ZRLT / ROLZ stages (e.g. "BWT+RANK+ZRLT", the transform chain of kanzi -l 5)
     // stages that read ctx["dataType"] in a way the block's magic number can change (LZ / LZX only look for DNA / small alphabets)
     bool uses_magic() const {
         for (int i = 0; i < nt; i++)
-            if (ids[i] == KZ_T_ROLZ || ids[i] == KZ_T_PACK || ids[i] == KZ_T_DNA || ids[i] == KZ_T_MM) return true;
+            if (ids[i] == KZ_T_ROLZ || ids[i] == KZ_T_PACK || ids[i] == KZ_T_DNA || ids[i] == KZ_T_MM || ids[i] == KZ_T_TEXT) return true;
         return false;
     }
     bool generic() const {
@@ -831,11 +832,11 @@ struct TransformPlan {
     }
 };
 
-// Stages written at the end of round 1 (PACK / DNA / MM, LZ / LZX inside sequences, the magic-number data type) had no GPU slot left to
-// be confirmed on: they are enabled by KZ_EXPERIMENTAL=1 (tests/test_gpu_pack.py sets it) until a GPU run has confirmed them.
+// The stages added last (PACK / DNA / MM, LZ / LZX inside sequences, the magic-number data type, TEXT) can be switched off with
+// KZ_EXPERIMENTAL=0: the library then answers "not available" for them, as it did before they existed.
 bool experimental_stages() {
     const char* e = getenv("KZ_EXPERIMENTAL");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
 }
 
 int plan_transforms(kz_ctx* ctx, uint64_t t48, TransformPlan& p, int err_code) {
@@ -843,10 +844,13 @@ int plan_transforms(kz_ctx* ctx, uint64_t t48, TransformPlan& p, int err_code) {
     if (!experimental_stages()) {
         for (int i = 0; i < p.nt; i++) {
             const uint64_t t = p.ids[i];
-            const bool newer = t == KZ_T_PACK || t == KZ_T_DNA || t == KZ_T_MM || ((t == KZ_T_LZ || t == KZ_T_LZX) && p.nt > 1);
-            if (newer) return ctx->fail(err_code, "transform stage awaiting GPU confirmation (set KZ_EXPERIMENTAL=1): PACK / DNA / MM, LZ / LZX inside a sequence");
+            const bool newer = t == KZ_T_PACK || t == KZ_T_DNA || t == KZ_T_MM || t == KZ_T_TEXT || ((t == KZ_T_LZ || t == KZ_T_LZX) && p.nt > 1);
+            if (newer) return ctx->fail(err_code, "transform stage switched off by KZ_EXPERIMENTAL=0: PACK / DNA / MM / TEXT, LZ / LZX inside a sequence");
         }
     }
+    for (int i = 0; i < p.nt; i++)
+        if (p.ids[i] == KZ_T_TEXT && !text_available())
+            return ctx->fail(err_code, "TEXT: the library was built without the static dictionary (kanzi-go_b200/gen_text_dict.py)");
     if (!(p.none() || p.bwt() || p.lz() || p.generic()))
         return ctx->fail(err_code, "transform sequence not available on the GPU path (sequences of BWT / BWTS / LZ / LZX / ROLZ / RANK / MTFT / ZRLT / PACK / DNA are)");
     return 0;
@@ -976,6 +980,51 @@ int apply_forward(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint64_t istride
                 applied[b] = 1;
                 len[b] = hres[b].out_len;
             }
+    } else if (t == KZ_T_TEXT) {  // TextCodec (encoding 2): declines unless the block looks like text
+        if (!text_available()) return ctx->fail(KZ_ERR_CREATE_CODEC, "TEXT: the library was built without the static dictionary");
+        const uint32_t SUB = 64;  // ~9 MB of dictionary per block
+        const uint64_t sbs = ctx->stream_bs ? ctx->stream_bs : *std::max_element(len.begin(), len.end());
+        for (uint32_t b0 = 0; b0 < nblocks; b0 += SUB) {
+            const uint32_t nb = std::min(SUB, nblocks - b0);
+            uint32_t max_len = 0;
+            for (uint32_t b = b0; b < b0 + nb; b++) max_len = std::max(max_len, active[b] ? len[b] : 0u);
+            if (max_len == 0) continue;
+            CK(ctx->d_ws.ensure(text_workspace(nb, sbs)));
+            std::vector<TextBlock> tb(nb);
+            for (uint32_t k = 0; k < nb; k++) {
+                const uint32_t b = b0 + k;
+                tb[k].src_off = b * istride;
+                tb[k].dst_off = b * ostride;
+                tb[k].len = active[b] ? len[b] : 0;
+                tb[k].cap = len[b];  // MaxEncodedLen = srcLen (:1720-1724)
+                tb[k].data_type = dts ? (*dts)[b] : 0;
+                tb[k].pad = 0;
+            }
+            Packer pk;
+            const size_t o_tb = pk.add(tb.data(), tb.size() * sizeof(TextBlock));
+            const size_t o_res = pk.reserve((size_t)nb * sizeof(TextResult));
+            int rc = upload(ctx, pk);
+            if (rc) return rc;
+            uint8_t* T = ctx->d_tables.as<uint8_t>();
+            {
+                LaunchScope ls(ctx, "text_forward");
+                cudaError_t e = text_forward_batch(d_in, d_out, (const TextBlock*)(T + o_tb), nb, max_len, sbs, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap,
+                                                   (TextResult*)(T + o_res), ctx->stream, &ctx->launches);
+                if (e != cudaSuccess) return ctx->cuda_fail(e, "text_forward");
+            }
+            std::vector<TextResult> hr(nb);
+            CK(cudaMemcpyAsync(hr.data(), T + o_res, (size_t)nb * sizeof(TextResult), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (uint32_t k = 0; k < nb; k++) {
+                const uint32_t b = b0 + k;
+                if (!active[b] || len[b] == 0) continue;
+                if (dts) (*dts)[b] = hr[k].data_type;
+                if (hr[k].status == 0) {
+                    applied[b] = 1;
+                    len[b] = hr[k].out_len;
+                }
+            }
+        }
     } else if (t == KZ_T_MM) {  // FSDCodec.Forward: declines unless a fixed-step delta lowers the sampled entropy
         const uint32_t SUB = 1024;
         for (uint32_t b0 = 0; b0 < nblocks; b0 += SUB) {
@@ -1280,6 +1329,48 @@ int apply_inverse(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint8_t* d_out, 
             if (!active[b] || len[b] == 0) continue;
             if (hs[b]) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "LZCodec inverse transform failed");
             len[b] = hl[b];
+        }
+    } else if (t == KZ_T_TEXT) {
+        if (!text_available()) return ctx->fail(KZ_ERR_CREATE_CODEC, "TEXT: the library was built without the static dictionary");
+        const uint32_t SUB = 64;
+        const uint64_t sbs = ctx->stream_bs ? ctx->stream_bs : cap;
+        for (uint32_t b0 = 0; b0 < nblocks; b0 += SUB) {
+            const uint32_t nb = std::min(SUB, nblocks - b0);
+            bool any = false;
+            for (uint32_t b = b0; b < b0 + nb; b++) any = any || (active[b] && len[b]);
+            if (!any) continue;
+            CK(ctx->d_ws.ensure(text_workspace(nb, sbs)));
+            std::vector<TextBlock> tb(nb);
+            for (uint32_t k = 0; k < nb; k++) {
+                const uint32_t b = b0 + k;
+                tb[k].src_off = b * stride;
+                tb[k].dst_off = b * stride;
+                tb[k].len = active[b] ? len[b] : 0;
+                tb[k].cap = cap;
+                tb[k].data_type = 0;
+                tb[k].pad = 0;
+            }
+            Packer pk;
+            const size_t o_tb = pk.add(tb.data(), tb.size() * sizeof(TextBlock));
+            const size_t o_res = pk.reserve((size_t)nb * sizeof(TextResult));
+            int rc = upload(ctx, pk);
+            if (rc) return rc;
+            uint8_t* T = ctx->d_tables.as<uint8_t>();
+            {
+                LaunchScope ls(ctx, "text_inverse");
+                cudaError_t e = text_inverse_batch(d_in, d_out, (const TextBlock*)(T + o_tb), nb, sbs, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap,
+                                                   (TextResult*)(T + o_res), ctx->stream, &ctx->launches);
+                if (e != cudaSuccess) return ctx->cuda_fail(e, "text_inverse");
+            }
+            std::vector<TextResult> hr(nb);
+            CK(cudaMemcpyAsync(hr.data(), T + o_res, (size_t)nb * sizeof(TextResult), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (uint32_t k = 0; k < nb; k++) {
+                const uint32_t b = b0 + k;
+                if (!active[b] || len[b] == 0) continue;
+                if (hr[k].status) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "Text transform failed: invalid data");
+                len[b] = hr[k].out_len;
+            }
         }
     } else if (t == KZ_T_MM) {
         std::vector<FsdBlock> fb(nblocks);
@@ -1767,6 +1858,10 @@ size_t kz_max_stream_output(size_t n, uint32_t block_size) {
     return n + (n >> 3) + 64 * (n / 16384 + 1) + 32 * nblocks + 1024 + 106496 * (n / (4u << 20) + nblocks + 1);
 }
 
+void kz_set_stream_block_size(kz_ctx* ctx, uint64_t block_size) {
+    if (ctx) ctx->user_stream_bs = block_size;
+}
+
 size_t kz_transform_max_encoded_len(uint64_t type, size_t n) {
     switch (type) {
         case KZ_T_NONE: return n;
@@ -1778,6 +1873,7 @@ size_t kz_transform_max_encoded_len(uint64_t type, size_t n) {
         case KZ_T_ROLZ: return n <= 512 ? n + 64 : n;  // transform/ROLZCodec.go:916-918
         case KZ_T_PACK: case KZ_T_DNA: return n + 1024;  // transform/AliasCodec.go:437-439
         case KZ_T_MM: return n + std::max<size_t>(n >> 4, 64);  // transform/FSDCodec.go:128-130
+        case KZ_T_TEXT: return n;  // transform/TextCodec.go:1720-1724
         case KZ_T_LZ:
         case KZ_T_LZX: return n <= 1024 ? n + 16 : n + n / 64;  // transform/LZCodec.go:935-941
         default: return 0;
@@ -1789,6 +1885,7 @@ int kz_compress_stream_device(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_
                               const void* d_src, size_t n, void* d_dst, size_t cap, size_t* out_n) {
     if (!ctx || !out_n) return -KZ_ERR_INVALID_PARAM;
     CK(cudaSetDevice(ctx->device));
+    ctx->stream_bs = block_size;
     if (block_size < 1024 || block_size > (1u << 30) || (block_size & 15)) return ctx->fail(KZ_ERR_INVALID_PARAM, "Invalid block size");
     if (checksum_bits != 0 && checksum_bits != 32 && checksum_bits != 64) return ctx->fail(KZ_ERR_INVALID_PARAM, "checksum must be 0, 32 or 64 bits");
     if (((uintptr_t)d_src & 15) || ((uintptr_t)d_dst & 15)) return ctx->fail(KZ_ERR_INVALID_PARAM, "device buffers must be 16-byte aligned");
@@ -1886,6 +1983,7 @@ int kz_decompress_stream_device(kz_ctx* ctx, const void* d_src, size_t n, void* 
         jobs[b].bit_off = boff[b];
         jobs[b].bits = bbits[b];
     }
+    ctx->stream_bs = sh.block_size;
     rc = decode_parse_headers(ctx, d_words, jobs, sh.checksum_bits, sh.block_size);
     if (rc) return rc;
     uint64_t out_off = 0;
@@ -1988,6 +2086,7 @@ int kz_encode_blocks(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_t checksu
                      const uint32_t* block_len, uint32_t nblocks, uint8_t* out, uint64_t out_stride, uint64_t* out_bits, int32_t* status) {
     if (!ctx || !slab || !block_len || !out || !out_bits) return -KZ_ERR_INVALID_PARAM;
     CK(cudaSetDevice(ctx->device));
+    ctx->stream_bs = ctx->user_stream_bs;
     if (checksum_bits != 0 && checksum_bits != 32 && checksum_bits != 64) return ctx->fail(KZ_ERR_INVALID_PARAM, "checksum must be 0, 32 or 64 bits");
     if (nblocks == 0) return 0;
     // device layout: block b at b * dstride (16-byte aligned)
@@ -2039,6 +2138,7 @@ int kz_decode_blocks(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_t checksu
                      int32_t* status) {
     if (!ctx || !in || !in_off || !in_bits || !out || !out_len) return -KZ_ERR_INVALID_PARAM;
     CK(cudaSetDevice(ctx->device));
+    ctx->stream_bs = block_size;
     if (checksum_bits != 0 && checksum_bits != 32 && checksum_bits != 64) return ctx->fail(KZ_ERR_INVALID_PARAM, "checksum must be 0, 32 or 64 bits");
     TransformPlan plan;
     {
@@ -2185,10 +2285,11 @@ int kz_entropy_decode(kz_ctx* ctx, uint32_t type, const uint8_t* src, size_t src
 }
 
 int kz_transform_forward(kz_ctx* ctx, uint64_t type, int* data_type, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n) {
-    if ((type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM) && ctx && !experimental_stages())
-        return ctx->fail(KZ_ERR_CREATE_CODEC, "transform awaiting GPU confirmation (set KZ_EXPERIMENTAL=1): PACK / DNA / MM");
+    if ((type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT) && ctx && !experimental_stages())
+        return ctx->fail(KZ_ERR_CREATE_CODEC, "transform switched off by KZ_EXPERIMENTAL=0: PACK / DNA / MM / TEXT");
     if (!ctx || (!src && n) || !dst || !out_n) return -KZ_ERR_INVALID_PARAM;
     CK(cudaSetDevice(ctx->device));
+    ctx->stream_bs = ctx->user_stream_bs;
     *out_n = 0;
     if (type == KZ_T_LZ || type == KZ_T_LZX) {  // LZXCodec.Forward (reads ctx["dataType"], never writes it)
         if (n == 0) return 0;
@@ -2211,7 +2312,7 @@ int kz_transform_forward(kz_ctx* ctx, uint64_t type, int* data_type, const uint8
         *out_n = jobs[0].post_len;
         return 0;
     }
-    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS || type == KZ_T_ROLZ || type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM) {  // SBRT / ZRLT / BWTS / ROLZ / Alias / FSD Forward
+    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS || type == KZ_T_ROLZ || type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT) {  // SBRT / ZRLT / BWTS / ROLZ / Alias / FSD / Text Forward
         if (n == 0) return 0;
         if (n > (1u << 30)) return ctx->fail(KZ_ERR_BLOCK_SIZE, "block too large");
         if (cap < kz_transform_max_encoded_len(type, n)) return 1;  // Forward returns an error: the sequence skips the transform
@@ -2259,10 +2360,11 @@ int kz_transform_forward(kz_ctx* ctx, uint64_t type, int* data_type, const uint8
 }
 
 int kz_transform_inverse(kz_ctx* ctx, uint64_t type, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n) {
-    if ((type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM) && ctx && !experimental_stages())
-        return ctx->fail(KZ_ERR_CREATE_CODEC, "transform awaiting GPU confirmation (set KZ_EXPERIMENTAL=1): PACK / DNA / MM");
+    if ((type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT) && ctx && !experimental_stages())
+        return ctx->fail(KZ_ERR_CREATE_CODEC, "transform switched off by KZ_EXPERIMENTAL=0: PACK / DNA / MM / TEXT");
     if (!ctx || (!src && n) || !dst || !out_n) return -KZ_ERR_INVALID_PARAM;
     CK(cudaSetDevice(ctx->device));
+    ctx->stream_bs = ctx->user_stream_bs;
     *out_n = 0;
     if (type == KZ_T_LZ || type == KZ_T_LZX) {  // LZXCodec.inverseV6; cap = len(dst) of the reference call
         if (n == 0) return 0;
@@ -2285,7 +2387,7 @@ int kz_transform_inverse(kz_ctx* ctx, uint64_t type, const uint8_t* src, size_t 
         *out_n = olen[0];
         return 0;
     }
-    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS || type == KZ_T_ROLZ || type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM) {  // SBRT / ZRLT / BWTS / ROLZ / Alias / FSD Inverse; cap = len(dst)
+    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS || type == KZ_T_ROLZ || type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT) {  // SBRT / ZRLT / BWTS / ROLZ / Alias / FSD / Text Inverse; cap = len(dst)
         if (n == 0 || cap == 0) return 0;
         if (n > (1u << 30) || cap > (1u << 30) + 4096) return ctx->fail(KZ_ERR_BLOCK_SIZE, "block too large");
         const uint64_t stride = ((uint64_t)std::max(n, cap) + 64 + 15) & ~15ull;

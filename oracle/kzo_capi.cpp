@@ -3,6 +3,7 @@
 #include <cstring>
 
 #include "kzo.hpp"
+#include "kzo_transforms.hpp"
 
 using namespace kzo;
 
@@ -52,6 +53,7 @@ int kzo_entropy_decode(uint32_t type, const uint8_t* src, size_t src_bytes, uint
 // ctx["blockSize"] for the single-transform calls below (0 = the call's own input length); thread local
 static thread_local size_t g_stream_block_size = 0;
 void kzo_set_stream_block_size(size_t n) { g_stream_block_size = n; }
+int kzo_text_available() { return text_available() ? 1 : 0; }
 
 int kzo_transform_forward(uint64_t type, int data_type, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n, int* out_data_type) {
     try {
