@@ -22,6 +22,7 @@
 #include "kz_alias.cuh"
 #include "kz_fsd.cuh"
 #include "kz_text.cuh"
+#include "kz_utf.cuh"
 
 #include <memory>
 
@@ -815,13 +816,13 @@ struct TransformPlan {
     bool lzx() const { return nt == 1 && ids[0] == KZ_T_LZX; }
     static bool seq_id(uint64_t t) {
         return t == KZ_T_BWT || t == KZ_T_BWTS || t == KZ_T_RANK || t == KZ_T_MTFT || t == KZ_T_ZRLT || t == KZ_T_ROLZ || t == KZ_T_PACK || t == KZ_T_DNA || t == KZ_T_LZ ||
-               t == KZ_T_LZX || t == KZ_T_MM || t == KZ_T_TEXT;
+               t == KZ_T_LZX || t == KZ_T_MM || t == KZ_T_TEXT || t == KZ_T_UTF;
     }
     // any sequence of BWT / BWTS / RANK / MTFT / ZRLT / ROLZ stages (e.g. "BWT+RANK+ZRLT", the transform chain of kanzi -l 5)
     // stages that read ctx["dataType"] in a way the block's magic number can change (LZ / LZX only look for DNA / small alphabets)
     bool uses_magic() const {
         for (int i = 0; i < nt; i++)
-            if (ids[i] == KZ_T_ROLZ || ids[i] == KZ_T_PACK || ids[i] == KZ_T_DNA || ids[i] == KZ_T_MM || ids[i] == KZ_T_TEXT) return true;
+            if (ids[i] == KZ_T_ROLZ || ids[i] == KZ_T_PACK || ids[i] == KZ_T_DNA || ids[i] == KZ_T_MM || ids[i] == KZ_T_TEXT || ids[i] == KZ_T_UTF) return true;
         return false;
     }
     bool generic() const {
@@ -844,7 +845,7 @@ int plan_transforms(kz_ctx* ctx, uint64_t t48, TransformPlan& p, int err_code) {
     if (!experimental_stages()) {
         for (int i = 0; i < p.nt; i++) {
             const uint64_t t = p.ids[i];
-            const bool newer = t == KZ_T_PACK || t == KZ_T_DNA || t == KZ_T_MM || t == KZ_T_TEXT || ((t == KZ_T_LZ || t == KZ_T_LZX) && p.nt > 1);
+            const bool newer = t == KZ_T_PACK || t == KZ_T_DNA || t == KZ_T_MM || t == KZ_T_TEXT || t == KZ_T_UTF || ((t == KZ_T_LZ || t == KZ_T_LZX) && p.nt > 1);
             if (newer) return ctx->fail(err_code, "transform stage switched off by KZ_EXPERIMENTAL=0: PACK / DNA / MM / TEXT, LZ / LZX inside a sequence");
         }
     }
@@ -1014,6 +1015,49 @@ int apply_forward(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint64_t istride
             }
             std::vector<TextResult> hr(nb);
             CK(cudaMemcpyAsync(hr.data(), T + o_res, (size_t)nb * sizeof(TextResult), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (uint32_t k = 0; k < nb; k++) {
+                const uint32_t b = b0 + k;
+                if (!active[b] || len[b] == 0) continue;
+                if (dts) (*dts)[b] = hr[k].data_type;
+                if (hr[k].status == 0) {
+                    applied[b] = 1;
+                    len[b] = hr[k].out_len;
+                }
+            }
+        }
+    } else if (t == KZ_T_UTF) {  // UTFCodec.Forward: declines unless the block is UTF-8 with enough multi-byte sequences
+        const uint32_t SUB = 32;  // 16 MB of code point counters per block
+        for (uint32_t b0 = 0; b0 < nblocks; b0 += SUB) {
+            const uint32_t nb = std::min(SUB, nblocks - b0);
+            bool any = false;
+            for (uint32_t b = b0; b < b0 + nb; b++) any = any || (active[b] && len[b]);
+            if (!any) continue;
+            CK(ctx->d_ws.ensure(utf_workspace(nb)));
+            std::vector<UtfBlock> ub(nb);
+            for (uint32_t k = 0; k < nb; k++) {
+                const uint32_t b = b0 + k;
+                ub[k].src_off = b * istride;
+                ub[k].dst_off = b * ostride;
+                ub[k].len = active[b] ? len[b] : 0;
+                ub[k].cap = (uint32_t)std::min<uint64_t>((uint64_t)len[b] + 8192, 0xFFFFFFF0u);  // MaxEncodedLen (:386-388)
+                ub[k].data_type = dts ? (*dts)[b] : 0;
+                ub[k].pad = 0;
+            }
+            Packer pk;
+            const size_t o_ub = pk.add(ub.data(), ub.size() * sizeof(UtfBlock));
+            const size_t o_res = pk.reserve((size_t)nb * sizeof(UtfResult));
+            int rc = upload(ctx, pk);
+            if (rc) return rc;
+            uint8_t* T = ctx->d_tables.as<uint8_t>();
+            {
+                LaunchScope ls(ctx, "utf_forward");
+                cudaError_t e = utf_forward_batch(d_in, d_out, (const UtfBlock*)(T + o_ub), nb, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap, (UtfResult*)(T + o_res),
+                                                  ctx->stream, &ctx->launches);
+                if (e != cudaSuccess) return ctx->cuda_fail(e, "utf_forward");
+            }
+            std::vector<UtfResult> hr(nb);
+            CK(cudaMemcpyAsync(hr.data(), T + o_res, (size_t)nb * sizeof(UtfResult), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
             for (uint32_t k = 0; k < nb; k++) {
                 const uint32_t b = b0 + k;
@@ -1202,7 +1246,7 @@ int forward_generic(kz_ctx* ctx, const TransformPlan& plan, const uint8_t* d_src
     uint32_t max_len = 0;
     for (uint32_t b = 0; b < nblocks; b++) max_len = std::max(max_len, blen[b]);
     // room for the largest stage output: +33 bytes per BWT / SBRT stage, n/64 + 128 for LZ, n/16 for MM, headers of PACK
-    const uint64_t gstride = ((uint64_t)max_len + max_len / 16 + 33ull * plan.nt + 1024 + 256 + 15) & ~15ull;
+    const uint64_t gstride = ((uint64_t)max_len + max_len / 16 + 33ull * plan.nt + 8192 + 1024 + 256 + 15) & ~15ull;
     CK(ctx->d_tmp.ensure(gstride * nblocks + 64));
     CK(ctx->d_tmp2.ensure(gstride * nblocks + 64));
     std::vector<uint32_t> len(blen);
@@ -1369,6 +1413,46 @@ int apply_inverse(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint8_t* d_out, 
                 const uint32_t b = b0 + k;
                 if (!active[b] || len[b] == 0) continue;
                 if (hr[k].status) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "Text transform failed: invalid data");
+                len[b] = hr[k].out_len;
+            }
+        }
+    } else if (t == KZ_T_UTF) {
+        const uint32_t SUB = 32;
+        for (uint32_t b0 = 0; b0 < nblocks; b0 += SUB) {
+            const uint32_t nb = std::min(SUB, nblocks - b0);
+            bool any = false;
+            for (uint32_t b = b0; b < b0 + nb; b++) any = any || (active[b] && len[b]);
+            if (!any) continue;
+            CK(ctx->d_ws.ensure(utf_workspace(nb)));
+            std::vector<UtfBlock> ub(nb);
+            for (uint32_t k = 0; k < nb; k++) {
+                const uint32_t b = b0 + k;
+                ub[k].src_off = b * stride;
+                ub[k].dst_off = b * stride;
+                ub[k].len = active[b] ? len[b] : 0;
+                ub[k].cap = cap;
+                ub[k].data_type = 0;
+                ub[k].pad = 0;
+            }
+            Packer pk;
+            const size_t o_ub = pk.add(ub.data(), ub.size() * sizeof(UtfBlock));
+            const size_t o_res = pk.reserve((size_t)nb * sizeof(UtfResult));
+            int rc = upload(ctx, pk);
+            if (rc) return rc;
+            uint8_t* T = ctx->d_tables.as<uint8_t>();
+            {
+                LaunchScope ls(ctx, "utf_inverse");
+                cudaError_t e = utf_inverse_batch(d_in, d_out, (const UtfBlock*)(T + o_ub), nb, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap, (UtfResult*)(T + o_res),
+                                                  ctx->stream, &ctx->launches);
+                if (e != cudaSuccess) return ctx->cuda_fail(e, "utf_inverse");
+            }
+            std::vector<UtfResult> hr(nb);
+            CK(cudaMemcpyAsync(hr.data(), T + o_res, (size_t)nb * sizeof(UtfResult), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (uint32_t k = 0; k < nb; k++) {
+                const uint32_t b = b0 + k;
+                if (!active[b] || len[b] == 0) continue;
+                if (hr[k].status) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "UTF inverse transform failed: invalid data");
                 len[b] = hr[k].out_len;
             }
         }
@@ -1874,6 +1958,7 @@ size_t kz_transform_max_encoded_len(uint64_t type, size_t n) {
         case KZ_T_PACK: case KZ_T_DNA: return n + 1024;  // transform/AliasCodec.go:437-439
         case KZ_T_MM: return n + std::max<size_t>(n >> 4, 64);  // transform/FSDCodec.go:128-130
         case KZ_T_TEXT: return n;  // transform/TextCodec.go:1720-1724
+        case KZ_T_UTF: return n + 8192;  // transform/UTFCodec.go:386-388
         case KZ_T_LZ:
         case KZ_T_LZX: return n <= 1024 ? n + 16 : n + n / 64;  // transform/LZCodec.go:935-941
         default: return 0;
@@ -2285,7 +2370,7 @@ int kz_entropy_decode(kz_ctx* ctx, uint32_t type, const uint8_t* src, size_t src
 }
 
 int kz_transform_forward(kz_ctx* ctx, uint64_t type, int* data_type, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n) {
-    if ((type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT) && ctx && !experimental_stages())
+    if ((type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT || type == KZ_T_UTF) && ctx && !experimental_stages())
         return ctx->fail(KZ_ERR_CREATE_CODEC, "transform switched off by KZ_EXPERIMENTAL=0: PACK / DNA / MM / TEXT");
     if (!ctx || (!src && n) || !dst || !out_n) return -KZ_ERR_INVALID_PARAM;
     CK(cudaSetDevice(ctx->device));
@@ -2312,11 +2397,11 @@ int kz_transform_forward(kz_ctx* ctx, uint64_t type, int* data_type, const uint8
         *out_n = jobs[0].post_len;
         return 0;
     }
-    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS || type == KZ_T_ROLZ || type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT) {  // SBRT / ZRLT / BWTS / ROLZ / Alias / FSD / Text Forward
+    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS || type == KZ_T_ROLZ || type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT || type == KZ_T_UTF) {  // SBRT / ZRLT / BWTS / ROLZ / Alias / FSD / Text / UTF Forward
         if (n == 0) return 0;
         if (n > (1u << 30)) return ctx->fail(KZ_ERR_BLOCK_SIZE, "block too large");
         if (cap < kz_transform_max_encoded_len(type, n)) return 1;  // Forward returns an error: the sequence skips the transform
-        const uint64_t stride = ((uint64_t)n + n / 16 + 1024 + 64 + 64 + 15) & ~15ull;
+        const uint64_t stride = ((uint64_t)n + n / 16 + 8192 + 1024 + 64 + 64 + 15) & ~15ull;
         CK(ctx->d_in.ensure(stride));
         CK(ctx->d_out.ensure(stride));
         CK(cudaMemcpyAsync(ctx->d_in.p, src, n, cudaMemcpyHostToDevice, ctx->stream));
@@ -2360,7 +2445,7 @@ int kz_transform_forward(kz_ctx* ctx, uint64_t type, int* data_type, const uint8
 }
 
 int kz_transform_inverse(kz_ctx* ctx, uint64_t type, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n) {
-    if ((type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT) && ctx && !experimental_stages())
+    if ((type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT || type == KZ_T_UTF) && ctx && !experimental_stages())
         return ctx->fail(KZ_ERR_CREATE_CODEC, "transform switched off by KZ_EXPERIMENTAL=0: PACK / DNA / MM / TEXT");
     if (!ctx || (!src && n) || !dst || !out_n) return -KZ_ERR_INVALID_PARAM;
     CK(cudaSetDevice(ctx->device));
@@ -2387,7 +2472,7 @@ int kz_transform_inverse(kz_ctx* ctx, uint64_t type, const uint8_t* src, size_t 
         *out_n = olen[0];
         return 0;
     }
-    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS || type == KZ_T_ROLZ || type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT) {  // SBRT / ZRLT / BWTS / ROLZ / Alias / FSD / Text Inverse; cap = len(dst)
+    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS || type == KZ_T_ROLZ || type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT || type == KZ_T_UTF) {  // SBRT / ZRLT / BWTS / ROLZ / Alias / FSD / Text / UTF Inverse; cap = len(dst)
         if (n == 0 || cap == 0) return 0;
         if (n > (1u << 30) || cap > (1u << 30) + 4096) return ctx->fail(KZ_ERR_BLOCK_SIZE, "block too large");
         const uint64_t stride = ((uint64_t)std::max(n, cap) + 64 + 15) & ~15ull;
