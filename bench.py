@@ -46,6 +46,12 @@ WORKLOADS = {
                "encode+decode MB/s (-t BWT+RANK+ZRLT -e ANS0, 4x32MiB text blocks: the GPU covered part of kanzi -l 5, configs[3] shape)"),
     "l5core4m": ("BWT+RANK+ZRLT", "ANS0", 4 << 20, 16, "text", "bwt_forward",
                  "encode+decode MB/s (-t BWT+RANK+ZRLT -e ANS0, 16x4MiB text blocks)"),
+    # complete level chains (app/BlockCompressor.go:664-700); TEXT / UTF walk their blocks with one thread each
+    "l2": ("DNA+LZ", "HUFFMAN", 4 << 20, 48, "text", "lz_parse", "encode+decode MB/s (kanzi -l 2 = -t DNA+LZ -e HUFFMAN, 48x4MiB text blocks)"),
+    "l3": ("TEXT+UTF+PACK+MM+LZX", "HUFFMAN", 4 << 20, 48, "text", "lz_parse",
+           "encode+decode MB/s (kanzi -l 3 = -t TEXT+UTF+PACK+MM+LZX -e HUFFMAN, 48x4MiB text blocks, configs[2] shape)"),
+    "l5": ("TEXT+UTF+BWT+RANK+ZRLT", "ANS0", 4 << 20, 16, "text", "bwt_forward",
+           "encode+decode MB/s (kanzi -l 5 = -t TEXT+UTF+BWT+RANK+ZRLT -e ANS0, 16x4MiB text blocks)"),
 }
 
 

@@ -36,7 +36,7 @@ enum {
 };
 
 enum { KZ_E_NONE = 0, KZ_E_HUFFMAN = 1, KZ_E_RANGE = 4, KZ_E_ANS0 = 5, KZ_E_ANS1 = 8 };
-enum { KZ_T_NONE = 0, KZ_T_BWT = 1, KZ_T_BWTS = 2, KZ_T_LZ = 3, KZ_T_ZRLT = 6, KZ_T_MTFT = 7, KZ_T_RANK = 8, KZ_T_TEXT = 10, KZ_T_ROLZ = 11, KZ_T_MM = 15, KZ_T_LZX = 16, KZ_T_UTF = 17, KZ_T_PACK = 18, KZ_T_DNA = 19 };
+enum { KZ_T_NONE = 0, KZ_T_BWT = 1, KZ_T_BWTS = 2, KZ_T_LZ = 3, KZ_T_ZRLT = 6, KZ_T_MTFT = 7, KZ_T_RANK = 8, KZ_T_EXE = 9, KZ_T_TEXT = 10, KZ_T_ROLZ = 11, KZ_T_MM = 15, KZ_T_LZX = 16, KZ_T_UTF = 17, KZ_T_PACK = 18, KZ_T_DNA = 19 };
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
 int kz_device_count(void);

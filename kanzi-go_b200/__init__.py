@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(_HERE, "libkanzi_b200.so")
 E_NONE, E_HUFFMAN, E_RANGE, E_ANS0, E_ANS1 = 0, 1, 4, 5, 8
 T_NONE, T_BWT, T_BWTS, T_LZ, T_ROLZ, T_LZX = 0, 1, 2, 3, 11, 16
 T_ZRLT, T_MTFT, T_RANK = 6, 7, 8
-T_PACK, T_DNA, T_MM, T_TEXT, T_UTF = 18, 19, 15, 10, 17
+T_PACK, T_DNA, T_MM, T_TEXT, T_UTF, T_EXE = 18, 19, 15, 10, 17, 9
 ENTROPY_IDS = {"NONE": 0, "HUFFMAN": 1, "FPAQ": 2, "RANGE": 4, "ANS0": 5, "CM": 6, "TPAQ": 7, "ANS1": 8, "TPAQX": 9}
 TRANSFORM_IDS = {"NONE": 0, "BWT": 1, "BWTS": 2, "LZ": 3, "RLT": 5, "ZRLT": 6, "MTFT": 7, "RANK": 8, "EXE": 9, "TEXT": 10, "ROLZ": 11,
                  "ROLZX": 12, "SRT": 13, "LZP": 14, "MM": 15, "LZX": 16, "UTF": 17, "PACK": 18, "DNA": 19}

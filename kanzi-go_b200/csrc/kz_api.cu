@@ -23,6 +23,7 @@
 #include "kz_fsd.cuh"
 #include "kz_text.cuh"
 #include "kz_utf.cuh"
+#include "kz_exe.cuh"
 
 #include <memory>
 
@@ -816,13 +817,13 @@ struct TransformPlan {
     bool lzx() const { return nt == 1 && ids[0] == KZ_T_LZX; }
     static bool seq_id(uint64_t t) {
         return t == KZ_T_BWT || t == KZ_T_BWTS || t == KZ_T_RANK || t == KZ_T_MTFT || t == KZ_T_ZRLT || t == KZ_T_ROLZ || t == KZ_T_PACK || t == KZ_T_DNA || t == KZ_T_LZ ||
-               t == KZ_T_LZX || t == KZ_T_MM || t == KZ_T_TEXT || t == KZ_T_UTF;
+               t == KZ_T_LZX || t == KZ_T_MM || t == KZ_T_TEXT || t == KZ_T_UTF || t == KZ_T_EXE || t == KZ_T_EXE;
     }
     // any sequence of BWT / BWTS / RANK / MTFT / ZRLT / ROLZ stages (e.g. "BWT+RANK+ZRLT", the transform chain of kanzi -l 5)
     // stages that read ctx["dataType"] in a way the block's magic number can change (LZ / LZX only look for DNA / small alphabets)
     bool uses_magic() const {
         for (int i = 0; i < nt; i++)
-            if (ids[i] == KZ_T_ROLZ || ids[i] == KZ_T_PACK || ids[i] == KZ_T_DNA || ids[i] == KZ_T_MM || ids[i] == KZ_T_TEXT || ids[i] == KZ_T_UTF) return true;
+            if (ids[i] == KZ_T_ROLZ || ids[i] == KZ_T_PACK || ids[i] == KZ_T_DNA || ids[i] == KZ_T_MM || ids[i] == KZ_T_TEXT || ids[i] == KZ_T_UTF || ids[i] == KZ_T_EXE) return true;
         return false;
     }
     bool generic() const {
@@ -845,7 +846,7 @@ int plan_transforms(kz_ctx* ctx, uint64_t t48, TransformPlan& p, int err_code) {
     if (!experimental_stages()) {
         for (int i = 0; i < p.nt; i++) {
             const uint64_t t = p.ids[i];
-            const bool newer = t == KZ_T_PACK || t == KZ_T_DNA || t == KZ_T_MM || t == KZ_T_TEXT || t == KZ_T_UTF || ((t == KZ_T_LZ || t == KZ_T_LZX) && p.nt > 1);
+            const bool newer = t == KZ_T_PACK || t == KZ_T_DNA || t == KZ_T_MM || t == KZ_T_TEXT || t == KZ_T_UTF || t == KZ_T_EXE || ((t == KZ_T_LZ || t == KZ_T_LZX) && p.nt > 1);
             if (newer) return ctx->fail(err_code, "transform stage switched off by KZ_EXPERIMENTAL=0: PACK / DNA / MM / TEXT, LZ / LZX inside a sequence");
         }
     }
@@ -1069,6 +1070,42 @@ int apply_forward(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint64_t istride
                 }
             }
         }
+    } else if (t == KZ_T_EXE) {  // EXECodec.Forward: declines unless the block is x86 / ARM64 code
+        std::vector<ExeBlock> eb(nblocks);
+        for (uint32_t b = 0; b < nblocks; b++) {
+            const uint64_t mel = len[b] <= 256 ? (uint64_t)len[b] + 32 : (uint64_t)len[b] + len[b] / 8;  // MaxEncodedLen (:701-708)
+            if (active[b] && mel > ostride) return ctx->fail(KZ_ERR_UNKNOWN, "internal: stage buffer too small for EXE");
+            eb[b].src_off = b * istride;
+            eb[b].dst_off = b * ostride;
+            eb[b].len = active[b] ? len[b] : 0;
+            eb[b].cap = (uint32_t)std::min<uint64_t>(mel, 0xFFFFFFF0u);
+            eb[b].data_type = dts ? (*dts)[b] : 0;
+            eb[b].pad = 0;
+        }
+        Packer pk;
+        const size_t o_eb = pk.add(eb.data(), eb.size() * sizeof(ExeBlock));
+        const size_t o_res = pk.reserve((size_t)nblocks * sizeof(ExeResult));
+        int rc = upload(ctx, pk);
+        if (rc) return rc;
+        uint8_t* T = ctx->d_tables.as<uint8_t>();
+        {
+            LaunchScope ls(ctx, "exe_forward");
+            exe_forward_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_in, (const ExeBlock*)(T + o_eb), (int)nblocks, d_out, (ExeResult*)(T + o_res));
+            ctx->launches++;
+        }
+        CK(cudaGetLastError());
+        std::vector<ExeResult> hr(nblocks);
+        CK(cudaMemcpyAsync(hr.data(), T + o_res, (size_t)nblocks * sizeof(ExeResult), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t b = 0; b < nblocks; b++) {
+            if (!active[b] || len[b] == 0) continue;
+            if (hr[b].status < 0) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "EXE codec: malformed executable header (the reference panics on this block)");
+            if (dts) (*dts)[b] = hr[b].data_type;
+            if (hr[b].status == 0) {
+                applied[b] = 1;
+                len[b] = hr[b].out_len;
+            }
+        }
     } else if (t == KZ_T_MM) {  // FSDCodec.Forward: declines unless a fixed-step delta lowers the sampled entropy
         const uint32_t SUB = 1024;
         for (uint32_t b0 = 0; b0 < nblocks; b0 += SUB) {
@@ -1246,7 +1283,7 @@ int forward_generic(kz_ctx* ctx, const TransformPlan& plan, const uint8_t* d_src
     uint32_t max_len = 0;
     for (uint32_t b = 0; b < nblocks; b++) max_len = std::max(max_len, blen[b]);
     // room for the largest stage output: +33 bytes per BWT / SBRT stage, n/64 + 128 for LZ, n/16 for MM, headers of PACK
-    const uint64_t gstride = ((uint64_t)max_len + max_len / 16 + 33ull * plan.nt + 8192 + 1024 + 256 + 15) & ~15ull;
+    const uint64_t gstride = ((uint64_t)max_len + max_len / 8 + 33ull * plan.nt + 8192 + 1024 + 256 + 15) & ~15ull;
     CK(ctx->d_tmp.ensure(gstride * nblocks + 64));
     CK(ctx->d_tmp2.ensure(gstride * nblocks + 64));
     std::vector<uint32_t> len(blen);
@@ -1455,6 +1492,36 @@ int apply_inverse(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint8_t* d_out, 
                 if (hr[k].status) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "UTF inverse transform failed: invalid data");
                 len[b] = hr[k].out_len;
             }
+        }
+    } else if (t == KZ_T_EXE) {
+        std::vector<ExeBlock> eb(nblocks);
+        for (uint32_t b = 0; b < nblocks; b++) {
+            eb[b].src_off = b * stride;
+            eb[b].dst_off = b * stride;
+            eb[b].len = active[b] ? len[b] : 0;
+            eb[b].cap = cap;
+            eb[b].data_type = 0;
+            eb[b].pad = 0;
+        }
+        Packer pk;
+        const size_t o_eb = pk.add(eb.data(), eb.size() * sizeof(ExeBlock));
+        const size_t o_res = pk.reserve((size_t)nblocks * sizeof(ExeResult));
+        int rc = upload(ctx, pk);
+        if (rc) return rc;
+        uint8_t* T = ctx->d_tables.as<uint8_t>();
+        {
+            LaunchScope ls(ctx, "exe_inverse");
+            exe_inverse_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_in, (const ExeBlock*)(T + o_eb), (int)nblocks, d_out, (ExeResult*)(T + o_res));
+            ctx->launches++;
+        }
+        CK(cudaGetLastError());
+        std::vector<ExeResult> hr(nblocks);
+        CK(cudaMemcpyAsync(hr.data(), T + o_res, (size_t)nblocks * sizeof(ExeResult), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t b = 0; b < nblocks; b++) {
+            if (!active[b] || len[b] == 0) continue;
+            if (hr[b].status) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "ExeCodec inverse transform failed: invalid data");
+            len[b] = hr[b].out_len;
         }
     } else if (t == KZ_T_MM) {
         std::vector<FsdBlock> fb(nblocks);
@@ -1959,6 +2026,7 @@ size_t kz_transform_max_encoded_len(uint64_t type, size_t n) {
         case KZ_T_MM: return n + std::max<size_t>(n >> 4, 64);  // transform/FSDCodec.go:128-130
         case KZ_T_TEXT: return n;  // transform/TextCodec.go:1720-1724
         case KZ_T_UTF: return n + 8192;  // transform/UTFCodec.go:386-388
+        case KZ_T_EXE: return n <= 256 ? n + 32 : n + n / 8;  // transform/EXECodec.go:701-708
         case KZ_T_LZ:
         case KZ_T_LZX: return n <= 1024 ? n + 16 : n + n / 64;  // transform/LZCodec.go:935-941
         default: return 0;
@@ -2370,7 +2438,7 @@ int kz_entropy_decode(kz_ctx* ctx, uint32_t type, const uint8_t* src, size_t src
 }
 
 int kz_transform_forward(kz_ctx* ctx, uint64_t type, int* data_type, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n) {
-    if ((type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT || type == KZ_T_UTF) && ctx && !experimental_stages())
+    if ((type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT || type == KZ_T_UTF || type == KZ_T_EXE) && ctx && !experimental_stages())
         return ctx->fail(KZ_ERR_CREATE_CODEC, "transform switched off by KZ_EXPERIMENTAL=0: PACK / DNA / MM / TEXT");
     if (!ctx || (!src && n) || !dst || !out_n) return -KZ_ERR_INVALID_PARAM;
     CK(cudaSetDevice(ctx->device));
@@ -2397,11 +2465,11 @@ int kz_transform_forward(kz_ctx* ctx, uint64_t type, int* data_type, const uint8
         *out_n = jobs[0].post_len;
         return 0;
     }
-    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS || type == KZ_T_ROLZ || type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT || type == KZ_T_UTF) {  // SBRT / ZRLT / BWTS / ROLZ / Alias / FSD / Text / UTF Forward
+    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS || type == KZ_T_ROLZ || type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT || type == KZ_T_UTF || type == KZ_T_EXE) {  // SBRT / ZRLT / BWTS / ROLZ / Alias / FSD / Text / UTF / EXE Forward
         if (n == 0) return 0;
         if (n > (1u << 30)) return ctx->fail(KZ_ERR_BLOCK_SIZE, "block too large");
         if (cap < kz_transform_max_encoded_len(type, n)) return 1;  // Forward returns an error: the sequence skips the transform
-        const uint64_t stride = ((uint64_t)n + n / 16 + 8192 + 1024 + 64 + 64 + 15) & ~15ull;
+        const uint64_t stride = ((uint64_t)n + n / 8 + 8192 + 1024 + 64 + 64 + 15) & ~15ull;
         CK(ctx->d_in.ensure(stride));
         CK(ctx->d_out.ensure(stride));
         CK(cudaMemcpyAsync(ctx->d_in.p, src, n, cudaMemcpyHostToDevice, ctx->stream));
@@ -2445,7 +2513,7 @@ int kz_transform_forward(kz_ctx* ctx, uint64_t type, int* data_type, const uint8
 }
 
 int kz_transform_inverse(kz_ctx* ctx, uint64_t type, const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_n) {
-    if ((type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT || type == KZ_T_UTF) && ctx && !experimental_stages())
+    if ((type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT || type == KZ_T_UTF || type == KZ_T_EXE) && ctx && !experimental_stages())
         return ctx->fail(KZ_ERR_CREATE_CODEC, "transform switched off by KZ_EXPERIMENTAL=0: PACK / DNA / MM / TEXT");
     if (!ctx || (!src && n) || !dst || !out_n) return -KZ_ERR_INVALID_PARAM;
     CK(cudaSetDevice(ctx->device));
@@ -2472,7 +2540,7 @@ int kz_transform_inverse(kz_ctx* ctx, uint64_t type, const uint8_t* src, size_t 
         *out_n = olen[0];
         return 0;
     }
-    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS || type == KZ_T_ROLZ || type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT || type == KZ_T_UTF) {  // SBRT / ZRLT / BWTS / ROLZ / Alias / FSD / Text / UTF Inverse; cap = len(dst)
+    if (type == KZ_T_RANK || type == KZ_T_MTFT || type == KZ_T_ZRLT || type == KZ_T_BWTS || type == KZ_T_ROLZ || type == KZ_T_PACK || type == KZ_T_DNA || type == KZ_T_MM || type == KZ_T_TEXT || type == KZ_T_UTF || type == KZ_T_EXE) {  // SBRT / ZRLT / BWTS / ROLZ / Alias / FSD / Text / UTF / EXE Inverse; cap = len(dst)
         if (n == 0 || cap == 0) return 0;
         if (n > (1u << 30) || cap > (1u << 30) + 4096) return ctx->fail(KZ_ERR_BLOCK_SIZE, "block too large");
         const uint64_t stride = ((uint64_t)std::max(n, cap) + 64 + 15) & ~15ull;
