@@ -263,7 +263,8 @@ def main():
     for name in ("ans0_decode", "ans0_tables", "ans0_encode", "ans0_stats", "ans_walk", "concat", "concat_zero", "scan", "stream_walk", "block_header", "block_prefix", "extract",
                  "huf_stats", "huf_encode", "huf_walk", "huf_decode", "ans1_hist", "ans1_stats", "ans1_encode", "ans1_decode", "range_encode", "range_decode",
                  "bwt_forward", "bwt_inverse", "bwts_forward", "bwts_inverse", "lz_parse", "lz_gather", "lz_inverse", "sbrt_last2", "sbrt_carry", "sbrt_rank",
-                 "sbrt_inverse", "zrlt_forward", "zrlt_inverse", "xxhash", "host:encode_batch", "host:enc_tables", "host:enc_sync"):
+                 "sbrt_inverse", "zrlt_forward", "zrlt_inverse", "xxhash", "rolz_forward", "rolz_inverse", "alias_forward", "alias_inverse", "fsd_forward",
+                 "fsd_inverse", "text_forward", "text_inverse", "utf_forward", "utf_inverse", "exe_forward", "exe_inverse", "host:encode_batch", "host:enc_tables", "host:enc_sync"):
         cnt, ms = ctx.kernel_time(name)
         if cnt:
             kern[name] = {"launches": cnt, "ms_avg": ms / cnt}

@@ -70,6 +70,9 @@ def test_exe_core_real_binaries_and_headers(xc):
         bad = exe[: 1 << 20].copy()
         bad[0x28:0x30] = 0xFF                          # section table offset out of range: the reference indexes out of bounds
         _check(xc, bad)
+        neg = exe[: 1 << 20].copy()
+        neg[0x28:0x30] = [0x9C, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF]  # section table at offset -100: the reference panics
+        assert _check(xc, neg) == "panic"
         bad2 = exe[: 1 << 20].copy()
         bad2[0x3C:0x3E] = [0xFF, 0x7F]                 # absurd section count
         _check(xc, bad2)

@@ -43,16 +43,40 @@ def test_exe_transform_parity(gpu, oracle, synth, kz, n):
             assert np.array_equal(back, x), (cname, n, dt)
 
 
-def test_exe_malformed_header_is_a_block_error(gpu, oracle, synth, kz):
+def test_exe_malformed_headers_behave_like_the_oracle(gpu, oracle, synth, kz):
+    """header fields pointing outside the block: where the reference indexes out of bounds (a panic, i.e. a block error) the GPU reports an
+    error too; where it reads garbage and carries on, the GPU produces the same bytes"""
     exe = np.fromfile(sys.executable, dtype=np.uint8)
     if len(exe) < (1 << 20) or bytes(exe[:4]) != b"\x7fELF":
         pytest.skip("no ELF interpreter to borrow a header from")
-    bad = exe[: 1 << 20].copy()
-    bad[0x28:0x30] = 0xFF  # section table offset out of range: the reference indexes out of bounds and the block fails
-    with pytest.raises(oracle.OracleError):
-        oracle.transform_forward(T_EXE, bad)
-    with pytest.raises(kz.KanziError):
-        gpu.transform_forward(T_EXE, bad)
+    variants = []
+    for lo, hi, val in [(0x28, 0x30, 0xFF), (0x3C, 0x3E, 0xFF), (0x28, 0x30, 0x7F), (0x3A, 0x3C, 0xFF), (0x28, 0x2C, 0xF0)]:
+        bad = exe[: 1 << 20].copy()
+        bad[lo:hi] = val
+        variants.append(bad)
+    neg = exe[: 1 << 20].copy()
+    neg[0x28:0x30] = [0x9C, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF]  # section table at offset -100: a negative slice index panics
+    variants.append(neg)
+    mz = _synth_x86(1 << 16, 5).copy()
+    mz[:2] = [0x4D, 0x5A]
+    mz[60:64] = [0xF0, 0xFF, 0, 0]  # PE header offset near the end of the block
+    variants.append(mz)
+    macho = _synth_x86(1 << 16, 6).copy()
+    macho[:4] = [0xCF, 0xFA, 0xED, 0xFE]
+    macho[12:16] = [2, 0, 0, 0]
+    macho[16:20] = [40, 0, 0, 0]  # 40 load commands of random sizes
+    variants.append(macho)
+    for i, bad in enumerate(variants):
+        try:
+            want, wdt = oracle.transform_forward(T_EXE, bad)
+        except oracle.OracleError:
+            with pytest.raises(kz.KanziError):
+                gpu.transform_forward(T_EXE, bad)
+            continue
+        got, gdt = gpu.transform_forward(T_EXE, bad)
+        assert (want is None) == (got is None) and gdt == wdt, i
+        if want is not None:
+            assert np.array_equal(got, want), i
 
 
 @pytest.mark.parametrize("bs", [8192, 1 << 17])
