@@ -1,0 +1,67 @@
+"""Next-round preparation, CPU only: the three-phase TEXT forward (kanzi-go_b200/csrc/next/kz_text_par_core.cuh: candidate words in
+parallel, dictionary pass over the candidates only, parallel emission) reproduces the one-pass walk the GPU runs today."""
+import ctypes as C
+import importlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from test_text_core_host import _words
+
+synth = importlib.import_module("kanzi-go_b200.synth")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "host", "text_par_host.cpp")
+SO = os.path.join(ROOT, "tests", "host", "_build", "libtext_par_host.so")
+
+
+@pytest.fixture(scope="module")
+def tp():
+    gen = importlib.import_module("kanzi-go_b200.gen_text_dict")
+    if not gen.main():
+        pytest.skip("static dictionary not available")
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    deps = [SRC, os.path.join(ROOT, "kanzi-go_b200", "csrc", "next", "kz_text_par_core.cuh"), os.path.join(ROOT, "kanzi-go_b200", "csrc", "kz_text_core.cuh")]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-o", SO, SRC])
+    lib = C.CDLL(SO)
+    lib.tp_walk.restype = C.c_int64
+    lib.tp_walk.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int]
+    lib.tp_phases.restype = C.c_int64
+    lib.tp_phases.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    return lib
+
+
+def _same(tp, x, bs, mode=0):
+    x = np.ascontiguousarray(x, np.uint8)
+    a = np.zeros(len(x) + 64, np.uint8)
+    b = np.zeros(len(x) + 64, np.uint8)
+    nc, nf = C.c_int(0), C.c_int(0)
+    na = tp.tp_walk(x.ctypes.data, len(x), a.ctypes.data, bs, mode)
+    nb = tp.tp_phases(x.ctypes.data, len(x), b.ctypes.data, bs, mode, C.byref(nc), C.byref(nf))
+    assert na == nb, (na, nb)
+    if na > 0:
+        assert np.array_equal(a[:na], b[:nb])
+    return na, nc.value, nf.value
+
+
+@pytest.mark.parametrize("n,bs", [(1024, 1024), (5000, 4096), (100000, 1 << 16), (1 << 20, 1 << 20), (3 << 20, 4 << 20)])
+def test_three_phases_match_the_walk(tp, n, bs):
+    for x in (synth.markov_text(n, seed=n), _words(n, 50, n + 1), _words(n, 5000, n + 2, crlf=True)):
+        for mode in (0, 0x40, 0x20):
+            na, nc, nf = _same(tp, x, bs, mode)
+            assert na > 0 and 0 < nf <= nc < n / 2  # the serial pass touches far fewer items than the block has bytes
+    spaces = np.concatenate([np.full(50, 0x20, np.uint8), synth.markov_text(n, seed=3)[: n - 50]])
+    _same(tp, spaces, bs)
+    dense = np.frombuffer((b"the and that have with " * (n // 23 + 1))[:n], np.uint8)  # every word is in the dictionary: single spaces implied
+    _same(tp, dense, bs)
+    hard = np.random.default_rng(n).integers(0, 256, n).astype(np.uint8)  # the walk itself does not care whether the block is text
+    _same(tp, hard, bs)
+    incompressible = _words(n, 200000, n + 4)  # few repeats: the output can exceed the bound -> both report the skip
+    _same(tp, incompressible, bs)
+
+
+def test_three_phases_dictionary_wrap(tp):
+    na, nc, nf = _same(tp, _words(12 << 20, 700000, 7), 16 << 20)
+    assert na > 0
