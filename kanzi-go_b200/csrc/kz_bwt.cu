@@ -210,11 +210,13 @@ KZ_D uint32_t ibwt_head_id(uint32_t t, uint32_t nstride, const uint32_t* prim, u
 // walk 1: one thread per sub-list head: length of the sub-list and id of the next head (END = 0xFFFFFFFF)
 __global__ void ibwt_measure_kernel(const uint32_t* __restrict__ next, uint32_t n, const uint32_t* __restrict__ prim_rank, uint32_t nprim,
                                     uint32_t nstride, uint32_t* __restrict__ succ, uint32_t* __restrict__ len) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nstride + nprim) return;
+    // the primary ranks are staged by the first 8 threads of EVERY CTA before any thread leaves: the last CTA holds the primary heads and
+    // may have fewer than 8 live threads (a block whose head count is 1..7 modulo the CTA size used to read stale shared memory here)
     __shared__ uint32_t s_prim[8];
     if (threadIdx.x < 8) s_prim[threadIdx.x] = threadIdx.x < nprim ? prim_rank[threadIdx.x] : 0xFFFFFFFFu;
     __syncthreads();
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nstride + nprim) return;
     uint32_t t = j < nstride ? j * IBWT_STRIDE : s_prim[j - nstride];
     if (t >= n || (j >= nstride && (t & (IBWT_STRIDE - 1)) == 0)) {  // duplicate head (primary rank on a stride multiple) or out of range
         succ[j] = 0xFFFFFFFEu;                                        // marks "unused"
