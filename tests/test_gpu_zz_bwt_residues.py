@@ -24,3 +24,49 @@ def test_bwt_inverse_head_count_residues(gpu, oracle, synth, kz, bs):
     for p in parts:
         w, _ = oracle.transform_forward(oracle.T_BWT, p)
         assert np.array_equal(gpu.transform_inverse(kz.T_BWT, w, bs + 64), p)
+
+
+def test_bwt_every_head_count_residue(gpu, oracle, synth, kz):
+    """BWT forward + inverse at 256 consecutive head counts (n = 15,000 + 64 k): every residue of the head count modulo the CTA size of the
+    list-ranking kernels, alternating data so that consecutive launches leave different values behind"""
+    for k in range(256):
+        n = 15000 + 64 * k
+        x = synth.markov_text(n, seed=k) if k % 3 else synth.zipf_bytes(n, 1.3, seed=k)
+        want, _ = oracle.transform_forward(oracle.T_BWT, x)
+        got, _ = gpu.transform_forward(kz.T_BWT, x)
+        assert np.array_equal(got, want), (k, n)
+        assert np.array_equal(gpu.transform_inverse(kz.T_BWT, want, n + 64), x), (k, n)
+
+
+@pytest.mark.parametrize("name", ["RANK", "MTFT", "ZRLT", "PACK", "MM", "LZ", "LZX", "ROLZ", "TEXT", "UTF"])
+def test_transform_size_sweep(gpu, oracle, synth, kz, name):
+    """sizes around the tile / segment / chunk sizes of the kernels (4096, 8192, 16384) and odd sizes in between, several blocks per call
+    through the stream path so that launches follow each other with different lengths"""
+    sizes = sorted({4096 * m + d for m in (1, 2, 4, 5) for d in (-17, -16, -1, 0, 1, 15, 16, 17, 511, 1023, 2047)})
+    r = np.random.default_rng(7)
+    for n in sizes:
+        if name == "UTF":
+            words = ["héllo", "wörld", "日本語", "данные", "abc", " ", "\n", "€"]
+            x = np.frombuffer("".join(r.choice(words, n)).encode("utf-8")[:n], np.uint8)
+        elif name == "MM":
+            t = np.arange(n)
+            x = (128 + 100 * np.sin(t / 40.0) + r.normal(0, 1.5, n)).astype(np.uint8)
+        elif name == "PACK":
+            x = np.frombuffer(b"0123456789abcdef", np.uint8)[r.integers(0, 16, n)] if n % 2 else synth.markov_text(n, seed=n)
+        else:
+            x = synth.markov_text(n, seed=n)
+        t = kz.TRANSFORM_IDS[name]
+        if name == "TEXT":
+            gpu.set_stream_block_size(1 << 16)
+            want, wdt = oracle.transform_forward(t, x, 0, block_size=1 << 16)
+        else:
+            want, wdt = oracle.transform_forward(t, x)
+        try:
+            got, gdt = gpu.transform_forward(t, x)
+            assert (want is None) == (got is None) and gdt == wdt, (name, n)
+            if want is not None:
+                assert np.array_equal(got, want), (name, n)
+                assert np.array_equal(gpu.transform_inverse(t, want, n + 4096), x), (name, n)
+        finally:
+            if name == "TEXT":
+                gpu.set_stream_block_size(0)
