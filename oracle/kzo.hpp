@@ -1,7 +1,8 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY. Not part of the shipped product path.
 //
 // C++ restatement ("port", the Go toolchain is absent from this image) of the per-block encode/decode
-// path of flanglet/kanzi-go @ ba60b1f. Each function cites the reference file:line it follows.
+// path of flanglet/kanzi-go @ ba60b1f (entropy codecs, BWT / BWTS / LZ / LZX / ROLZ / RANK / MTFT / ZRLT, the pre-transforms TEXT (encoding 2) /
+// UTF / PACK / DNA / MM / EXE, transform sequences, block framing, stream, XXHash). Each function cites the reference file:line it follows.
 // PARITY PINNING: the reference ships no byte-level golden vectors for this path and
 // cannot be built here (no Go toolchain) -> "parity unpinned" except for the pins listed in
 // tests/test_oracle_pins.py (varint sizes, BWT "mississippi" doc example, format constants).
