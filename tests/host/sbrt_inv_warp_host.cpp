@@ -1,32 +1,49 @@
-// NEXT ROUND — CPU model of the planned warp-resident RANK / MTFT inverse (tests/test_sbrt_inv_warp_host.py): the list lives in 32 lanes
-// x 8 consecutive ranks, the new rank of the decoded symbol is the number of entries above it whose q is larger than the new q (a ballot /
-// popc over a comparison, valid because the list is always sorted by q), and the move-up is a shift of the ranks in between.
-// Reference: v2/transform/SBRT.go:177-226 (Inverse), modes :93-111.
+// NEXT ROUND — CPU model of the planned warp-resident RANK / MTFT inverse (tests/test_sbrt_inv_warp_host.py), written lane by lane the way
+// the kernel (kanzi-go_b200/csrc/next/kz_sbrt_warp.cu) moves data: 32 lanes x 8 consecutive ranks of 64-bit entries
+// (q << 35 | p << 8 | symbol), the decoded symbol fetched with one shuffle, the new rank from a popc over "entry above rank r with a larger q"
+// (valid because the list is always sorted by q), the move-up as a predicated register shift per lane plus one shuffle-up for the lane
+// boundaries. Reference: v2/transform/SBRT.go:177-226 (Inverse), modes :93-111.
 #include <cstdint>
 
+namespace {
+inline uint64_t pack(int64_t q, int64_t p, uint32_t sym) { return (uint64_t(q) << 35) | (uint64_t(p) << 8) | sym; }  // q, p < 2^27
+inline int64_t ent_q(uint64_t e) { return int64_t(e >> 35); }
+inline int64_t ent_p(uint64_t e) { return int64_t((e >> 8) & ((1ull << 27) - 1)); }
+}  // namespace
+
 extern "C" int64_t sbrt_inverse_warp_model(int mode, const uint8_t* src, int64_t n, uint8_t* dst) {
-    const int m2 = mode == 2 ? -1 : 0, s = mode == 2 ? 1 : 0;  // MTFT: qc = i; RANK: qc = (i + p[c]) >> 1
-    struct E {
-        int32_t q, p;
-        uint8_t sym;
-    };
-    E lane[32][8];  // lane l holds ranks 8 l .. 8 l + 7
-    for (int r = 0; r < 256; r++) lane[r >> 3][r & 7] = E{0, 0, uint8_t(r)};
+    const bool rank_mode = mode == 2;  // MTFT: qc = i; RANK: qc = (i + p[c]) >> 1
+    uint64_t e[32][8];
+    for (int l = 0; l < 32; l++)
+        for (int k = 0; k < 8; k++) e[l][k] = pack(0, 0, uint32_t(8 * l + k));
     for (int64_t i = 0; i < n; i++) {
         const int r = src[i];
-        const E cur = lane[r >> 3][r & 7];  // one shuffle from lane r / 8
-        dst[i] = cur.sym;
-        const int32_t qc = int32_t(((i & -1) + (int64_t(cur.p) & m2)) >> s);
-        // every lane counts its entries above rank r with q > qc; the sum is the new rank (one popc-add reduction)
+        // shuffle: lane r >> 3 selects its register r & 7 and broadcasts it
+        const uint64_t cur = e[r >> 3][r & 7];
+        dst[i] = uint8_t(cur);
+        const int64_t qc = rank_mode ? ((i + ent_p(cur)) >> 1) : i;
+        // per lane: entries at ranks < r with q > qc; warp sum = new rank
         int nr = 0;
-        for (int l = 0; l < 32; l++)
-            for (int k = 0; k < 8; k++) {
+        for (int l = 0; l < 32; l++) {
+            int c = 0;
+            for (int k = 0; k < 8; k++)
+                if (8 * l + k < r && ent_q(e[l][k]) > qc) c++;
+            nr += c;
+        }
+        // per lane, in place: the last register of every lane before the shift (for the shuffle-up), then k = 7 .. 1, then k = 0
+        uint64_t last[32];
+        for (int l = 0; l < 32; l++) last[l] = e[l][7];
+        const uint64_t fresh = pack(qc, i, uint32_t(cur & 0xFF));
+        for (int l = 0; l < 32; l++) {
+            for (int k = 7; k >= 1; k--) {
                 const int rank = 8 * l + k;
-                if (rank < r && lane[l][k].q > qc) nr++;
+                if (rank > nr && rank <= r) e[l][k] = e[l][k - 1];
             }
-        // ranks nr .. r-1 move down by one: inside a lane a register shift, across lanes one shuffle of the lane's last entry
-        for (int rank = r; rank > nr; rank--) lane[rank >> 3][rank & 7] = lane[(rank - 1) >> 3][(rank - 1) & 7];
-        lane[nr >> 3][nr & 7] = E{qc, int32_t(i), cur.sym};
+            const int rank0 = 8 * l;
+            if (rank0 > nr && rank0 <= r) e[l][0] = last[l - 1];  // shuffle-up by one lane (lane 0 never takes this branch: rank0 = 0)
+            for (int k = 0; k < 8; k++)
+                if (8 * l + k == nr) e[l][k] = fresh;
+        }
     }
     return n;
 }
