@@ -1,17 +1,23 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200 block-compression engine (contract: see the task statement / DESIGN.md).
 
-Workload at N=1 (BASELINE.json configs[1]): `-e ANS0 -t NONE`, 256 MiB of Zipf(1.0) bytes, 64 x 4 MiB blocks.
-A "step" is one pass of the hot path over that batch: compress the whole slab to a kanzi bitstream, then decompress it.
+Default workload at N=1 = the configuration BASELINE.json's `metric` is quoted on: a 200,000,000-byte silesia.tar-shaped
+slab (kanzi-go_b200/synth.py: silesia_shaped), 4 MiB blocks (48 blocks), compressed and decompressed at
+kanzi `-l 3` (TEXT+UTF+PACK+MM+LZX & HUFFMAN) AND `-l 5` (TEXT+UTF+BWT+RANK+ZRLT & ANS0) (app/BlockCompressor.go:665-700).
+A "step" is one pass of the hot path over that slab: compress + decompress at -l 3, then compress + decompress at -l 5.
 
-  value  = uncompressed bytes through (encode + decode) per second with inputs resident in HBM (device API), MB = 1e6 B
+  value  = uncompressed bytes through the four passes per second (MB = 1e6 B), inputs resident in HBM (device API);
+           config.levels holds encode / decode / combined MB/s of each level
   e2e    = the same through the host-buffer C ABI (kz_compress_stream / kz_decompress_stream) from pinned host
            memory, host<->device copies inside the timed region
-  roofline: dominant kernel ans0_decode, achieved = (compressed bytes read + decoded bytes written) / CUDA-event time
+  roofline: the kernel with the largest share of the step; achieved = algorithmic bytes of its stage (stage input +
+           stage output bytes over the batch) / CUDA-event time of the launch
   cpu_baseline / --impl reference: the C++ restatement of the reference path (oracle/, "port": no Go toolchain here)
-           with one worker per block on all host cores, on a bounded sample of the same workload.
-With N > 1 ranks every rank processes its own 64-block slab (weak scaling, no data-path collective: blocks are
-independent); time = max over ranks.
+           with one worker per block on all host cores, same slab, same levels.
+With N > 1 ranks: see --mode. "weak" (default): every rank processes its own slab (no data-path collective: blocks are
+independent); "sharded": ONE slab on rank 0, block ranges scattered over NCCL, encoded shards gathered and
+committed in order on rank 0 (and the mirror for decode) — reported inside the same line under "sharded".
+Other workloads (--workload) are single-pass lines used for profiles/ (configs[1], configs[4] points, sub-pipelines).
 """
 import argparse
 import importlib
@@ -28,31 +34,36 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-BLOCK = 4 << 20
-NBLOCKS = 64
-METRIC = "encode+decode MB/s (ANS0/NONE, 64x4MiB Zipf(1.0) blocks per GPU)"
-
-# The default workload is BASELINE.json configs[1] (the configuration the roofline target is quoted on). The others are
-# the GPU-covered parts of the remaining configs, run by hand with --workload and recorded under profiles/ (they are
-# parity-test cases first; the driver's bench line is always the default).
-#   name: (transform, entropy, block size, blocks per GPU, data generator, dominant kernel for the roofline, metric label)
+L3 = ("l3", "TEXT+UTF+PACK+MM+LZX", "HUFFMAN")
+L5 = ("l5", "TEXT+UTF+BWT+RANK+ZRLT", "ANS0")
+# name: (passes [(label, transform, entropy)], block size, bytes per GPU, data generator, metric label)
 WORKLOADS = {
-    "ans0": ("NONE", "ANS0", 4 << 20, 64, "zipf1", "ans0_decode", METRIC),
-    "huffman": ("NONE", "HUFFMAN", 4 << 20, 64, "zipf1", "huf_decode", "encode+decode MB/s (HUFFMAN/NONE, 64x4MiB Zipf(1.0) blocks per GPU)"),
-    "ans1": ("NONE", "ANS1", 4 << 20, 64, "text", "ans1_decode", "encode+decode MB/s (ANS1/NONE, 64x4MiB order-1 text blocks per GPU; configs[4] at 4 MiB)"),
-    "l3core": ("LZX", "HUFFMAN", 4 << 20, 48, "text", "lz_parse",
-               "encode+decode MB/s (-t LZX -e HUFFMAN, 48x4MiB text blocks: the GPU covered part of kanzi -l 3, configs[2] shape)"),
-    "l5core": ("BWT+RANK+ZRLT", "ANS0", 32 << 20, 4, "text", "bwt_forward",
-               "encode+decode MB/s (-t BWT+RANK+ZRLT -e ANS0, 4x32MiB text blocks: the GPU covered part of kanzi -l 5, configs[3] shape)"),
-    "l5core4m": ("BWT+RANK+ZRLT", "ANS0", 4 << 20, 16, "text", "bwt_forward",
-                 "encode+decode MB/s (-t BWT+RANK+ZRLT -e ANS0, 16x4MiB text blocks)"),
-    # complete level chains (app/BlockCompressor.go:664-700); TEXT / UTF walk their blocks with one thread each
-    "l2": ("DNA+LZ", "HUFFMAN", 4 << 20, 48, "text", "lz_parse", "encode+decode MB/s (kanzi -l 2 = -t DNA+LZ -e HUFFMAN, 48x4MiB text blocks)"),
-    "l3": ("TEXT+UTF+PACK+MM+LZX", "HUFFMAN", 4 << 20, 48, "text", "lz_parse",
-           "encode+decode MB/s (kanzi -l 3 = -t TEXT+UTF+PACK+MM+LZX -e HUFFMAN, 48x4MiB text blocks, configs[2] shape)"),
-    "l5": ("TEXT+UTF+BWT+RANK+ZRLT", "ANS0", 4 << 20, 16, "text", "bwt_forward",
-           "encode+decode MB/s (kanzi -l 5 = -t TEXT+UTF+BWT+RANK+ZRLT -e ANS0, 16x4MiB text blocks)"),
+    "silesia": ([L3, L5], 4 << 20, 200_000_000, "silesia",
+                "encode+decode MB/s, 200 MB silesia-shaped slab, kanzi -l 3 and -l 5, 4 MiB blocks"),
+    "silesia_l3": ([L3], 4 << 20, 200_000_000, "silesia", "encode+decode MB/s, 200 MB silesia-shaped slab, kanzi -l 3"),
+    "silesia_l5": ([L5], 4 << 20, 200_000_000, "silesia", "encode+decode MB/s, 200 MB silesia-shaped slab, kanzi -l 5"),
+    "enwik_l5": ([L5], 32 << 20, 256 << 20, "enwik", "encode+decode MB/s, 256 MiB enwik-shaped text, kanzi -l 5 -b 32m (configs[3] shape, 8 blocks)"),
+    "ans0": ([("ans0", "NONE", "ANS0")], 4 << 20, 64 * (4 << 20), "zipf1", "encode+decode MB/s (ANS0/NONE, 64x4MiB Zipf(1.0) blocks per GPU; BASELINE.json configs[1])"),
+    "huffman": ([("huffman", "NONE", "HUFFMAN")], 4 << 20, 64 * (4 << 20), "zipf1", "encode+decode MB/s (HUFFMAN/NONE, 64x4MiB Zipf(1.0) blocks per GPU)"),
+    "ans1": ([("ans1", "NONE", "ANS1")], 4 << 20, 64 * (4 << 20), "text", "encode+decode MB/s (ANS1/NONE, 64x4MiB order-1 text blocks per GPU; configs[4] at 4 MiB)"),
+    "l3core": ([("l3core", "LZX", "HUFFMAN")], 4 << 20, 48 * (4 << 20), "text", "encode+decode MB/s (-t LZX -e HUFFMAN, 48x4MiB text blocks)"),
+    "l5core": ([("l5core", "BWT+RANK+ZRLT", "ANS0")], 32 << 20, 4 * (32 << 20), "text", "encode+decode MB/s (-t BWT+RANK+ZRLT -e ANS0, 4x32MiB text blocks)"),
+    "l5core4m": ([("l5core4m", "BWT+RANK+ZRLT", "ANS0")], 4 << 20, 16 * (4 << 20), "text", "encode+decode MB/s (-t BWT+RANK+ZRLT -e ANS0, 16x4MiB text blocks)"),
+    "l2": ([("l2", "DNA+LZ", "HUFFMAN")], 4 << 20, 48 * (4 << 20), "text", "encode+decode MB/s (kanzi -l 2 = -t DNA+LZ -e HUFFMAN, 48x4MiB text blocks)"),
+    "l1": ([("l1", "LZX", "NONE")], 4 << 20, 200_000_000, "silesia", "encode+decode MB/s, 200 MB silesia-shaped slab, kanzi -l 1"),
+    "l4": ([("l4", "TEXT+UTF+EXE+PACK+MM+ROLZ", "NONE")], 4 << 20, 200_000_000, "silesia", "encode+decode MB/s, 200 MB silesia-shaped slab, kanzi -l 4"),
+    "l3": ([L3], 4 << 20, 48 * (4 << 20), "text", "encode+decode MB/s (kanzi -l 3, 48x4MiB markov text blocks)"),
+    "l5": ([L5], 4 << 20, 16 * (4 << 20), "text", "encode+decode MB/s (kanzi -l 5, 16x4MiB markov text blocks)"),
 }
+for _bs in (1, 2, 4, 8, 16, 32, 64):  # BASELINE.json configs[4]: ANS1 block-size sweep over 256 MiB of order-1 text
+    WORKLOADS["ans1_%dm" % _bs] = ([("ans1", "NONE", "ANS1")], _bs << 20, 256 << 20, "text",
+                                   "encode+decode MB/s (ANS1/NONE, 256 MiB order-1 text, %d MiB blocks; configs[4])" % _bs)
+
+# kernel name -> (stage the kernel belongs to, as kz_stage_bytes names it) for the roofline's algorithmic bytes
+STAGE_OF = {"lz_parse": "fwd:16", "lz_gather": "fwd:16", "lz_inverse": "inv:16", "text_forward": "fwd:10", "text_inverse": "inv:10", "utf_forward": "fwd:17",
+            "utf_inverse": "inv:17", "bwt_forward": "fwd:1", "bwt_inverse": "inv:1", "sbrt_rank": "fwd:8", "sbrt_inverse": "inv:8", "zrlt_forward": "fwd:6",
+            "zrlt_inverse": "inv:6", "alias_forward": "fwd:18", "alias_inverse": "inv:18", "fsd_forward": "fwd:15", "fsd_inverse": "inv:15",
+            "rolz_forward": "fwd:11", "rolz_inverse": "inv:11", "exe_forward": "fwd:9", "exe_inverse": "inv:9"}
 
 
 def make_data(kind, n, seed):
@@ -61,6 +72,10 @@ def make_data(kind, n, seed):
         return synth.zipf_bytes(n, 1.0, seed=seed)
     if kind == "text":
         return synth.markov_text(n, seed=seed)
+    if kind == "silesia":
+        return synth.silesia_shaped(n, seed=seed)
+    if kind == "enwik":
+        return synth.enwik_shaped(n, seed=seed)
     raise ValueError(kind)
 
 
@@ -70,7 +85,7 @@ def measured_traffic(kernel):
     import glob
 
     best = None
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu*summary*.json")), key=lambda f: ("final" in os.path.basename(f), os.path.basename(f)))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02*ncu*summary*.json")), key=lambda f: ("final" in os.path.basename(f), os.path.basename(f)))
     for f in files:  # the capture named "final" wins, otherwise the highest generation
         try:
             for k in json.load(open(f)).get("kernels", []):
@@ -122,38 +137,48 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def cpu_reference(steps, warmup, sample_blocks=None, workload="ans0"):
-    """Times the CPU restatement of the reference path (oracle) with one worker per block on all host cores."""
+def cpu_reference(steps, warmup, workload, max_seconds=60.0):
+    """Times the CPU restatement of the reference path (oracle) with one worker per block on all host cores: the same slab and the
+    same passes as the GPU arm. Bounded: stops taking further steps once max_seconds of CPU work were spent."""
     from oracle import pyoracle
 
     synth = importlib.import_module("kanzi-go_b200.synth")
-    transform, entropy, BLOCK, NBLOCKS, kind = WORKLOADS[workload][:5]
+    passes, BLOCK, n, kind, _ = WORKLOADS[workload]
     cores = os.cpu_count() or 1
     jobs = min(64, cores)
-    if sample_blocks is None:
-        sample_blocks = NBLOCKS  # the full batch is ~1-3 s of CPU work per step on a multi-core host
-    n = sample_blocks * BLOCK
     x = make_data(kind, n, synth.SEED + 1)
-    times = []
+    times, per = [], {}
+    t_all = time.perf_counter()
     for it in range(warmup + steps):
-        te, td = [], []
-        s = pyoracle.compress(x, transform, entropy, block_size=BLOCK, jobs=jobs, input_size=n, timing=te)
-        y = pyoracle.decompress(s, n + 64, jobs=jobs, timing=td)
-        if it == 0:
-            assert np.array_equal(y, x)
+        tot = 0.0
+        for label, transform, entropy in passes:
+            te, td = [], []
+            s = pyoracle.compress(x, transform, entropy, block_size=BLOCK, jobs=jobs, input_size=n, timing=te)
+            y = pyoracle.decompress(s, n + 64, jobs=jobs, timing=td)
+            if it == 0:
+                assert np.array_equal(y, x)
+            tot += te[0] + td[0]
+            if it >= warmup or it == warmup + steps - 1:
+                per[label] = {"encode_MBps": n / te[0] / 1e6, "decode_MBps": n / td[0] / 1e6, "MBps": 2 * n / (te[0] + td[0]) / 1e6, "compressed_bytes": int(len(s))}
         if it >= warmup:
-            times.append(te[0] + td[0])
+            times.append(tot)
+        if time.perf_counter() - t_all > max_seconds and times:
+            break
     t = float(np.mean(times))
-    return {"value": 2 * n / t / 1e6, "unit": "MB/s", "cores": jobs, "kind": "port",
-            "sample": "%d x %d MiB %s blocks (%d MiB), -t %s -e %s, compress+decompress in memory, %d worker threads, C++ restatement of kanzi-go (no Go toolchain)"
-                      % (sample_blocks, BLOCK >> 20, kind, n >> 20, transform, entropy, jobs),
-            "ms_per_step": t * 1e3}
+    return {"value": 2 * n * len(passes) / t / 1e6, "unit": "MB/s", "cores": jobs, "kind": "port",
+            "sample": "the whole workload (%d bytes of %s data, %d-byte blocks; %s), compress+decompress in memory, %d worker threads, %d timed step(s); "
+                      "C++ restatement of kanzi-go (no Go toolchain in this image)"
+                      % (n, kind, BLOCK, " and ".join("-t %s -e %s" % (p[1], p[2]) for p in passes), jobs, len(times)),
+            "ms_per_step": t * 1e3, "levels": per, "steps": len(times)}
 
 
 def workload_label(name):
-    transform, entropy, block, nblocks, kind = WORKLOADS[name][:5]
-    label = "%s/%s %dx%dMiB %s" % (entropy, transform, nblocks, block >> 20, {"zipf1": "Zipf(1.0)", "text": "order-1 text"}[kind])
-    return label + (" (BASELINE.json configs[1])" if name == "ans0" else "")
+    passes, block, n, kind, _ = WORKLOADS[name]
+    data = {"zipf1": "Zipf(1.0) bytes", "text": "order-1 markov text", "silesia": "silesia.tar-shaped mix (synth.silesia_shaped: 35% text, 25% x86-like, 15% records, 10% 16-bit walks, 10% XML, 5% random)",
+            "enwik": "enwik9-shaped text (synth.enwik_shaped)"}[kind]
+    lv = " and ".join("%s (-t %s -e %s)" % (p[0], p[1], p[2]) for p in passes)
+    return "%d bytes of %s, %d blocks of %d MiB, %s" % (n, data, (n + block - 1) // block, block >> 20, lv) + \
+        (" (BASELINE.json metric configuration)" if name == "silesia" else "")
 
 
 def emit(line):
@@ -169,13 +194,16 @@ os.dup2(2, 1)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="ans0", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mode", default="auto", choices=["auto", "weak", "sharded"])
+    ap.add_argument("--workload", default="silesia", choices=sorted(WORKLOADS))
     args = ap.parse_args()
-    transform, entropy, BLOCK, NBLOCKS, kind, roof_kernel, METRIC = WORKLOADS[args.workload]
+    passes, BLOCK, n, kind, METRIC = WORKLOADS[args.workload]
+    NBLOCKS = (n + BLOCK - 1) // BLOCK
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -185,11 +213,11 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        steps = min(args.steps, 5)
-        r = cpu_reference(steps, min(args.warmup, 1), workload=args.workload)
-        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "MB/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        steps = min(args.steps, 3)
+        r = cpu_reference(steps, 1, args.workload)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "MB/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": 1,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "%s, CPU path" % workload_label(args.workload), "block_size": BLOCK, "blocks": NBLOCKS},
+                "config": {"workload": workload_label(args.workload), "block_size": BLOCK, "blocks_per_gpu": NBLOCKS, "levels": r["levels"], "path": "CPU"},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         emit(line)
@@ -207,23 +235,17 @@ def main():
     synth = importlib.import_module("kanzi-go_b200.synth")
     torch.cuda.set_device(local_rank)
     ctx = kz.Context(local_rank)
-    n = NBLOCKS * BLOCK
     x = make_data(kind, n, synth.SEED + 1 + rank)
-    t48, et = kz.transform_type(transform), kz.entropy_type(entropy)
     cap = int(ctx.lib.kz_max_stream_output(n, BLOCK))
+    P = [(label, kz.transform_type(tr), kz.entropy_type(en)) for label, tr, en in passes]
 
     # ---------------- device-resident pass (value) ----------------
     d_src = torch.empty(n + 256, dtype=torch.uint8, device="cuda")
-    d_cmp = torch.zeros(cap + 256, dtype=torch.uint8, device="cuda")
+    d_cmp = [torch.zeros(cap + 256, dtype=torch.uint8, device="cuda") for _ in P]
     d_dec = torch.empty(n + 256, dtype=torch.uint8, device="cuda")
     d_src[:n].copy_(torch.from_numpy(x))
     torch.cuda.synchronize()
     ext = torch.cuda.ExternalStream(ctx.cuda_stream())
-
-    def step_device():
-        m = ctx.compress_device(d_src.data_ptr(), n, d_cmp.data_ptr(), cap, t48, et, BLOCK, 0, n)
-        k = ctx.decompress_device(d_cmp.data_ptr(), m, d_dec.data_ptr(), n)
-        return m, k
 
     def barrier():
         torch.cuda.synchronize()
@@ -231,10 +253,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    m = 0
+    m = [0] * len(P)
     for _ in range(args.warmup):
-        m, k = step_device()
-    assert k == n and torch.equal(d_dec[:n], d_src[:n]), "round trip mismatch"
+        for i, (label, t48, et) in enumerate(P):
+            m[i] = ctx.compress_device(d_src.data_ptr(), n, d_cmp[i].data_ptr(), cap, t48, et, BLOCK, 0, n)
+            d_dec.zero_()
+            k = ctx.decompress_device(d_cmp[i].data_ptr(), m[i], d_dec.data_ptr(), n)
+            assert k == n and torch.equal(d_dec[:n], d_src[:n]), "round trip mismatch at %s" % label
     sampler = ClockSampler(local_rank)
     sampler.start()
     ctx.profile(True)
@@ -242,109 +267,135 @@ def main():
     ctx.launch_count(reset=True)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    enc_ms = dec_ms = 0.0
+    enc_ms = [0.0] * len(P)
+    dec_ms = [0.0] * len(P)
     with torch.cuda.stream(ext):
         e0.record()
         for _ in range(args.steps):
-            a, b, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            m = ctx.compress_device(d_src.data_ptr(), n, d_cmp.data_ptr(), cap, t48, et, BLOCK, 0, n)
-            b.record()
-            ctx.decompress_device(d_cmp.data_ptr(), m, d_dec.data_ptr(), n)
-            c.record()
-            c.synchronize()
-            enc_ms += a.elapsed_time(b)
-            dec_ms += b.elapsed_time(c)
+            for i, (label, t48, et) in enumerate(P):
+                a, b, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                m[i] = ctx.compress_device(d_src.data_ptr(), n, d_cmp[i].data_ptr(), cap, t48, et, BLOCK, 0, n)
+                b.record()
+                ctx.decompress_device(d_cmp[i].data_ptr(), m[i], d_dec.data_ptr(), n)
+                c.record()
+                c.synchronize()
+                enc_ms[i] += a.elapsed_time(b)
+                dec_ms[i] += b.elapsed_time(c)
         e1.record()
     barrier()
     dev_ms = e0.elapsed_time(e1)
     launches = ctx.launch_count(reset=True)
     kern = {}
-    for name in ("ans0_decode", "ans0_tables", "ans0_encode", "ans0_stats", "ans_walk", "concat", "concat_zero", "scan", "stream_walk", "block_header", "block_prefix", "extract",
-                 "huf_stats", "huf_encode", "huf_walk", "huf_decode", "ans1_hist", "ans1_stats", "ans1_encode", "ans1_decode", "range_encode", "range_decode",
-                 "bwt_forward", "bwt_inverse", "bwts_forward", "bwts_inverse", "lz_parse", "lz_gather", "lz_inverse", "sbrt_last2", "sbrt_carry", "sbrt_rank",
-                 "sbrt_inverse", "zrlt_forward", "zrlt_inverse", "xxhash", "rolz_forward", "rolz_inverse", "alias_forward", "alias_inverse", "fsd_forward",
-                 "fsd_inverse", "text_forward", "text_inverse", "utf_forward", "utf_inverse", "exe_forward", "exe_inverse", "host:encode_batch", "host:enc_tables", "host:enc_sync"):
+    for name in ctx.profile_names():
+        if name.startswith("stage:"):
+            continue
         cnt, ms = ctx.kernel_time(name)
         if cnt:
-            kern[name] = {"launches": cnt, "ms_avg": ms / cnt}
+            kern[name] = {"launches": cnt, "ms_avg": ms / cnt, "ms_per_step": ms / args.steps}
+    stages = {}
+    for name in ctx.profile_names():
+        if name.startswith("stage:"):
+            cnt, bi, bo = ctx.stage_bytes(name)
+            if cnt:
+                stages[name[6:]] = {"bytes_in": bi / cnt, "bytes_out": bo / cnt, "batches_per_step": cnt / args.steps}
     ctx.profile(False)
 
     # ---------------- end-to-end pass through the host-buffer C ABI (pinned host memory) ----------------
-    h_src = torch.empty(n, dtype=torch.uint8).pin_memory()
-    h_cmp = torch.empty(cap, dtype=torch.uint8).pin_memory()
-    h_dec = torch.empty(n + 64, dtype=torch.uint8).pin_memory()
-    h_src.numpy()[:] = x
-    e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(2):
-        mm = ctx.compress_host(h_src.data_ptr(), n, h_cmp.data_ptr(), cap, t48, et, BLOCK, 0, n)
-        kk = ctx.decompress_host(h_cmp.data_ptr(), mm, h_dec.data_ptr(), n + 64)
-    assert kk == n and np.array_equal(h_dec.numpy()[:n], x), "e2e round trip mismatch"
-    barrier()
-    t0 = time.perf_counter()
-    with torch.cuda.stream(ext):
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(e2e_steps):
-            mm = ctx.compress_host(h_src.data_ptr(), n, h_cmp.data_ptr(), cap, t48, et, BLOCK, 0, n)
-            ctx.decompress_host(h_cmp.data_ptr(), mm, h_dec.data_ptr(), n + 64)
-        f1.record()
-    barrier()
-    e2e_ms = f0.elapsed_time(f1)
-    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms, e2e_wall_ms, e2e_steps = 0.0, 0.0, 0
+    if not args.no_e2e:
+        h_src = torch.empty(n, dtype=torch.uint8).pin_memory()
+        h_cmp = [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in P]
+        h_dec = torch.empty(n + 64, dtype=torch.uint8).pin_memory()
+        h_src.numpy()[:] = x
+        e2e_steps = max(1, min(args.steps, 3))
+        for i, (label, t48, et) in enumerate(P):
+            mm = ctx.compress_host(h_src.data_ptr(), n, h_cmp[i].data_ptr(), cap, t48, et, BLOCK, 0, n)
+            kk = ctx.decompress_host(h_cmp[i].data_ptr(), mm, h_dec.data_ptr(), n + 64)
+            assert kk == n and np.array_equal(h_dec.numpy()[:n], x), "e2e round trip mismatch"
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(ext):
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(e2e_steps):
+                for i, (label, t48, et) in enumerate(P):
+                    mm = ctx.compress_host(h_src.data_ptr(), n, h_cmp[i].data_ptr(), cap, t48, et, BLOCK, 0, n)
+                    ctx.decompress_host(h_cmp[i].data_ptr(), mm, h_dec.data_ptr(), n + 64)
+            f1.record()
+        barrier()
+        e2e_ms = f0.elapsed_time(f1)
+        e2e_wall_ms = (time.perf_counter() - t0) * 1e3
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
     # ---------------- max over ranks ----------------
-    vals = torch.tensor([dev_ms, e2e_ms, enc_ms, dec_ms], dtype=torch.float64, device="cuda")
+    vals = torch.tensor([dev_ms, e2e_ms] + enc_ms + dec_ms, dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, enc_ms, dec_ms = [float(v) for v in vals.tolist()]
+    vals = [float(v) for v in vals.tolist()]
+    dev_ms, e2e_ms = vals[0], vals[1]
+    enc_ms, dec_ms = vals[2:2 + len(P)], vals[2 + len(P):]
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
-    total_bytes = 2.0 * n * world  # uncompressed bytes through encode and through decode, all ranks
+    npass = len(P)
+    total_bytes = 2.0 * n * npass * world  # uncompressed bytes through encode and through decode of every level, all ranks
     ms_per_step = dev_ms / args.steps
     value = total_bytes * args.steps / (dev_ms / 1e3) / 1e6
-    e2e_value = total_bytes * e2e_steps / (e2e_ms / 1e3) / 1e6
+    e2e_value = total_bytes * e2e_steps / (e2e_ms / 1e3) / 1e6 if e2e_steps else None
     peak, peak_src = peaks()
+    levels = {}
+    for i, (label, t48, et) in enumerate(P):
+        levels[label] = {"transform": passes[i][1], "entropy": passes[i][2], "compressed_bytes": int(m[i]), "ratio": m[i] / n,
+                         "encode_MBps": n * world * args.steps / (enc_ms[i] / 1e3) / 1e6, "decode_MBps": n * world * args.steps / (dec_ms[i] / 1e3) / 1e6,
+                         "MBps": 2.0 * n * world * args.steps / ((enc_ms[i] + dec_ms[i]) / 1e3) / 1e6}
+    # dominant kernel of the step = largest ms_per_step among device kernels
     roof = None
-    if roof_kernel in kern:
-        # algorithmic bytes per launch: entropy stage = compressed + uncompressed bytes of the batch; a transform
-        # launched per block (BWT) = 2 x block bytes; the serial LZ parse = block bytes in + out of the batch
-        per_block = roof_kernel in ("bwt_forward", "bwt_inverse")
-        alg = float(2 * BLOCK) if per_block else float(n + m)
-        ach = alg / (kern[roof_kernel]["ms_avg"] / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": roof_kernel + ("_device (all kernels of one block)" if per_block else "_kernel"), "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                "ms_per_launch": kern[roof_kernel]["ms_avg"]}
-        if args.workload == "ans0":
-            t = measured_traffic("ans0_decode")
-            if t:
-                roof["traffic"] = t[0]
-                roof["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/" + t[1]
+    dev_kern = {k: v for k, v in kern.items() if not k.startswith("host:")}
+    if dev_kern:
+        top = max(dev_kern, key=lambda k: dev_kern[k]["ms_per_step"])
+        st = stages.get(STAGE_OF.get(top, ""))
+        if st is not None:
+            # a stage runs once per pass that contains it; per launch of the kernel = stage bytes of one batch / launches per batch
+            per_batch_launches = max(1.0, dev_kern[top]["launches"] / args.steps / max(st["batches_per_step"], 1e-9))
+            alg = (st["bytes_in"] + st["bytes_out"]) / per_batch_launches
+            how = "stage input + output bytes of one batch (%s) / launches per batch" % STAGE_OF[top]
+        else:
+            alg = float(n + sum(m) / max(len(m), 1))
+            how = "uncompressed + compressed bytes of the batch"
+        ach = alg / (dev_kern[top]["ms_avg"] / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg, "algorithmic_bytes": how, "ms_per_launch": dev_kern[top]["ms_avg"],
+                "share_of_step": dev_kern[top]["ms_per_step"] / ms_per_step}
+        t = measured_traffic(top)
+        if t:
+            roof["traffic"] = t[0]
+            roof["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/" + t[1]
     line = {
         "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload_label(args.workload), "block_size": BLOCK, "blocks_per_gpu": NBLOCKS,
-                   "uncompressed_bytes_per_gpu": n, "compressed_bytes_per_gpu": int(m),
-                   "l2": "inputs (%d MiB in, %d MiB compressed) larger than the 126 MB L2" % (n >> 20, m >> 20),
-                   "encode_MBps": n * world * args.steps / (enc_ms / 1e3) / 1e6, "decode_MBps": n * world * args.steps / (dec_ms / 1e3) / 1e6,
+                   "uncompressed_bytes_per_gpu": n, "levels": levels,
+                   "l2": "slab (%d MB) and compressed streams larger than the 126 MB L2" % (n // 1000000),
                    "parallelism": "1 process per GPU, %d blocks per GPU, no data-path collective" % NBLOCKS},
         "clocks": sampler.summary(),
-        "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": int(n + m), "d2h_bytes_per_step": int(m + n), "steps": e2e_steps,
-                "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": e2e_wall_ms / e2e_steps, "api": "kz_compress_stream + kz_decompress_stream, pinned host buffers"},
         "gpu_launches": int(launches),
-        "kernels": kern,
+        "kernels": dict(sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])),
+        "stages": stages,
     }
+    if e2e_steps:
+        line["e2e"] = {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": int(n * npass + sum(m)), "d2h_bytes_per_step": int(sum(m) + n * npass),
+                       "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": e2e_wall_ms / e2e_steps,
+                       "api": "kz_compress_stream + kz_decompress_stream per level, pinned host buffers"}
     if roof:
         line["roofline"] = roof
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = cpu_reference(2, 1, sample_blocks=NBLOCKS, workload=args.workload)
-            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            r = cpu_reference(1, 1, args.workload, max_seconds=30.0)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "levels")}
         except Exception as e:  # the checker is absent: report, never substitute
             line["cpu_baseline"] = {"value": None, "unit": "MB/s", "cores": 0, "kind": "port", "sample": "unavailable: %s" % e}
     emit(line)

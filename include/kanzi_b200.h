@@ -113,6 +113,12 @@ int kz_decompress_stream_device(kz_ctx* ctx, const void* d_src, size_t n, void* 
 void kz_profile(kz_ctx* ctx, int enable);
 uint32_t kz_kernel_time(kz_ctx* ctx, const char* name, double* total_ms);
 void kz_profile_reset(kz_ctx* ctx);
+/* Algorithmic bytes of a transform stage accumulated since the last reset: name = "stage:fwd:<transform id>" or
+ * "stage:inv:<transform id>" (ids of transform/Factory.go:31-50); *bytes_in / *bytes_out = stage input / output bytes summed over
+ * the blocks the stage ran on. Returns the number of batches accumulated (0 = unknown name). Only with kz_profile(ctx,1).
+ * Also "kernel names" (enumeration): kz_profile_names writes up to cap bytes of newline separated names, returns the full size. */
+uint32_t kz_stage_bytes(kz_ctx* ctx, const char* name, uint64_t* bytes_in, uint64_t* bytes_out);
+size_t kz_profile_names(kz_ctx* ctx, char* buf, size_t cap);
 
 /* ctx["blockSize"] of the stream the following kz_encode_blocks / kz_transform_forward / kz_transform_inverse calls belong to
  * (io/CompressedStream.go:220,1406). Only TEXT reads it (it sizes its hash map from it, transform/TextCodec.go:1143-1156);

@@ -34,6 +34,7 @@ ABI_SYMBOLS = [
     "kz_entropy_encode", "kz_entropy_decode", "kz_transform_forward", "kz_transform_inverse", "kz_transform_max_encoded_len",
     "kz_encode_blocks", "kz_decode_blocks", "kz_max_block_output", "kz_compress_stream", "kz_decompress_stream", "kz_max_stream_output",
     "kz_compress_stream_device", "kz_decompress_stream_device", "kz_profile", "kz_kernel_time", "kz_profile_reset", "kz_set_stream_block_size",
+    "kz_stage_bytes", "kz_profile_names",
 ]
 
 
@@ -120,6 +121,10 @@ def load_library(build_if_missing=True):
     L.kz_profile_reset.argtypes = [vp]
     L.kz_profile_reset.restype = None
     L.kz_set_stream_block_size.argtypes = [vp, C.c_uint64]
+    L.kz_stage_bytes.argtypes = [vp, C.c_char_p, C.POINTER(u64), C.POINTER(u64)]
+    L.kz_stage_bytes.restype = u32
+    L.kz_profile_names.argtypes = [vp, C.c_char_p, sz]
+    L.kz_profile_names.restype = sz
     L.kz_set_stream_block_size.restype = None
     _lib = L
     return L
@@ -292,6 +297,18 @@ class Context:
         ms = C.c_double(0)
         n = self.lib.kz_kernel_time(self.h, name.encode(), C.byref(ms))
         return n, ms.value
+
+    def stage_bytes(self, name):
+        """-> (batches, bytes_in, bytes_out) of "stage:fwd:<id>" / "stage:inv:<id>" since the last profile_reset"""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        k = self.lib.kz_stage_bytes(self.h, name.encode(), C.byref(a), C.byref(b))
+        return k, a.value, b.value
+
+    def profile_names(self):
+        n = self.lib.kz_profile_names(self.h, None, 0)
+        buf = C.create_string_buffer(n + 16)
+        self.lib.kz_profile_names(self.h, buf, n + 16)
+        return [x for x in buf.value.decode().split("\n") if x]
 
     def launch_count(self, reset=False):
         return self.lib.kz_launch_count(self.h, 1 if reset else 0)

@@ -88,6 +88,15 @@ struct LaunchScope {
     }
 };
 
+// algorithmic bytes of one transform stage over a batch (stage input + stage output), kept under "stage:fwd:<id>" / "stage:inv:<id>"
+void note_stage_bytes(kz_ctx* ctx, const char* dir, uint64_t id, uint64_t bytes_in, uint64_t bytes_out) {
+    if (!ctx->profile) return;
+    auto& e = ctx->prof[std::string("stage:") + dir + ":" + std::to_string((unsigned long long)id)];
+    e.bytes_in += bytes_in;
+    e.bytes_out += bytes_out;
+    e.launches++;
+}
+
 void drain_profile(kz_ctx* ctx) {
     if (ctx->pending.empty()) return;
     cudaStreamSynchronize(ctx->stream);
@@ -1294,8 +1303,12 @@ int forward_generic(kz_ctx* ctx, const TransformPlan& plan, const uint8_t* d_src
     uint64_t cur_stride = stride;
     for (int i = 0; i < plan.nt; i++) {
         uint8_t* outb = (i & 1) ? ctx->d_tmp2.as<uint8_t>() : ctx->d_tmp.as<uint8_t>();
+        uint64_t bytes_in = 0, bytes_out = 0;
+        for (uint32_t b = 0; b < nblocks; b++) bytes_in += active[b] ? len[b] : 0;
         int rc = apply_forward(ctx, plan.ids[i], cur, cur_stride, outb, gstride, len, active, applied, &dts);
         if (rc) return rc;
+        for (uint32_t b = 0; b < nblocks; b++) bytes_out += active[b] ? len[b] : 0;
+        note_stage_bytes(ctx, "fwd", plan.ids[i], bytes_in, bytes_out);
         for (uint32_t b = 0; b < nblocks; b++) {
             if (applied[b]) flags[b] &= (uint8_t)~(1u << (7 - i));
             else if (len[b]) CK(cudaMemcpyAsync(outb + b * gstride, cur + b * cur_stride, len[b], cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1675,8 +1688,12 @@ int inverse_generic(kz_ctx* ctx, const TransformPlan& plan, std::vector<DecJob>&
             any = any || active[b];
         }
         if (!any) continue;
+        uint64_t bytes_in = 0, bytes_out = 0;
+        for (uint32_t b = 0; b < nblocks; b++) bytes_in += active[b] ? len[b] : 0;
         int rc = apply_inverse(ctx, plan.ids[i], cur, other, pstride, blk_cap, len, active);
         if (rc) return rc;
+        for (uint32_t b = 0; b < nblocks; b++) bytes_out += active[b] ? len[b] : 0;
+        note_stage_bytes(ctx, "inv", plan.ids[i], bytes_in, bytes_out);
         for (uint32_t b = 0; b < nblocks; b++)
             if (!active[b] && len[b]) CK(cudaMemcpyAsync(other + b * pstride, cur + b * pstride, len[b], cudaMemcpyDeviceToDevice, ctx->stream));
         std::swap(cur, other);
@@ -2000,6 +2017,23 @@ uint32_t kz_kernel_time(kz_ctx* ctx, const char* name, double* total_ms) {
 void kz_profile_reset(kz_ctx* ctx) {
     drain_profile(ctx);
     ctx->prof.clear();
+}
+size_t kz_profile_names(kz_ctx* ctx, char* buf, size_t cap) {
+    drain_profile(ctx);
+    std::string all;
+    for (auto& kv : ctx->prof) all += kv.first + "\n";
+    if (buf && cap) {
+        const size_t k = std::min(cap - 1, all.size());
+        memcpy(buf, all.data(), k);
+        buf[k] = 0;
+    }
+    return all.size() + 1;
+}
+uint32_t kz_stage_bytes(kz_ctx* ctx, const char* name, uint64_t* bytes_in, uint64_t* bytes_out) {
+    auto it = ctx->prof.find(name);
+    if (bytes_in) *bytes_in = it == ctx->prof.end() ? 0 : it->second.bytes_in;
+    if (bytes_out) *bytes_out = it == ctx->prof.end() ? 0 : it->second.bytes_out;
+    return it == ctx->prof.end() ? 0 : it->second.launches;
 }
 
 // worst cases: ANS0/Huffman ~440/550 header bytes per 16 KiB chunk; ANS1 256 context tables (<= 104 KiB) per 4 MiB chunk

@@ -92,6 +92,7 @@ struct EncPlan {
 struct ProfEntry {
     double ms = 0;
     uint32_t launches = 0;
+    uint64_t bytes_in = 0, bytes_out = 0;  // "stage:*" entries only
 };
 
 struct EncJob {          // one block handed to the entropy stage
