@@ -1622,9 +1622,9 @@ int apply_inverse(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint8_t* d_out, 
         if (rc) return rc;
         {
             LaunchScope ls(ctx, "sbrt_inverse");
-            bool packed = true;
-            for (uint32_t b = 0; b < nblocks; b++) packed = packed && len[b] < (1u << 27);
-            sbrt_inverse_launch(d_in, (const SbrtBlock*)(ctx->d_tables.as<uint8_t>() + o_sb), (int)nblocks, t == KZ_T_MTFT ? 1 : 2, d_out, packed, ctx->stream);
+            uint32_t longest = 0;
+            for (uint32_t b = 0; b < nblocks; b++) longest = std::max(longest, len[b]);
+            sbrt_inverse_launch_len(d_in, (const SbrtBlock*)(ctx->d_tables.as<uint8_t>() + o_sb), (int)nblocks, t == KZ_T_MTFT ? 1 : 2, d_out, longest, ctx->stream);
         }
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(ctx->stream));

@@ -304,10 +304,156 @@ __global__ void __launch_bounds__(32) sbrt_inverse_kernel_t(const uint8_t* __res
     for (uint32_t i = n16 << 4; i < n; i++) dst[i] = (uint8_t)step(i, src[i]);
 }
 
-// host entry: packed entries when every block is shorter than 128 MiB
+// ---- inverse, warp-resident (default): the 256-entry list lives in the registers of one warp, lane l holds ranks 8 l .. 8 l + 7
+// as (q, p << 8 | symbol). The list is always sorted by q (descending; SBRT.go:214-220 only ever moves the accessed symbol up, and its
+// new q is never below its old one), so the move-up is a LOCAL decision per list position j <= r:
+//     q[j] >  qc                 -> stays
+//     q[j] <= qc, q[j-1] >  qc   -> receives the accessed symbol (this is the new rank)
+//     q[j] <= qc, q[j-1] <= qc   -> receives the entry of rank j - 1
+// i.e. one predicated register shift per lane plus one shuffle for the lane boundary (issued before qc is known): no reduction, no loop
+// over ranks, a fixed short dependent chain per byte whatever the rank (after TEXT+BWT half of the ranks are >= 4 and their mean is 50).
+// Ranks < 8 never leave lane 0 (no shuffle on the chain); a run of L zero ranks is one step (entry 0 keeps its place: p = i + L - 1,
+// q = i + L - 2). 32 input ranks per round, one per lane, handed out by a shuffle issued one step ahead; the decoded symbols of a round
+// go through 32 bytes of shared memory and leave as one coalesced store.
+template <typename X_t>
+__global__ void __launch_bounds__(32) sbrt_inverse_warp_kernel(const uint8_t* __restrict__ data, const SbrtBlock* __restrict__ blocks, int nblocks, int mode,
+                                                                uint8_t* __restrict__ out) {
+    __shared__ uint8_t s_out[32];
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (b >= nblocks) return;
+    const SbrtBlock blk = blocks[b];
+    if (!blk.active) return;
+    const uint8_t* src = data + blk.src_off;
+    uint8_t* dst = out + blk.dst_off;
+    const uint32_t n = blk.len;
+    const bool rank_mode = mode == 2;
+    uint32_t Q[8];
+    X_t X[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        Q[k] = 0;
+        X[k] = (X_t)(8 * lane + k);
+    }
+    const uint32_t base = 8u * (uint32_t)lane;
+    uint32_t nxt = lane < (int)n ? src[lane] : 0u;
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+        const uint32_t mine = nxt;
+        nxt = i0 + 32 + lane < n ? src[i0 + 32 + lane] : 0u;  // next round's ranks in flight
+        const uint32_t cnt = min(32u, n - i0);
+        const uint32_t valid = cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u);
+        const uint32_t zmask = __ballot_sync(0xFFFFFFFFu, mine == 0) & valid;
+        uint32_t runmask = 0;  // bit j set: position j repeats the symbol of position j - 1 (inside a zero run)
+        uint32_t j = 0;
+        uint32_t r = __shfl_sync(0xFFFFFFFFu, mine, 0);
+        while (j < cnt) {
+            const uint32_t i = i0 + j;
+            if (r == 0) {
+                const uint32_t rest = ~(zmask >> j);  // bit 0 is clear (position j is a zero)
+                const uint32_t L = rest ? (uint32_t)__ffs((int)rest) - 1u : 32u - j;
+                const uint32_t jn = j + L;
+                const uint32_t rn = __shfl_sync(0xFFFFFFFFu, mine, (int)(jn & 31u));
+                if (lane == 0) {
+                    const uint32_t sym = (uint32_t)X[0] & 0xFFu;
+                    const uint32_t pl = i + L - 1;
+                    s_out[j] = (uint8_t)sym;
+                    Q[0] = rank_mode ? (L >= 2 ? pl - 1 : (uint32_t)(((uint64_t)i + (uint64_t)(X[0] >> 8)) >> 1)) : pl;
+                    X[0] = ((X_t)pl << 8) | sym;
+                }
+                if (L >= 2) runmask |= (uint32_t)(((1ull << (L - 1)) - 1ull) << (j + 1));
+                j = jn;
+                r = rn;
+                continue;
+            }
+            const uint32_t rn = __shfl_sync(0xFFFFFFFFu, mine, (int)((j + 1) & 31u));
+            // the entry of rank r: select inside the owner lane (a tree over the three low bits of r), then one shuffle unless r < 8
+            X_t x;
+            {
+                const X_t a0 = (r & 1) ? X[1] : X[0], a1 = (r & 1) ? X[3] : X[2], a2 = (r & 1) ? X[5] : X[4], a3 = (r & 1) ? X[7] : X[6];
+                const X_t b0 = (r & 2) ? a1 : a0, b1 = (r & 2) ? a3 : a2;
+                x = (r & 4) ? b1 : b0;
+            }
+            if (r < 8) {
+                if (lane == 0) {
+                    const uint32_t sym = (uint32_t)x & 0xFFu;
+                    const uint32_t qc = rank_mode ? (uint32_t)(((uint64_t)i + (uint64_t)(x >> 8)) >> 1) : i;
+                    const X_t fresh = ((X_t)i << 8) | sym;
+                    s_out[j] = (uint8_t)sym;
+                    bool g[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) g[k] = Q[k] > qc;
+#pragma unroll
+                    for (int k = 7; k >= 1; k--) {
+                        if ((uint32_t)k <= r && !g[k]) {
+                            Q[k] = g[k - 1] ? qc : Q[k - 1];
+                            X[k] = g[k - 1] ? fresh : X[k - 1];
+                        }
+                    }
+                    if (!g[0]) {
+                        Q[0] = qc;
+                        X[0] = fresh;
+                    }
+                }
+            } else {
+                const uint32_t up_q = __shfl_up_sync(0xFFFFFFFFu, Q[7], 1);
+                const X_t up_x = __shfl_up_sync(0xFFFFFFFFu, X[7], 1);
+                x = __shfl_sync(0xFFFFFFFFu, x, (int)(r >> 3));
+                const uint32_t sym = (uint32_t)x & 0xFFu;
+                const uint32_t qc = rank_mode ? (uint32_t)(((uint64_t)i + (uint64_t)(x >> 8)) >> 1) : i;
+                const X_t fresh = ((X_t)i << 8) | sym;
+                if (lane == 0) s_out[j] = (uint8_t)sym;
+                bool g[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) g[k] = Q[k] > qc;
+                const bool g_up = lane == 0 ? true : up_q > qc;
+#pragma unroll
+                for (int k = 7; k >= 1; k--) {
+                    if (base + (uint32_t)k <= r && !g[k]) {
+                        Q[k] = g[k - 1] ? qc : Q[k - 1];
+                        X[k] = g[k - 1] ? fresh : X[k - 1];
+                    }
+                }
+                if (base <= r && !g[0]) {
+                    Q[0] = g_up ? qc : up_q;
+                    X[0] = g_up ? fresh : up_x;
+                }
+            }
+            j++;
+            r = rn;
+        }
+        __syncwarp();
+        if ((uint32_t)lane < cnt) {
+            const uint32_t own = ~runmask & (lane == 31 ? 0xFFFFFFFFu : ((2u << lane) - 1u));  // positions <= lane that hold a symbol of their own
+            dst[i0 + lane] = s_out[31 - __clz((int)own)];
+        }
+        __syncwarp();
+    }
+}
+
+// host entry. KZ_SBRT_INV=lane selects the round-1 kernel (lane 0 walks the chain; kept for comparison); packed = every block < 128 MiB
 void sbrt_inverse_launch(const uint8_t* data, const SbrtBlock* d_blocks, int nblocks, int mode, uint8_t* out, bool packed, cudaStream_t stream) {
+    static const bool old_kernel = [] {
+        const char* e = getenv("KZ_SBRT_INV");
+        return e && e[0] == 'l';
+    }();
+    if (!old_kernel) {  // the block lengths are not known here: 64-bit entries (sbrt_inverse_launch_len picks 32-bit ones for blocks <= 16 MiB)
+        sbrt_inverse_warp_kernel<uint64_t><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, mode, out);
+        return;
+    }
     if (packed) sbrt_inverse_kernel_t<true><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, mode, out);
     else sbrt_inverse_kernel_t<false><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, mode, out);
+}
+
+void sbrt_inverse_launch_len(const uint8_t* data, const SbrtBlock* d_blocks, int nblocks, int mode, uint8_t* out, uint32_t max_len, cudaStream_t stream) {
+    static const bool old_kernel = [] {
+        const char* e = getenv("KZ_SBRT_INV");
+        return e && e[0] == 'l';
+    }();
+    if (old_kernel) {
+        sbrt_inverse_launch(data, d_blocks, nblocks, mode, out, max_len < (1u << 27), stream);
+        return;
+    }
+    if (max_len <= (1u << 24)) sbrt_inverse_warp_kernel<uint32_t><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, mode, out);
+    else sbrt_inverse_warp_kernel<uint64_t><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, mode, out);
 }
 
 }  // namespace kz

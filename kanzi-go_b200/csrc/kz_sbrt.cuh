@@ -21,5 +21,7 @@ __global__ void sbrt_rank_kernel(const uint8_t* data, const SbrtBlock* blocks, i
                                  const int32_t* table, uint8_t* out);
 // packed = every block of the batch is shorter than 128 MiB (64-bit list entries then carry q, p and the symbol)
 void sbrt_inverse_launch(const uint8_t* data, const SbrtBlock* d_blocks, int nblocks, int mode, uint8_t* out, bool packed, cudaStream_t stream);
+// default entry: warp-resident list kernel (32-bit entries for blocks up to 16 MiB, 64-bit above); max_len = longest block of the batch
+void sbrt_inverse_launch_len(const uint8_t* data, const SbrtBlock* d_blocks, int nblocks, int mode, uint8_t* out, uint32_t max_len, cudaStream_t stream);
 
 }  // namespace kz
