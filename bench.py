@@ -60,7 +60,7 @@ for _bs in (1, 2, 4, 8, 16, 32, 64):  # BASELINE.json configs[4]: ANS1 block-siz
                                    "encode+decode MB/s (ANS1/NONE, 256 MiB order-1 text, %d MiB blocks; configs[4])" % _bs)
 
 # kernel name -> (stage the kernel belongs to, as kz_stage_bytes names it) for the roofline's algorithmic bytes
-STAGE_OF = {"lz_parse": "fwd:16", "lz_gather": "fwd:16", "lz_inverse": "inv:16", "text_forward": "fwd:10", "text_inverse": "inv:10", "utf_forward": "fwd:17",
+STAGE_OF = {"lz_parse": "fwd:16", "lz_gather": "fwd:16", "lz_hash": "fwd:16", "lz_sort": "fwd:16", "lz_link": "fwd:16", "lz_spec": "fwd:16", "lz_stitch": "fwd:16", "lz_emit": "fwd:16", "lz_inverse": "inv:16", "text_forward": "fwd:10", "text_inverse": "inv:10", "utf_forward": "fwd:17",
             "utf_inverse": "inv:17", "bwt_forward": "fwd:1", "bwt_inverse": "inv:1", "sbrt_rank": "fwd:8", "sbrt_inverse": "inv:8", "zrlt_forward": "fwd:6",
             "zrlt_inverse": "inv:6", "alias_forward": "fwd:18", "alias_inverse": "inv:18", "fsd_forward": "fwd:15", "fsd_inverse": "inv:15",
             "rolz_forward": "fwd:11", "rolz_inverse": "inv:11", "exe_forward": "fwd:9", "exe_inverse": "inv:9"}

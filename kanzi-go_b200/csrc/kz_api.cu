@@ -113,6 +113,31 @@ void drain_profile(kz_ctx* ctx) {
     ctx->pending.clear();
 }
 
+// adaptors for the data-parallel LZ forward path (kz_lz_par.cu): scratch from ctx->d_ws, every pass timed under its own name
+struct CtxLzWorkspace : LzWorkspace {
+    kz_ctx* ctx;
+    explicit CtxLzWorkspace(kz_ctx* c) : ctx(c) {}
+    uint8_t* ensure(size_t bytes) override { return ctx->d_ws.ensure(bytes) == cudaSuccess ? ctx->d_ws.as<uint8_t>() : nullptr; }
+};
+struct CtxLzHook : LzHook {
+    kz_ctx* ctx;
+    LaunchScope* cur = nullptr;
+    explicit CtxLzHook(kz_ctx* c) : ctx(c) {}
+    void begin(const char* name) override { cur = new LaunchScope(ctx, name); }
+    void end() override {
+        delete cur;
+        cur = nullptr;
+    }
+};
+// KZ_LZ_PARSE=serial selects the round-1 parse (one lane per block replays the reference loop); default: the data-parallel path
+bool lz_serial_parse() {
+    static const bool v = [] {
+        const char* e = getenv("KZ_LZ_PARSE");
+        return e && e[0] == 's';
+    }();
+    return v;
+}
+
 int upload(kz_ctx* ctx, Packer& pk) {
     CK(ctx->h_stage.ensure(pk.bytes.size() + 256));
     CK(ctx->d_tables.ensure(pk.bytes.size() + 256));
@@ -953,8 +978,6 @@ int apply_forward(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint64_t istride
         if ((uint64_t)max_len + max_len / 64 + 128 > ostride) return ctx->fail(KZ_ERR_UNKNOWN, "internal: stage buffer too small for LZ");
         const uint64_t sstride = (lz_scratch_bytes(max_len) + 255) & ~size_t(255);
         const size_t hbytes = ((size_t)nblocks << (extra ? 19 : 16)) * 4;
-        CK(ctx->d_ws.ensure(sstride * nblocks + hbytes + 4096));
-        CK(ctx->d_lens.ensure((size_t)nblocks * sizeof(LzResult) + 64));
         std::vector<LzBlock> lb(nblocks);
         for (uint32_t b = 0; b < nblocks; b++) {
             lb[b].src_off = b * istride;
@@ -965,27 +988,35 @@ int apply_forward(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint64_t istride
             lb[b].data_type = dts ? (*dts)[b] : 0;
             lb[b].pad = 0;
         }
-        Packer pk;
-        const size_t o_lb = pk.add(lb.data(), lb.size() * sizeof(LzBlock));
-        int rc = upload(ctx, pk);
-        if (rc) return rc;
-        uint8_t* ws = ctx->d_ws.as<uint8_t>();
-        int32_t* d_hash = (int32_t*)(ws + sstride * nblocks);
-        CK(cudaMemsetAsync(d_hash, 0, hbytes, ctx->stream));
-        LzBlock* d_lb = (LzBlock*)(ctx->d_tables.as<uint8_t>() + o_lb);
-        LzResult* d_res = ctx->d_lens.as<LzResult>();
-        {
-            LaunchScope ls(ctx, "lz_parse");
-            lz_parse_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_in, d_lb, (int)nblocks, extra ? 1 : 0, d_hash, ws, d_out, d_res);
-        }
-        {
-            LaunchScope ls(ctx, "lz_gather");
-            lz_gather_kernel<<<dim3(nblocks, 8), 256, 0, ctx->stream>>>(d_in, d_lb, (int)nblocks, ws, d_res, d_out);
-        }
-        CK(cudaGetLastError());
         std::vector<LzResult> hres(nblocks);
-        CK(cudaMemcpyAsync(hres.data(), d_res, (size_t)nblocks * sizeof(LzResult), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        if (!lz_serial_parse()) {
+            CtxLzWorkspace W(ctx);
+            CtxLzHook H(ctx);
+            CK(lz_forward_parallel(d_in, d_out, lb, extra, W, ctx->stream, hres, &H));
+        } else {
+            CK(ctx->d_ws.ensure(sstride * nblocks + hbytes + 4096));
+            CK(ctx->d_lens.ensure((size_t)nblocks * sizeof(LzResult) + 64));
+            Packer pk;
+            const size_t o_lb = pk.add(lb.data(), lb.size() * sizeof(LzBlock));
+            int rc = upload(ctx, pk);
+            if (rc) return rc;
+            uint8_t* ws = ctx->d_ws.as<uint8_t>();
+            int32_t* d_hash = (int32_t*)(ws + sstride * nblocks);
+            CK(cudaMemsetAsync(d_hash, 0, hbytes, ctx->stream));
+            LzBlock* d_lb = (LzBlock*)(ctx->d_tables.as<uint8_t>() + o_lb);
+            LzResult* d_res = ctx->d_lens.as<LzResult>();
+            {
+                LaunchScope ls(ctx, "lz_parse");
+                lz_parse_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_in, d_lb, (int)nblocks, extra ? 1 : 0, d_hash, ws, d_out, d_res);
+            }
+            {
+                LaunchScope ls(ctx, "lz_gather");
+                lz_gather_kernel<<<dim3(nblocks, 8), 256, 0, ctx->stream>>>(d_in, d_lb, (int)nblocks, ws, d_res, d_out);
+            }
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(hres.data(), d_res, (size_t)nblocks * sizeof(LzResult), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
         for (uint32_t b = 0; b < nblocks; b++)
             if (active[b] && len[b] && hres[b].status == 0) {
                 applied[b] = 1;
@@ -1745,8 +1776,6 @@ int forward_stage(kz_ctx* ctx, const TransformPlan& plan, const uint8_t* d_src, 
         const uint64_t sstride = (lz_scratch_bytes(max_len) + 255) & ~size_t(255);
         const size_t hbytes = ((size_t)nblocks << (extra ? 19 : 16)) * 4;
         CK(ctx->d_tmp.ensure(tstride * nblocks + 64));
-        CK(ctx->d_ws.ensure(sstride * nblocks + hbytes + 4096));
-        CK(ctx->d_lens.ensure((size_t)nblocks * sizeof(LzResult) + 64));
         std::vector<LzBlock> lb(nblocks);
         for (uint32_t b = 0; b < nblocks; b++) {
             lb[b].src_off = (uint64_t)b * stride;
@@ -1757,26 +1786,34 @@ int forward_stage(kz_ctx* ctx, const TransformPlan& plan, const uint8_t* d_src, 
             lb[b].data_type = dts[b];
             lb[b].pad = 0;
         }
-        Packer pk;
-        const size_t o_lb = pk.add(lb.data(), lb.size() * sizeof(LzBlock));
-        int rc = upload(ctx, pk);
-        if (rc) return rc;
-        uint8_t* ws = ctx->d_ws.as<uint8_t>();
-        int32_t* d_hash = (int32_t*)(ws + sstride * nblocks);
-        CK(cudaMemsetAsync(d_hash, 0, hbytes, ctx->stream));
-        LzBlock* d_lb = (LzBlock*)(ctx->d_tables.as<uint8_t>() + o_lb);
-        LzResult* d_res = ctx->d_lens.as<LzResult>();
-        {
-            LaunchScope ls(ctx, "lz_parse");
-            lz_parse_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_src, d_lb, (int)nblocks, extra ? 1 : 0, d_hash, ws, ctx->d_tmp.as<uint8_t>(), d_res);
-        }
-        {
-            LaunchScope ls(ctx, "lz_gather");
-            lz_gather_kernel<<<dim3(nblocks, 8), 256, 0, ctx->stream>>>(d_src, d_lb, (int)nblocks, ws, d_res, ctx->d_tmp.as<uint8_t>());
-        }
         std::vector<LzResult> hres(nblocks);
-        CK(cudaMemcpyAsync(hres.data(), d_res, (size_t)nblocks * sizeof(LzResult), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        if (!lz_serial_parse()) {
+            CtxLzWorkspace W(ctx);
+            CtxLzHook H(ctx);
+            CK(lz_forward_parallel(d_src, ctx->d_tmp.as<uint8_t>(), lb, extra, W, ctx->stream, hres, &H));
+        } else {
+            CK(ctx->d_ws.ensure(sstride * nblocks + hbytes + 4096));
+            CK(ctx->d_lens.ensure((size_t)nblocks * sizeof(LzResult) + 64));
+            Packer pk;
+            const size_t o_lb = pk.add(lb.data(), lb.size() * sizeof(LzBlock));
+            int rc = upload(ctx, pk);
+            if (rc) return rc;
+            uint8_t* ws = ctx->d_ws.as<uint8_t>();
+            int32_t* d_hash = (int32_t*)(ws + sstride * nblocks);
+            CK(cudaMemsetAsync(d_hash, 0, hbytes, ctx->stream));
+            LzBlock* d_lb = (LzBlock*)(ctx->d_tables.as<uint8_t>() + o_lb);
+            LzResult* d_res = ctx->d_lens.as<LzResult>();
+            {
+                LaunchScope ls(ctx, "lz_parse");
+                lz_parse_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_src, d_lb, (int)nblocks, extra ? 1 : 0, d_hash, ws, ctx->d_tmp.as<uint8_t>(), d_res);
+            }
+            {
+                LaunchScope ls(ctx, "lz_gather");
+                lz_gather_kernel<<<dim3(nblocks, 8), 256, 0, ctx->stream>>>(d_src, d_lb, (int)nblocks, ws, d_res, ctx->d_tmp.as<uint8_t>());
+            }
+            CK(cudaMemcpyAsync(hres.data(), d_res, (size_t)nblocks * sizeof(LzResult), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
         for (uint32_t b = 0; b < nblocks; b++) {
             EncJob& j = jobs[b];
             j.data_off = (uint64_t)b * tstride;

@@ -1,5 +1,7 @@
 // LZ / LZX kernels (kz_lz.cu)
 #pragma once
+#include <vector>
+
 #include "kz_common.cuh"
 
 namespace kz {
@@ -26,6 +28,32 @@ static inline size_t lz_scratch_bytes(size_t count) {
     s = (s + 15) & ~size_t(15);
     return s + (count / 4 + 8) * sizeof(LzRun) + 256;
 }
+
+// ---- data-parallel forward path (kz_lz_par.cu) ----
+struct LzWorkspace {  // device scratch provider: returns a base pointer with at least `bytes` bytes (contents need not survive a call)
+    virtual uint8_t* ensure(size_t bytes) = 0;
+    virtual ~LzWorkspace() {}
+};
+struct LzHook {  // optional per pass instrumentation (kz_api.cu times the passes with CUDA events)
+    virtual void begin(const char* name) = 0;
+    virtual void end() = 0;
+    virtual ~LzHook() {}
+};
+struct LzHookScope {
+    LzHook* h;
+    LzHookScope(LzHook* hook, const char* name) : h(hook) {
+        if (h) h->begin(name);
+    }
+    ~LzHookScope() {
+        if (h) h->end();
+    }
+};
+// LZ / LZX forward of a batch: block b = lb[b] (len == 0: skipped). res[b].status 0 = transformed (out_len bytes at dst_off), 1 = the transform
+// declines (block too small, small alphabet, no compression). Synchronises the stream before it returns.
+cudaError_t lz_forward_parallel(const uint8_t* d_in, uint8_t* d_out, const std::vector<LzBlock>& lb, bool extra, LzWorkspace& W, cudaStream_t stream,
+                                std::vector<LzResult>& res, LzHook* hook);
+cudaError_t lz_forward_parallel_sub(const uint8_t* d_in, uint8_t* d_out, const LzBlock* lb, uint32_t nblocks, bool extra, LzWorkspace& W, cudaStream_t stream,
+                                    LzResult* res, LzHook* hook);
 
 __global__ void lz_parse_kernel(const uint8_t* in, const LzBlock* blocks, int nblocks, int extra, int32_t* hashes_all, uint8_t* scratch_all, uint8_t* out,
                                 LzResult* res);

@@ -1,0 +1,573 @@
+// Data-parallel LZ / LZX forward transform on sm_100a (the parse logic itself is kz_lz_par_core.cuh, shared with the CPU harness
+// tests/host/lz_par_host.cpp). Reference: v2/transform/LZCodec.go:249-591. Passes, all blocks of a batch together:
+//
+//   hash      position -> (block << hash_bits | hash) key                                   [streaming, 8-byte loads]
+//   sort      stable radix sort of (key, position) pairs by key (cub::DeviceRadixSort — the one library call of this path)
+//   link      neighbours of the sorted order with equal keys -> prev[] / next[] per position  [scatter]
+//   info      common prefix / suffix lengths of (i, prev[i]), saturated at 255               [streaming compares]
+//   spec      one warp (lane 0) per 16 KiB segment: speculative parse from a guessed state -> match log of the segment
+//   stitch    one warp (lane 0) per block: the true parse only until it meets a segment's log; piece list of the final match list
+//   flatten   pieces -> contiguous match list
+//   sizes / tilescan / emit   per match token, distance bytes, length bytes, literal run: sizes, block-wide exclusive scans, final bytes
+//   literals  warp-wide copies of the literal runs
+#include <cub/device/device_radix_sort.cuh>
+
+#include <vector>
+
+#include "kz_lz.cuh"
+#include "kz_lz_par_core.cuh"
+
+namespace kz {
+
+using namespace lzp;
+
+namespace {
+
+const int SEG = 16384;               // bytes per speculative segment
+const int SEG_CAP = SEG / 4 + 8;     // log entries per segment (a match is at least 4 bytes long)
+const uint32_t TAINT_CAP = 1024;
+const int TILE = 1024;               // matches per emission tile
+const uint32_t LONG_RUN = 4096;      // literal runs above this length are copied by all warps of the block's CTAs together
+
+struct PBlock {  // device descriptor of one block of the batch
+    uint64_t src_off, dst_off;
+    uint64_t pos_off;    // first entry of the block in rec[] / next[] and (bit index) in the bitmaps; a multiple of 64
+    uint64_t match_off;  // first entry of the block in fix[] / ml[] / runs[]
+    uint32_t count, src_end, npos;
+    int32_t max_dist, min_match;
+    uint32_t seg_base, nsegs;
+    uint32_t piece_off;  // first entry in pieces[]
+    uint32_t tile_base, ntiles_cap;
+    uint32_t active, flags;
+    uint32_t long_off, pad;  // first entry of the block in the list of long literal runs
+};
+struct PState {  // per block results of the stitch / scan passes
+    uint32_t np, fix_n, nmatch;
+    int32_t final_anchor;
+    uint32_t m_total, mlen_total, lit_total, too_many;
+};
+
+__device__ __forceinline__ Params make_params(const uint8_t* in, const PBlock& B, int extra, const Rec* rec, const uint32_t* next, uint32_t* skipmap, uint32_t* taintmap,
+                                              uint32_t* seg_taint, int b) {
+    Params P;
+    P.src = in + B.src_off;
+    P.count = (int)B.count;
+    P.src_end = (int)B.src_end;
+    P.max_dist = B.max_dist;
+    P.min_match = B.min_match;
+    P.extra = extra;
+    P.rec = rec + B.pos_off;
+    P.next = next + B.pos_off;
+    P.skipmap = skipmap + (B.pos_off >> 5);
+    P.taintmap = taintmap + (B.pos_off >> 5);
+    P.seg_taint = seg_taint + 4 * b;
+    P.seg_size = SEG;
+    P.taint_cap = TAINT_CAP;
+    return P;
+}
+
+// ---- pass 0 --------------------------------------------------------------------------------------------------------------------------
+// one thread per position of the concatenated position space; blk_of_tile gives the block of each 1024-position tile
+__global__ void __launch_bounds__(256) lzp_hash_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_chunk,
+                                                        int extra, int hash_bits, uint32_t nblocks, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                        uint64_t total) {
+    const uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (g >= total) return;
+    const uint32_t b = blk_of_chunk[g >> 10];
+    const PBlock& B = blocks[b];
+    const uint32_t i = (uint32_t)(g - B.pos_off);
+    // positions >= npos (and the padding up to the next multiple of 1024) carry the block index `nblocks`: they sort behind every real key
+    uint32_t key = nblocks << hash_bits;
+    if (B.active && i < B.npos) key = (b << hash_bits) | lz_hash(ld64(in + B.src_off + i), extra != 0);
+    keys[g] = key;
+    vals[g] = i;
+}
+__global__ void __launch_bounds__(256) lzp_link_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const PBlock* __restrict__ blocks, int hash_bits,
+                                                        uint32_t nblocks, Rec* __restrict__ rec, uint32_t* __restrict__ next, uint64_t total) {
+    const uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (g >= total) return;
+    const uint32_t key = keys[g];
+    const uint32_t b = key >> hash_bits;
+    if (b >= nblocks) return;
+    const uint64_t base = blocks[b].pos_off;
+    const uint32_t i = vals[g];
+    const bool has_prev = g > 0 && keys[g - 1] == key;
+    const bool has_next = g + 1 < total && keys[g + 1] == key;
+    rec[base + i].prev = has_prev ? vals[g - 1] : NONE;
+    next[base + i] = has_next ? vals[g + 1] : NONE;
+}
+__global__ void __launch_bounds__(256) lzp_info_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_chunk,
+                                                        Rec* __restrict__ rec, uint32_t* __restrict__ next, uint64_t total) {
+    const uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (g >= total) return;
+    const uint32_t b = blk_of_chunk[g >> 10];
+    const PBlock& B = blocks[b];
+    const uint32_t i = (uint32_t)(g - B.pos_off);
+    if (!B.active || i >= B.npos) {  // never probed: no candidate
+        rec[g].prev = NONE;
+        rec[g].info = 0;
+        next[g] = NONE;
+        return;
+    }
+    rec[g].info = make_info(in + B.src_off, (int)B.count, (int)i, rec[g].prev);
+}
+
+// ---- pass 1: speculative segment parses (lane 0 of one warp per segment) -----------------------------------------------------------------
+__global__ void __launch_bounds__(32) lzp_spec_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_seg, int extra,
+                                                       const Rec* __restrict__ rec, const uint32_t* __restrict__ next, uint32_t* skipmap, uint32_t* taintmap, uint32_t* seg_taint,
+                                                       Match* __restrict__ logs, SegDesc* __restrict__ desc) {
+    if (threadIdx.x != 0) return;
+    const uint32_t s = blockIdx.x;
+    const uint32_t b = blk_of_seg[s];
+    const PBlock B = blocks[b];
+    if (!B.active) return;
+    const uint32_t k = s - B.seg_base;
+    const Params P = make_params(in, B, extra, rec, next, skipmap, taintmap, seg_taint, (int)b);
+    const int s0 = (int)(k * SEG);
+    const int s1 = k == B.nsegs - 1 ? 0x7FFFFFFF : s0 + SEG;
+    SegDesc d;
+    spec_parse_segment(P, s0, s1, logs + (size_t)s * SEG_CAP, d);
+    desc[s] = d;
+}
+
+// ---- pass 2: stitch (lane 0 of one warp per block) -----------------------------------------------------------------------------------------
+struct SegLogAt {
+    const Match* base;
+    __device__ const Match* operator()(int k) const { return base + (size_t)k * SEG_CAP; }
+};
+__global__ void __launch_bounds__(32) lzp_stitch_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, int nblocks, int extra, const Rec* __restrict__ rec,
+                                                         const uint32_t* __restrict__ next, uint32_t* skipmap, uint32_t* taintmap, uint32_t* seg_taint,
+                                                         const Match* __restrict__ logs, const SegDesc* __restrict__ desc, Match* __restrict__ fix, Piece* __restrict__ pieces,
+                                                         uint32_t* __restrict__ piece_start, PState* __restrict__ pst) {
+    const int b = blockIdx.x;
+    if (b >= nblocks || threadIdx.x != 0) return;
+    const PBlock B = blocks[b];
+    PState S;
+    S.np = S.fix_n = S.nmatch = 0;
+    S.final_anchor = 0;
+    S.m_total = S.mlen_total = S.lit_total = S.too_many = 0;
+    if (B.active) {
+        const Params P = make_params(in, B, extra, rec, next, skipmap, taintmap, seg_taint, b);
+        SegLogAt sl;
+        sl.base = logs + (size_t)B.seg_base * SEG_CAP;
+        Piece* pc = pieces + B.piece_off;
+        S.np = stitch_block(P, (int)B.nsegs, desc + B.seg_base, sl, fix + B.match_off, pc, &S.fix_n, &S.final_anchor);
+        uint32_t acc = 0;
+        for (uint32_t p = 0; p < S.np; p++) {  // exclusive scan of the piece lengths (a few hundred pieces)
+            piece_start[B.piece_off + p] = acc;
+            acc += pc[p].end - pc[p].begin;
+        }
+        piece_start[B.piece_off + S.np] = acc;
+        S.nmatch = acc;
+    }
+    pst[b] = S;
+}
+
+// ---- pass 3: flatten the pieces into the block's match list -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lzp_flatten_kernel(const PBlock* __restrict__ blocks, const PState* __restrict__ pst, const Piece* __restrict__ pieces,
+                                                           const uint32_t* __restrict__ piece_start, const Match* __restrict__ logs, const Match* __restrict__ fix,
+                                                           Match* __restrict__ ml) {
+    const int b = blockIdx.y;
+    const PBlock& B = blocks[b];
+    const PState& S = pst[b];
+    const Piece* pc = pieces + B.piece_off;
+    const uint32_t* ps = piece_start + B.piece_off;
+    for (uint32_t t = blockIdx.x * 256 + threadIdx.x; t < S.nmatch; t += gridDim.x * 256) {
+        uint32_t lo = 0, hi = S.np;  // last piece with start <= t
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (ps[mid] <= t) lo = mid;
+            else hi = mid;
+        }
+        const Piece p = pc[lo];
+        const uint32_t e = p.begin + (t - ps[lo]);
+        ml[B.match_off + t] = p.spec ? logs[(size_t)(B.seg_base + p.seg) * SEG_CAP + e] : fix[B.match_off + e];
+    }
+}
+
+// ---- pass 4: emission -------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void match_context(const Match* __restrict__ ml, uint32_t t, int count, int& prev_anchor, int& r0, int& r1) {
+    if (t >= 1) {
+        const Match a = ml[t - 1];
+        prev_anchor = (int)(a.start + a.len);
+        r0 = (int)a.dist;
+    } else {
+        prev_anchor = 0;
+        r0 = count;
+    }
+    r1 = t >= 2 ? (int)ml[t - 2].dist : count;
+}
+// block-wide exclusive scan of three 32-bit values over TILE threads; returns the tile totals through tot[]
+__device__ __forceinline__ void tile_scan3(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t* sm /* 3 * 32 */, uint32_t tot[3]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t ia = a, ib = b, ic = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t xa = __shfl_up_sync(0xFFFFFFFFu, ia, d), xb = __shfl_up_sync(0xFFFFFFFFu, ib, d), xc = __shfl_up_sync(0xFFFFFFFFu, ic, d);
+        if (lane >= d) ia += xa, ib += xb, ic += xc;
+    }
+    if (lane == 31) sm[warp] = ia, sm[32 + warp] = ib, sm[64 + warp] = ic;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t wa = sm[lane], wb = sm[32 + lane], wc = sm[64 + lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t xa = __shfl_up_sync(0xFFFFFFFFu, wa, d), xb = __shfl_up_sync(0xFFFFFFFFu, wb, d), xc = __shfl_up_sync(0xFFFFFFFFu, wc, d);
+            if (lane >= d) wa += xa, wb += xb, wc += xc;
+        }
+        sm[lane] = wa, sm[32 + lane] = wb, sm[64 + lane] = wc;
+    }
+    __syncthreads();
+    const uint32_t oa = warp ? sm[warp - 1] : 0, ob = warp ? sm[32 + warp - 1] : 0, oc = warp ? sm[64 + warp - 1] : 0;
+    tot[0] = sm[31], tot[1] = sm[63], tot[2] = sm[95];
+    a = oa + ia - a;
+    b = ob + ib - b;
+    c = oc + ic - c;
+    __syncthreads();
+}
+__global__ void __launch_bounds__(TILE) lzp_sizes_kernel(const PBlock* __restrict__ blocks, const PState* __restrict__ pst, const Match* __restrict__ ml_all,
+                                                          uint32_t* __restrict__ tile_sums /* 4 per tile */) {
+    __shared__ uint32_t sm[96];
+    const int b = blockIdx.y;
+    const PBlock& B = blocks[b];
+    const uint32_t nm = pst[b].nmatch;
+    if (blockIdx.x * TILE >= nm && blockIdx.x > 0) return;
+    const Match* ml = ml_all + B.match_off;
+    const uint32_t t = blockIdx.x * TILE + threadIdx.x;
+    uint32_t a = 0, bb = 0, c = 0;
+    bool too_many = false;
+    if (t < nm) {
+        int pa, r0, r1;
+        match_context(ml, t, (int)B.count, pa, r0, r1);
+        Sizes s;
+        match_sizes(ml[t], pa, r0, r1, B.min_match, s, too_many);
+        a = s.m_bytes, bb = s.mlen_bytes, c = s.lit_bytes;
+    }
+    const int any_too_many = __syncthreads_or(too_many ? 1 : 0);
+    uint32_t tot[3];
+    tile_scan3(a, bb, c, sm, tot);
+    if (threadIdx.x == 0) {
+        uint32_t* ts = tile_sums + 4 * (size_t)(B.tile_base + blockIdx.x);
+        ts[0] = tot[0], ts[1] = tot[1], ts[2] = tot[2], ts[3] = (uint32_t)any_too_many;
+    }
+}
+// one warp per block: exclusive scan of the tile sums, totals, the reference's two "no compression" tests, header
+__global__ void __launch_bounds__(32) lzp_tilescan_kernel(const PBlock* __restrict__ blocks, int nblocks, PState* __restrict__ pst, uint32_t* __restrict__ tile_sums,
+                                                           uint8_t* __restrict__ out, LzResult* __restrict__ res) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (b >= nblocks) return;
+    const PBlock B = blocks[b];
+    PState S = pst[b];
+    LzResult r;
+    r.status = 1;
+    r.out_len = r.n_runs = r.lit_end = r.tk_n = r.m_n = r.mlen_n = 0;
+    if (!B.active) {
+        if (lane == 0) res[b] = r;
+        return;
+    }
+    const uint32_t ntiles = (S.nmatch + TILE - 1) / TILE;
+    uint32_t ca = 0, cb = 0, cc = 0, bad = 0;
+    for (uint32_t t0 = 0; t0 < ntiles; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        uint32_t* ts = tile_sums + 4 * (size_t)(B.tile_base + t);
+        uint32_t a = 0, bb = 0, c = 0;
+        if (t < ntiles) a = ts[0], bb = ts[1], c = ts[2], bad |= ts[3];
+        uint32_t ia = a, ib = bb, ic = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t xa = __shfl_up_sync(0xFFFFFFFFu, ia, d), xb = __shfl_up_sync(0xFFFFFFFFu, ib, d), xc = __shfl_up_sync(0xFFFFFFFFu, ic, d);
+            if (lane >= d) ia += xa, ib += xb, ic += xc;
+        }
+        if (t < ntiles) ts[0] = ca + ia - a, ts[1] = cb + ib - bb, ts[2] = cc + ic - c;
+        ca += __shfl_sync(0xFFFFFFFFu, ia, 31);
+        cb += __shfl_sync(0xFFFFFFFFu, ib, 31);
+        cc += __shfl_sync(0xFFFFFFFFu, ic, 31);
+    }
+    bad = __reduce_or_sync(0xFFFFFFFFu, bad);
+    if (lane != 0) return;
+    S.m_total = ca, S.mlen_total = cb, S.lit_total = cc, S.too_many = bad;
+    const uint32_t count = B.count;
+    const int lit_len = (int)count - S.final_anchor;
+    const uint64_t dst_idx = 13ull + cc, tk_idx = S.nmatch, m_idx = ca;
+    const uint64_t lit_end = dst_idx + (uint64_t)lit_len + (lit_len >= 7 ? (uint64_t)length_bytes(lit_len - 7) : 0ull);
+    const uint64_t total = lit_end + (tk_idx + 1) + m_idx + cb;
+    if (!bad && dst_idx + (uint64_t)lit_len + tk_idx + m_idx < count && total <= count - count / 100) {
+        uint8_t* dst = out + B.dst_off;
+        const uint32_t a = (uint32_t)lit_end, bb = (uint32_t)(tk_idx + 1), c = (uint32_t)m_idx;
+        for (int i = 0; i < 4; i++) {
+            dst[i] = (uint8_t)(a >> (8 * i));
+            dst[4 + i] = (uint8_t)(bb >> (8 * i));
+            dst[8 + i] = (uint8_t)(c >> (8 * i));
+        }
+        dst[12] = (uint8_t)B.flags;
+        r.lit_end = a, r.tk_n = bb, r.m_n = c, r.mlen_n = cb;
+        r.n_runs = S.nmatch + 1;
+        if (total <= count - count / 100) {  // otherwise the reference declines after writing (:582-588): nothing is emitted here
+            r.status = 0;
+            r.out_len = (uint32_t)total;
+        }
+    }
+    pst[b] = S;
+    res[b] = r;
+}
+__global__ void __launch_bounds__(TILE) lzp_emit_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const PState* __restrict__ pst,
+                                                         const Match* __restrict__ ml_all, const uint32_t* __restrict__ tile_sums, const LzResult* __restrict__ res,
+                                                         uint8_t* __restrict__ out, LzRun* __restrict__ runs_all, uint32_t* __restrict__ long_runs,
+                                                         uint32_t* __restrict__ long_n) {
+    __shared__ uint32_t sm[96];
+    const int b = blockIdx.y;
+    const PBlock& B = blocks[b];
+    const PState& S = pst[b];
+    const LzResult R = res[b];
+    if (R.status != 0) return;
+    const uint32_t nm = S.nmatch;
+    if (blockIdx.x * TILE > nm) return;  // tile blockIdx.x holds matches [x * TILE, ...) and, behind the last match, the final literals
+    const Match* ml = ml_all + B.match_off;
+    LzRun* runs = runs_all + B.match_off;
+    uint8_t* dst = out + B.dst_off;
+    const uint32_t t = blockIdx.x * TILE + threadIdx.x;
+    uint32_t a = 0, bb = 0, c = 0;
+    int pa = 0, r0 = 0, r1 = 0;
+    Match m;
+    m.start = m.len = m.dist = m.pad = 0;
+    Sizes s;
+    s.m_bytes = s.mlen_bytes = s.lit_bytes = 0;
+    if (t < nm) {
+        match_context(ml, t, (int)B.count, pa, r0, r1);
+        m = ml[t];
+        bool tm;
+        match_sizes(m, pa, r0, r1, B.min_match, s, tm);
+        a = s.m_bytes, bb = s.mlen_bytes, c = s.lit_bytes;
+    }
+    uint32_t tot[3];
+    tile_scan3(a, bb, c, sm, tot);
+    const uint32_t* ts = tile_sums + 4 * (size_t)(B.tile_base + blockIdx.x);
+    const uint32_t has_tile = blockIdx.x * TILE < nm;
+    const uint32_t m_at = (has_tile ? ts[0] : S.m_total) + a, mlen_at = (has_tile ? ts[1] : S.mlen_total) + bb, lit_at = 13u + (has_tile ? ts[2] : S.lit_total) + c;
+    uint8_t* tk = dst + R.lit_end;
+    uint8_t* mb = tk + R.tk_n;
+    uint8_t* mlenb = mb + R.m_n;
+    if (t < nm) {
+        match_emit(m, pa, r0, r1, B.min_match, tk + t, mb + m_at, mlenb + mlen_at, dst + lit_at);
+        const uint32_t lit_len = m.start - (uint32_t)pa;
+        runs[t].src = (uint32_t)pa;
+        runs[t].dst = lit_at + (s.lit_bytes - lit_len);
+        runs[t].len = lit_len;
+        if (lit_len > LONG_RUN) long_runs[B.long_off + atomicAdd(&long_n[b], 1u)] = t;
+    } else if (t == nm) {  // final literals (:538-551)
+        const int lit_len = (int)B.count - S.final_anchor;
+        uint32_t at = lit_at;
+        if (lit_len >= 7) {
+            tk[t] = (uint8_t)(7 << 5);
+            at += (uint32_t)emit_length(dst + at, lit_len - 7);
+        } else {
+            tk[t] = (uint8_t)(lit_len << 5);
+        }
+        runs[t].src = (uint32_t)S.final_anchor;
+        runs[t].dst = at;
+        runs[t].len = (uint32_t)lit_len;
+        if ((uint32_t)lit_len > LONG_RUN) long_runs[B.long_off + atomicAdd(&long_n[b], 1u)] = t;
+    }
+}
+// literal runs: warps of grid.x CTAs per block take runs round robin; long runs are cut into 4 KiB pieces over all warps
+__global__ void __launch_bounds__(256) lzp_literals_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const LzResult* __restrict__ res,
+                                                            const LzRun* __restrict__ runs_all, const uint32_t* __restrict__ long_runs,
+                                                            const uint32_t* __restrict__ long_n, uint8_t* __restrict__ out) {
+    const int b = blockIdx.y;
+    const LzResult R = res[b];
+    if (R.status != 0) return;
+    const PBlock& B = blocks[b];
+    const uint8_t* src = in + B.src_off;
+    uint8_t* dst = out + B.dst_off;
+    const LzRun* runs = runs_all + B.match_off;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = (gridDim.x * 256) >> 5;
+    for (uint32_t i = warp; i < R.n_runs; i += nwarps) {
+        const LzRun run = runs[i];
+        if (run.len > LONG_RUN) continue;  // long runs: second loop
+        for (uint32_t k = lane; k < run.len; k += 32) dst[run.dst + k] = src[run.src + k];
+    }
+    const uint32_t nl = long_n[b];
+    for (uint32_t i = 0; i < nl; i++) {
+        const LzRun run = runs[long_runs[B.long_off + i]];
+        for (uint32_t k0 = warp * 4096u; k0 < run.len; k0 += nwarps * 4096u) {
+            const uint32_t k1 = min(k0 + 4096u, run.len);
+            for (uint32_t k = k0 + lane; k < k1; k += 32) dst[run.dst + k] = src[run.src + k];
+        }
+    }
+}
+
+size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+}  // namespace
+
+cudaError_t lz_forward_parallel_sub(const uint8_t* d_in, uint8_t* d_out, const LzBlock* lb, uint32_t nblocks, bool extra, LzWorkspace& W, cudaStream_t stream,
+                                    LzResult* res, LzHook* hook) {
+    const int hash_bits = extra ? 19 : 16;
+    std::vector<PBlock> pb(nblocks);
+    std::vector<uint32_t> blk_of_chunk, blk_of_seg;
+    uint64_t pos = 0, matches = 0;
+    uint32_t segs = 0, pieces = 0, tiles = 0, longs = 0;
+    for (uint32_t b = 0; b < nblocks; b++) {
+        PBlock& B = pb[b];
+        const uint32_t count = lb[b].len;
+        B.src_off = lb[b].src_off;
+        B.dst_off = lb[b].dst_off;
+        B.count = count;
+        B.active = count >= (uint32_t)MIN_BLOCK && lb[b].data_type != 9 /*DT_SMALL_ALPHABET*/;
+        B.src_end = B.active ? count - 16 - 2 : 0;
+        B.max_dist = MAX_DISTANCE2;
+        B.flags = 1;
+        if ((int)B.src_end < 4 * MAX_DISTANCE1) {
+            B.max_dist = MAX_DISTANCE1;
+            B.flags = 0;
+        }
+        B.min_match = lb[b].data_type == 6 /*DT_DNA*/ ? 6 : 4;
+        B.flags |= (uint32_t)(((B.min_match - 2) & 7) << 1);
+        B.npos = B.active ? (uint32_t)std::min<int64_t>((int64_t)count - 8, (int64_t)B.src_end + 2) : 0;
+        B.pos_off = pos;
+        const uint64_t padded = ((uint64_t)count + 1023) & ~1023ull;
+        for (uint64_t c = 0; c < padded; c += 1024) blk_of_chunk.push_back(b);
+        pos += padded;
+        B.match_off = matches;
+        matches += (uint64_t)count / 4 + 32;
+        B.seg_base = segs;
+        B.nsegs = B.active ? std::max<uint32_t>(1, (B.src_end + SEG - 1) / SEG) : 0;
+        for (uint32_t k = 0; k < B.nsegs; k++) blk_of_seg.push_back(b);
+        segs += B.nsegs;
+        B.piece_off = pieces;
+        pieces += piece_capacity(B.nsegs, TAINT_CAP) + 1;
+        B.tile_base = tiles;
+        B.ntiles_cap = (uint32_t)((count / 4 + 32 + TILE - 1) / TILE) + 1;
+        tiles += B.ntiles_cap;
+        B.long_off = longs;
+        B.pad = 0;
+        longs += count / LONG_RUN + 2;
+    }
+    const uint64_t total = pos;
+    if (total == 0 || segs == 0) {
+        for (uint32_t b = 0; b < nblocks; b++) res[b] = LzResult{1, 0, 0, 0, 0, 0, 0};
+        return cudaSuccess;
+    }
+    // ---- workspace layout
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t at = off;
+        off = align256(off + bytes);
+        return at;
+    };
+    const size_t o_pb = take(nblocks * sizeof(PBlock)), o_boc = take(blk_of_chunk.size() * 4), o_bos = take(blk_of_seg.size() * 4);
+    const size_t o_keys_a = take(total * 4), o_keys_b = take(total * 4), o_vals_a = take(total * 4), o_vals_b = take(total * 4);
+    const size_t o_rec = take(total * sizeof(Rec)), o_next = take(total * 4), o_skip = take(total / 8 + 64), o_taint = take(total / 8 + 64);
+    const size_t o_segt = take((size_t)nblocks * 16), o_longn = take((size_t)nblocks * 4), o_long = take((size_t)longs * 4), o_logs = take((size_t)segs * SEG_CAP * sizeof(Match)), o_desc = take((size_t)segs * sizeof(SegDesc));
+    const size_t o_fix = take(matches * sizeof(Match)), o_ml = take(matches * sizeof(Match)), o_runs = take(matches * sizeof(LzRun));
+    const size_t o_pieces = take((size_t)pieces * sizeof(Piece)), o_pstart = take((size_t)pieces * 4), o_pst = take(nblocks * sizeof(PState));
+    const size_t o_tiles = take((size_t)tiles * 16), o_res = take(nblocks * sizeof(LzResult));
+    size_t cub_bytes = 0;
+    {
+        cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
+        cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, k, v, (int)total, 0, 32);
+    }
+    const size_t o_cub = take(cub_bytes + 256);
+    uint8_t* ws = W.ensure(off + 4096);
+    if (!ws) return cudaErrorMemoryAllocation;
+    // ---- host tables
+    std::vector<uint8_t> host(o_keys_a);
+    memcpy(host.data() + o_pb, pb.data(), nblocks * sizeof(PBlock));
+    memcpy(host.data() + o_boc, blk_of_chunk.data(), blk_of_chunk.size() * 4);
+    memcpy(host.data() + o_bos, blk_of_seg.data(), blk_of_seg.size() * 4);
+    cudaError_t e = cudaMemcpyAsync(ws, host.data(), host.size(), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(stream);  // `host` goes out of scope at return; the copy is small
+    if (e != cudaSuccess) return e;
+    const PBlock* d_pb = (const PBlock*)(ws + o_pb);
+    const uint32_t* d_boc = (const uint32_t*)(ws + o_boc);
+    const uint32_t* d_bos = (const uint32_t*)(ws + o_bos);
+    uint32_t *keys_a = (uint32_t*)(ws + o_keys_a), *keys_b = (uint32_t*)(ws + o_keys_b), *vals_a = (uint32_t*)(ws + o_vals_a), *vals_b = (uint32_t*)(ws + o_vals_b);
+    Rec* d_rec = (Rec*)(ws + o_rec);
+    uint32_t* d_next = (uint32_t*)(ws + o_next);
+    uint32_t *d_skip = (uint32_t*)(ws + o_skip), *d_taint = (uint32_t*)(ws + o_taint), *d_segt = (uint32_t*)(ws + o_segt);
+    Match *d_logs = (Match*)(ws + o_logs), *d_fix = (Match*)(ws + o_fix), *d_ml = (Match*)(ws + o_ml);
+    SegDesc* d_desc = (SegDesc*)(ws + o_desc);
+    LzRun* d_runs = (LzRun*)(ws + o_runs);
+    Piece* d_pieces = (Piece*)(ws + o_pieces);
+    uint32_t* d_pstart = (uint32_t*)(ws + o_pstart);
+    PState* d_pst = (PState*)(ws + o_pst);
+    uint32_t* d_tiles = (uint32_t*)(ws + o_tiles);
+    uint32_t *d_longn = (uint32_t*)(ws + o_longn), *d_long = (uint32_t*)(ws + o_long);
+    LzResult* d_res = (LzResult*)(ws + o_res);
+    const uint32_t G = (uint32_t)((total + 255) / 256);
+    int key_bits = hash_bits;
+    while ((1u << (key_bits - hash_bits)) <= nblocks) key_bits++;  // block indices 0 .. nblocks (the last one: padding)
+    // ---- passes
+    cudaMemsetAsync(ws + o_skip, 0, o_longn + (size_t)nblocks * 4 - o_skip, stream);  // skipmap, taintmap, taint counters, long run counters
+    {
+        LzHookScope hs(hook, "lz_hash");
+        lzp_hash_kernel<<<G, 256, 0, stream>>>(d_in, d_pb, d_boc, extra ? 1 : 0, hash_bits, nblocks, keys_a, vals_a, total);
+    }
+    cub::DoubleBuffer<uint32_t> dk(keys_a, keys_b), dv(vals_a, vals_b);
+    {
+        LzHookScope hs(hook, "lz_sort");
+        size_t tb = cub_bytes;
+        e = cub::DeviceRadixSort::SortPairs(ws + o_cub, tb, dk, dv, (int)total, 0, std::min(32, key_bits), stream);
+        if (e != cudaSuccess) return e;
+    }
+    {
+        LzHookScope hs(hook, "lz_link");
+        lzp_link_kernel<<<G, 256, 0, stream>>>(dk.Current(), dv.Current(), d_pb, hash_bits, nblocks, d_rec, d_next, total);
+        lzp_info_kernel<<<G, 256, 0, stream>>>(d_in, d_pb, d_boc, d_rec, d_next, total);
+    }
+    {
+        LzHookScope hs(hook, "lz_spec");
+        lzp_spec_kernel<<<segs, 32, 0, stream>>>(d_in, d_pb, d_bos, extra ? 1 : 0, d_rec, d_next, d_skip, d_taint, d_segt, d_logs, d_desc);
+    }
+    {
+        LzHookScope hs(hook, "lz_stitch");
+        lzp_stitch_kernel<<<nblocks, 32, 0, stream>>>(d_in, d_pb, (int)nblocks, extra ? 1 : 0, d_rec, d_next, d_skip, d_taint, d_segt, d_logs, d_desc, d_fix, d_pieces, d_pstart,
+                                                      d_pst);
+    }
+    uint32_t max_tiles = 1;
+    for (uint32_t b = 0; b < nblocks; b++) max_tiles = std::max(max_tiles, pb[b].ntiles_cap);
+    {
+        LzHookScope hs(hook, "lz_emit");
+        lzp_flatten_kernel<<<dim3(64, nblocks), 256, 0, stream>>>(d_pb, d_pst, d_pieces, d_pstart, d_logs, d_fix, d_ml);
+        lzp_sizes_kernel<<<dim3(max_tiles, nblocks), TILE, 0, stream>>>(d_pb, d_pst, d_ml, d_tiles);
+        lzp_tilescan_kernel<<<nblocks, 32, 0, stream>>>(d_pb, (int)nblocks, d_pst, d_tiles, d_out, d_res);
+        lzp_emit_kernel<<<dim3(max_tiles, nblocks), TILE, 0, stream>>>(d_in, d_pb, d_pst, d_ml, d_tiles, d_res, d_out, d_runs, d_long, d_longn);
+        lzp_literals_kernel<<<dim3(16, nblocks), 256, 0, stream>>>(d_in, d_pb, d_res, d_runs, d_long, d_longn, d_out);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(res, d_res, nblocks * sizeof(LzResult), cudaMemcpyDeviceToHost, stream);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+// Host entry: LZ / LZX forward of a batch. blocks[b].len == 0 -> the block is skipped (status 1). res[b] as lz_parse_kernel + lz_gather_kernel
+// leave it (status 0: transformed, out_len bytes at dst_off). ws / ws_bytes: device workspace, grown through `grow` (returns the new base).
+cudaError_t lz_forward_parallel(const uint8_t* d_in, uint8_t* d_out, const std::vector<LzBlock>& lb, bool extra, LzWorkspace& W, cudaStream_t stream,
+                                std::vector<LzResult>& res, LzHook* hook) {
+    const uint32_t nblocks = (uint32_t)lb.size();
+    res.assign(nblocks, LzResult{1, 0, 0, 0, 0, 0, 0});
+    if (nblocks == 0) return cudaSuccess;
+    const int hash_bits = extra ? 19 : 16;
+    cudaError_t e = cudaSuccess;
+    for (uint32_t b0 = 0; b0 < nblocks && e == cudaSuccess;) {  // sub-batches: block index bits + hash bits fit a 32-bit key, position space < 2^31
+        uint32_t nb = 0;
+        uint64_t total = 0;
+        while (b0 + nb < nblocks && nb < (1u << (31 - hash_bits)) - 1) {
+            const uint64_t add = ((uint64_t)lb[b0 + nb].len + 1023) & ~1023ull;
+            if (nb > 0 && total + add > (1ull << 30)) break;
+            total += add;
+            nb++;
+        }
+        e = lz_forward_parallel_sub(d_in, d_out, lb.data() + b0, nb, extra, W, stream, res.data() + b0, hook);
+        b0 += nb;
+    }
+    return e;
+}
+
+
+}  // namespace kz

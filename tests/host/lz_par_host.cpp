@@ -1,0 +1,138 @@
+// CPU harness of the data-parallel LZ / LZX parse: runs kanzi-go_b200/csrc/kz_lz_par_core.cuh (the code the kernels of kz_lz_par.cu run) pass by
+// pass on the host, segments one after another, so that tests/test_lz_par_host.py can compare its output with the oracle byte for byte.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../kanzi-go_b200/csrc/kz_lz_par_core.cuh"
+
+using namespace kz::lzp;
+
+extern "C" {
+// returns the encoded length, -1 when the transform declines. stats: [0] matches, [1] fix-up matches (true parse work of the stitch pass),
+// [2] pieces, [3] 1 when the block entered skip mode
+int64_t lz_forward_par(int extra_i, int data_type, const uint8_t* src_in, int64_t n, uint8_t* dst, int64_t cap, int seg_size, int64_t* stats) {
+    if (n == 0) return 0;
+    const int count = int(n);
+    if (cap < (n <= 1024 ? n + 16 : n + n / 64)) return -1;
+    if (count < MIN_BLOCK) return -1;
+    if (data_type == 9) return -1;
+    std::vector<uint8_t> padded(size_t(n) + 64, 0);
+    memcpy(padded.data(), src_in, size_t(n));
+    const uint8_t* src = padded.data();
+    Params P;
+    P.src = src;
+    P.count = count;
+    P.src_end = count - 16 - 2;
+    P.max_dist = MAX_DISTANCE2;
+    uint8_t flags = 1;
+    if (P.src_end < 4 * MAX_DISTANCE1) {
+        P.max_dist = MAX_DISTANCE1;
+        flags = 0;
+    }
+    P.min_match = data_type == 6 ? 6 : 4;
+    flags |= uint8_t(((P.min_match - 2) & 7) << 1);
+    P.extra = extra_i;
+    // pass 0: prev[] (what the stable sort by hash produces), T / B
+    const int npos = std::max(0, std::min(count - 8, P.src_end + 2));
+    std::vector<Rec> rec(size_t(count) + 8);
+    std::vector<uint32_t> next(size_t(count) + 8, NONE);
+    {
+        std::vector<uint32_t> last(size_t(1) << (extra_i ? 19 : 16), NONE);
+        for (int i = 0; i < count; i++) rec[i].prev = NONE, rec[i].info = 0;
+        for (int i = 0; i < npos; i++) {
+            const uint32_t h = lz_hash(ld64(src + i), extra_i != 0);
+            rec[i].prev = last[h];
+            if (last[h] != NONE) next[last[h]] = uint32_t(i);
+            last[h] = uint32_t(i);
+            rec[i].info = make_info(src, count, i, rec[i].prev);
+        }
+    }
+    P.rec = rec.data();
+    P.next = next.data();
+    std::vector<uint32_t> skipmap(size_t(count) / 32 + 4, 0), taintmap(size_t(count) / 32 + 4, 0);
+    P.skipmap = skipmap.data();
+    P.taintmap = taintmap.data();
+    // pass 1: speculative parse of every segment
+    const int nsegs = std::max(1, (P.src_end + seg_size - 1) / seg_size);
+    std::vector<uint32_t> seg_taint(4, 0);
+    P.seg_taint = seg_taint.data();
+    P.seg_size = seg_size;
+    P.taint_cap = 256;
+    const int seg_cap = seg_size / 4 + 4;
+    std::vector<Match> logs(size_t(nsegs) * seg_cap);
+    std::vector<SegDesc> desc(nsegs);
+    for (int k = 0; k < nsegs; k++) {
+        const int s0 = k * seg_size;
+        const int s1 = k == nsegs - 1 ? 0x7FFFFFFF : s0 + seg_size;
+        spec_parse_segment(P, s0, s1, logs.data() + size_t(k) * seg_cap, desc[k]);
+        if (int(desc[k].n) > seg_cap) return -2;
+    }
+    // pass 2: stitch
+    std::vector<Match> fix(size_t(count) / 4 + 16);
+    std::vector<Piece> pieces(piece_capacity(uint32_t(nsegs), P.taint_cap));
+    uint32_t fix_n = 0;
+    int32_t final_anchor = 0;
+    Match* lp = logs.data();
+    const uint32_t np = stitch_block(P, nsegs, desc.data(), [lp, seg_cap](int k) { return (const Match*)(lp + size_t(k) * seg_cap); }, fix.data(),
+                                     pieces.data(), &fix_n, &final_anchor);
+    // pass 3: flatten + emit
+    std::vector<Match> ml;
+    for (uint32_t p = 0; p < np; p++) {
+        const Match* base = pieces[p].spec ? logs.data() + size_t(pieces[p].seg) * seg_cap : fix.data();
+        for (uint32_t e = pieces[p].begin; e < pieces[p].end; e++) ml.push_back(base[e]);
+    }
+    if (stats) {
+        stats[0] = int64_t(ml.size());
+        stats[1] = fix_n;
+        stats[2] = np;
+        stats[3] = seg_taint[0];
+    }
+    std::vector<uint8_t> tk(ml.size() + 8), mb(3 * ml.size() + 8), mlenb(4 * ml.size() + 8);
+    size_t tk_idx = 0, m_idx = 0, mlen_idx = 0, dst_idx = 13;
+    int prev_anchor = 0, r0 = count, r1 = count;
+    for (const Match& m : ml) {
+        Sizes s;
+        bool too_many;
+        match_sizes(m, prev_anchor, r0, r1, P.min_match, s, too_many);
+        if (too_many) return -1;
+        match_emit(m, prev_anchor, r0, r1, P.min_match, &tk[tk_idx], &mb[m_idx], &mlenb[mlen_idx], dst + dst_idx);
+        const int lit_len = int(m.start) - prev_anchor;
+        memcpy(dst + dst_idx + (s.lit_bytes - lit_len), src + prev_anchor, size_t(lit_len));
+        tk_idx++;
+        m_idx += s.m_bytes;
+        mlen_idx += s.mlen_bytes;
+        dst_idx += s.lit_bytes;
+        prev_anchor = int(m.start + m.len);
+        r1 = r0;
+        r0 = int(m.dist);
+    }
+    if (prev_anchor != final_anchor && !ml.empty()) return -3;
+    const int lit_len = count - prev_anchor;
+    if (dst_idx + size_t(lit_len) + tk_idx + m_idx >= size_t(count)) return -1;
+    if (lit_len >= 7) {
+        tk[tk_idx++] = uint8_t(7 << 5);
+        dst_idx += size_t(emit_length(dst + dst_idx, lit_len - 7));
+    } else {
+        tk[tk_idx++] = uint8_t(lit_len << 5);
+    }
+    memcpy(dst + dst_idx, src + prev_anchor, size_t(lit_len));
+    dst_idx += size_t(lit_len);
+    const uint32_t a = uint32_t(dst_idx), b = uint32_t(tk_idx), c = uint32_t(m_idx);
+    for (int i = 0; i < 4; i++) {
+        dst[i] = uint8_t(a >> (8 * i));
+        dst[4 + i] = uint8_t(b >> (8 * i));
+        dst[8 + i] = uint8_t(c >> (8 * i));
+    }
+    dst[12] = flags;
+    memcpy(dst + dst_idx, tk.data(), tk_idx);
+    dst_idx += tk_idx;
+    memcpy(dst + dst_idx, mb.data(), m_idx);
+    dst_idx += m_idx;
+    memcpy(dst + dst_idx, mlenb.data(), mlen_idx);
+    dst_idx += mlen_idx;
+    if (dst_idx > size_t(count - count / 100)) return -1;
+    return int64_t(dst_idx);
+}
+}
