@@ -1031,7 +1031,7 @@ int apply_forward(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint64_t istride
             uint32_t max_len = 0;
             for (uint32_t b = b0; b < b0 + nb; b++) max_len = std::max(max_len, active[b] ? len[b] : 0u);
             if (max_len == 0) continue;
-            CK(ctx->d_ws.ensure(text_workspace(nb, sbs)));
+            CK(ctx->d_ws.ensure(text_workspace(nb, sbs, max_len)));
             std::vector<TextBlock> tb(nb);
             for (uint32_t k = 0; k < nb; k++) {
                 const uint32_t b = b0 + k;
@@ -1050,7 +1050,7 @@ int apply_forward(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint64_t istride
             uint8_t* T = ctx->d_tables.as<uint8_t>();
             {
                 LaunchScope ls(ctx, "text_forward");
-                cudaError_t e = text_forward_batch(d_in, d_out, (const TextBlock*)(T + o_tb), nb, max_len, sbs, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap,
+                cudaError_t e = text_forward_batch(d_in, d_out, (const TextBlock*)(T + o_tb), tb.data(), nb, max_len, sbs, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap,
                                                    (TextResult*)(T + o_res), ctx->stream, &ctx->launches);
                 if (e != cudaSuccess) return ctx->cuda_fail(e, "text_forward");
             }
@@ -1464,7 +1464,7 @@ int apply_inverse(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint8_t* d_out, 
             bool any = false;
             for (uint32_t b = b0; b < b0 + nb; b++) any = any || (active[b] && len[b]);
             if (!any) continue;
-            CK(ctx->d_ws.ensure(text_workspace(nb, sbs)));
+            CK(ctx->d_ws.ensure(text_workspace_serial(nb, sbs)));
             std::vector<TextBlock> tb(nb);
             for (uint32_t k = 0; k < nb; k++) {
                 const uint32_t b = b0 + k;

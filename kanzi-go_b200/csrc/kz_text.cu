@@ -7,6 +7,7 @@
 
 #include "kz_text.cuh"
 #include "kz_text_core.cuh"
+#include "kz_text_par.cuh"
 
 #if __has_include("_gen/kz_text_dict.inc")
 #include "_gen/kz_text_dict.inc"
@@ -226,21 +227,31 @@ __global__ void __launch_bounds__(32) text_inverse_walk_kernel(const uint8_t* __
 
 }  // namespace
 
-size_t text_workspace(uint32_t nblocks, uint64_t stream_block_size) {
+bool text_serial_walk() {  // KZ_TEXT_FORWARD=serial: the round-1 path (one thread per block walks the words)
+    static const bool v = [] {
+        const char* e = getenv("KZ_TEXT_FORWARD");
+        return e && e[0] == 's';
+    }();
+    return v;
+}
+
+size_t text_workspace_serial(uint32_t nblocks, uint64_t stream_block_size) {
     const uint32_t lg = log_hash_size(stream_block_size);
     return align256(sizeof(Entry) * STATIC_WORDS) + align256(SWORDS_BYTES) + align256((size_t)nblocks * 256 * 4) + align256((size_t)nblocks * 65536 * 4) +
            align256((size_t)nblocks * 4) + align256(((size_t)nblocks << lg) * 4) + align256((size_t)nblocks * MAX_DICT_SIZE * sizeof(Entry)) + 256;
 }
+size_t text_workspace(uint32_t nblocks, uint64_t stream_block_size, uint32_t max_len) {
+    return align256(text_workspace_serial(nblocks, stream_block_size)) + text_parallel_workspace(nblocks, max_len, stream_block_size) + 256;
+}
 
-cudaError_t text_forward_batch(const uint8_t* d_in, uint8_t* d_out, const TextBlock* d_blocks, uint32_t nblocks, uint32_t max_len, uint64_t stream_block_size,
-                               uint8_t* ws, size_t ws_bytes, TextResult* d_res, cudaStream_t stream, uint64_t* launches) {
+cudaError_t text_forward_batch(const uint8_t* d_in, uint8_t* d_out, const TextBlock* d_blocks, const TextBlock* h_blocks, uint32_t nblocks, uint32_t max_len,
+                               uint64_t stream_block_size, uint8_t* ws, size_t ws_bytes, TextResult* d_res, cudaStream_t stream, uint64_t* launches) {
 #if !KZ_HAVE_TEXT_DICT
-    (void)d_in; (void)d_out; (void)d_blocks; (void)nblocks; (void)max_len; (void)stream_block_size; (void)ws; (void)ws_bytes; (void)d_res; (void)stream; (void)launches;
+    (void)d_in; (void)d_out; (void)d_blocks; (void)h_blocks; (void)nblocks; (void)max_len; (void)stream_block_size; (void)ws; (void)ws_bytes; (void)d_res; (void)stream; (void)launches;
     return cudaErrorNotSupported;
 #else
     if (nblocks == 0) return cudaSuccess;
-    (void)max_len;
-    if (ws_bytes < text_workspace(nblocks, stream_block_size)) return cudaErrorInvalidValue;
+    if (ws_bytes < text_workspace(nblocks, stream_block_size, max_len)) return cudaErrorInvalidValue;
     const Ws w = carve(ws, nblocks, stream_block_size);
     const HostStatic& S = host_static();
     cudaError_t e;
@@ -250,6 +261,23 @@ cudaError_t text_forward_batch(const uint8_t* d_in, uint8_t* d_out, const TextBl
     if ((e = cudaMemsetAsync(w.hist1, 0, (size_t)nblocks * 65536 * 4, stream)) != cudaSuccess) return e;
     text_hist_kernel<<<dim3(HIST_SLICES, nblocks), 256, 0, stream>>>(d_in, d_blocks, w.hist0, w.hist1);
     text_plan_kernel<<<nblocks, 32, 0, stream>>>(d_in, d_blocks, (int)nblocks, w.hist0, w.hist1, w.go, d_res);
+    if (!text_serial_walk() && h_blocks) {
+        // data-parallel path (kz_text_par.cu); blocks it does not cover come back in `fallback` and take the serial walk below
+        uint8_t* pws = ws + align256(text_workspace_serial(nblocks, stream_block_size));
+        const size_t pws_bytes = ws_bytes - align256(text_workspace_serial(nblocks, stream_block_size));
+        std::vector<TextBlock> tb(h_blocks, h_blocks + nblocks);
+        std::vector<uint32_t> fallback;
+        if ((e = text_forward_parallel(d_in, d_out, tb, w.go, stream_block_size, w.sdict, w.swords, S.n, pws, pws_bytes, d_res, stream, fallback, launches)) != cudaSuccess)
+            return e;
+        bool any = false;
+        for (uint32_t b = 0; b < nblocks; b++) any = any || fallback[b];
+        if (!any) return cudaGetLastError();
+        std::vector<uint32_t> go(nblocks);
+        if ((e = cudaMemcpy(go.data(), w.go, nblocks * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+        for (uint32_t b = 0; b < nblocks; b++)
+            if (!fallback[b]) go[b] = 0;
+        if ((e = cudaMemcpy(w.go, go.data(), nblocks * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    }
     text_init_kernel<<<dim3(INIT_SLICES, nblocks), 256, 0, stream>>>(w.go, w.sdict, S.n, w.map, w.log, w.list);
     text_forward_walk_kernel<<<nblocks, 32, 0, stream>>>(d_in, d_blocks, (int)nblocks, w.go, S.n, w.swords, w.map, w.log, w.list, d_out, d_res);
     if (launches) *launches += 4;
@@ -264,7 +292,7 @@ cudaError_t text_inverse_batch(const uint8_t* d_in, uint8_t* d_out, const TextBl
     return cudaErrorNotSupported;
 #else
     if (nblocks == 0) return cudaSuccess;
-    if (ws_bytes < text_workspace(nblocks, stream_block_size)) return cudaErrorInvalidValue;
+    if (ws_bytes < text_workspace_serial(nblocks, stream_block_size)) return cudaErrorInvalidValue;
     const Ws w = carve(ws, nblocks, stream_block_size);
     const HostStatic& S = host_static();
     cudaError_t e;

@@ -1,17 +1,22 @@
-// NEXT ROUND — not part of the build (kanzi-go_b200/build.py does not list this directory).
-//
-// TEXT forward (kz_text_core.cuh forward_walk) split into the three phases a GPU wants; tests/test_text_par_host.py checks on the CPU
-// that the phases reproduce forward_walk byte for byte, so that the kernels of the next round only have to wrap them:
+// TEXT forward (kz_text_core.cuh forward_walk) split into the phases a GPU wants; tests/test_text_par_host.py checks on the CPU
+// that the phases reproduce forward_walk byte for byte; the kernels of kz_text_par.cu wrap them:
 //   A. per byte, data parallel: the candidate words — maximal letter runs of 2..31 letters that end on a delimiter — with both hashes
 //      (as written, first letter case-flipped). A word is identified by the position p of the delimiter that ends it.
-//   B. per candidate, in order, one thread per block: the dictionary walk (look-up, insert, recycle). This is the only serial part, and it
-//      touches one map slot, one entry and at most 31 bytes per candidate instead of every byte of the block; its inputs are known
-//      ahead of time, so the map slots of the next candidates can be prefetched.
+//   B. the dictionary. Serial statement: dictionary_pass (look-up, insert, recycle, one candidate after the other). Parallel statement
+//      (dictionary rounds, below): as long as the entry list does not wrap around (fewer than 2^19 - 1024 inserts in a block) a map slot
+//      that has been filled keeps its word for ever (add_word only fires on an EMPTY slot), so "which word owns slot s" is the first
+//      candidate of that slot that is inserted at all, and a candidate is inserted iff it qualifies by length, its slot is still empty
+//      and it is not found through its case-flipped hash. Those conditions refer to EARLIER candidates only, so the true outcome is the
+//      unique fixed point of  ins' = F(ins)  where F looks every candidate up in the slot owners that `ins` implies; every round is data
+//      parallel (atomicMin per slot, one thread per candidate) and round r is right for every candidate whose decision hangs on a chain
+//      of at most r earlier decisions (in text: a handful). Two quirks of the reference are part of F: fresh list entries carry hash 0,
+//      so EVERY insert empties map slot 0 (:1302-1310 via add_word), and words of 3 letters are only inserted while fewer than
+//      16384 - 1024 words were (THRESHOLD2, :1303).
 //   C. per found word, data parallel after a prefix sum: the literal span in front of the word (with the escapes of emitSymbols and the
 //      "single space between two dictionary words is implied" rule), the 1-3 byte word index, and the size checks of Forward :1338-1344,
 //      :1382-1389.
 #pragma once
-#include "../kz_text_core.cuh"
+#include "kz_text_core.cuh"
 
 namespace kz {
 namespace textc {
@@ -130,6 +135,74 @@ KZ_TEXT_HD int emit_pass(const uint8_t* src, int count, uint8_t mode, const Foun
     if (dst_idx > dst_end) return -1;
     return dst_idx;
 }
+
+// ---- phase B, parallel statement: dictionary rounds ------------------------------------------------------------------------------------------------
+static const int32_t OCC_EMPTY = 0x7FFFFFFF;
+static const int Z0_MAX = 16;
+struct SlotZero {  // the inserted candidates whose slot is 0, with the next insert behind each of them (slot 0 is emptied by every insert)
+    int32_t n;
+    int32_t first_ins;  // first inserted candidate of the block (INT32_MAX: none): the static word of slot 0 lives until then
+    int32_t idx[Z0_MAX];
+    int32_t nx[Z0_MAX];
+};
+struct DictView {
+    const uint8_t* src;
+    const Candidate* cand;
+    const int32_t* owner;  // [mask + 1]: OCC_EMPTY, a static word -(index + 1), or the first inserted candidate of the slot (slot 0: static / empty only)
+    uint32_t mask;
+    const Entry* sdict;
+    const uint8_t* swords;
+    const SlotZero* z0;
+};
+// what map[slot] holds when candidate k is looked up
+KZ_TEXT_HD int32_t occupant(const DictView& V, uint32_t slot, int k) {
+    if (slot != 0) {
+        const int32_t o = V.owner[slot];
+        return (o >= 0 && o >= k) ? OCC_EMPTY : o;
+    }
+    const int32_t st = V.owner[0];
+    if (st != OCC_EMPTY && k <= V.z0->first_ins) return st;
+    for (int z = 0; z < V.z0->n && z < Z0_MAX; z++)
+        if (V.z0->idx[z] < k && k <= V.z0->nx[z]) return V.z0->idx[z];
+    return OCC_EMPTY;
+}
+KZ_TEXT_HD bool occupant_is(const DictView& V, int32_t o, uint32_t hash, int32_t length) {
+    if (o == OCC_EMPTY) return false;
+    if (o < 0) {
+        const Entry& e = V.sdict[-(o + 1)];
+        return e.hash == (int32_t)hash && (e.data >> 24) == length;
+    }
+    const Candidate& c = V.cand[o];
+    return c.h1 == hash && c.end - c.start == length;
+}
+KZ_TEXT_HD const uint8_t* occupant_bytes(const DictView& V, int32_t o) {
+    if (o < 0) return V.swords + (~V.sdict[-(o + 1)].ptr);
+    return V.src + V.cand[o].start;
+}
+// One candidate of one round. ins_before = inserted candidates in front of k under the previous round's decisions. Returns the new decision;
+// *found_occ = the word it is (OCC_EMPTY: not in the dictionary), *flip = found through the case-flipped hash.
+KZ_TEXT_HD bool eval_candidate(const DictView& V, int k, uint32_t ins_before, int32_t* found_occ, int32_t* flip) {
+    const Candidate& c = V.cand[k];
+    const int32_t length = c.end - c.start;
+    const int32_t o1 = occupant(V, c.h1 & V.mask, k);
+    int32_t pe = OCC_EMPTY;
+    *flip = 0;
+    if (occupant_is(V, o1, c.h1, length)) {
+        pe = o1;
+    } else {
+        const int32_t o2 = occupant(V, c.h2 & V.mask, k);
+        if (occupant_is(V, o2, c.h2, length)) {
+            pe = o2;
+            *flip = 1;
+        }
+    }
+    if (pe != OCC_EMPTY && !same_words(occupant_bytes(V, pe) + 1, V.src + c.start + 1, length - 1)) pe = OCC_EMPTY;
+    *found_occ = pe;
+    if (pe != OCC_EMPTY) return false;
+    const int words = STATIC_WORDS + (int)ins_before;
+    return (length > 3 || (length == 3 && words < THRESHOLD2)) && o1 == OCC_EMPTY;
+}
+KZ_TEXT_HD int32_t occupant_index(int32_t o, const uint32_t* rank) { return o < 0 ? -(o + 1) : STATIC_WORDS + (int32_t)rank[o]; }
 
 }  // namespace textc
 }  // namespace kz

@@ -1,5 +1,6 @@
-"""Next-round preparation, CPU only: the three-phase TEXT forward (kanzi-go_b200/csrc/next/kz_text_par_core.cuh: candidate words in
-parallel, dictionary pass over the candidates only, parallel emission) reproduces the one-pass walk the GPU runs today."""
+"""CPU check of the parallel TEXT forward (kanzi-go_b200/csrc/kz_text_par_core.cuh, what the kernels of kz_text_par.cu run): candidate words in
+parallel, the dictionary either as one pass over the candidates or as data-parallel rounds to a fixed point, emission through prefix
+sums — all reproduce the one-pass walk (kz_text_core.cuh forward_walk, itself checked against the oracle) byte for byte."""
 import ctypes as C
 import importlib
 import os
@@ -22,7 +23,7 @@ def tp():
     if not gen.main():
         pytest.skip("static dictionary not available")
     os.makedirs(os.path.dirname(SO), exist_ok=True)
-    deps = [SRC, os.path.join(ROOT, "kanzi-go_b200", "csrc", "next", "kz_text_par_core.cuh"), os.path.join(ROOT, "kanzi-go_b200", "csrc", "kz_text_core.cuh")]
+    deps = [SRC, os.path.join(ROOT, "kanzi-go_b200", "csrc", "kz_text_par_core.cuh"), os.path.join(ROOT, "kanzi-go_b200", "csrc", "kz_text_core.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-o", SO, SRC])
     lib = C.CDLL(SO)
@@ -30,7 +31,45 @@ def tp():
     lib.tp_walk.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int]
     lib.tp_phases.restype = C.c_int64
     lib.tp_phases.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.tp_parallel.restype = C.c_int64
+    lib.tp_parallel.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     return lib
+
+
+def _same_parallel(tp, x, bs, mode=0):
+    x = np.ascontiguousarray(x, np.uint8)
+    a = np.zeros(len(x) + 64, np.uint8)
+    b = np.zeros(len(x) + 64, np.uint8)
+    rounds, nc, nf = C.c_int(0), C.c_int(0), C.c_int(0)
+    na = tp.tp_walk(x.ctypes.data, len(x), a.ctypes.data, bs, mode)
+    nb = tp.tp_parallel(x.ctypes.data, len(x), b.ctypes.data, bs, mode, C.byref(rounds), C.byref(nc), C.byref(nf))
+    assert nb != -2, "the parallel statement declined"
+    assert na == nb, (na, nb, rounds.value)
+    if na > 0:
+        assert np.array_equal(a[:na], b[:nb]), int(np.argmax(a[:na] != b[:nb]))
+    return na, rounds.value, nc.value, nf.value
+
+
+@pytest.mark.parametrize("n,bs", [(1024, 1024), (5000, 4096), (100000, 1 << 16), (1 << 20, 1 << 20), (4 << 20, 4 << 20)])
+def test_dictionary_rounds_match_the_walk(tp, n, bs):
+    """the data-parallel dictionary (fixed point of the insert decisions) + prefix-sum emission == the serial walk"""
+    texts = [synth.markov_text(n, seed=n), _words(n, 50, n + 1), _words(n, 5000, n + 2, crlf=True), synth.english_text(n, seed=n + 3),
+             synth.english_text(n, seed=n + 4, crlf=False, html=True), synth.enwik_shaped(n, seed=n + 5), synth.xml_like(n, seed=n + 6)]
+    worst = 0
+    for x in texts:
+        for mode in (0, 0x40):
+            na, rounds, nc, nf = _same_parallel(tp, x, bs, mode)
+            worst = max(worst, rounds)
+    print("n", n, "rounds (max)", worst)
+    assert worst <= 24
+    spaces = np.concatenate([np.full(50, 0x20, np.uint8), synth.markov_text(n, seed=3)[: n - 50]])
+    _same_parallel(tp, spaces, bs)
+    dense = np.frombuffer((b"the and that have with " * (n // 23 + 1))[:n], np.uint8)
+    _same_parallel(tp, dense, bs)
+    caps = np.frombuffer((b"Hello hello HELLO hello Hello world World wOrld world abc Abc abc aBc " * (n // 70 + 1))[:n], np.uint8)
+    _same_parallel(tp, caps, bs)
+    hard = np.random.default_rng(n).integers(0, 256, n).astype(np.uint8)
+    _same_parallel(tp, hard, bs)
 
 
 def _same(tp, x, bs, mode=0):
