@@ -138,6 +138,57 @@ bool lz_serial_parse() {
     return v;
 }
 
+// LZ / LZX forward of a batch: the data-parallel path (kz_lz_par.cu); blocks it hands back (status 3: no fixed point of the table
+// membership within its round limit) and everything under KZ_LZ_PARSE=serial go through the serial parse of kz_lz.cu.
+int upload(kz_ctx* ctx, Packer& pk);
+int lz_forward_batch(kz_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, std::vector<LzBlock>& lb, bool extra, std::vector<LzResult>& hres) {
+    const uint32_t nblocks = (uint32_t)lb.size();
+    hres.assign(nblocks, LzResult{1, 0, 0, 0, 0, 0, 0});
+    bool serial = lz_serial_parse();
+    if (!serial) {
+        CtxLzWorkspace W(ctx);
+        CtxLzHook H(ctx);
+        CK(lz_forward_parallel(d_in, d_out, lb, extra, W, ctx->stream, hres, &H));
+        for (uint32_t b = 0; b < nblocks; b++) serial = serial || hres[b].status == 3;
+        if (!serial) return 0;
+    }
+    uint32_t max_len = 0;
+    std::vector<LzBlock> sb(lb);
+    for (uint32_t b = 0; b < nblocks; b++) {
+        if (!lz_serial_parse() && hres[b].status != 3) sb[b].len = 0;  // done by the parallel path
+        max_len = std::max(max_len, sb[b].len);
+    }
+    const uint64_t sstride = (lz_scratch_bytes(max_len) + 255) & ~size_t(255);
+    const size_t hbytes = ((size_t)nblocks << (extra ? 19 : 16)) * 4;
+    for (uint32_t b = 0; b < nblocks; b++) sb[b].scratch_off = (uint64_t)b * sstride;
+    CK(ctx->d_ws.ensure(sstride * nblocks + hbytes + 4096));
+    CK(ctx->d_lens.ensure((size_t)nblocks * sizeof(LzResult) + 64));
+    Packer pk;
+    const size_t o_lb = pk.add(sb.data(), sb.size() * sizeof(LzBlock));
+    int rc = upload(ctx, pk);
+    if (rc) return rc;
+    uint8_t* ws = ctx->d_ws.as<uint8_t>();
+    int32_t* d_hash = (int32_t*)(ws + sstride * nblocks);
+    CK(cudaMemsetAsync(d_hash, 0, hbytes, ctx->stream));
+    LzBlock* d_lb = (LzBlock*)(ctx->d_tables.as<uint8_t>() + o_lb);
+    LzResult* d_res = ctx->d_lens.as<LzResult>();
+    {
+        LaunchScope ls(ctx, "lz_parse");
+        lz_parse_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_in, d_lb, (int)nblocks, extra ? 1 : 0, d_hash, ws, d_out, d_res);
+    }
+    {
+        LaunchScope ls(ctx, "lz_gather");
+        lz_gather_kernel<<<dim3(nblocks, 8), 256, 0, ctx->stream>>>(d_in, d_lb, (int)nblocks, ws, d_res, d_out);
+    }
+    CK(cudaGetLastError());
+    std::vector<LzResult> sres(nblocks);
+    CK(cudaMemcpyAsync(sres.data(), d_res, (size_t)nblocks * sizeof(LzResult), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t b = 0; b < nblocks; b++)
+        if (lz_serial_parse() || hres[b].status == 3) hres[b] = sres[b];
+    return 0;
+}
+
 int upload(kz_ctx* ctx, Packer& pk) {
     CK(ctx->h_stage.ensure(pk.bytes.size() + 256));
     CK(ctx->d_tables.ensure(pk.bytes.size() + 256));
@@ -988,34 +1039,10 @@ int apply_forward(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint64_t istride
             lb[b].data_type = dts ? (*dts)[b] : 0;
             lb[b].pad = 0;
         }
-        std::vector<LzResult> hres(nblocks);
-        if (!lz_serial_parse()) {
-            CtxLzWorkspace W(ctx);
-            CtxLzHook H(ctx);
-            CK(lz_forward_parallel(d_in, d_out, lb, extra, W, ctx->stream, hres, &H));
-        } else {
-            CK(ctx->d_ws.ensure(sstride * nblocks + hbytes + 4096));
-            CK(ctx->d_lens.ensure((size_t)nblocks * sizeof(LzResult) + 64));
-            Packer pk;
-            const size_t o_lb = pk.add(lb.data(), lb.size() * sizeof(LzBlock));
-            int rc = upload(ctx, pk);
+        std::vector<LzResult> hres;
+        {
+            int rc = lz_forward_batch(ctx, d_in, d_out, lb, extra, hres);
             if (rc) return rc;
-            uint8_t* ws = ctx->d_ws.as<uint8_t>();
-            int32_t* d_hash = (int32_t*)(ws + sstride * nblocks);
-            CK(cudaMemsetAsync(d_hash, 0, hbytes, ctx->stream));
-            LzBlock* d_lb = (LzBlock*)(ctx->d_tables.as<uint8_t>() + o_lb);
-            LzResult* d_res = ctx->d_lens.as<LzResult>();
-            {
-                LaunchScope ls(ctx, "lz_parse");
-                lz_parse_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_in, d_lb, (int)nblocks, extra ? 1 : 0, d_hash, ws, d_out, d_res);
-            }
-            {
-                LaunchScope ls(ctx, "lz_gather");
-                lz_gather_kernel<<<dim3(nblocks, 8), 256, 0, ctx->stream>>>(d_in, d_lb, (int)nblocks, ws, d_res, d_out);
-            }
-            CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(hres.data(), d_res, (size_t)nblocks * sizeof(LzResult), cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
         }
         for (uint32_t b = 0; b < nblocks; b++)
             if (active[b] && len[b] && hres[b].status == 0) {
@@ -1786,33 +1813,10 @@ int forward_stage(kz_ctx* ctx, const TransformPlan& plan, const uint8_t* d_src, 
             lb[b].data_type = dts[b];
             lb[b].pad = 0;
         }
-        std::vector<LzResult> hres(nblocks);
-        if (!lz_serial_parse()) {
-            CtxLzWorkspace W(ctx);
-            CtxLzHook H(ctx);
-            CK(lz_forward_parallel(d_src, ctx->d_tmp.as<uint8_t>(), lb, extra, W, ctx->stream, hres, &H));
-        } else {
-            CK(ctx->d_ws.ensure(sstride * nblocks + hbytes + 4096));
-            CK(ctx->d_lens.ensure((size_t)nblocks * sizeof(LzResult) + 64));
-            Packer pk;
-            const size_t o_lb = pk.add(lb.data(), lb.size() * sizeof(LzBlock));
-            int rc = upload(ctx, pk);
+        std::vector<LzResult> hres;
+        {
+            int rc = lz_forward_batch(ctx, d_src, ctx->d_tmp.as<uint8_t>(), lb, extra, hres);
             if (rc) return rc;
-            uint8_t* ws = ctx->d_ws.as<uint8_t>();
-            int32_t* d_hash = (int32_t*)(ws + sstride * nblocks);
-            CK(cudaMemsetAsync(d_hash, 0, hbytes, ctx->stream));
-            LzBlock* d_lb = (LzBlock*)(ctx->d_tables.as<uint8_t>() + o_lb);
-            LzResult* d_res = ctx->d_lens.as<LzResult>();
-            {
-                LaunchScope ls(ctx, "lz_parse");
-                lz_parse_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_src, d_lb, (int)nblocks, extra ? 1 : 0, d_hash, ws, ctx->d_tmp.as<uint8_t>(), d_res);
-            }
-            {
-                LaunchScope ls(ctx, "lz_gather");
-                lz_gather_kernel<<<dim3(nblocks, 8), 256, 0, ctx->stream>>>(d_src, d_lb, (int)nblocks, ws, d_res, ctx->d_tmp.as<uint8_t>());
-            }
-            CK(cudaMemcpyAsync(hres.data(), d_res, (size_t)nblocks * sizeof(LzResult), cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
         }
         for (uint32_t b = 0; b < nblocks; b++) {
             EncJob& j = jobs[b];

@@ -3,11 +3,14 @@
 //
 //   hash      position -> (block << hash_bits | hash) key                                   [streaming, 8-byte loads]
 //   sort      stable radix sort of (key, position) pairs by key (cub::DeviceRadixSort — the one library call of this path)
-//   link      neighbours of the sorted order with equal keys -> prev[] / next[] per position  [scatter]
+//   link      neighbours of the sorted order with equal keys -> prev[] per position           [scatter]
 //   info      common prefix / suffix lengths of (i, prev[i]), saturated at 255               [streaming compares]
-//   spec      one warp (lane 0) per 16 KiB segment: speculative parse from a guessed state -> match log of the segment
-//   stitch    one warp (lane 0) per block: the true parse only until it meets a segment's log; piece list of the final match list
-//   flatten   pieces -> contiguous match list
+//   rounds to the fixed point of the table membership vf[] (kz_lz_par_core.cuh, 3.; two rounds for ordinary blocks):
+//     filter    candidates under the previous round's vf (round 0: as linked)
+//     spec      one warp (lane 0) per 16 KiB segment: speculative parse from a guessed state -> match log of the segment
+//     stitch    one warp (lane 0) per block: the true parse only until it meets a segment's log; piece list of the match list
+//     flatten   pieces -> contiguous match list
+//     derive    per position: vf' from the match list (closed form for the probe pattern of a literal run); changed?
 //   sizes / tilescan / emit   per match token, distance bytes, length bytes, literal run: sizes, block-wide exclusive scans, final bytes
 //   literals  warp-wide copies of the literal runs
 #include <cub/device/device_radix_sort.cuh>
@@ -25,7 +28,7 @@ namespace {
 
 const int SEG = 16384;               // bytes per speculative segment
 const int SEG_CAP = SEG / 4 + 8;     // log entries per segment (a match is at least 4 bytes long)
-const uint32_t TAINT_CAP = 1024;
+const int MAX_ROUNDS = 8;
 const int TILE = 1024;               // matches per emission tile
 const uint32_t LONG_RUN = 4096;      // literal runs above this length are copied by all warps of the block's CTAs together
 
@@ -47,8 +50,7 @@ struct PState {  // per block results of the stitch / scan passes
     uint32_t m_total, mlen_total, lit_total, too_many;
 };
 
-__device__ __forceinline__ Params make_params(const uint8_t* in, const PBlock& B, int extra, const Rec* rec, const uint32_t* next, uint32_t* skipmap, uint32_t* taintmap,
-                                              uint32_t* seg_taint, int b) {
+__device__ __forceinline__ Params make_params(const uint8_t* in, const PBlock& B, int extra, const Rec* rec) {
     Params P;
     P.src = in + B.src_off;
     P.count = (int)B.count;
@@ -57,12 +59,7 @@ __device__ __forceinline__ Params make_params(const uint8_t* in, const PBlock& B
     P.min_match = B.min_match;
     P.extra = extra;
     P.rec = rec + B.pos_off;
-    P.next = next + B.pos_off;
-    P.skipmap = skipmap + (B.pos_off >> 5);
-    P.taintmap = taintmap + (B.pos_off >> 5);
-    P.seg_taint = seg_taint + 4 * b;
     P.seg_size = SEG;
-    P.taint_cap = TAINT_CAP;
     return P;
 }
 
@@ -83,7 +80,7 @@ __global__ void __launch_bounds__(256) lzp_hash_kernel(const uint8_t* __restrict
     vals[g] = i;
 }
 __global__ void __launch_bounds__(256) lzp_link_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const PBlock* __restrict__ blocks, int hash_bits,
-                                                        uint32_t nblocks, Rec* __restrict__ rec, uint32_t* __restrict__ next, uint64_t total) {
+                                                        uint32_t nblocks, Rec* __restrict__ rec, uint64_t total) {
     const uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x;
     if (g >= total) return;
     const uint32_t key = keys[g];
@@ -92,12 +89,10 @@ __global__ void __launch_bounds__(256) lzp_link_kernel(const uint32_t* __restric
     const uint64_t base = blocks[b].pos_off;
     const uint32_t i = vals[g];
     const bool has_prev = g > 0 && keys[g - 1] == key;
-    const bool has_next = g + 1 < total && keys[g + 1] == key;
     rec[base + i].prev = has_prev ? vals[g - 1] : NONE;
-    next[base + i] = has_next ? vals[g + 1] : NONE;
 }
 __global__ void __launch_bounds__(256) lzp_info_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_chunk,
-                                                        Rec* __restrict__ rec, uint32_t* __restrict__ next, uint64_t total) {
+                                                        Rec* __restrict__ rec, uint64_t total) {
     const uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x;
     if (g >= total) return;
     const uint32_t b = blk_of_chunk[g >> 10];
@@ -106,23 +101,55 @@ __global__ void __launch_bounds__(256) lzp_info_kernel(const uint8_t* __restrict
     if (!B.active || i >= B.npos) {  // never probed: no candidate
         rec[g].prev = NONE;
         rec[g].info = 0;
-        next[g] = NONE;
         return;
     }
     rec[g].info = make_info(in + B.src_off, (int)B.count, (int)i, rec[g].prev);
 }
+// candidates of a round: the first position of the prev[] chain that is in the table (vf) when the position is probed
+__global__ void __launch_bounds__(256) lzp_filter_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_chunk,
+                                                          const uint32_t* __restrict__ done, const Rec* __restrict__ rec0, const uint32_t* __restrict__ vf,
+                                                          Rec* __restrict__ rec, uint64_t total) {
+    const uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (g >= total) return;
+    const uint32_t b = blk_of_chunk[g >> 10];
+    if (done[b]) return;
+    const PBlock& B = blocks[b];
+    const uint32_t i = (uint32_t)(g - B.pos_off);
+    if (!B.active || i >= B.npos) {
+        rec[g] = rec0[g];
+        return;
+    }
+    rec[g] = filter_candidate(in + B.src_off, (int)B.count, rec0 + B.pos_off, vf + B.pos_off, (int)i);
+}
+// vf' of every position from the block's match list; changed[b] |= (vf' != vf)
+__global__ void __launch_bounds__(256) lzp_derive_kernel(const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_chunk, const uint32_t* __restrict__ done,
+                                                          const PState* __restrict__ pst, const Match* __restrict__ ml_all, const uint32_t* __restrict__ vf,
+                                                          uint32_t* __restrict__ vf2, uint32_t* __restrict__ changed, uint64_t total) {
+    const uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    const uint32_t b = blk_of_chunk[min(g, total - 1) >> 10];  // a chunk of 1024 positions belongs to one block: uniform per CTA
+    bool diff = false;
+    if (g < total && !done[b]) {
+        const PBlock& B = blocks[b];
+        const uint32_t i = (uint32_t)(g - B.pos_off);
+        uint32_t v = 0;
+        if (B.active && i < B.count) v = derive_vf(ml_all + B.match_off, pst[b].nmatch, (int)B.src_end, (int)i);
+        vf2[g] = v;
+        diff = v != vf[g];
+    }
+    if (__syncthreads_or(diff ? 1 : 0) && threadIdx.x == 0) atomicOr(&changed[b], 1u);
+}
 
 // ---- pass 1: speculative segment parses (lane 0 of one warp per segment) -----------------------------------------------------------------
 __global__ void __launch_bounds__(32) lzp_spec_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_seg, int extra,
-                                                       const Rec* __restrict__ rec, const uint32_t* __restrict__ next, uint32_t* skipmap, uint32_t* taintmap, uint32_t* seg_taint,
-                                                       Match* __restrict__ logs, SegDesc* __restrict__ desc) {
+                                                       const uint32_t* __restrict__ done, const Rec* __restrict__ rec, Match* __restrict__ logs, SegDesc* __restrict__ desc) {
     if (threadIdx.x != 0) return;
     const uint32_t s = blockIdx.x;
     const uint32_t b = blk_of_seg[s];
+    if (done[b]) return;
     const PBlock B = blocks[b];
     if (!B.active) return;
     const uint32_t k = s - B.seg_base;
-    const Params P = make_params(in, B, extra, rec, next, skipmap, taintmap, seg_taint, (int)b);
+    const Params P = make_params(in, B, extra, rec);
     const int s0 = (int)(k * SEG);
     const int s1 = k == B.nsegs - 1 ? 0x7FFFFFFF : s0 + SEG;
     SegDesc d;
@@ -135,19 +162,19 @@ struct SegLogAt {
     const Match* base;
     __device__ const Match* operator()(int k) const { return base + (size_t)k * SEG_CAP; }
 };
-__global__ void __launch_bounds__(32) lzp_stitch_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, int nblocks, int extra, const Rec* __restrict__ rec,
-                                                         const uint32_t* __restrict__ next, uint32_t* skipmap, uint32_t* taintmap, uint32_t* seg_taint,
-                                                         const Match* __restrict__ logs, const SegDesc* __restrict__ desc, Match* __restrict__ fix, Piece* __restrict__ pieces,
+__global__ void __launch_bounds__(32) lzp_stitch_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, int nblocks, int extra,
+                                                         const uint32_t* __restrict__ done, const Rec* __restrict__ rec, const Match* __restrict__ logs,
+                                                         const SegDesc* __restrict__ desc, Match* __restrict__ fix, Piece* __restrict__ pieces,
                                                          uint32_t* __restrict__ piece_start, PState* __restrict__ pst) {
     const int b = blockIdx.x;
-    if (b >= nblocks || threadIdx.x != 0) return;
+    if (b >= nblocks || threadIdx.x != 0 || done[b]) return;
     const PBlock B = blocks[b];
     PState S;
     S.np = S.fix_n = S.nmatch = 0;
     S.final_anchor = 0;
     S.m_total = S.mlen_total = S.lit_total = S.too_many = 0;
     if (B.active) {
-        const Params P = make_params(in, B, extra, rec, next, skipmap, taintmap, seg_taint, b);
+        const Params P = make_params(in, B, extra, rec);
         SegLogAt sl;
         sl.base = logs + (size_t)B.seg_base * SEG_CAP;
         Piece* pc = pieces + B.piece_off;
@@ -164,10 +191,11 @@ __global__ void __launch_bounds__(32) lzp_stitch_kernel(const uint8_t* __restric
 }
 
 // ---- pass 3: flatten the pieces into the block's match list -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lzp_flatten_kernel(const PBlock* __restrict__ blocks, const PState* __restrict__ pst, const Piece* __restrict__ pieces,
-                                                           const uint32_t* __restrict__ piece_start, const Match* __restrict__ logs, const Match* __restrict__ fix,
-                                                           Match* __restrict__ ml) {
+__global__ void __launch_bounds__(256) lzp_flatten_kernel(const PBlock* __restrict__ blocks, const uint32_t* __restrict__ done, const PState* __restrict__ pst,
+                                                           const Piece* __restrict__ pieces, const uint32_t* __restrict__ piece_start, const Match* __restrict__ logs,
+                                                           const Match* __restrict__ fix, Match* __restrict__ ml) {
     const int b = blockIdx.y;
+    if (done[b]) return;
     const PBlock& B = blocks[b];
     const PState& S = pst[b];
     const Piece* pc = pieces + B.piece_off;
@@ -252,8 +280,8 @@ __global__ void __launch_bounds__(TILE) lzp_sizes_kernel(const PBlock* __restric
     }
 }
 // one warp per block: exclusive scan of the tile sums, totals, the reference's two "no compression" tests, header
-__global__ void __launch_bounds__(32) lzp_tilescan_kernel(const PBlock* __restrict__ blocks, int nblocks, PState* __restrict__ pst, uint32_t* __restrict__ tile_sums,
-                                                           uint8_t* __restrict__ out, LzResult* __restrict__ res) {
+__global__ void __launch_bounds__(32) lzp_tilescan_kernel(const PBlock* __restrict__ blocks, int nblocks, const uint32_t* __restrict__ done, PState* __restrict__ pst,
+                                                           uint32_t* __restrict__ tile_sums, uint8_t* __restrict__ out, LzResult* __restrict__ res) {
     const int b = blockIdx.x, lane = threadIdx.x;
     if (b >= nblocks) return;
     const PBlock B = blocks[b];
@@ -261,7 +289,8 @@ __global__ void __launch_bounds__(32) lzp_tilescan_kernel(const PBlock* __restri
     LzResult r;
     r.status = 1;
     r.out_len = r.n_runs = r.lit_end = r.tk_n = r.m_n = r.mlen_n = 0;
-    if (!B.active) {
+    if (!B.active || !done[b]) {
+        if (B.active) r.status = 3;  // no fixed point within MAX_ROUNDS: the caller parses this block serially
         if (lane == 0) res[b] = r;
         return;
     }
@@ -329,7 +358,7 @@ __global__ void __launch_bounds__(TILE) lzp_emit_kernel(const uint8_t* __restric
     uint32_t a = 0, bb = 0, c = 0;
     int pa = 0, r0 = 0, r1 = 0;
     Match m;
-    m.start = m.len = m.dist = m.pad = 0;
+    m.start = m.len = m.dist = m.probe = 0;
     Sizes s;
     s.m_bytes = s.mlen_bytes = s.lit_bytes = 0;
     if (t < nm) {
@@ -436,7 +465,7 @@ cudaError_t lz_forward_parallel_sub(const uint8_t* d_in, uint8_t* d_out, const L
         for (uint32_t k = 0; k < B.nsegs; k++) blk_of_seg.push_back(b);
         segs += B.nsegs;
         B.piece_off = pieces;
-        pieces += piece_capacity(B.nsegs, TAINT_CAP) + 1;
+        pieces += 2 * B.nsegs + 8;
         B.tile_base = tiles;
         B.ntiles_cap = (uint32_t)((count / 4 + 32 + TILE - 1) / TILE) + 1;
         tiles += B.ntiles_cap;
@@ -458,8 +487,8 @@ cudaError_t lz_forward_parallel_sub(const uint8_t* d_in, uint8_t* d_out, const L
     };
     const size_t o_pb = take(nblocks * sizeof(PBlock)), o_boc = take(blk_of_chunk.size() * 4), o_bos = take(blk_of_seg.size() * 4);
     const size_t o_keys_a = take(total * 4), o_keys_b = take(total * 4), o_vals_a = take(total * 4), o_vals_b = take(total * 4);
-    const size_t o_rec = take(total * sizeof(Rec)), o_next = take(total * 4), o_skip = take(total / 8 + 64), o_taint = take(total / 8 + 64);
-    const size_t o_segt = take((size_t)nblocks * 16), o_longn = take((size_t)nblocks * 4), o_long = take((size_t)longs * 4), o_logs = take((size_t)segs * SEG_CAP * sizeof(Match)), o_desc = take((size_t)segs * sizeof(SegDesc));
+    const size_t o_rec = take(total * sizeof(Rec)), o_rec2 = take(total * sizeof(Rec)), o_vf = take(total * 4), o_vf2 = take(total * 4);
+    const size_t o_done = take((size_t)nblocks * 4), o_changed = take((size_t)nblocks * 4), o_longn = take((size_t)nblocks * 4), o_long = take((size_t)longs * 4), o_logs = take((size_t)segs * SEG_CAP * sizeof(Match)), o_desc = take((size_t)segs * sizeof(SegDesc));
     const size_t o_fix = take(matches * sizeof(Match)), o_ml = take(matches * sizeof(Match)), o_runs = take(matches * sizeof(LzRun));
     const size_t o_pieces = take((size_t)pieces * sizeof(Piece)), o_pstart = take((size_t)pieces * 4), o_pst = take(nblocks * sizeof(PState));
     const size_t o_tiles = take((size_t)tiles * 16), o_res = take(nblocks * sizeof(LzResult));
@@ -484,9 +513,8 @@ cudaError_t lz_forward_parallel_sub(const uint8_t* d_in, uint8_t* d_out, const L
     const uint32_t* d_boc = (const uint32_t*)(ws + o_boc);
     const uint32_t* d_bos = (const uint32_t*)(ws + o_bos);
     uint32_t *keys_a = (uint32_t*)(ws + o_keys_a), *keys_b = (uint32_t*)(ws + o_keys_b), *vals_a = (uint32_t*)(ws + o_vals_a), *vals_b = (uint32_t*)(ws + o_vals_b);
-    Rec* d_rec = (Rec*)(ws + o_rec);
-    uint32_t* d_next = (uint32_t*)(ws + o_next);
-    uint32_t *d_skip = (uint32_t*)(ws + o_skip), *d_taint = (uint32_t*)(ws + o_taint), *d_segt = (uint32_t*)(ws + o_segt);
+    Rec *d_rec = (Rec*)(ws + o_rec), *d_rec2 = (Rec*)(ws + o_rec2);
+    uint32_t *d_vf = (uint32_t*)(ws + o_vf), *d_vf2 = (uint32_t*)(ws + o_vf2), *d_done = (uint32_t*)(ws + o_done), *d_changed = (uint32_t*)(ws + o_changed);
     Match *d_logs = (Match*)(ws + o_logs), *d_fix = (Match*)(ws + o_fix), *d_ml = (Match*)(ws + o_ml);
     SegDesc* d_desc = (SegDesc*)(ws + o_desc);
     LzRun* d_runs = (LzRun*)(ws + o_runs);
@@ -500,7 +528,8 @@ cudaError_t lz_forward_parallel_sub(const uint8_t* d_in, uint8_t* d_out, const L
     int key_bits = hash_bits;
     while ((1u << (key_bits - hash_bits)) <= nblocks) key_bits++;  // block indices 0 .. nblocks (the last one: padding)
     // ---- passes
-    cudaMemsetAsync(ws + o_skip, 0, o_longn + (size_t)nblocks * 4 - o_skip, stream);  // skipmap, taintmap, taint counters, long run counters
+    cudaMemsetAsync(d_vf, 0, total * 4, stream);
+    cudaMemsetAsync(ws + o_done, 0, o_longn + (size_t)nblocks * 4 - o_done, stream);  // done, changed, long run counters
     {
         LzHookScope hs(hook, "lz_hash");
         lzp_hash_kernel<<<G, 256, 0, stream>>>(d_in, d_pb, d_boc, extra ? 1 : 0, hash_bits, nblocks, keys_a, vals_a, total);
@@ -514,25 +543,55 @@ cudaError_t lz_forward_parallel_sub(const uint8_t* d_in, uint8_t* d_out, const L
     }
     {
         LzHookScope hs(hook, "lz_link");
-        lzp_link_kernel<<<G, 256, 0, stream>>>(dk.Current(), dv.Current(), d_pb, hash_bits, nblocks, d_rec, d_next, total);
-        lzp_info_kernel<<<G, 256, 0, stream>>>(d_in, d_pb, d_boc, d_rec, d_next, total);
+        lzp_link_kernel<<<G, 256, 0, stream>>>(dk.Current(), dv.Current(), d_pb, hash_bits, nblocks, d_rec, total);
+        lzp_info_kernel<<<G, 256, 0, stream>>>(d_in, d_pb, d_boc, d_rec, total);
     }
-    {
-        LzHookScope hs(hook, "lz_spec");
-        lzp_spec_kernel<<<segs, 32, 0, stream>>>(d_in, d_pb, d_bos, extra ? 1 : 0, d_rec, d_next, d_skip, d_taint, d_segt, d_logs, d_desc);
+    std::vector<uint32_t> h_changed(nblocks), h_done(nblocks, 0);
+    for (int round = 0; round < MAX_ROUNDS; round++) {
+        const Rec* rec_r = d_rec;
+        if (round > 0) {
+            LzHookScope hs(hook, "lz_filter");
+            lzp_filter_kernel<<<G, 256, 0, stream>>>(d_in, d_pb, d_boc, d_done, d_rec, d_vf, d_rec2, total);
+            rec_r = d_rec2;
+        }
+        {
+            LzHookScope hs(hook, "lz_spec");
+            lzp_spec_kernel<<<segs, 32, 0, stream>>>(d_in, d_pb, d_bos, extra ? 1 : 0, d_done, rec_r, d_logs, d_desc);
+        }
+        {
+            LzHookScope hs(hook, "lz_stitch");
+            lzp_stitch_kernel<<<nblocks, 32, 0, stream>>>(d_in, d_pb, (int)nblocks, extra ? 1 : 0, d_done, rec_r, d_logs, d_desc, d_fix, d_pieces, d_pstart, d_pst);
+        }
+        {
+            LzHookScope hs(hook, "lz_derive");
+            lzp_flatten_kernel<<<dim3(64, nblocks), 256, 0, stream>>>(d_pb, d_done, d_pst, d_pieces, d_pstart, d_logs, d_fix, d_ml);
+            cudaMemsetAsync(d_changed, 0, (size_t)nblocks * 4, stream);
+            lzp_derive_kernel<<<G, 256, 0, stream>>>(d_pb, d_boc, d_done, d_pst, d_ml, d_vf, d_vf2, d_changed, total);
+        }
+        e = cudaMemcpyAsync(h_changed.data(), d_changed, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return e;
+        bool all = true;
+        for (uint32_t b = 0; b < nblocks; b++) {
+            if (!h_done[b] && !h_changed[b]) h_done[b] = 1;  // vf' == vf: this round's match list is the parse
+            all = all && (h_done[b] || !pb[b].active);
+        }
+        e = cudaMemcpyAsync(d_done, h_done.data(), (size_t)nblocks * 4, cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) return e;
+        if (all) break;
+        std::swap(d_vf, d_vf2);  // blocks that are done have identical halves
     }
-    {
-        LzHookScope hs(hook, "lz_stitch");
-        lzp_stitch_kernel<<<nblocks, 32, 0, stream>>>(d_in, d_pb, (int)nblocks, extra ? 1 : 0, d_rec, d_next, d_skip, d_taint, d_segt, d_logs, d_desc, d_fix, d_pieces, d_pstart,
-                                                      d_pst);
-    }
+    for (uint32_t b = 0; b < nblocks; b++)
+        if (!pb[b].active) h_done[b] = 1;
+    e = cudaMemcpyAsync(d_done, h_done.data(), (size_t)nblocks * 4, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
     uint32_t max_tiles = 1;
     for (uint32_t b = 0; b < nblocks; b++) max_tiles = std::max(max_tiles, pb[b].ntiles_cap);
     {
         LzHookScope hs(hook, "lz_emit");
-        lzp_flatten_kernel<<<dim3(64, nblocks), 256, 0, stream>>>(d_pb, d_pst, d_pieces, d_pstart, d_logs, d_fix, d_ml);
         lzp_sizes_kernel<<<dim3(max_tiles, nblocks), TILE, 0, stream>>>(d_pb, d_pst, d_ml, d_tiles);
-        lzp_tilescan_kernel<<<nblocks, 32, 0, stream>>>(d_pb, (int)nblocks, d_pst, d_tiles, d_out, d_res);
+        lzp_tilescan_kernel<<<nblocks, 32, 0, stream>>>(d_pb, (int)nblocks, d_done, d_pst, d_tiles, d_out, d_res);
         lzp_emit_kernel<<<dim3(max_tiles, nblocks), TILE, 0, stream>>>(d_in, d_pb, d_pst, d_ml, d_tiles, d_res, d_out, d_runs, d_long, d_longn);
         lzp_literals_kernel<<<dim3(16, nblocks), 256, 0, stream>>>(d_in, d_pb, d_res, d_runs, d_long, d_longn, d_out);
     }

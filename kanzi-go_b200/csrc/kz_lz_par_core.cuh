@@ -20,13 +20,17 @@
 //     first byte by its own warp (all segments of all blocks at once); a stitch pass then walks the block once: it continues the true
 //     parse into a segment only until it meets that segment's speculative log (a few matches), and takes the rest of the log as is.
 //
-// When the skip acceleration fires (64 probes in a row without a match — at the start of every block, and in incompressible regions)
-// positions are left out of the table. Speculative parses stop there; the true parse (stitch pass) goes on in "skip mode": a bitmap holds
-// the skipped positions and a candidate that points to one is replaced by the next inserted position of the prev[] chain. A skipped
-// position j falsifies exactly one stored candidate, the one of next[j] (the next position with j's hash): that position is marked
-// "tainted", and a speculative log is only taken up to the first match whose literal run or match bytes contain a tainted position; the
-// true parse steps over it and merges again behind it.
+//  3. The skip acceleration (64 probes in a row without a match: at the start of every block, in incompressible regions) leaves positions
+//     out of the table, and a backward-extended match puts some of them back later (:403-407, :497-531). Which positions, and from when on,
+//     is a function of the parse itself: vf[j] = 0 (inserted when the cursor passed), NEVER, or the end of the match that inserted j
+//     late (usable for probes at or behind that point). So the parse is the fixed point of
+//         vf -> candidates filtered by vf (first usable position of the prev[] chain, T / B recomputed) -> parse -> vf'
+//     and that fixed point is unique (induction over the position of the first difference). Round 0 starts from vf = 0; every round is
+//     the same data-parallel pipeline (filter, speculative segments, stitch, vf' per position with a closed form for the probe pattern
+//     of a literal run: group g of 64 probes has stride g + 1 and starts 32 g (g + 1) bytes behind the run's first byte).
+//     Blocks converge after two or three rounds in practice; one that has not after the last round goes to the serial parse of kz_lz.cu.
 #pragma once
+#include <math.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -52,7 +56,7 @@ struct Rec {  // per position: nearest earlier position with the same hash (all 
     uint32_t prev, info;
 };
 struct Match {
-    uint32_t start, len, dist, pad;
+    uint32_t start, len, dist, probe;  // probe = position of the probe that found the match
 };
 struct State {
     int32_t src_idx, anchor, repd0, repd1, repd_idx, src_inc;
@@ -61,18 +65,12 @@ struct Params {
     const uint8_t* src;
     int32_t count, src_end, max_dist, min_match;
     int32_t extra;
-    const Rec* rec;
-    const uint32_t* next;  // next position with the same hash (NONE at the end of a chain)
-    uint32_t* skipmap;     // one bit per position, all zero until the skip acceleration fires
-    uint32_t* taintmap;    // one bit per position whose stored candidate is a skipped position
-    uint32_t* seg_taint;   // [0] = number of tainted positions of the block (merging stops when it exceeds taint_cap)
+    const Rec* rec;  // candidates of this round (filtered by the previous round's vf)
     int32_t seg_size;
-    uint32_t taint_cap;
 };
-// capacity of the piece list of a block: every speculative piece is a whole segment log or ends at a tainted position
-KZL_HD uint32_t piece_capacity(uint32_t nsegs, uint32_t taint_cap) { return 2u * (nsegs + taint_cap) + 16u; }
-enum { R_MATCH = 0, R_END = 1, R_SKIP = 2 };
-enum { END_POST_MATCH = 0, END_BLOCK = 1, END_STOP_SKIP = 2 };
+const uint32_t VF_NEVER = 0xFFFFFFFFu;
+enum { R_MATCH = 0, R_END = 1 };
+enum { END_POST_MATCH = 0, END_BLOCK = 1 };
 struct SegDesc {  // result of the speculative parse of one segment
     uint32_t n;    // log entries
     uint32_t end;  // END_*
@@ -160,24 +158,12 @@ KZL_HD uint32_t make_info(const uint8_t* src, int count, int i, uint32_t c) {
     return (uint32_t)t | ((uint32_t)b << 8);
 }
 
-KZL_HD bool skipped(const Params& P, int pos) { return (P.skipmap[pos >> 5] >> (pos & 31)) & 1u; }
-
-// the table entry a probe at position i reads: cand (NONE / 0 = nothing usable), its prefix length t and suffix length b (saturated)
-KZL_HD void lookup(const Params& P, int i, bool skipmode, int& cand, int& t, int& b) {
+// the table entry a probe at position i reads: cand (0 = nothing usable), its prefix length t and suffix length b (saturated)
+KZL_HD void lookup(const Params& P, int i, int& cand, int& t, int& b) {
     const Rec r = P.rec[i];
-    uint32_t c = r.prev;
     t = (int)(r.info & 0xFF);
     b = (int)((r.info >> 8) & 0xFF);
-    if (skipmode && c != NONE && skipped(P, (int)c)) {
-        do c = P.rec[c].prev;
-        while (c != NONE && skipped(P, (int)c));
-        if (c != NONE) {
-            const uint32_t info = make_info(P.src, P.count, i, c);
-            t = (int)(info & 0xFF);
-            b = (int)((info >> 8) & 0xFF);
-        }
-    }
-    cand = c == NONE ? 0 : (int)c;  // position 0 is never accepted (ref > minRef >= 0), like an empty table slot
+    cand = r.prev == NONE ? 0 : (int)r.prev;  // position 0 is never accepted (ref > minRef >= 0), like an empty table slot
 }
 // true prefix length as far as `limit` matters (the stored one saturates at T_CAP)
 KZL_HD int full_t(const Params& P, int i, int cand, int t, int limit) {
@@ -195,52 +181,55 @@ KZL_HD int match_len(const Params& P, int i, int cand, int t, int maxm) {
     return tt < m8 ? tt : m8;
 }
 
-KZL_HD void mark_skipped(const Params& P, int from, int to) {  // [from, to)
-    for (int p = from; p < to; p++) {
-        P.skipmap[p >> 5] |= 1u << (p & 31);
-        const uint32_t t = P.next[p];
-        if (t != NONE && !((P.taintmap[t >> 5] >> (t & 31)) & 1u)) {
-            P.taintmap[t >> 5] |= 1u << (t & 31);
-            P.seg_taint[0]++;
-        }
+// candidate of position i under vf: the first position of the prev[] chain that is in the table when i is probed
+KZL_HD Rec filter_candidate(const uint8_t* src, int count, const Rec* rec0, const uint32_t* vf, int i) {
+    Rec r = rec0[i];
+    uint32_t c = r.prev;
+    bool moved = false;
+    while (c != NONE) {
+        const uint32_t v = vf[c];
+        if (v == 0 || (uint32_t)i >= v) break;  // in the table
+        c = rec0[c].prev;
+        moved = true;
     }
+    if (moved) {
+        r.prev = c;
+        r.info = make_info(src, count, i, c);
+    }
+    return r;
 }
-// first tainted position in [from, to), or -1
-KZL_HD int next_tainted(const Params& P, int from, int to) {
-    if (from >= to) return -1;
-    int w = from >> 5;
-    const int wl = (to - 1) >> 5;
-    uint32_t bits = P.taintmap[w] & (0xFFFFFFFFu << (from & 31));
-    for (;;) {
-        if (bits) {
-            const int pos = (w << 5) + ctz64((uint64_t)bits);
-            return pos < to ? pos : -1;
-        }
-        if (++w > wl) return -1;
-        bits = P.taintmap[w];
+// is the byte at offset d of a literal run probed (true) or jumped over? The j-th probe of a run is followed by a stride of 1 + (j >> 6).
+KZL_HD bool run_offset_probed(uint32_t d) {
+    uint32_t g = 0;
+    if (d >= 64) {  // largest g with 32 g (g + 1) <= d
+        g = (uint32_t)((sqrt(1.0 + (double)d / 8.0) - 1.0) * 0.5);
+        while (32ull * (g + 1) * (g + 2) <= d) g++;
+        while (g > 0 && 32ull * g * (g + 1) > d) g--;
     }
+    return (d - 32u * g * (g + 1)) % (g + 1) == 0;
 }
-KZL_HD void clear_skipped(const Params& P, int from, int to) {  // [from, to): these positions are inserted by the in-match loop
-    if (from >= to) return;
-    int p = from;
-    while (p < to && (p & 31)) {
-        P.skipmap[p >> 5] &= ~(1u << (p & 31));
-        p++;
+// vf of position j given the block's final match list ml[0..nm) (ascending): see the header comment
+KZL_HD uint32_t derive_vf(const Match* ml, uint32_t nm, int src_end, int j) {
+    uint32_t lo = 0, hi = nm;  // t = number of matches that end at or before j
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((int)(ml[mid].start + ml[mid].len) <= j) lo = mid + 1;
+        else hi = mid;
     }
-    while (p + 32 <= to) {
-        P.skipmap[p >> 5] = 0;
-        p += 32;
+    const uint32_t t = lo;
+    const int a = t ? (int)(ml[t - 1].start + ml[t - 1].len) : 0;
+    if (t == nm) {
+        if (j >= src_end) return 0;
+        return run_offset_probed((uint32_t)(j - a)) ? 0u : VF_NEVER;
     }
-    while (p < to) {
-        P.skipmap[p >> 5] &= ~(1u << (p & 31));
-        p++;
-    }
+    const Match m = ml[t];
+    if (j >= (int)m.probe) return 0;
+    if (run_offset_probed((uint32_t)(j - a))) return 0;
+    return j > (int)m.start ? m.start + m.len : VF_NEVER;
 }
 
-// Runs the parse from `st` to the next match. R_MATCH: m is the match, st the state behind it. R_END: the cursor reached srcEnd (st.src_idx
-// >= src_end). R_SKIP (only when !skipmode): the probe at st.src_idx misses and would be followed by a stride > 1 — st is the state BEFORE
-// that probe, so that the caller can repeat it in skip mode.
-KZL_HD int parse_one(const Params& P, State& st, bool skipmode, Match& m) {
+// Runs the parse from `st` to the next match. R_MATCH: m is the match, st the state behind it. R_END: the cursor reached srcEnd.
+KZL_HD int parse_one(const Params& P, State& st, Match& m) {
     const uint8_t* src = P.src;
     const int src_end = P.src_end, min_match = P.min_match;
     while (st.src_idx < src_end) {
@@ -259,19 +248,14 @@ KZL_HD int parse_one(const Params& P, State& st, bool skipmode, Match& m) {
         }
         if (best_len < min_match) {
             int cand, t, b;
-            lookup(P, src_idx, skipmode, cand, t, b);
+            lookup(P, src_idx, cand, t, b);
             bool found = false;
             if (cand > min_ref && t >= 4) {
                 best_len = match_len(P, src_idx, cand, t, imin(src_end - src_idx, MAX_MATCH));
                 found = best_len >= min_match;
             }
             if (!found) {
-                const int stride = st.src_inc >> 6;
-                if (stride > 0) {
-                    if (!skipmode) return R_SKIP;
-                    mark_skipped(P, src_idx1, imin(src_idx1 + stride, P.count));
-                }
-                st.src_idx = src_idx1 + stride;
+                st.src_idx = src_idx1 + (st.src_inc >> 6);
                 st.src_inc++;
                 st.repd_idx = 0;
                 continue;
@@ -280,7 +264,7 @@ KZL_HD int parse_one(const Params& P, State& st, bool skipmode, Match& m) {
             int bsel = b, isel = src_idx;  // suffix length / position of the selected candidate pair
             if (ref != src_idx - st.repd0 && ref != src_idx - st.repd1) {
                 int c1, t1, b1;
-                lookup(P, src_idx1, skipmode, c1, t1, b1);
+                lookup(P, src_idx1, c1, t1, b1);
                 if (c1 > min_ref + 1) {
                     const int m8 = max_match & ~7;
                     if (m8 >= best_len && full_t(P, src_idx1, c1, t1, best_len + 1) >= best_len + 1) {
@@ -295,7 +279,7 @@ KZL_HD int parse_one(const Params& P, State& st, bool skipmode, Match& m) {
                 if (P.extra) {
                     const int src_idx2 = src_idx1 + 1;
                     int c2, t2, b2;
-                    lookup(P, src_idx2, skipmode, c2, t2, b2);
+                    lookup(P, src_idx2, c2, t2, b2);
                     if (c2 > min_ref + 2) {
                         const int m8 = imin(src_end - src_idx2, MAX_MATCH) & ~7;
                         if (m8 >= best_len && full_t(P, src_idx2, c2, t2, best_len + 1) >= best_len + 1) {
@@ -335,13 +319,12 @@ KZL_HD int parse_one(const Params& P, State& st, bool skipmode, Match& m) {
         m.start = (uint32_t)src_idx;
         m.len = (uint32_t)best_len;
         m.dist = (uint32_t)dist;
-        m.pad = 0;
+        m.probe = (uint32_t)st.src_idx;
         st.repd1 = st.repd0;
         st.repd0 = dist;
         st.repd_idx = 1;
         st.src_inc = 0;
         st.anchor = src_idx + best_len;
-        if (skipmode) clear_skipped(P, src_idx + 1, st.anchor);
         st.src_idx = st.anchor;
         return R_MATCH;
     }
@@ -366,13 +349,9 @@ KZL_HD void spec_parse_segment(const Params& P, int seg_start, int seg_end, Matc
     uint32_t end = END_BLOCK;
     for (;;) {
         Match m;
-        const int r = parse_one(P, st, false, m);
+        const int r = parse_one(P, st, m);
         if (r == R_END) {
             end = END_BLOCK;
-            break;
-        }
-        if (r == R_SKIP) {
-            end = END_STOP_SKIP;
             break;
         }
         log[n++] = m;
@@ -386,91 +365,52 @@ KZL_HD void spec_parse_segment(const Params& P, int seg_start, int seg_end, Matc
     d.fin = st;
 }
 
-// Stitch pass over one block. seg_log(k) = speculative log of segment k, desc[k] its result. Writes the fix-up log and the piece list.
-// Returns the number of pieces; *fix_n = fix-up entries; *final_anchor = anchor behind the last match (start of the final literals).
+// Stitch pass over one block. seg_log(k) = speculative log of segment k, desc[k] its result. Writes the fix-up log and the piece list
+// (at most 2 * nsegs + 2 pieces). Returns the number of pieces; *fix_n = fix-up entries; *final_anchor = anchor behind the last match.
 template <class SegLog>
 KZL_HD uint32_t stitch_block(const Params& P, int nsegs, const SegDesc* desc, SegLog seg_log, Match* fix, Piece* pieces, uint32_t* fix_n, int32_t* final_anchor) {
     const int seg_size = P.seg_size;
     State st = initial_state(P.count, 0);
-    bool skipmode = false;
     uint32_t np = 0, fn = 0, fbegin = 0;
-    bool post = true;    // st stands behind a match (or at the block start): a merge is possible
-    bool first = true;   // block start: segment 0 was parsed from exactly this state
+    bool first = true;  // block start: segment 0 was parsed from exactly this state
     int cur_seg = -1;
     uint32_t cursor = 0;
     while (st.src_idx < P.src_end) {
-        if (post && P.seg_taint[0] <= P.taint_cap) {
-            const int k = imin(st.src_idx / seg_size, nsegs - 1);
-            if (k != cur_seg) {
-                cur_seg = k;
-                cursor = 0;
-            }
-            const SegDesc& d = desc[k];
-            const Match* lg = seg_log(k);
-            int j = -2;  // -2: no merge; -1: the whole log (block start); >= 0: entries behind j
-            if (first && k == 0) {
-                j = -1;
-            } else {
-                while (cursor < d.n && (int)(lg[cursor].start + lg[cursor].len) < st.anchor) cursor++;
-                if (cursor >= 1 && cursor < d.n && (int)(lg[cursor].start + lg[cursor].len) == st.anchor && (int)lg[cursor].dist == st.repd0 &&
-                    (int)lg[cursor - 1].dist == st.repd1)
-                    j = (int)cursor;
-            }
-            first = false;
-            if (j != -2) {
-                // how much of the log behind j is free of tainted positions (their stored candidates are wrong)?
-                int e = (int)d.n;  // first entry that is NOT taken
-                bool whole = true;
-                if (skipmode) {
-                    const int cover_end = (int)d.n > j + 1 ? (int)(lg[d.n - 1].start + lg[d.n - 1].len) : st.anchor;
-                    // the speculative parse may also have probed up to 66 positions behind its last match (END_STOP_SKIP / END_BLOCK)
-                    const int probe_end = d.end == END_POST_MATCH ? cover_end : imin(imax(cover_end, d.fin.src_idx) + 3, P.count);
-                    const int t = next_tainted(P, st.anchor, probe_end);
-                    if (t >= 0) {
-                        whole = false;
-                        e = j + 1;
-                        while (e < (int)d.n && (int)(lg[e].start + lg[e].len) <= t) e++;
-                        // entry e (or the tail of the parse behind the last entry) looked at position t
-                    }
-                }
-                if (whole || e > j + 1) {
-                    if (fn > fbegin) {
-                        pieces[np].spec = 0, pieces[np].seg = 0, pieces[np].begin = fbegin, pieces[np].end = fn;
-                        np++;
-                        fbegin = fn;
-                    }
-                    if (e > j + 1) {
-                        pieces[np].spec = 1, pieces[np].seg = (uint32_t)k, pieces[np].begin = (uint32_t)(j + 1), pieces[np].end = (uint32_t)e;
-                        np++;
-                    }
-                    if (whole) {  // the state behind the segment's log = the state its speculative parse stopped in
-                        st = d.fin;
-                        post = d.end == END_POST_MATCH;
-                        if (d.end == END_BLOCK) break;
-                        continue;
-                    }
-                    // state behind entry e - 1
-                    st.repd1 = e - 2 >= 0 ? (int)lg[e - 2].dist : P.count;
-                    st.repd0 = (int)lg[e - 1].dist;
-                    st.anchor = (int)(lg[e - 1].start + lg[e - 1].len);
-                    st.src_idx = st.anchor;
-                    st.repd_idx = 1;
-                    st.src_inc = 0;
-                    cursor = (uint32_t)(e - 1);
-                }
-                // fall through: one step of the true parse over the tainted position
-            }
+        // st stands behind a match (or at the block start): can it join the speculative log of the segment it is in?
+        const int k = imin(st.src_idx / seg_size, nsegs - 1);
+        if (k != cur_seg) {
+            cur_seg = k;
+            cursor = 0;
         }
-        Match m;
-        const int r = parse_one(P, st, skipmode, m);
-        if (r == R_SKIP) {
-            skipmode = true;
-            post = false;
+        const SegDesc& d = desc[k];
+        const Match* lg = seg_log(k);
+        int j = -2;  // -2: no; -1: the whole log (block start); >= 0: the entries behind j
+        if (first && k == 0) {
+            j = -1;
+        } else {
+            while (cursor < d.n && (int)(lg[cursor].start + lg[cursor].len) < st.anchor) cursor++;
+            if (cursor >= 1 && cursor < d.n && (int)(lg[cursor].start + lg[cursor].len) == st.anchor && (int)lg[cursor].dist == st.repd0 &&
+                (int)lg[cursor - 1].dist == st.repd1)
+                j = (int)cursor;
+        }
+        first = false;
+        if (j != -2) {
+            if (fn > fbegin) {
+                pieces[np].spec = 0, pieces[np].seg = 0, pieces[np].begin = fbegin, pieces[np].end = fn;
+                np++;
+                fbegin = fn;
+            }
+            if ((int)d.n > j + 1) {
+                pieces[np].spec = 1, pieces[np].seg = (uint32_t)k, pieces[np].begin = (uint32_t)(j + 1), pieces[np].end = d.n;
+                np++;
+            }
+            st = d.fin;  // the state the segment's speculative parse stopped in
+            if (d.end == END_BLOCK) break;
             continue;
         }
-        if (r == R_END) break;
+        Match m;
+        if (parse_one(P, st, m) == R_END) break;
         fix[fn++] = m;
-        post = true;
     }
     if (fn > fbegin) {
         pieces[np].spec = 0, pieces[np].seg = 0, pieces[np].begin = fbegin, pieces[np].end = fn;

@@ -10,9 +10,10 @@
 using namespace kz::lzp;
 
 extern "C" {
-// returns the encoded length, -1 when the transform declines. stats: [0] matches, [1] fix-up matches (true parse work of the stitch pass),
-// [2] pieces, [3] 1 when the block entered skip mode
+// returns the encoded length, -1 when the transform declines. stats: [0] matches, [1] fix-up matches (true parse work of the stitch passes, all
+// rounds), [2] pieces, [3] rounds to the fixed point
 int64_t lz_forward_par(int extra_i, int data_type, const uint8_t* src_in, int64_t n, uint8_t* dst, int64_t cap, int seg_size, int64_t* stats) {
+    const int max_rounds = 64;
     if (n == 0) return 0;
     const int count = int(n);
     if (cap < (n <= 1024 ? n + 16 : n + n / 64)) return -1;
@@ -36,58 +37,68 @@ int64_t lz_forward_par(int extra_i, int data_type, const uint8_t* src_in, int64_
     P.extra = extra_i;
     // pass 0: prev[] (what the stable sort by hash produces), T / B
     const int npos = std::max(0, std::min(count - 8, P.src_end + 2));
-    std::vector<Rec> rec(size_t(count) + 8);
-    std::vector<uint32_t> next(size_t(count) + 8, NONE);
+    std::vector<Rec> rec0(size_t(count) + 8), rec(size_t(count) + 8);
     {
         std::vector<uint32_t> last(size_t(1) << (extra_i ? 19 : 16), NONE);
-        for (int i = 0; i < count; i++) rec[i].prev = NONE, rec[i].info = 0;
+        for (int i = 0; i < count; i++) rec0[i].prev = NONE, rec0[i].info = 0;
         for (int i = 0; i < npos; i++) {
             const uint32_t h = lz_hash(ld64(src + i), extra_i != 0);
-            rec[i].prev = last[h];
-            if (last[h] != NONE) next[last[h]] = uint32_t(i);
+            rec0[i].prev = last[h];
             last[h] = uint32_t(i);
-            rec[i].info = make_info(src, count, i, rec[i].prev);
+            rec0[i].info = make_info(src, count, i, rec0[i].prev);
         }
     }
-    P.rec = rec.data();
-    P.next = next.data();
-    std::vector<uint32_t> skipmap(size_t(count) / 32 + 4, 0), taintmap(size_t(count) / 32 + 4, 0);
-    P.skipmap = skipmap.data();
-    P.taintmap = taintmap.data();
-    // pass 1: speculative parse of every segment
-    const int nsegs = std::max(1, (P.src_end + seg_size - 1) / seg_size);
-    std::vector<uint32_t> seg_taint(4, 0);
-    P.seg_taint = seg_taint.data();
     P.seg_size = seg_size;
-    P.taint_cap = 256;
+    const int nsegs = std::max(1, (P.src_end + seg_size - 1) / seg_size);
     const int seg_cap = seg_size / 4 + 4;
     std::vector<Match> logs(size_t(nsegs) * seg_cap);
     std::vector<SegDesc> desc(nsegs);
-    for (int k = 0; k < nsegs; k++) {
-        const int s0 = k * seg_size;
-        const int s1 = k == nsegs - 1 ? 0x7FFFFFFF : s0 + seg_size;
-        spec_parse_segment(P, s0, s1, logs.data() + size_t(k) * seg_cap, desc[k]);
-        if (int(desc[k].n) > seg_cap) return -2;
-    }
-    // pass 2: stitch
     std::vector<Match> fix(size_t(count) / 4 + 16);
-    std::vector<Piece> pieces(piece_capacity(uint32_t(nsegs), P.taint_cap));
-    uint32_t fix_n = 0;
-    int32_t final_anchor = 0;
-    Match* lp = logs.data();
-    const uint32_t np = stitch_block(P, nsegs, desc.data(), [lp, seg_cap](int k) { return (const Match*)(lp + size_t(k) * seg_cap); }, fix.data(),
-                                     pieces.data(), &fix_n, &final_anchor);
-    // pass 3: flatten + emit
+    std::vector<Piece> pieces(size_t(2) * nsegs + 4);
+    std::vector<uint32_t> vf(size_t(count) + 8, 0), vf2(size_t(count) + 8, 0);
     std::vector<Match> ml;
-    for (uint32_t p = 0; p < np; p++) {
-        const Match* base = pieces[p].spec ? logs.data() + size_t(pieces[p].seg) * seg_cap : fix.data();
-        for (uint32_t e = pieces[p].begin; e < pieces[p].end; e++) ml.push_back(base[e]);
+    uint32_t fix_n = 0, np = 0;
+    int32_t final_anchor = 0;
+    int rounds = 0;
+    int64_t fix_total = 0;
+    for (;; rounds++) {
+        if (rounds >= max_rounds) return -4;
+        // filter the candidates by the previous round's vf (round 0: vf = 0, nothing moves)
+        for (int i = 0; i < count; i++) rec[i] = rounds == 0 ? rec0[i] : filter_candidate(src, count, rec0.data(), vf.data(), i);
+        P.rec = rec.data();
+        // speculative parse of every segment
+        for (int k = 0; k < nsegs; k++) {
+            const int s0 = k * seg_size;
+            const int s1 = k == nsegs - 1 ? 0x7FFFFFFF : s0 + seg_size;
+            spec_parse_segment(P, s0, s1, logs.data() + size_t(k) * seg_cap, desc[k]);
+            if (int(desc[k].n) > seg_cap) return -2;
+        }
+        // stitch
+        Match* lp = logs.data();
+        np = stitch_block(P, nsegs, desc.data(), [lp, seg_cap](int k) { return (const Match*)(lp + size_t(k) * seg_cap); }, fix.data(), pieces.data(), &fix_n,
+                          &final_anchor);
+        if (np > pieces.size()) return -5;
+        fix_total += fix_n;
+        // flatten
+        ml.clear();
+        for (uint32_t p = 0; p < np; p++) {
+            const Match* base = pieces[p].spec ? logs.data() + size_t(pieces[p].seg) * seg_cap : fix.data();
+            for (uint32_t e = pieces[p].begin; e < pieces[p].end; e++) ml.push_back(base[e]);
+        }
+        // the table membership this parse implies
+        bool same = true;
+        for (int j = 0; j < count; j++) {
+            vf2[j] = derive_vf(ml.data(), uint32_t(ml.size()), P.src_end, j);
+            same = same && vf2[j] == vf[j];
+        }
+        if (same) break;
+        vf.swap(vf2);
     }
     if (stats) {
         stats[0] = int64_t(ml.size());
-        stats[1] = fix_n;
+        stats[1] = fix_total;
         stats[2] = np;
-        stats[3] = seg_taint[0];
+        stats[3] = rounds + 1;
     }
     std::vector<uint8_t> tk(ml.size() + 8), mb(3 * ml.size() + 8), mlenb(4 * ml.size() + 8);
     size_t tk_idx = 0, m_idx = 0, mlen_idx = 0, dst_idx = 13;

@@ -1,6 +1,6 @@
 """CPU check of the data-parallel LZ / LZX parse (kanzi-go_b200/csrc/kz_lz_par_core.cuh, the code the kernels of kz_lz_par.cu execute): precomputed
-candidates + speculative segment parses + stitch pass + emission produce exactly the oracle's bytes, for several segment sizes, including
-blocks that enter skip mode (long incompressible stretches) and degenerate data (constant, periodic)."""
+candidates + speculative segment parses + stitch pass, iterated to the fixed point of the table membership (skip acceleration), + emission
+produce exactly the oracle's bytes, for several segment sizes, including blocks with long incompressible stretches and degenerate data."""
 import ctypes as C
 import importlib
 import os
@@ -86,6 +86,6 @@ def test_large_blocks_and_stitch_work(lz):
             assert r == -1, cname
             continue
         assert r == len(want) and np.array_equal(dst[:r], want), (cname, r, len(want), st)
-        print(cname, "matches", st[0], "fix-up", st[1], "pieces", st[2], "skip mode", st[3])
+        print(cname, "matches", st[0], "fix-up (all rounds)", st[1], "pieces", st[2], "rounds", st[3])
         if cname == "text":
-            assert st[1] < st[0] // 20
+            assert st[1] < st[0] // 10 and st[3] <= 4
