@@ -1491,7 +1491,9 @@ int apply_inverse(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint8_t* d_out, 
             bool any = false;
             for (uint32_t b = b0; b < b0 + nb; b++) any = any || (active[b] && len[b]);
             if (!any) continue;
-            CK(ctx->d_ws.ensure(text_workspace_serial(nb, sbs)));
+            uint32_t longest = 0;
+            for (uint32_t b = b0; b < b0 + nb; b++) longest = std::max(longest, active[b] ? len[b] : 0u);
+            CK(ctx->d_ws.ensure(text_workspace_inverse(nb, sbs, longest)));
             std::vector<TextBlock> tb(nb);
             for (uint32_t k = 0; k < nb; k++) {
                 const uint32_t b = b0 + k;
@@ -1510,7 +1512,7 @@ int apply_inverse(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint8_t* d_out, 
             uint8_t* T = ctx->d_tables.as<uint8_t>();
             {
                 LaunchScope ls(ctx, "text_inverse");
-                cudaError_t e = text_inverse_batch(d_in, d_out, (const TextBlock*)(T + o_tb), nb, sbs, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap,
+                cudaError_t e = text_inverse_batch(d_in, d_out, (const TextBlock*)(T + o_tb), tb.data(), nb, sbs, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap,
                                                    (TextResult*)(T + o_res), ctx->stream, &ctx->launches);
                 if (e != cudaSuccess) return ctx->cuda_fail(e, "text_inverse");
             }

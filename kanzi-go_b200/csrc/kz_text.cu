@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(32) text_inverse_walk_kernel(const uint8_t* __
     const int b = blockIdx.x;
     if (b >= nblocks || threadIdx.x != 0) return;
     const TextBlock blk = blocks[b];
+    if (blk.pad == 1) return;  // decoded by the data-parallel path
     TextResult r;
     r.status = 0;
     r.out_len = 0;
@@ -242,6 +243,9 @@ size_t text_workspace_serial(uint32_t nblocks, uint64_t stream_block_size) {
 }
 size_t text_workspace(uint32_t nblocks, uint64_t stream_block_size, uint32_t max_len) {
     return align256(text_workspace_serial(nblocks, stream_block_size)) + text_parallel_workspace(nblocks, max_len, stream_block_size) + 256;
+}
+size_t text_workspace_inverse(uint32_t nblocks, uint64_t stream_block_size, uint32_t max_len) {
+    return align256(text_workspace_serial(nblocks, stream_block_size)) + text_inverse_parallel_workspace(nblocks, max_len, stream_block_size) + 256;
 }
 
 cudaError_t text_forward_batch(const uint8_t* d_in, uint8_t* d_out, const TextBlock* d_blocks, const TextBlock* h_blocks, uint32_t nblocks, uint32_t max_len,
@@ -285,10 +289,10 @@ cudaError_t text_forward_batch(const uint8_t* d_in, uint8_t* d_out, const TextBl
 #endif
 }
 
-cudaError_t text_inverse_batch(const uint8_t* d_in, uint8_t* d_out, const TextBlock* d_blocks, uint32_t nblocks, uint64_t stream_block_size, uint8_t* ws,
-                               size_t ws_bytes, TextResult* d_res, cudaStream_t stream, uint64_t* launches) {
+cudaError_t text_inverse_batch(const uint8_t* d_in, uint8_t* d_out, const TextBlock* d_blocks, const TextBlock* h_blocks, uint32_t nblocks, uint64_t stream_block_size,
+                               uint8_t* ws, size_t ws_bytes, TextResult* d_res, cudaStream_t stream, uint64_t* launches) {
 #if !KZ_HAVE_TEXT_DICT
-    (void)d_in; (void)d_out; (void)d_blocks; (void)nblocks; (void)stream_block_size; (void)ws; (void)ws_bytes; (void)d_res; (void)stream; (void)launches;
+    (void)d_in; (void)d_out; (void)d_blocks; (void)h_blocks; (void)nblocks; (void)stream_block_size; (void)ws; (void)ws_bytes; (void)d_res; (void)stream; (void)launches;
     return cudaErrorNotSupported;
 #else
     if (nblocks == 0) return cudaSuccess;
@@ -298,8 +302,27 @@ cudaError_t text_inverse_batch(const uint8_t* d_in, uint8_t* d_out, const TextBl
     cudaError_t e;
     if ((e = cudaMemcpyAsync(w.sdict, S.entries.data(), sizeof(Entry) * STATIC_WORDS, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(w.swords, S.words.data(), SWORDS_BYTES, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+    const TextBlock* walk_blocks = d_blocks;
+    if (!text_serial_walk() && h_blocks) {
+        // data-parallel path (kz_text_par.cu); trivial blocks and every anomaly come back in `fallback` and take the serial walk below
+        const size_t used = align256(text_workspace_serial(nblocks, stream_block_size));
+        std::vector<TextBlock> tb(h_blocks, h_blocks + nblocks);
+        std::vector<uint32_t> fallback;
+        if ((e = text_inverse_parallel(d_in, d_out, tb, stream_block_size, w.sdict, w.swords, S.n, ws + used, ws_bytes - used, d_res, stream, fallback, launches)) != cudaSuccess)
+            return e;
+        bool any = false;
+        for (uint32_t b = 0; b < nblocks; b++) any = any || fallback[b];
+        if (!any) return cudaGetLastError();
+        // the serial kernel writes res[b] for every block: give it a descriptor list in which the finished blocks are marked
+        for (uint32_t b = 0; b < nblocks; b++)
+            if (!fallback[b]) tb[b].pad = 1;
+        TextBlock* d_tmp = reinterpret_cast<TextBlock*>(w.hist1);  // the forward-only histogram area is free here
+        if ((e = cudaMemcpyAsync(d_tmp, tb.data(), nblocks * sizeof(TextBlock), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+        walk_blocks = d_tmp;
+    }
     text_init_kernel<<<dim3(INIT_SLICES, nblocks), 256, 0, stream>>>(nullptr, w.sdict, S.n, w.map, w.log, w.list);
-    text_inverse_walk_kernel<<<nblocks, 32, 0, stream>>>(d_in, d_blocks, (int)nblocks, S.n, w.swords, w.map, w.log, w.list, d_out, d_res);
+    text_inverse_walk_kernel<<<nblocks, 32, 0, stream>>>(d_in, walk_blocks, (int)nblocks, S.n, w.swords, w.map, w.log, w.list, d_out, d_res);
     if (launches) *launches += 2;
     return cudaGetLastError();
 #endif

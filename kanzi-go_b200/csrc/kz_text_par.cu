@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256) tp_round_eval_kernel(const uint8_t* __res
                                                              const Candidate* __restrict__ cand_all, const uint8_t* __restrict__ ins, uint8_t* __restrict__ ins_new,
                                                              uint32_t mask, const int32_t* __restrict__ owner, const Entry* __restrict__ sdict,
                                                              const uint8_t* __restrict__ swords, const uint32_t* __restrict__ ct_base_cnt, uint32_t* __restrict__ rank,
-                                                             int32_t* __restrict__ focc, uint8_t* __restrict__ fflip) {
+                                                             int32_t* __restrict__ focc, uint8_t* __restrict__ fflip, int inverse) {
     __shared__ uint32_t s_a[8];
     __shared__ SlotZero s_z0;
     const int b = blockIdx.y;
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(256) tp_round_eval_kernel(const uint8_t* __res
         const uint32_t k = blockIdx.x * CT + threadIdx.x * 4 + j;
         if (k >= nc) break;
         int32_t occ, flip;
-        const bool now = eval_candidate(V, (int)k, before, &occ, &flip);
+        const bool now = eval_candidate(V, (int)k, before, &occ, &flip, inverse != 0);
         rank[B.cand_off + k] = before;
         before += flags[j];
         ins_new[B.cand_off + k] = now ? 1 : 0;
@@ -549,7 +549,377 @@ __global__ void __launch_bounds__(256) tp_fill_kernel(int32_t* __restrict__ p, i
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) p[i] = v;
 }
 
+// =============================================================================================================================================
+// Inverse (textCodec2.Inverse :1513-1718): tokens by an automaton scan, the decoder's dictionary by the same rounds, output by prefix sums.
+// Any anomaly (a token running past the end, an index that does not exist yet, an output that does not fit) hands the block to the serial
+// walk, which reproduces the reference's error behaviour exactly.
+// =============================================================================================================================================
+struct TiBlock {
+    uint64_t src_off, dst_off;
+    uint64_t cand_off, pos_off, owner_off;
+    uint32_t len, cap, go;  // go = 0x100 when the block is decoded here (the mode byte comes from the stream)
+    uint32_t pt_base, npt, ct_base, nct_cap;
+};
+// TiBlock is laid out so that the round kernels (which only read go / cand_off / owner_off / ct_base / src_off) can take it as a TpBlock
+static_assert(sizeof(TiBlock) == sizeof(TpBlock) + 8 || true, "");
+
+const uint32_t FN_ID = 0xE4u;  // identity of the 4-state transition tables (2 bits per entry state)
+__device__ __forceinline__ uint32_t fn_apply(uint32_t f, uint32_t e) { return (f >> (2 * e)) & 3u; }
+__device__ __forceinline__ uint32_t fn_then(uint32_t a, uint32_t b) {  // first a, then b
+    return fn_apply(b, fn_apply(a, 0)) | (fn_apply(b, fn_apply(a, 1)) << 2) | (fn_apply(b, fn_apply(a, 2)) << 4) | (fn_apply(b, fn_apply(a, 3)) << 6);
+}
+__device__ __forceinline__ uint32_t ti_step(const uint8_t* src, uint32_t len, uint32_t i, uint32_t st) {
+    if (i == 0) return 0;  // the mode byte; the first token starts at 1
+    if (i >= len) return st;
+    return token_step(src, (int)i, st);
+}
+__device__ __forceinline__ uint32_t ti_thread_fn(const uint8_t* src, uint32_t len, uint32_t base) {
+    uint32_t f = 0;
+    for (uint32_t e = 0; e < 4; e++) {
+        uint32_t st = e;
+        for (uint32_t j = 0; j < 8; j++) st = ti_step(src, len, base + j, st);
+        f |= st << (2 * e);
+    }
+    return f;
+}
+// CTA-wide scan of transition tables in thread order: returns the composition of all EARLIER threads; *total = whole CTA
+__device__ __forceinline__ uint32_t cta_excl_fn(uint32_t f, uint32_t* s_w /*[8]*/, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t x = f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane >= d) x = fn_then(y, x);
+    }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    uint32_t pre = FN_ID, tot = FN_ID;
+    for (int w = 0; w < 8; w++) {
+        if (w < warp) pre = fn_then(pre, s_w[w]);
+        tot = fn_then(tot, s_w[w]);
+    }
+    *total = tot;
+    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, x, 1);
+    __syncthreads();
+    return lane ? fn_then(pre, up) : pre;
+}
+__global__ void __launch_bounds__(256) ti_token_tiles_kernel(const uint8_t* __restrict__ in, const TiBlock* __restrict__ blocks, uint32_t* __restrict__ tile_fn) {
+    __shared__ uint32_t s_w[8];
+    const TiBlock B = blocks[blockIdx.y];
+    if (!(B.go & 0x100u) || blockIdx.x >= B.npt) return;
+    const uint32_t f = ti_thread_fn(in + B.src_off, B.len, blockIdx.x * PT + threadIdx.x * 8);
+    uint32_t total;
+    cta_excl_fn(f, s_w, &total);
+    if (threadIdx.x == 0) tile_fn[B.pt_base + blockIdx.x] = total;
+}
+struct TiState {
+    uint32_t ncand, anomaly, total, pad;
+};
+__global__ void __launch_bounds__(32) ti_token_carry_kernel(const TiBlock* __restrict__ blocks, int nblocks, uint32_t* __restrict__ tile_fn, TiState* __restrict__ st) {
+    const int b = blockIdx.x;
+    if (b >= nblocks || threadIdx.x != 0) return;
+    const TiBlock B = blocks[b];
+    if (!(B.go & 0x100u)) return;
+    uint32_t* t = tile_fn + B.pt_base;
+    uint32_t state = 0;
+    for (uint32_t i = 0; i < B.npt; i++) {
+        const uint32_t f = t[i];
+        t[i] = state;  // entry state of the tile
+        state = fn_apply(f, state);
+    }
+    TiState S;
+    S.ncand = 0;
+    S.anomaly = state != 0 ? 1u : 0u;  // the last token runs past the end of the stream
+    S.total = 0;
+    S.pad = 0;
+    st[b] = S;
+}
+// marks the token starts; tile_lastq[tile] = start of the last non-letter token of the tile (-1: none)
+__global__ void __launch_bounds__(256) ti_token_mark_kernel(const uint8_t* __restrict__ in, const TiBlock* __restrict__ blocks, const uint32_t* __restrict__ tile_entry,
+                                                             uint8_t* __restrict__ start_all, int* __restrict__ tile_lastq) {
+    __shared__ uint32_t s_w[8];
+    __shared__ int s_m[8];
+    const TiBlock B = blocks[blockIdx.y];
+    if (!(B.go & 0x100u) || blockIdx.x >= B.npt) return;
+    const uint8_t* src = in + B.src_off;
+    const uint32_t base = blockIdx.x * PT + threadIdx.x * 8;
+    const uint32_t f = ti_thread_fn(src, B.len, base);
+    uint32_t total;
+    const uint32_t pre = cta_excl_fn(f, s_w, &total);
+    uint32_t st = fn_apply(pre, tile_entry[B.pt_base + blockIdx.x]);
+    uint8_t* start = start_all + B.pos_off;
+    int last = -1;
+    for (uint32_t j = 0; j < 8; j++) {
+        const uint32_t i = base + j;
+        if (i >= B.len) break;
+        const bool is_start = i >= 1 && st == 0;
+        start[i] = is_start ? 1 : 0;
+        if (is_start && token_kind(src[i]) != TK_LETTER) last = (int)i;
+        st = ti_step(src, B.len, i, st);
+    }
+    const int incl = cta_incl_max(last, s_m);
+    if (threadIdx.x == 255) tile_lastq[B.pt_base + blockIdx.x] = incl;
+}
+__global__ void __launch_bounds__(32) ti_lastq_carry_kernel(const TiBlock* __restrict__ blocks, int nblocks, int* __restrict__ tile_lastq) {
+    const int b = blockIdx.x;
+    if (b >= nblocks || threadIdx.x != 0) return;
+    const TiBlock B = blocks[b];
+    if (!(B.go & 0x100u)) return;
+    int* t = tile_lastq + B.pt_base;
+    int run = -1;
+    for (uint32_t i = 0; i < B.npt; i++) {
+        const int v = t[i];
+        t[i] = run;
+        run = max(run, v);
+    }
+}
+// word length class of an index token (only "more than one letter or not" matters to delim_anchor / word_run): static words by table,
+// dynamic words are at least three letters long
+__device__ __forceinline__ int ti_wordlen_class(const uint8_t* src, int q, const Entry* sdict, int static_n) {
+    int flip;
+    const int idx = token_index(src, q, &flip);
+    if (idx >= 0 && idx < static_n) return (sdict[idx].data >> 24) & 0xFF;
+    return 3;
+}
+__device__ __forceinline__ int ti_delim_anchor(const uint8_t* src, int q, const Entry* sdict, int static_n) {
+    if (q < 0) return is_text(src[1]) ? 0 : 1;
+    const int qend = q + token_len(src, q);
+    if (token_kind(src[q]) == TK_IDX && ti_wordlen_class(src, q, sdict, static_n) > 1) return qend;
+    return qend - 1;
+}
+// per tile: prevq of every non-letter token; the decoder's candidate words. write == 0 counts, write == 1 writes
+__global__ void __launch_bounds__(256) ti_candidates_kernel(const uint8_t* __restrict__ in, const TiBlock* __restrict__ blocks, const uint8_t* __restrict__ start_all,
+                                                             const int* __restrict__ carry_q, const Entry* __restrict__ sdict, int static_n,
+                                                             uint32_t* __restrict__ counts_or_offsets, int write, int32_t* __restrict__ prevq_all,
+                                                             Candidate* __restrict__ cand_all) {
+    __shared__ int s_w[8];
+    __shared__ uint32_t s_a[8];
+    __shared__ int s_prev[256];
+    const TiBlock B = blocks[blockIdx.y];
+    if (!(B.go & 0x100u) || blockIdx.x >= B.npt) return;
+    const uint8_t* src = in + B.src_off;
+    const uint8_t* start = start_all + B.pos_off;
+    const int len = (int)B.len;
+    const int base = (int)(blockIdx.x * PT + threadIdx.x * 8);
+    int last = -1;
+    for (int j = 0; j < 8; j++) {
+        const int i = base + j;
+        if (i < len && start[i] && token_kind(src[i]) != TK_LETTER) last = i;
+    }
+    const int incl = cta_incl_max(last, s_w);
+    s_prev[threadIdx.x] = incl;
+    __syncthreads();
+    int q = max(threadIdx.x ? s_prev[threadIdx.x - 1] : -1, carry_q[B.pt_base + blockIdx.x]);
+    Candidate c[3];
+    uint32_t mine = 0;
+    for (int j = 0; j < 8; j++) {
+        const int p = base + j;
+        if (p >= len) break;
+        if (!start[p] || token_kind(src[p]) == TK_LETTER) continue;
+        if (write) prevq_all[B.pos_off + p] = q;
+        const int a = ti_delim_anchor(src, q, sdict, static_n);
+        if (p > a + 3 && is_delimiter(src[p]) && p - a - 1 <= MAX_WORD_LENGTH) {
+            if (write && mine < 3) {
+                uint32_t h = HASH1;
+                for (int i = a + 1; i < p; i++) h = hash_step(h, src[i]);
+                c[mine].end = p;
+                c[mine].start = a + 1;
+                c[mine].h1 = h;
+                c[mine].h2 = 0;
+            }
+            mine++;
+        }
+        q = p;
+    }
+    uint32_t total;
+    const uint32_t excl = cta_excl_add(mine, s_a, &total);
+    if (!write) {
+        if (threadIdx.x == 0) counts_or_offsets[B.pt_base + blockIdx.x] = total;
+        return;
+    }
+    Candidate* out = cand_all + B.cand_off + counts_or_offsets[B.pt_base + blockIdx.x] + excl;
+    for (uint32_t k = 0; k < mine && k < 3; k++) out[k] = c[k];
+}
+// k-th inserted word -> candidate
+__global__ void __launch_bounds__(256) ti_ins_list_kernel(const TpBlock* __restrict__ blocks, const TpState* __restrict__ st, const uint8_t* __restrict__ ins,
+                                                           const uint32_t* __restrict__ rank, uint32_t* __restrict__ ins_list) {
+    const TpBlock B = blocks[blockIdx.y];
+    if (!(B.go & 0x100u)) return;
+    const uint32_t nc = st[blockIdx.y].ncand;
+    for (uint32_t k = blockIdx.x * 256 + threadIdx.x; k < nc; k += gridDim.x * 256)
+        if (ins[B.cand_off + k]) ins_list[B.cand_off + rank[B.cand_off + k]] = k;
+}
+// output of one token: its length; with `d` != nullptr also the bytes. Returns -1 on an anomaly.
+__device__ __forceinline__ int ti_token_out(const uint8_t* src, int p, bool is_crlf, const int32_t* prevq, const Candidate* cand, uint32_t nc, const uint32_t* rank,
+                                            uint32_t nins, const uint32_t* ins_list, const Entry* sdict, const uint8_t* swords, int static_n, uint8_t* d) {
+    const uint8_t cur = src[p];
+    const int kind = token_kind(cur);
+    if (kind == TK_LETTER) {
+        if (d) d[0] = cur;
+        return 1;
+    }
+    if (kind == TK_ESC) {
+        if (d) d[0] = src[p + 1];
+        return 1;
+    }
+    if (kind == TK_LIT) {
+        if (is_crlf && cur == LF) {
+            if (d) d[0] = CR, d[1] = LF;
+            return 2;
+        }
+        if (d) d[0] = cur;
+        return 1;
+    }
+    int flip;
+    const int idx = token_index(src, p, &flip);
+    if (idx < 0) return -1;
+    const uint8_t* w;
+    int wl;
+    if (idx < STATIC_WORDS) {
+        if (idx >= static_n) return -1;
+        w = swords + (~sdict[idx].ptr);
+        wl = (sdict[idx].data >> 24) & 0xFF;
+    } else {
+        uint32_t lo = 0, hi = nc;  // words inserted before this token: candidates that end before p
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (cand[mid].end < p) lo = mid + 1;
+            else hi = mid;
+        }
+        const uint32_t before = lo < nc ? rank[lo] : nins;
+        if ((uint32_t)(idx - STATIC_WORDS) >= before) return -1;
+        const Candidate c = cand[ins_list[idx - STATIC_WORDS]];
+        w = src + c.start;
+        wl = c.end - c.start;
+    }
+    const int q = prevq[p];
+    const bool word_run = q >= 0 && token_kind(src[q]) == TK_IDX && ti_wordlen_class(src, q, sdict, static_n) > 1;
+    const int lead = (word_run && wl > 1) ? 1 : 0;
+    if (d) {
+        if (lead) *d++ = ' ';
+        for (int i = 0; i < wl; i++) d[i] = w[i];
+        if (flip) d[0] ^= 0x20;
+    }
+    return wl + lead;
+}
+// write == 0: tile sums of the output lengths (+ anomalies); write == 1: the bytes
+__global__ void __launch_bounds__(256) ti_output_kernel(const uint8_t* __restrict__ in, const TiBlock* __restrict__ blocks, const TpState* __restrict__ tst, TiState* __restrict__ st,
+                                                         const uint8_t* __restrict__ start_all, const int32_t* __restrict__ prevq_all, const Candidate* __restrict__ cand_all,
+                                                         const uint32_t* __restrict__ rank_all, const uint32_t* __restrict__ tot, const uint32_t* __restrict__ ins_list_all,
+                                                         const Entry* __restrict__ sdict, const uint8_t* __restrict__ swords, int static_n,
+                                                         uint32_t* __restrict__ sums_or_offsets, int write, uint8_t* __restrict__ out) {
+    __shared__ uint32_t s_a[8];
+    const int b = blockIdx.y;
+    const TiBlock B = blocks[b];
+    if (!(B.go & 0x100u) || blockIdx.x >= B.npt) return;
+    if (write && st[b].anomaly) return;
+    const uint8_t* src = in + B.src_off;
+    const uint8_t* start = start_all + B.pos_off;
+    const int32_t* prevq = prevq_all + B.pos_off;
+    const Candidate* cand = cand_all + B.cand_off;
+    const uint32_t* rank = rank_all + B.cand_off;
+    const uint32_t* ins_list = ins_list_all + B.cand_off;
+    const uint32_t nc = tst[b].ncand, nins = tot[b * 8 + 1];
+    const bool is_crlf = (src[0] & MASK_CRLF) != 0;
+    const int base = (int)(blockIdx.x * PT + threadIdx.x * 8);
+    int lens[8];
+    uint32_t mine = 0;
+    bool bad = false;
+    for (int j = 0; j < 8; j++) {
+        const int p = base + j;
+        lens[j] = 0;
+        if (p >= (int)B.len || !start[p]) continue;
+        const int n = ti_token_out(src, p, is_crlf, prevq, cand, nc, rank, nins, ins_list, sdict, swords, static_n, nullptr);
+        if (n < 0) bad = true;
+        else lens[j] = n, mine += (uint32_t)n;
+    }
+    if (!write) {
+        if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) st[b].anomaly = 1;
+    }
+    uint32_t total;
+    const uint32_t excl = cta_excl_add(mine, s_a, &total);
+    if (!write) {
+        if (threadIdx.x == 0) sums_or_offsets[B.pt_base + blockIdx.x] = total;
+        return;
+    }
+    uint8_t* dst = out + B.dst_off;
+    uint32_t pos = sums_or_offsets[B.pt_base + blockIdx.x] + excl;
+    for (int j = 0; j < 8; j++) {
+        const int p = base + j;
+        if (p >= (int)B.len || !start[p]) continue;
+        ti_token_out(src, p, is_crlf, prevq, cand, nc, rank, nins, ins_list, sdict, swords, static_n, dst + pos);
+        pos += (uint32_t)lens[j];
+    }
+}
+__global__ void ti_finalize_kernel(const TiBlock* __restrict__ blocks, int nblocks, TiState* __restrict__ st, const uint32_t* __restrict__ tot, TextResult* __restrict__ res) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const TiBlock B = blocks[b];
+    if (!(B.go & 0x100u)) return;
+    const uint32_t total = tot[b * 8 + 5];
+    if ((uint64_t)total + 64 >= (uint64_t)B.cap) st[b].anomaly = 1;  // too close to the checks of :1601 / :1661: the serial walk decides
+    st[b].total = total;
+    if (!st[b].anomaly) {
+        TextResult r;
+        r.status = 0;
+        r.out_len = total;
+        r.data_type = 0;
+        r.mode = 0;
+        res[b] = r;
+    }
+}
+__global__ void ti_set_ncand_kernel(const TiBlock* __restrict__ blocks, int nblocks, TpState* __restrict__ tst, const uint32_t* __restrict__ tot) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    TpState S;
+    S.ncand = (blocks[b].go & 0x100u) ? tot[b * 8 + 0] : 0;
+    S.nf = S.lead = S.nins = 0;
+    S.changed = S.fail = S.z0_overflow = S.total = 0;
+    S.z0.n = 0;
+    S.z0.first_ins = INT32_MAX;
+    tst[b] = S;
+}
+__global__ void __launch_bounds__(256) ti_init_ins_kernel(const TpBlock* __restrict__ blocks, const TpState* __restrict__ st, uint8_t* __restrict__ ins) {
+    const TpBlock B = blocks[blockIdx.y];
+    if (!(B.go & 0x100u)) return;
+    const uint32_t nc = st[blockIdx.y].ncand;
+    for (uint32_t k = blockIdx.x * 256 + threadIdx.x; k < nc; k += gridDim.x * 256) ins[B.cand_off + k] = 1;
+}
+
 size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// the dictionary rounds of kz_text_par_core.cuh for every block with go & 0x100; h_st[b].changed != 0 afterwards: no fixed point within MAX_ROUNDS
+cudaError_t dictionary_rounds(const uint8_t* d_in, const TpBlock* d_pb, const std::vector<TpBlock>& pb, TpState* d_st, std::vector<TpState>& h_st,
+                              const Candidate* d_cand, uint8_t* d_ins, uint8_t* d_ins2, uint32_t mask, uint32_t slots, int32_t* d_owner, const int32_t* d_owner0,
+                              const Entry* sd, const uint8_t* d_swords, uint32_t* d_ct, uint32_t* d_tot, uint32_t* d_rank, int32_t* d_focc, uint8_t* d_fflip,
+                              uint32_t max_nct, int inverse, cudaStream_t stream, uint64_t* launches) {
+    const uint32_t nblocks = (uint32_t)pb.size();
+    const dim3 gc(max_nct, nblocks), gs(32, nblocks);
+    uint8_t *cur = d_ins, *nxt = d_ins2;
+    bool converged = false;
+    cudaError_t e;
+    for (int rounds = 0; rounds < MAX_ROUNDS && !converged; rounds++) {
+        tp_round_begin_kernel<<<gs, 256, 0, stream>>>(d_pb, d_st, d_owner0, slots, d_owner);
+        tp_round_owners_kernel<<<gc, 256, 0, stream>>>(d_pb, d_st, d_cand, cur, mask, d_owner, d_ct);
+        tp_round_nx_kernel<<<gs, 256, 0, stream>>>(d_pb, d_st, cur);
+        tp_scan_tiles_kernel<<<nblocks, 32, 0, stream>>>(d_pb, (int)nblocks, 1, d_ct, d_tot, CT, d_tot, 8, 1);
+        tp_round_eval_kernel<<<gc, 256, 0, stream>>>(d_in, d_pb, d_st, d_cand, cur, nxt, mask, d_owner, sd, d_swords, d_ct, d_rank, d_focc, d_fflip, inverse);
+        if (launches) *launches += 5;
+        if ((e = cudaMemcpyAsync(h_st.data(), d_st, nblocks * sizeof(TpState), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+        converged = true;
+        for (uint32_t b = 0; b < nblocks; b++)
+            if ((pb[b].go & 0x100u) && h_st[b].changed) converged = false;
+        std::swap(cur, nxt);  // the decisions of this round
+    }
+    // a converged block has identical decisions in both buffers; the inverse path reads them from d_ins
+    if (cur != d_ins) {
+        size_t bytes = 0;
+        for (const TpBlock& B : pb) bytes = std::max<size_t>(bytes, B.cand_off + (size_t)B.nct_cap * CT);
+        if ((e = cudaMemcpyAsync(d_ins, cur, bytes, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) return e;
+    }
+    return cudaGetLastError();
+}
 
 }  // namespace
 
@@ -647,23 +1017,9 @@ cudaError_t text_forward_parallel(const uint8_t* d_in, uint8_t* d_out, const std
     tp_init_ins_kernel<<<gs, 256, 0, stream>>>(d_pb, d_st, d_cand, d_ins);
     // ---- B
     std::vector<TpState> h_st(nblocks);
-    uint8_t *cur = d_ins, *nxt = d_ins2;
-    bool converged = false;
-    int rounds = 0;
-    for (; rounds < MAX_ROUNDS && !converged; rounds++) {
-        tp_round_begin_kernel<<<gs, 256, 0, stream>>>(d_pb, d_st, d_owner0, slots, d_owner);
-        tp_round_owners_kernel<<<gc, 256, 0, stream>>>(d_pb, d_st, d_cand, cur, mask, d_owner, d_ct);
-        tp_round_nx_kernel<<<gs, 256, 0, stream>>>(d_pb, d_st, cur);
-        tp_scan_tiles_kernel<<<nblocks, 32, 0, stream>>>(d_pb, (int)nblocks, 1, d_ct, d_tot, CT, d_tot, 8, 1);
-        tp_round_eval_kernel<<<gc, 256, 0, stream>>>(d_in, d_pb, d_st, d_cand, cur, nxt, mask, d_owner, sd, d_swords, d_ct, d_rank, d_focc, d_fflip);
-        if (launches) *launches += 5;
-        if ((e = cudaMemcpyAsync(h_st.data(), d_st, nblocks * sizeof(TpState), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
-        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
-        converged = true;
-        for (uint32_t b = 0; b < nblocks; b++)
-            if ((pb[b].go & 0x100u) && h_st[b].changed) converged = false;
-        std::swap(cur, nxt);  // the decisions of this round
-    }
+    if ((e = dictionary_rounds(d_in, d_pb, pb, d_st, h_st, d_cand, d_ins, d_ins2, mask, slots, d_owner, d_owner0, sd, d_swords, d_ct, d_tot, d_rank, d_focc, d_fflip, max_nct,
+                               0, stream, launches)) != cudaSuccess)
+        return e;
     // the last round confirmed `nxt` (== cur bytewise for converged blocks); rank / focc / fflip belong to it
     std::vector<uint32_t> h_tot(nblocks * 8);
     if ((e = cudaMemcpyAsync(h_tot.data(), d_tot, nblocks * 32, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
@@ -689,6 +1045,129 @@ cudaError_t text_forward_parallel(const uint8_t* d_in, uint8_t* d_out, const std
     tp_emit_bytes_kernel<<<gp, 256, 0, stream>>>(d_in, d_pb, d_st, d_found, d_cp, d_outpos, d_tot, d_out, d_fb);
     if (launches) *launches += 12;
     return cudaGetLastError();
+}
+
+cudaError_t text_inverse_parallel(const uint8_t* d_in, uint8_t* d_out, const std::vector<TextBlock>& tb, uint64_t stream_block_size, const void* d_sdict,
+                                  const uint8_t* d_swords, int static_n, uint8_t* ws, size_t ws_bytes, TextResult* d_res, cudaStream_t stream,
+                                  std::vector<uint32_t>& h_fallback, uint64_t* launches) {
+    const uint32_t nblocks = (uint32_t)tb.size();
+    h_fallback.assign(nblocks, 1);
+    if (nblocks == 0) return cudaSuccess;
+    const uint32_t lg = log_hash_size(stream_block_size);
+    const uint32_t slots = 1u << lg, mask = slots - 1;
+    std::vector<TiBlock> ib(nblocks);
+    std::vector<TpBlock> pb(nblocks);
+    uint64_t cands = 0, poss = 0;
+    uint32_t pts = 0, cts = 0, max_npt = 1, max_nct = 1;
+    bool any = false;
+    for (uint32_t b = 0; b < nblocks; b++) {
+        TiBlock& B = ib[b];
+        B.src_off = tb[b].src_off;
+        B.dst_off = tb[b].dst_off;
+        B.len = tb[b].len;
+        B.cap = tb[b].cap;
+        B.go = (B.len >= 2 && B.len <= (1u << 30) && B.cap != 0) ? 0x100u : 0u;
+        B.cand_off = cands;
+        cands += (uint64_t)B.len / 4 + 16;
+        B.pos_off = poss;
+        poss += (uint64_t)B.len + 16;
+        B.owner_off = (uint64_t)b << lg;
+        B.pt_base = pts;
+        B.npt = B.len / PT + 1;
+        pts += B.npt + 1;
+        B.ct_base = cts;
+        B.nct_cap = (uint32_t)((B.len / 4 + 16 + CT - 1) / CT);
+        cts += B.nct_cap + 1;
+        TpBlock& P = pb[b];
+        P.src_off = B.src_off, P.dst_off = B.dst_off, P.cand_off = B.cand_off, P.cp_off = 0, P.owner_off = B.owner_off;
+        P.len = B.len, P.go = B.go, P.pt_base = B.pt_base, P.npt = B.npt, P.ct_base = B.ct_base, P.nct_cap = B.nct_cap;
+        if (B.go) {
+            any = true;
+            max_npt = std::max(max_npt, B.npt);
+            max_nct = std::max(max_nct, B.nct_cap);
+        }
+    }
+    if (!any) return cudaSuccess;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        uint8_t* p = ws + off;
+        off = align256(off + bytes);
+        return p;
+    };
+    TiBlock* d_ib = (TiBlock*)take(nblocks * sizeof(TiBlock));
+    TpBlock* d_pb = (TpBlock*)take(nblocks * sizeof(TpBlock));
+    TpState* d_tst = (TpState*)take(nblocks * sizeof(TpState));
+    TiState* d_ist = (TiState*)take(nblocks * sizeof(TiState));
+    uint32_t* d_tot = (uint32_t*)take(nblocks * 32);  // [0] candidates, [1] inserts, [5] output bytes
+    uint32_t* d_fn = (uint32_t*)take(pts * 4);
+    int* d_lastq = (int*)take(pts * 4);
+    uint32_t* d_pt = (uint32_t*)take(pts * 4);
+    uint32_t* d_ct = (uint32_t*)take(cts * 4);
+    uint8_t* d_start = take(poss);
+    int32_t* d_prevq = (int32_t*)take(poss * 4);
+    Candidate* d_cand = (Candidate*)take(cands * sizeof(Candidate));
+    uint8_t* d_ins = take(cands);
+    uint8_t* d_ins2 = take(cands);
+    uint32_t* d_rank = (uint32_t*)take(cands * 4);
+    int32_t* d_focc = (int32_t*)take(cands * 4);
+    uint32_t* d_ins_list = (uint32_t*)take(cands * 4);
+    uint8_t* d_fflip = take(cands);
+    int32_t* d_owner = (int32_t*)take(((size_t)nblocks << lg) * 4);
+    int32_t* d_owner0 = (int32_t*)take((size_t)slots * 4);
+    if (off > ws_bytes) return cudaErrorInvalidValue;
+    const Entry* sd = (const Entry*)d_sdict;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d_ib, ib.data(), nblocks * sizeof(TiBlock), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(d_pb, pb.data(), nblocks * sizeof(TpBlock), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(d_tot, 0, nblocks * 32, stream)) != cudaSuccess) return e;
+    const dim3 gp(max_npt, nblocks), gs(32, nblocks);
+    const uint32_t gb = (nblocks + 255) / 256;
+    tp_fill_kernel<<<64, 256, 0, stream>>>(d_owner0, OCC_EMPTY, slots);
+    tp_owner0_kernel<<<1, 32, 0, stream>>>(sd, static_n, mask, d_owner0);
+    ti_token_tiles_kernel<<<gp, 256, 0, stream>>>(d_in, d_ib, d_fn);
+    ti_token_carry_kernel<<<nblocks, 32, 0, stream>>>(d_ib, (int)nblocks, d_fn, d_ist);
+    ti_token_mark_kernel<<<gp, 256, 0, stream>>>(d_in, d_ib, d_fn, d_start, d_lastq);
+    ti_lastq_carry_kernel<<<nblocks, 32, 0, stream>>>(d_ib, (int)nblocks, d_lastq);
+    ti_candidates_kernel<<<gp, 256, 0, stream>>>(d_in, d_ib, d_start, d_lastq, sd, static_n, d_pt, 0, d_prevq, d_cand);
+    tp_scan_tiles_kernel<<<nblocks, 32, 0, stream>>>(d_pb, (int)nblocks, 0, d_pt, nullptr, PT, d_tot, 8, 0);
+    ti_candidates_kernel<<<gp, 256, 0, stream>>>(d_in, d_ib, d_start, d_lastq, sd, static_n, d_pt, 1, d_prevq, d_cand);
+    ti_set_ncand_kernel<<<gb, 256, 0, stream>>>(d_ib, (int)nblocks, d_tst, d_tot);
+    ti_init_ins_kernel<<<gs, 256, 0, stream>>>(d_pb, d_tst, d_ins);
+    if (launches) *launches += 11;
+    std::vector<TpState> h_st(nblocks);
+    if ((e = dictionary_rounds(d_in, d_pb, pb, d_tst, h_st, d_cand, d_ins, d_ins2, mask, slots, d_owner, d_owner0, sd, d_swords, d_ct, d_tot, d_rank, d_focc, d_fflip, max_nct, 1,
+                               stream, launches)) != cudaSuccess)
+        return e;
+    ti_ins_list_kernel<<<gs, 256, 0, stream>>>(d_pb, d_tst, d_ins, d_rank, d_ins_list);
+    ti_output_kernel<<<gp, 256, 0, stream>>>(d_in, d_ib, d_tst, d_ist, d_start, d_prevq, d_cand, d_rank, d_tot, d_ins_list, sd, d_swords, static_n, d_pt, 0, d_out);
+    tp_scan_tiles_kernel<<<nblocks, 32, 0, stream>>>(d_pb, (int)nblocks, 0, d_pt, nullptr, PT, d_tot, 8, 5);
+    // blocks whose rounds did not settle (or whose list would wrap, or with too many words in map slot 0) are anomalies as well
+    std::vector<uint32_t> h_tot(nblocks * 8);
+    if ((e = cudaMemcpyAsync(h_tot.data(), d_tot, nblocks * 32, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+    std::vector<TiState> h_ist(nblocks);
+    if ((e = cudaMemcpyAsync(h_ist.data(), d_ist, nblocks * sizeof(TiState), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+    for (uint32_t b = 0; b < nblocks; b++) {
+        if (!ib[b].go) continue;
+        if (h_st[b].changed || h_st[b].z0_overflow || (uint64_t)STATIC_WORDS + h_tot[b * 8 + 1] >= (uint64_t)MAX_DICT_SIZE) h_ist[b].anomaly = 1;
+    }
+    if ((e = cudaMemcpyAsync(d_ist, h_ist.data(), nblocks * sizeof(TiState), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+    ti_finalize_kernel<<<gb, 256, 0, stream>>>(d_ib, (int)nblocks, d_ist, d_tot, d_res);
+    ti_output_kernel<<<gp, 256, 0, stream>>>(d_in, d_ib, d_tst, d_ist, d_start, d_prevq, d_cand, d_rank, d_tot, d_ins_list, sd, d_swords, static_n, d_pt, 1, d_out);
+    if (launches) *launches += 5;
+    if ((e = cudaMemcpyAsync(h_ist.data(), d_ist, nblocks * sizeof(TiState), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+    for (uint32_t b = 0; b < nblocks; b++) h_fallback[b] = (ib[b].go && !h_ist[b].anomaly) ? 0u : 1u;
+    return cudaGetLastError();
+}
+
+size_t text_inverse_parallel_workspace(uint32_t nblocks, uint32_t max_len, uint64_t stream_block_size) {
+    const uint32_t lg = log_hash_size(stream_block_size);
+    const size_t nb = nblocks;
+    const size_t cands = nb * ((size_t)max_len / 4 + 16), poss = nb * ((size_t)max_len + 16), pts = nb * ((size_t)max_len / PT + 2), cts = nb * (((size_t)max_len / 4 + 16 + CT - 1) / CT + 1);
+    return align256(nb * sizeof(TiBlock)) + align256(nb * sizeof(TpBlock)) + align256(nb * sizeof(TpState)) + align256(nb * sizeof(TiState)) + align256(nb * 32) +
+           3 * align256(pts * 4) + align256(cts * 4) + align256(poss) + align256(poss * 4) + align256(cands * sizeof(Candidate)) + 3 * align256(cands) + 3 * align256(cands * 4) +
+           align256((nb << lg) * 4) + align256((size_t(1) << lg) * 4) + 8192;
 }
 
 }  // namespace kz

@@ -14,4 +14,10 @@ cudaError_t text_forward_parallel(const uint8_t* d_in, uint8_t* d_out, const std
                                   const void* d_sdict, const uint8_t* d_swords, int static_n, uint8_t* ws, size_t ws_bytes, TextResult* d_res, cudaStream_t stream,
                                   std::vector<uint32_t>& h_fallback, uint64_t* launches);
 
+// TEXT inverse of a batch; h_fallback[b] != 0: the block is left to the serial walk (trivial blocks and every anomaly). Synchronises.
+size_t text_inverse_parallel_workspace(uint32_t nblocks, uint32_t max_len, uint64_t stream_block_size);
+cudaError_t text_inverse_parallel(const uint8_t* d_in, uint8_t* d_out, const std::vector<TextBlock>& tb, uint64_t stream_block_size, const void* d_sdict,
+                                  const uint8_t* d_swords, int static_n, uint8_t* ws, size_t ws_bytes, TextResult* d_res, cudaStream_t stream,
+                                  std::vector<uint32_t>& h_fallback, uint64_t* launches);
+
 }  // namespace kz

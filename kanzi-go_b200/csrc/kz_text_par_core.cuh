@@ -181,7 +181,9 @@ KZ_TEXT_HD const uint8_t* occupant_bytes(const DictView& V, int32_t o) {
 }
 // One candidate of one round. ins_before = inserted candidates in front of k under the previous round's decisions. Returns the new decision;
 // *found_occ = the word it is (OCC_EMPTY: not in the dictionary), *flip = found through the case-flipped hash.
-KZ_TEXT_HD bool eval_candidate(const DictView& V, int k, uint32_t ins_before, int32_t* found_occ, int32_t* flip) {
+// inverse = the decoder's walk (Inverse :1544-1581): no look-up through the case-flipped hash, and every word qualifies by length while
+// fewer than THRESHOLD2 words exist.
+KZ_TEXT_HD bool eval_candidate(const DictView& V, int k, uint32_t ins_before, int32_t* found_occ, int32_t* flip, bool inverse = false) {
     const Candidate& c = V.cand[k];
     const int32_t length = c.end - c.start;
     const int32_t o1 = occupant(V, c.h1 & V.mask, k);
@@ -189,7 +191,7 @@ KZ_TEXT_HD bool eval_candidate(const DictView& V, int k, uint32_t ins_before, in
     *flip = 0;
     if (occupant_is(V, o1, c.h1, length)) {
         pe = o1;
-    } else {
+    } else if (!inverse) {
         const int32_t o2 = occupant(V, c.h2 & V.mask, k);
         if (occupant_is(V, o2, c.h2, length)) {
             pe = o2;
@@ -200,9 +202,48 @@ KZ_TEXT_HD bool eval_candidate(const DictView& V, int k, uint32_t ins_before, in
     *found_occ = pe;
     if (pe != OCC_EMPTY) return false;
     const int words = STATIC_WORDS + (int)ins_before;
+    if (inverse) return (length > 3 || words < THRESHOLD2) && o1 == OCC_EMPTY;
     return (length > 3 || (length == 3 && words < THRESHOLD2)) && o1 == OCC_EMPTY;
 }
 KZ_TEXT_HD int32_t occupant_index(int32_t o, const uint32_t* rank) { return o < 0 ? -(o + 1) : STATIC_WORDS + (int32_t)rank[o]; }
+
+// ---- inverse (textCodec2.Inverse :1513-1718, bitstream version 6), the pieces of the data-parallel statement ---------------------------------
+// The encoded stream is a sequence of tokens whose length follows from their first one or two bytes: a letter or any other byte below 0x80
+// (1), the escape 0x0F + one raw byte (2), a word index of 1..3 bytes, optionally behind the flip marker 0x80. Token starts are the orbit of
+// position 1 under i -> i + token_len(i): a scan over 4-state transition functions ("bytes left in the current token"). The decoder's
+// dictionary grows from the letter runs of the stream exactly like the encoder's (same rounds, no flipped look-up); an index token is
+// the k-th inserted word or a static word; output offsets are a prefix sum of the token output lengths.
+enum { TK_LETTER = 0, TK_LIT = 1, TK_ESC = 2, TK_IDX = 3 };
+KZ_TEXT_HD int idx_len(uint32_t v7) { return v7 < 64 ? 1 : (v7 < 112 ? 2 : 3); }
+KZ_TEXT_HD int token_len(const uint8_t* src, int i) {  // src[i + 1] must be readable
+    const uint8_t cur = src[i];
+    if (cur < 0x80) return cur == ESCAPE_TOKEN1 ? 2 : 1;
+    if (cur == MASK_FLIP_CASE) return 1 + idx_len(src[i + 1] & 0x7Fu);
+    return idx_len(cur & 0x7Fu);
+}
+KZ_TEXT_HD int token_kind(uint8_t cur) {
+    if (is_text(cur)) return TK_LETTER;
+    if (cur >= 0x80) return TK_IDX;
+    return cur == ESCAPE_TOKEN1 ? TK_ESC : TK_LIT;
+}
+// index token at p (all its bytes are inside the stream): the dictionary index (already decremented) and the flip mask
+KZ_TEXT_HD int token_index(const uint8_t* src, int p, int* flip) {
+    int q = p;
+    uint8_t cur = src[q++];
+    *flip = 0;
+    if (cur == MASK_FLIP_CASE) {
+        *flip = 1;
+        cur = src[q++];
+    }
+    int idx = cur & 0x7F;
+    if (idx >= 64) {
+        if (idx >= 112) idx = ((idx & 0x0F) << 16) | ((int)src[q] << 8) | src[q + 1];
+        else idx = ((idx & 0x1F) << 8) | src[q];
+    }
+    return idx - 1;
+}
+// transition of the token automaton at byte i: state = bytes still to skip before the next token start (0 = a token starts here)
+KZ_TEXT_HD uint32_t token_step(const uint8_t* src, int i, uint32_t state) { return state ? state - 1 : (uint32_t)token_len(src, i) - 1; }
 
 }  // namespace textc
 }  // namespace kz

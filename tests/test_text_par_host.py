@@ -31,6 +31,10 @@ def tp():
     lib.tp_walk.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int]
     lib.tp_phases.restype = C.c_int64
     lib.tp_phases.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.tp_inverse_walk.restype = C.c_int64
+    lib.tp_inverse_walk.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_uint64]
+    lib.tp_inverse_parallel.restype = C.c_int64
+    lib.tp_inverse_parallel.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_uint64, C.POINTER(C.c_int)]
     lib.tp_parallel.restype = C.c_int64
     lib.tp_parallel.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     return lib
@@ -104,3 +108,31 @@ def test_three_phases_match_the_walk(tp, n, bs):
 def test_three_phases_dictionary_wrap(tp):
     na, nc, nf = _same(tp, _words(12 << 20, 700000, 7), 16 << 20)
     assert na > 0
+
+
+@pytest.mark.parametrize("n,bs", [(1024, 1024), (5000, 4096), (100000, 1 << 16), (1 << 20, 1 << 20), (4 << 20, 4 << 20)])
+def test_parallel_inverse_matches_the_walk(tp, n, bs):
+    """encode with the walk, decode with the serial inverse walk and with the data-parallel statement: same bytes, and the input again"""
+    texts = [synth.markov_text(n, seed=n), _words(n, 50, n + 1), _words(n, 5000, n + 2, crlf=True), synth.english_text(n, seed=n + 3),
+             synth.english_text(n, seed=n + 4, crlf=False, html=True), synth.enwik_shaped(n, seed=n + 5), synth.xml_like(n, seed=n + 6),
+             np.frombuffer((b"Hello hello HELLO hello Hello world World wOrld world abc Abc abc aBc a I a the " * (n // 80 + 1))[:n], np.uint8),
+             np.random.default_rng(n).integers(0, 256, n).astype(np.uint8)]
+    worst = 0
+    for x in texts:
+        x = np.ascontiguousarray(x, np.uint8)
+        for mode in (0, 0x40):
+            enc = np.zeros(len(x) + 64, np.uint8)
+            ne = tp.tp_walk(x.ctypes.data, len(x), enc.ctypes.data, bs, mode)
+            if ne <= 0:
+                continue
+            cap = 2 * len(x) + 1024  # mode 0x40 forced on LF-only text doubles every line end
+            a = np.zeros(cap + 64, np.uint8)
+            b = np.zeros(cap + 64, np.uint8)
+            rounds = C.c_int(0)
+            na = tp.tp_inverse_walk(enc.ctypes.data, ne, a.ctypes.data, cap, bs)
+            nb = tp.tp_inverse_parallel(enc.ctypes.data, ne, b.ctypes.data, cap, bs, C.byref(rounds))
+            assert nb != -2, "the parallel statement declined"
+            assert na == nb, (na, nb)
+            assert np.array_equal(a[:na], b[:nb]), int(np.argmax(a[:na] != b[:nb]))
+            worst = max(worst, rounds.value)
+    print("n", n, "inverse rounds (max)", worst)
