@@ -106,6 +106,22 @@ int kz_compress_stream_device(kz_ctx* ctx, uint64_t transform48, uint32_t entrop
 /* Decompresses the complete stream of n bytes at d_src (must be followed by >= 64 readable bytes) into d_dst. */
 int kz_decompress_stream_device(kz_ctx* ctx, const void* d_src, size_t n, void* d_dst, size_t cap, size_t* out_n);
 
+/* ---- sharded streams (io.Writer / io.Reader with the blocks of ONE stream spread over several GPUs; the NCCL scatter / gather of the
+ *      byte ranges is the host side's business, kanzi-go_b200/parallel.py; blocks are independent: io/CompressedStream.go:896-898) ---------- */
+/* Block records (5 b | lw b | payload each, :951-976) of the n bytes at d_src: no stream header, no end marker. *out_bits = exact length. */
+int kz_compress_fragment_device(kz_ctx* ctx, uint64_t transform48, uint32_t entropy, uint32_t block_size, uint32_t checksum_bits, const void* d_src, size_t n,
+                                void* d_dst, size_t cap, uint64_t* out_bits);
+/* Stream header (Writer.writeHeader :429-519) as bytes (out: >= 32 bytes) + its bit length. Host only. */
+int kz_stream_header(uint64_t transform48, uint32_t entropy, uint32_t block_size, uint32_t checksum_bits, int64_t input_size_hint, uint8_t* out, uint32_t* out_bits);
+/* Ordered, bit-granular commit: concatenates nseg device bit strings (4-byte aligned bases) into d_dst. */
+int kz_concat_bits_device(kz_ctx* ctx, uint32_t nseg, const void* const* d_seg, const uint64_t* seg_bits, void* d_dst, size_t cap, uint64_t* total_bits);
+/* Header fields and record boundaries of the complete stream at d_src: rec_bit[0 .. *nblocks] (max_blocks + 1 entries). */
+int kz_stream_index_device(kz_ctx* ctx, const void* d_src, size_t n, uint32_t max_blocks, uint64_t* transform48, uint32_t* entropy, uint32_t* block_size,
+                           uint32_t* checksum_bits, int64_t* input_size, uint64_t* rec_bit, uint32_t* nblocks);
+/* Decodes nblocks records starting at bit start_bit of the fragment at d_src (16-byte aligned, >= 64 readable bytes behind frag_bytes). */
+int kz_decompress_fragment_device(kz_ctx* ctx, uint64_t transform48, uint32_t entropy, uint32_t block_size, uint32_t checksum_bits, const void* d_src,
+                                  size_t frag_bytes, uint64_t start_bit, uint32_t nblocks, void* d_dst, size_t cap, size_t* out_n);
+
 /* ---- instrumentation ------------------------------------------------------------------------------------- */
 /* Milliseconds (CUDA events on the context's stream) spent in named kernels since the last reset; names:
  * "ans0_decode", "ans0_encode", "ans0_stats", "ans_walk", "concat", "huf_encode", "huf_decode", ...  Returns

@@ -35,6 +35,7 @@ ABI_SYMBOLS = [
     "kz_encode_blocks", "kz_decode_blocks", "kz_max_block_output", "kz_compress_stream", "kz_decompress_stream", "kz_max_stream_output",
     "kz_compress_stream_device", "kz_decompress_stream_device", "kz_profile", "kz_kernel_time", "kz_profile_reset", "kz_set_stream_block_size",
     "kz_stage_bytes", "kz_profile_names",
+    "kz_compress_fragment_device", "kz_stream_header", "kz_concat_bits_device", "kz_stream_index_device", "kz_decompress_fragment_device",
 ]
 
 
@@ -121,6 +122,12 @@ def load_library(build_if_missing=True):
     L.kz_profile_reset.argtypes = [vp]
     L.kz_profile_reset.restype = None
     L.kz_set_stream_block_size.argtypes = [vp, C.c_uint64]
+    L.kz_compress_fragment_device.argtypes = [vp, u64, u32, u32, u32, vp, sz, vp, sz, C.POINTER(u64)]
+    L.kz_stream_header.argtypes = [u64, u32, u32, u32, C.c_int64, vp, C.POINTER(u32)]
+    L.kz_concat_bits_device.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64), vp, sz, C.POINTER(u64)]
+    L.kz_stream_index_device.argtypes = [vp, vp, sz, u32, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_int64), C.POINTER(u64),
+                                         C.POINTER(u32)]
+    L.kz_decompress_fragment_device.argtypes = [vp, u64, u32, u32, u32, vp, sz, u64, u32, vp, sz, C.POINTER(sz)]
     L.kz_stage_bytes.argtypes = [vp, C.c_char_p, C.POINTER(u64), C.POINTER(u64)]
     L.kz_stage_bytes.restype = u32
     L.kz_profile_names.argtypes = [vp, C.c_char_p, sz]
@@ -281,6 +288,42 @@ class Context:
     def decompress_host(self, src_ptr, n, dst_ptr, cap):
         out_n = C.c_size_t(0)
         self._check(self.lib.kz_decompress_stream(self.h, src_ptr, n, dst_ptr, cap, C.byref(out_n)))
+        return out_n.value
+
+    # ---- sharded streams (one stream, blocks spread over ranks; kanzi-go_b200/parallel.py drives these) ---------------------
+    def compress_fragment_device(self, d_src, n, d_dst, cap, transform48, etype, block_size, checksum_bits=0):
+        bits = C.c_uint64(0)
+        self._check(self.lib.kz_compress_fragment_device(self.h, transform48, etype, block_size, checksum_bits, d_src, n, d_dst, cap, C.byref(bits)))
+        return bits.value
+
+    def stream_header(self, transform48, etype, block_size, checksum_bits=0, input_size=0):
+        out = np.zeros(32, np.uint8)
+        bits = C.c_uint32(0)
+        rc = self.lib.kz_stream_header(transform48, etype, block_size, checksum_bits, input_size, out.ctypes.data, C.byref(bits))
+        if rc:
+            raise KanziError(-rc, "kz_stream_header")
+        return out, bits.value
+
+    def concat_bits_device(self, seg_ptrs, seg_bits, d_dst, cap):
+        n = len(seg_ptrs)
+        ptrs = (C.c_void_p * max(n, 1))(*seg_ptrs)
+        bits = (C.c_uint64 * max(n, 1))(*seg_bits)
+        total = C.c_uint64(0)
+        self._check(self.lib.kz_concat_bits_device(self.h, n, ptrs, bits, d_dst, cap, C.byref(total)))
+        return total.value
+
+    def stream_index_device(self, d_src, n, max_blocks):
+        t48, et, bs, ck, isz, nb = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_int64(0), C.c_uint32(0)
+        rec = (C.c_uint64 * (max_blocks + 1))()
+        self._check(self.lib.kz_stream_index_device(self.h, d_src, n, max_blocks, C.byref(t48), C.byref(et), C.byref(bs), C.byref(ck), C.byref(isz), rec,
+                                                    C.byref(nb)))
+        return {"transform48": t48.value, "entropy": et.value, "block_size": bs.value, "checksum_bits": ck.value, "input_size": isz.value,
+                "rec_bit": [int(rec[i]) for i in range(nb.value + 1)], "nblocks": nb.value}
+
+    def decompress_fragment_device(self, d_src, frag_bytes, start_bit, nblocks, d_dst, cap, transform48, etype, block_size, checksum_bits=0):
+        out_n = C.c_size_t(0)
+        self._check(self.lib.kz_decompress_fragment_device(self.h, transform48, etype, block_size, checksum_bits, d_src, frag_bytes, start_bit, nblocks, d_dst,
+                                                           cap, C.byref(out_n)))
         return out_n.value
 
     def cuda_stream(self):

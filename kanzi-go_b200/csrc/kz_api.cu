@@ -279,7 +279,7 @@ int encode_batch(kz_ctx* ctx, EncLayout layout, uint32_t etype, uint32_t checksu
             const uint8_t* q = (const uint8_t*)p;
             key.insert(key.end(), q, q + n);
         };
-        const uint64_t scal[8] = {(uint64_t)layout, etype, checksum_bits, (uint64_t)(uintptr_t)d_data, (uint64_t)(uintptr_t)d_small, (uint64_t)nblocks,
+        const uint64_t scal[8] = {(uint64_t)layout | (ctx->fragment ? 0x100u : 0u), etype, checksum_bits, (uint64_t)(uintptr_t)d_data, (uint64_t)(uintptr_t)d_small, (uint64_t)nblocks,
                                   stream_hdr_bits, (uint64_t)stream_hdr.size()};
         key.reserve(sizeof(scal) + stream_hdr.size() + jobs.size() * 40 + blk_base_bits.size() * 8);
         put(scal, sizeof(scal));
@@ -373,7 +373,7 @@ int encode_batch(kz_ctx* ctx, EncLayout layout, uint32_t etype, uint32_t checksu
                 }
             }
             if (layout == LAYOUT_STREAM) {
-                add_seg((uint64_t)(uintptr_t)(d_small + small_zero_off), 8);  // end marker: 5+3 zero bits (Close :593-594)
+                add_seg((uint64_t)(uintptr_t)(d_small + small_zero_off), ctx->fragment ? 0 : 8);  // end marker: 5+3 zero bits (Close :593-594); none behind a fragment
                 blk_first[nblocks] = (uint32_t)seg_src.size();
             } else {
                 blk_first[nblocks] = (uint32_t)seg_src.size();
@@ -564,13 +564,15 @@ __global__ void block_header_kernel(const uint32_t* __restrict__ words, const ui
 }
 
 // Serial walk over the block length prefixes of a complete stream (decodingTask.decode :1816-1852). One thread.
+// stop_after != 0: a fragment of that many block records (no end marker behind them)
 __global__ void stream_walk_kernel(const uint32_t* __restrict__ words, uint64_t start_bit, uint64_t end_bit, uint32_t max_blocks,
-                                   uint64_t* __restrict__ bit_off, uint64_t* __restrict__ bits, uint32_t* __restrict__ count_status) {
+                                   uint64_t* __restrict__ bit_off, uint64_t* __restrict__ bits, uint32_t* __restrict__ count_status, uint32_t stop_after = 0) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     BitReader br(words, start_bit, end_bit);
     uint32_t n = 0;
     int32_t st = 0;
     for (;;) {
+        if (stop_after && n == stop_after) break;
         const uint32_t lr = br.read(5) + 3;
         uint64_t len;
         if (lr > 32) {
@@ -926,8 +928,14 @@ bool experimental_stages() {
     return !(e && e[0] == '0');
 }
 
-int plan_transforms(kz_ctx* ctx, uint64_t t48, TransformPlan& p, int err_code) {
+// etype: the entropy codec of the stream. The reference picks the TEXT encoding from it (transform/Factory.go:99-119): encoding 2 for NONE /
+// ANS0 / HUFFMAN / RANGE, encoding 1 otherwise; only encoding 2 (textCodec2) exists here, so TEXT with any other codec is refused
+// rather than written in a form the reference could not read.
+int plan_transforms(kz_ctx* ctx, uint64_t t48, uint32_t etype, TransformPlan& p, int err_code) {
     p.nt = count_transforms(t48, p.ids);
+    for (int i = 0; i < p.nt; i++)
+        if (p.ids[i] == KZ_T_TEXT && !(etype == KZ_E_NONE || etype == KZ_E_ANS0 || etype == KZ_E_HUFFMAN || etype == KZ_E_RANGE))
+            return ctx->fail(err_code, "TEXT with this entropy codec selects the reference's text encoding 1, which the GPU path does not implement (NONE / ANS0 / HUFFMAN / RANGE select encoding 2)");
     if (!experimental_stages()) {
         for (int i = 0; i < p.nt; i++) {
             const uint64_t t = p.ids[i];
@@ -2111,8 +2119,22 @@ size_t kz_transform_max_encoded_len(uint64_t type, size_t n) {
 }
 
 // ---- whole stream, device resident ---------------------------------------------------------------------------
+static int compress_device_impl(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_t block_size, uint32_t checksum_bits, int64_t input_size, const void* d_src,
+                                size_t n, void* d_dst, size_t cap, size_t* out_n, bool fragment, uint64_t* out_bits);
 int kz_compress_stream_device(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_t block_size, uint32_t checksum_bits, int64_t input_size,
                               const void* d_src, size_t n, void* d_dst, size_t cap, size_t* out_n) {
+    return compress_device_impl(ctx, t48, etype, block_size, checksum_bits, input_size, d_src, n, d_dst, cap, out_n, false, nullptr);
+}
+// The block records (5 b | lw b | payload each) of n bytes at d_src, without stream header and without end marker: what one rank of a sharded
+// compression contributes (blocks are independent, io/CompressedStream.go:896-898). *out_bits = exact bit length.
+int kz_compress_fragment_device(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_t block_size, uint32_t checksum_bits, const void* d_src, size_t n, void* d_dst,
+                                size_t cap, uint64_t* out_bits) {
+    size_t bytes = 0;
+    if (!out_bits) return -KZ_ERR_INVALID_PARAM;
+    return compress_device_impl(ctx, t48, etype, block_size, checksum_bits, 0, d_src, n, d_dst, cap, &bytes, true, out_bits);
+}
+static int compress_device_impl(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_t block_size, uint32_t checksum_bits, int64_t input_size, const void* d_src,
+                                size_t n, void* d_dst, size_t cap, size_t* out_n, bool fragment, uint64_t* out_bits) {
     if (!ctx || !out_n) return -KZ_ERR_INVALID_PARAM;
     CK(cudaSetDevice(ctx->device));
     ctx->stream_bs = block_size;
@@ -2122,7 +2144,7 @@ int kz_compress_stream_device(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_
     const uint32_t nblocks = (uint32_t)((n + block_size - 1) / block_size);
     std::vector<EncJob> jobs;
     TransformPlan plan;
-    int rc = plan_transforms(ctx, t48, plan, KZ_ERR_CREATE_CODEC);
+    int rc = plan_transforms(ctx, t48, etype, plan, KZ_ERR_CREATE_CODEC);
     if (rc) return rc;
     const uint8_t* d_data = nullptr;
     std::vector<int32_t> init_dt;
@@ -2152,18 +2174,100 @@ int kz_compress_stream_device(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_
     }
     std::vector<uint8_t> hdr;
     uint32_t hdr_bits = build_stream_header(hdr, t48, etype, block_size, checksum_bits, input_size);
+    if (fragment) hdr_bits = 0;
     EncResult res;
+    ctx->fragment = fragment;
     rc = encode_batch(ctx, LAYOUT_STREAM, etype, checksum_bits, d_data, jobs, hdr, hdr_bits, (uint8_t*)d_dst, cap, {}, res);
+    ctx->fragment = false;
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     *out_n = (size_t)((res.total_bits + 7) / 8);
+    if (out_bits) *out_bits = res.total_bits;
     return 0;
 }
 
-int kz_decompress_stream_device(kz_ctx* ctx, const void* d_src, size_t n, void* d_dst, size_t cap, size_t* out_n) {
-    if (!ctx || !out_n) return -KZ_ERR_INVALID_PARAM;
+// Stream header bytes (Writer.writeHeader, io/CompressedStream.go:429-519) for the rank that commits a sharded stream. out: >= 32 bytes.
+int kz_stream_header(uint64_t t48, uint32_t etype, uint32_t block_size, uint32_t checksum_bits, int64_t input_size, uint8_t* out, uint32_t* out_bits) {
+    if (!out || !out_bits) return -KZ_ERR_INVALID_PARAM;
+    std::vector<uint8_t> hdr;
+    *out_bits = build_stream_header(hdr, t48, etype, block_size, checksum_bits, input_size);
+    memset(out, 0, 32);
+    memcpy(out, hdr.data(), std::min<size_t>(hdr.size(), 32));
+    return 0;
+}
+
+// Bit-granular concatenation of nseg device bit strings (MSB first) into d_dst: the ordered commit of Writer.processBlock (:951-976) for
+// fragments gathered from other ranks. Segments are cut into 64 KiB pieces, one CTA each. *total_bits = length of the result.
+int kz_concat_bits_device(kz_ctx* ctx, uint32_t nseg, const void* const* d_seg, const uint64_t* seg_bits, void* d_dst, size_t cap, uint64_t* total_bits) {
+    if (!ctx || !total_bits || (nseg && (!d_seg || !seg_bits)) || !d_dst) return -KZ_ERR_INVALID_PARAM;
     CK(cudaSetDevice(ctx->device));
-    if (((uintptr_t)d_src & 15) || ((uintptr_t)d_dst & 15)) return ctx->fail(KZ_ERR_INVALID_PARAM, "device buffers must be 16-byte aligned");
+    std::vector<uint64_t> src, bits;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < nseg; i++) {
+        if (((uintptr_t)d_seg[i] & 3) != 0) return ctx->fail(KZ_ERR_INVALID_PARAM, "segments must be 4-byte aligned");
+        const uint64_t nbytes = (seg_bits[i] + 7) / 8;
+        for (uint64_t o = 0; o < nbytes; o += RAW_PIECE) {
+            src.push_back((uint64_t)(uintptr_t)((const uint8_t*)d_seg[i] + o));
+            bits.push_back(std::min<uint64_t>(8 * RAW_PIECE, seg_bits[i] - 8 * o));
+        }
+        total += seg_bits[i];
+    }
+    *total_bits = total;
+    if ((total + 7) / 8 + 8 > cap) return ctx->fail(KZ_ERR_WRITE_FILE, "output buffer too small");
+    const int nsegs = (int)src.size();
+    if (nsegs == 0) return 0;
+    Packer pk;
+    const size_t o_src = pk.add(src.data(), src.size() * 8);
+    const size_t o_bits = pk.add(bits.data(), bits.size() * 8);
+    const size_t o_dst = pk.reserve((size_t)(nsegs + 1) * 8);
+    const size_t o_total = pk.reserve(8);
+    int rc = upload(ctx, pk);
+    if (rc) return rc;
+    uint8_t* T = ctx->d_tables.as<uint8_t>();
+    {
+        LaunchScope ls(ctx, "scan");
+        scan_bits_kernel<<<1, 1024, 0, ctx->stream>>>((const uint64_t*)(T + o_bits), (uint64_t*)(T + o_dst), nsegs + 1, 0, (uint64_t*)(T + o_total));
+    }
+    {
+        LaunchScope ls(ctx, "concat_zero");
+        concat_zero_kernel<<<(nsegs + 255) / 256, 256, 0, ctx->stream>>>((const uint64_t*)(T + o_bits), (const uint64_t*)(T + o_dst), nsegs, (uint32_t*)d_dst);
+    }
+    {
+        LaunchScope ls(ctx, "concat");
+        concat_copy_kernel<<<nsegs, 128, 0, ctx->stream>>>((const uint64_t*)(T + o_src), (const uint64_t*)(T + o_bits), (const uint64_t*)(T + o_dst), nsegs, (uint32_t*)d_dst);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int decompress_device_impl(kz_ctx* ctx, const StreamHeader* given, uint64_t start_bit, uint32_t stop_after, const void* d_src, size_t n, void* d_dst,
+                                  size_t cap, size_t* out_n);
+int kz_decompress_stream_device(kz_ctx* ctx, const void* d_src, size_t n, void* d_dst, size_t cap, size_t* out_n) {
+    return decompress_device_impl(ctx, nullptr, 0, 0, d_src, n, d_dst, cap, out_n);
+}
+// Decodes `nblocks` block records that start at bit `start_bit` of the fragment at d_src (frag_bytes bytes, >= 64 readable bytes behind them):
+// what one rank of a sharded decompression does with its part of the stream. The stream parameters come from the header rank 0 parsed.
+int kz_decompress_fragment_device(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_t block_size, uint32_t checksum_bits, const void* d_src, size_t frag_bytes,
+                                  uint64_t start_bit, uint32_t nblocks, void* d_dst, size_t cap, size_t* out_n) {
+    if (!ctx || !out_n) return -KZ_ERR_INVALID_PARAM;
+    *out_n = 0;
+    if (nblocks == 0) return 0;
+    StreamHeader sh;
+    sh.t48 = t48;
+    sh.etype = etype;
+    sh.block_size = block_size;
+    sh.checksum_bits = checksum_bits;
+    sh.input_size = 0;
+    sh.bits = 0;
+    return decompress_device_impl(ctx, &sh, start_bit, nblocks, d_src, frag_bytes, d_dst, cap, out_n);
+}
+// Parses the header of the stream at d_src and walks its block records: rec_bit[b] = first bit of record b (its 5-bit prefix), rec_bit[nblocks] =
+// first bit behind the last record (the end marker). rec_bit must hold max_blocks + 1 entries.
+int kz_stream_index_device(kz_ctx* ctx, const void* d_src, size_t n, uint32_t max_blocks, uint64_t* t48, uint32_t* etype, uint32_t* block_size,
+                           uint32_t* checksum_bits, int64_t* input_size, uint64_t* rec_bit, uint32_t* nblocks) {
+    if (!ctx || !d_src || !rec_bit || !nblocks) return -KZ_ERR_INVALID_PARAM;
+    CK(cudaSetDevice(ctx->device));
     uint8_t head[64];
     memset(head, 0, sizeof(head));
     CK(cudaMemcpyAsync(head, d_src, std::min<size_t>(n, 64), cudaMemcpyDeviceToHost, ctx->stream));
@@ -2171,8 +2275,55 @@ int kz_decompress_stream_device(kz_ctx* ctx, const void* d_src, size_t n, void* 
     StreamHeader sh;
     int rc = parse_stream_header(ctx, head, n, sh);
     if (rc) return rc;
+    if (t48) *t48 = sh.t48;
+    if (etype) *etype = sh.etype;
+    if (block_size) *block_size = sh.block_size;
+    if (checksum_bits) *checksum_bits = sh.checksum_bits;
+    if (input_size) *input_size = sh.input_size;
+    CK(ctx->d_dl.ensure((size_t)max_blocks * 16 + 64));
+    uint64_t* d_boff = ctx->d_dl.as<uint64_t>();
+    uint64_t* d_bbits = d_boff + max_blocks;
+    uint32_t* d_cnt = (uint32_t*)(d_bbits + max_blocks);
+    {
+        LaunchScope ls(ctx, "stream_walk");
+        stream_walk_kernel<<<1, 32, 0, ctx->stream>>>((const uint32_t*)d_src, sh.bits, 8ull * n, max_blocks, d_boff, d_bbits, d_cnt);
+    }
+    uint32_t cs[2] = {0, 0};
+    CK(cudaMemcpyAsync(cs, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if ((int32_t)cs[1] != 0) return ctx->fail(-(int32_t)cs[1], "Invalid bitstream: corrupted block length");
+    const uint32_t nb = cs[0];
+    std::vector<uint64_t> boff(nb), bbits(nb);
+    if (nb) {
+        CK(cudaMemcpyAsync(boff.data(), d_boff, (size_t)nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(bbits.data(), d_bbits, (size_t)nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    rec_bit[0] = sh.bits;
+    for (uint32_t b = 0; b < nb; b++) rec_bit[b + 1] = boff[b] + bbits[b];
+    *nblocks = nb;
+    return 0;
+}
+static int decompress_device_impl(kz_ctx* ctx, const StreamHeader* given, uint64_t start_bit, uint32_t stop_after, const void* d_src, size_t n, void* d_dst,
+                                  size_t cap, size_t* out_n) {
+    if (!ctx || !out_n) return -KZ_ERR_INVALID_PARAM;
+    CK(cudaSetDevice(ctx->device));
+    if (((uintptr_t)d_src & 15) || ((uintptr_t)d_dst & 15)) return ctx->fail(KZ_ERR_INVALID_PARAM, "device buffers must be 16-byte aligned");
+    StreamHeader sh;
+    int rc = 0;
+    if (given) {
+        sh = *given;
+        sh.bits = start_bit;
+    } else {
+        uint8_t head[64];
+        memset(head, 0, sizeof(head));
+        CK(cudaMemcpyAsync(head, d_src, std::min<size_t>(n, 64), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        rc = parse_stream_header(ctx, head, n, sh);
+        if (rc) return rc;
+    }
     TransformPlan plan;
-    rc = plan_transforms(ctx, sh.t48, plan, KZ_ERR_INVALID_CODEC);
+    rc = plan_transforms(ctx, sh.t48, sh.etype, plan, KZ_ERR_INVALID_CODEC);
     if (rc) return rc;
     const uint32_t* d_words = (const uint32_t*)d_src;
     const uint64_t words_len = (n + 3) / 4 + 16;  // callers guarantee >= 64 readable bytes past n
@@ -2184,7 +2335,7 @@ int kz_decompress_stream_device(kz_ctx* ctx, const void* d_src, size_t n, void* 
     uint32_t* d_cnt = (uint32_t*)(d_bbits + max_blocks);
     {
         LaunchScope ls(ctx, "stream_walk");
-        stream_walk_kernel<<<1, 32, 0, ctx->stream>>>(d_words, sh.bits, 8ull * n, max_blocks, d_boff, d_bbits, d_cnt);
+        stream_walk_kernel<<<1, 32, 0, ctx->stream>>>(d_words, sh.bits, 8ull * n, max_blocks, d_boff, d_bbits, d_cnt, stop_after);
     }
     // count + the first SPEC block descriptors in one round trip (streams with more blocks pay a second copy)
     const uint32_t SPEC = std::min<uint32_t>(max_blocks, 1024);
@@ -2332,7 +2483,7 @@ int kz_encode_blocks(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_t checksu
             CK(cudaMemcpyAsync((uint8_t*)ctx->d_in.p + b * dstride, slab + b * block_stride, block_len[b], cudaMemcpyHostToDevice, ctx->stream));
     std::vector<EncJob> jobs;
     TransformPlan plan;
-    int rc = plan_transforms(ctx, t48, plan, KZ_ERR_CREATE_CODEC);
+    int rc = plan_transforms(ctx, t48, etype, plan, KZ_ERR_CREATE_CODEC);
     if (rc) return rc;
     const uint8_t* d_data = nullptr;
     std::vector<int32_t> init_dt(nblocks, 0);
@@ -2372,7 +2523,7 @@ int kz_decode_blocks(kz_ctx* ctx, uint64_t t48, uint32_t etype, uint32_t checksu
     if (checksum_bits != 0 && checksum_bits != 32 && checksum_bits != 64) return ctx->fail(KZ_ERR_INVALID_PARAM, "checksum must be 0, 32 or 64 bits");
     TransformPlan plan;
     {
-        int prc = plan_transforms(ctx, t48, plan, KZ_ERR_INVALID_CODEC);
+        int prc = plan_transforms(ctx, t48, etype, plan, KZ_ERR_INVALID_CODEC);
         if (prc) return prc;
     }
     if (nblocks == 0) return 0;

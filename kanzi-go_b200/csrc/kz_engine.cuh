@@ -129,6 +129,7 @@ struct kz_ctx {
     bool profile = false;
     int ans0_dec_version = 5;  // 6 = thread-per-chunk kernel (correct, measured slower: 0.94 vs 0.68 ms), 4 / 3 = older generations
     kz::EncPlan enc_plan;
+    bool fragment = false;        // encode_batch: LAYOUT_STREAM without the end marker (kz_compress_fragment_device)
     uint64_t user_stream_bs = 0;  // kz_set_stream_block_size: ctx["blockSize"] for the block / single-transform entry points
     uint64_t stream_bs = 0;       // ctx["blockSize"] of the call in progress (TEXT sizes its hash map from it)
     std::map<std::string, kz::ProfEntry> prof;

@@ -107,3 +107,23 @@ def test_block_batch_uses_stream_block_size(gpu, oracle, synth, kz):
     for b, d in zip(blocks, dec):
         assert np.array_equal(b, d)
     assert np.array_equal(gpu.decompress(stream, 3 * bs), np.concatenate(blocks))
+
+
+def test_text_with_encoding1_codecs_is_refused(gpu, kz, synth):
+    """The reference picks the TEXT encoding from the entropy codec (transform/Factory.go:99-119): encoding 2 for NONE / ANS0 / HUFFMAN /
+    RANGE, encoding 1 for everything else. Only encoding 2 exists on the GPU path, so `TEXT & ANS1` must be refused, both ways."""
+    x = synth.markov_text(1 << 16, seed=5)
+    for entropy in ("ANS1",):
+        with pytest.raises(kz.KanziError):
+            gpu.compress(x, "TEXT", entropy, block_size=1 << 16, input_size=len(x))
+        with pytest.raises(kz.KanziError):
+            gpu.encode_blocks(kz.transform_type("TEXT+UTF"), kz.entropy_type(entropy), [x])
+    ok = gpu.compress(x, "TEXT", "ANS0", block_size=1 << 16, input_size=len(x))
+    assert np.array_equal(gpu.decompress(ok, len(x) + 64), x)
+    # a stream whose header says TEXT & ANS1 (written by the reference with encoding 1) is refused as well, not mis-decoded
+    bad = gpu.compress(x, "TEXT", "ANS0", block_size=1 << 16, input_size=len(x)).copy()
+    # entropy type lives in header bits 38..42 (after 32 b magic, 4 b version, 2 b checksum): ANS0 = 5 -> ANS1 = 8; the header checksum then
+    # no longer matches either, so any error is fine as long as nothing is decoded
+    bad[4] ^= 0x01
+    with pytest.raises(kz.KanziError):
+        gpu.decompress(bad, len(x) + 64)
