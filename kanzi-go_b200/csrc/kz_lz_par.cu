@@ -7,8 +7,10 @@
 //   info      common prefix / suffix lengths of (i, prev[i]), saturated at 255               [streaming compares]
 //   rounds to the fixed point of the table membership vf[] (kz_lz_par_core.cuh, 3.; two rounds for ordinary blocks):
 //     filter    candidates under the previous round's vf (round 0: as linked)
-//     spec      one warp (lane 0) per 16 KiB segment: speculative parse from a guessed state -> match log of the segment
-//     stitch    one warp (lane 0) per block: the true parse only until it meets a segment's log; piece list of the match list
+//     spec      one LANE per 1 KiB segment: speculative parse from a guessed state -> match log of the segment
+//     junction  one lane per segment: from the state the segment's log stopped in, the parse until it meets the log of the segment it is in
+//     walk      one CTA per block: junction records staged in shared memory, one thread follows them -> piece list of the match list
+//     stitch    (only blocks with a live junction that hit its cap) one lane per block: the serial stitch of kz_lz_par_core.cuh
 //     flatten   pieces -> contiguous match list
 //     derive    per position: vf' from the match list (closed form for the probe pattern of a literal run); changed?
 //   sizes / tilescan / emit   per match token, distance bytes, length bytes, literal run: sizes, block-wide exclusive scans, final bytes
@@ -26,9 +28,11 @@ using namespace lzp;
 
 namespace {
 
-const int SEG = 16384;               // bytes per speculative segment
+const int SEG = 1024;                // bytes per speculative segment (one lane each)
 const int SEG_CAP = SEG / 4 + 8;     // log entries per segment (a match is at least 4 bytes long)
-const int MAX_ROUNDS = 8;
+const int JCAP = 64;                 // fix-up matches per junction before it gives up (a live one that does sends the block to the serial stitch)
+const int WALK_WIN = 4096;           // junction records staged in shared memory per window of the walk
+const int MAX_ROUNDS = 96;
 const int TILE = 1024;               // matches per emission tile
 const uint32_t LONG_RUN = 4096;      // literal runs above this length are copied by all warps of the block's CTAs together
 
@@ -107,12 +111,11 @@ __global__ void __launch_bounds__(256) lzp_info_kernel(const uint8_t* __restrict
 }
 // candidates of a round: the first position of the prev[] chain that is in the table (vf) when the position is probed
 __global__ void __launch_bounds__(256) lzp_filter_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_chunk,
-                                                          const uint32_t* __restrict__ done, const Rec* __restrict__ rec0, const uint32_t* __restrict__ vf,
+                                                          const uint32_t* __restrict__ act_chunks, const Rec* __restrict__ rec0, const uint32_t* __restrict__ vf,
                                                           Rec* __restrict__ rec, uint64_t total) {
-    const uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    const uint64_t g = (uint64_t)act_chunks[blockIdx.x >> 2] * 1024 + (blockIdx.x & 3) * 256 + threadIdx.x;  // only chunks of unfinished blocks are launched
     if (g >= total) return;
     const uint32_t b = blk_of_chunk[g >> 10];
-    if (done[b]) return;
     const PBlock& B = blocks[b];
     const uint32_t i = (uint32_t)(g - B.pos_off);
     if (!B.active || i >= B.npos) {
@@ -122,13 +125,13 @@ __global__ void __launch_bounds__(256) lzp_filter_kernel(const uint8_t* __restri
     rec[g] = filter_candidate(in + B.src_off, (int)B.count, rec0 + B.pos_off, vf + B.pos_off, (int)i);
 }
 // vf' of every position from the block's match list; changed[b] |= (vf' != vf)
-__global__ void __launch_bounds__(256) lzp_derive_kernel(const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_chunk, const uint32_t* __restrict__ done,
+__global__ void __launch_bounds__(256) lzp_derive_kernel(const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_chunk, const uint32_t* __restrict__ act_chunks,
                                                           const PState* __restrict__ pst, const Match* __restrict__ ml_all, const uint32_t* __restrict__ vf,
                                                           uint32_t* __restrict__ vf2, uint32_t* __restrict__ changed, uint64_t total) {
-    const uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    const uint64_t g = (uint64_t)act_chunks[blockIdx.x >> 2] * 1024 + (blockIdx.x & 3) * 256 + threadIdx.x;
     const uint32_t b = blk_of_chunk[min(g, total - 1) >> 10];  // a chunk of 1024 positions belongs to one block: uniform per CTA
     bool diff = false;
-    if (g < total && !done[b]) {
+    if (g < total) {
         const PBlock& B = blocks[b];
         const uint32_t i = (uint32_t)(g - B.pos_off);
         uint32_t v = 0;
@@ -139,15 +142,15 @@ __global__ void __launch_bounds__(256) lzp_derive_kernel(const PBlock* __restric
     if (__syncthreads_or(diff ? 1 : 0) && threadIdx.x == 0) atomicOr(&changed[b], 1u);
 }
 
-// ---- pass 1: speculative segment parses (lane 0 of one warp per segment) -----------------------------------------------------------------
-__global__ void __launch_bounds__(32) lzp_spec_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_seg, int extra,
-                                                       const uint32_t* __restrict__ done, const Rec* __restrict__ rec, Match* __restrict__ logs, SegDesc* __restrict__ desc) {
-    if (threadIdx.x != 0) return;
-    const uint32_t s = blockIdx.x;
+// ---- pass 1: speculative segment parses (one lane per segment; act_segs lists the segments of the unfinished blocks) ---------------------
+__global__ void __launch_bounds__(128) lzp_spec_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_seg, int extra,
+                                                        const uint32_t* __restrict__ act_segs, uint32_t n_act, const Rec* __restrict__ rec, Match* __restrict__ logs,
+                                                        SegDesc* __restrict__ desc) {
+    const uint32_t t = blockIdx.x * 128 + threadIdx.x;
+    if (t >= n_act) return;
+    const uint32_t s = act_segs[t];
     const uint32_t b = blk_of_seg[s];
-    if (done[b]) return;
-    const PBlock B = blocks[b];
-    if (!B.active) return;
+    const PBlock& B = blocks[b];
     const uint32_t k = s - B.seg_base;
     const Params P = make_params(in, B, extra, rec);
     const int s0 = (int)(k * SEG);
@@ -157,45 +160,145 @@ __global__ void __launch_bounds__(32) lzp_spec_kernel(const uint8_t* __restrict_
     desc[s] = d;
 }
 
-// ---- pass 2: stitch (lane 0 of one warp per block) -----------------------------------------------------------------------------------------
+// ---- pass 2: junctions (one lane per segment), the walk over them (one CTA per block), the serial stitch for what the walk could not do ---------
 struct SegLogAt {
     const Match* base;
     __device__ const Match* operator()(int k) const { return base + (size_t)k * SEG_CAP; }
 };
-__global__ void __launch_bounds__(32) lzp_stitch_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, int nblocks, int extra,
-                                                         const uint32_t* __restrict__ done, const Rec* __restrict__ rec, const Match* __restrict__ logs,
-                                                         const SegDesc* __restrict__ desc, Match* __restrict__ fix, Piece* __restrict__ pieces,
-                                                         uint32_t* __restrict__ piece_start, PState* __restrict__ pst) {
-    const int b = blockIdx.x;
-    if (b >= nblocks || threadIdx.x != 0 || done[b]) return;
+__global__ void __launch_bounds__(128) lzp_junction_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_seg, int extra,
+                                                            const uint32_t* __restrict__ act_segs, uint32_t n_act, const Rec* __restrict__ rec, const Match* __restrict__ logs,
+                                                            const SegDesc* __restrict__ desc, Match* __restrict__ jfix, Junction* __restrict__ junc) {
+    const uint32_t t = blockIdx.x * 128 + threadIdx.x;
+    if (t >= n_act) return;
+    const uint32_t s = act_segs[t];
+    const uint32_t b = blk_of_seg[s];
+    const PBlock& B = blocks[b];
+    const Params P = make_params(in, B, extra, rec);
+    SegLogAt sl;
+    sl.base = logs + (size_t)B.seg_base * SEG_CAP;
+    Junction J;
+    junction_parse(P, (int)(s - B.seg_base), (int)B.nsegs, desc + B.seg_base, sl, jfix + (size_t)s * JCAP, (uint32_t)JCAP, J);
+    junc[s] = J;
+}
+// packed junction record of the walk: n (9 bits) | END_BLOCK << 9 | status << 10 | fix_n << 12 | idx << 19; second word: joined segment
+__global__ void __launch_bounds__(256) lzp_walk_kernel(const PBlock* __restrict__ blocks, const uint32_t* __restrict__ act_blocks, const SegDesc* __restrict__ desc_all,
+                                                        const Junction* __restrict__ junc_all, Piece* __restrict__ pieces, uint32_t* __restrict__ piece_start,
+                                                        PState* __restrict__ pst) {
+    __shared__ uint32_t s_w0[WALK_WIN], s_w1[WALK_WIN];
+    __shared__ int s_k, s_stop;
+    const uint32_t b = act_blocks[blockIdx.x];
+    const PBlock B = blocks[b];
+    if (!B.active) {
+        if (threadIdx.x == 0) {
+            PState S;
+            S.np = S.fix_n = S.nmatch = 0, S.final_anchor = 0, S.m_total = S.mlen_total = S.lit_total = S.too_many = 0;
+            pst[b] = S;
+        }
+        return;
+    }
+    const SegDesc* desc = desc_all + B.seg_base;
+    const Junction* junc = junc_all + B.seg_base;
+    Piece* pc = pieces + B.piece_off;
+    uint32_t* ps = piece_start + B.piece_off;
+    uint32_t np = 0, total = 0, begin = 0;  // thread 0's walk state
+    int32_t final_anchor = 0;
+    bool overflow = false;
+    if (threadIdx.x == 0) s_k = 0, s_stop = 0;
+    __syncthreads();
+    for (;;) {
+        const int base = s_k;
+        for (int i = threadIdx.x; i < WALK_WIN && base + i < (int)B.nsegs; i += 256) {
+            const SegDesc d = desc[base + i];
+            const Junction J = junc[base + i];
+            s_w0[i] = d.n | (d.end == END_BLOCK ? 1u << 9 : 0u) | (J.status << 10) | (J.fix_n << 12) | (J.idx << 19);
+            s_w1[i] = J.seg;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int k = base;
+            while (k < base + WALK_WIN) {
+                const uint32_t w0 = s_w0[k - base];
+                const uint32_t n = w0 & 0x1FFu, status = (w0 >> 10) & 3u, fix_n = (w0 >> 12) & 0x7Fu;
+                if (n > begin) {
+                    Piece p;
+                    p.spec = 1, p.seg = (uint32_t)k, p.begin = begin, p.end = n;
+                    pc[np] = p;
+                    ps[np] = total;
+                    np++;
+                    total += n - begin;
+                }
+                if (w0 & (1u << 9)) {
+                    final_anchor = desc[k].fin.anchor;
+                    s_stop = 1;
+                    break;
+                }
+                if (status == J_OVERFLOW) {
+                    overflow = true;
+                    s_stop = 1;
+                    break;
+                }
+                if (fix_n) {
+                    Piece p;
+                    p.spec = 2, p.seg = (uint32_t)k, p.begin = 0, p.end = fix_n;
+                    pc[np] = p;
+                    ps[np] = total;
+                    np++;
+                    total += fix_n;
+                }
+                if (status == J_TERMINAL) {
+                    final_anchor = junc[k].anchor;
+                    s_stop = 1;
+                    break;
+                }
+                k = (int)s_w1[k - base];
+                begin = (w0 >> 19) + 1;
+            }
+            s_k = k;
+        }
+        __syncthreads();
+        if (s_stop) break;
+    }
+    if (threadIdx.x == 0) {
+        PState S;
+        S.np = overflow ? 0xFFFFFFFFu : np;
+        S.fix_n = 0;
+        S.nmatch = total;
+        S.final_anchor = final_anchor;
+        S.m_total = S.mlen_total = S.lit_total = S.too_many = 0;
+        ps[np] = total;
+        pst[b] = S;
+    }
+}
+__global__ void __launch_bounds__(32) lzp_stitch_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const uint32_t* __restrict__ act_blocks, int extra,
+                                                         const Rec* __restrict__ rec, const Match* __restrict__ logs, const SegDesc* __restrict__ desc, Match* __restrict__ fix,
+                                                         Piece* __restrict__ pieces, uint32_t* __restrict__ piece_start, PState* __restrict__ pst) {
+    const uint32_t b = act_blocks[blockIdx.x];
+    if (threadIdx.x != 0 || pst[b].np != 0xFFFFFFFFu) return;  // only blocks the walk gave up on
     const PBlock B = blocks[b];
     PState S;
     S.np = S.fix_n = S.nmatch = 0;
     S.final_anchor = 0;
     S.m_total = S.mlen_total = S.lit_total = S.too_many = 0;
-    if (B.active) {
-        const Params P = make_params(in, B, extra, rec);
-        SegLogAt sl;
-        sl.base = logs + (size_t)B.seg_base * SEG_CAP;
-        Piece* pc = pieces + B.piece_off;
-        S.np = stitch_block(P, (int)B.nsegs, desc + B.seg_base, sl, fix + B.match_off, pc, &S.fix_n, &S.final_anchor);
-        uint32_t acc = 0;
-        for (uint32_t p = 0; p < S.np; p++) {  // exclusive scan of the piece lengths (a few hundred pieces)
-            piece_start[B.piece_off + p] = acc;
-            acc += pc[p].end - pc[p].begin;
-        }
-        piece_start[B.piece_off + S.np] = acc;
-        S.nmatch = acc;
+    const Params P = make_params(in, B, extra, rec);
+    SegLogAt sl;
+    sl.base = logs + (size_t)B.seg_base * SEG_CAP;
+    Piece* pc = pieces + B.piece_off;
+    S.np = stitch_block(P, (int)B.nsegs, desc + B.seg_base, sl, fix + B.match_off, pc, &S.fix_n, &S.final_anchor);
+    uint32_t acc = 0;
+    for (uint32_t p = 0; p < S.np; p++) {
+        piece_start[B.piece_off + p] = acc;
+        acc += pc[p].end - pc[p].begin;
     }
+    piece_start[B.piece_off + S.np] = acc;
+    S.nmatch = acc;
     pst[b] = S;
 }
 
 // ---- pass 3: flatten the pieces into the block's match list -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lzp_flatten_kernel(const PBlock* __restrict__ blocks, const uint32_t* __restrict__ done, const PState* __restrict__ pst,
+__global__ void __launch_bounds__(256) lzp_flatten_kernel(const PBlock* __restrict__ blocks, const uint32_t* __restrict__ act_blocks, const PState* __restrict__ pst,
                                                            const Piece* __restrict__ pieces, const uint32_t* __restrict__ piece_start, const Match* __restrict__ logs,
-                                                           const Match* __restrict__ fix, Match* __restrict__ ml) {
-    const int b = blockIdx.y;
-    if (done[b]) return;
+                                                           const Match* __restrict__ jfix, const Match* __restrict__ fix, Match* __restrict__ ml) {
+    const uint32_t b = act_blocks[blockIdx.y];
     const PBlock& B = blocks[b];
     const PState& S = pst[b];
     const Piece* pc = pieces + B.piece_off;
@@ -209,7 +312,7 @@ __global__ void __launch_bounds__(256) lzp_flatten_kernel(const PBlock* __restri
         }
         const Piece p = pc[lo];
         const uint32_t e = p.begin + (t - ps[lo]);
-        ml[B.match_off + t] = p.spec ? logs[(size_t)(B.seg_base + p.seg) * SEG_CAP + e] : fix[B.match_off + e];
+        ml[B.match_off + t] = p.spec == 1 ? logs[(size_t)(B.seg_base + p.seg) * SEG_CAP + e] : p.spec == 2 ? jfix[(size_t)(B.seg_base + p.seg) * JCAP + e] : fix[B.match_off + e];
     }
 }
 
@@ -491,6 +594,8 @@ cudaError_t lz_forward_parallel_sub(const uint8_t* d_in, uint8_t* d_out, const L
     const size_t o_done = take((size_t)nblocks * 4), o_changed = take((size_t)nblocks * 4), o_longn = take((size_t)nblocks * 4), o_long = take((size_t)longs * 4), o_logs = take((size_t)segs * SEG_CAP * sizeof(Match)), o_desc = take((size_t)segs * sizeof(SegDesc));
     const size_t o_fix = take(matches * sizeof(Match)), o_ml = take(matches * sizeof(Match)), o_runs = take(matches * sizeof(LzRun));
     const size_t o_pieces = take((size_t)pieces * sizeof(Piece)), o_pstart = take((size_t)pieces * 4), o_pst = take(nblocks * sizeof(PState));
+    const size_t o_junc = take((size_t)segs * sizeof(Junction)), o_jfix = take((size_t)segs * JCAP * sizeof(Match));
+    const size_t o_actc = take(blk_of_chunk.size() * 4), o_acts = take((size_t)segs * 4), o_actb = take((size_t)nblocks * 4);
     const size_t o_tiles = take((size_t)tiles * 16), o_res = take(nblocks * sizeof(LzResult));
     size_t cub_bytes = 0;
     {
@@ -546,27 +651,54 @@ cudaError_t lz_forward_parallel_sub(const uint8_t* d_in, uint8_t* d_out, const L
         lzp_link_kernel<<<G, 256, 0, stream>>>(dk.Current(), dv.Current(), d_pb, hash_bits, nblocks, d_rec, total);
         lzp_info_kernel<<<G, 256, 0, stream>>>(d_in, d_pb, d_boc, d_rec, total);
     }
+    Junction* d_junc = (Junction*)(ws + o_junc);
+    Match* d_jfix = (Match*)(ws + o_jfix);
+    uint32_t *d_actc = (uint32_t*)(ws + o_actc), *d_acts = (uint32_t*)(ws + o_acts), *d_actb = (uint32_t*)(ws + o_actb);
+    cudaMemsetAsync(d_pst, 0, nblocks * sizeof(PState), stream);
     std::vector<uint32_t> h_changed(nblocks), h_done(nblocks, 0);
+    // the passes of a round run over the chunks / segments / blocks that have not reached their fixed point yet
+    std::vector<uint32_t> act_c, act_s, act_b;
+    bool lists_stale = true;
+    for (uint32_t b = 0; b < nblocks; b++)
+        if (!pb[b].active) h_done[b] = 1;
     for (int round = 0; round < MAX_ROUNDS; round++) {
+        if (lists_stale) {
+            act_c.clear(), act_s.clear(), act_b.clear();
+            for (uint32_t b = 0; b < nblocks; b++) {
+                if (h_done[b]) continue;
+                act_b.push_back(b);
+                for (uint64_t c = pb[b].pos_off >> 10, ce = (pb[b].pos_off + pb[b].count + 1023) >> 10; c < ce; c++) act_c.push_back((uint32_t)c);
+                for (uint32_t k = 0; k < pb[b].nsegs; k++) act_s.push_back(pb[b].seg_base + k);
+            }
+            if (act_b.empty()) break;
+            // pageable source: the copies are staged before the call returns, the vectors may change afterwards
+            if ((e = cudaMemcpyAsync(d_actc, act_c.data(), act_c.size() * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+            if ((e = cudaMemcpyAsync(d_acts, act_s.data(), act_s.size() * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+            if ((e = cudaMemcpyAsync(d_actb, act_b.data(), act_b.size() * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+            lists_stale = false;
+        }
+        const uint32_t GA = (uint32_t)act_c.size() * 4, NS = (uint32_t)act_s.size(), NB = (uint32_t)act_b.size();
         const Rec* rec_r = d_rec;
         if (round > 0) {
             LzHookScope hs(hook, "lz_filter");
-            lzp_filter_kernel<<<G, 256, 0, stream>>>(d_in, d_pb, d_boc, d_done, d_rec, d_vf, d_rec2, total);
+            lzp_filter_kernel<<<GA, 256, 0, stream>>>(d_in, d_pb, d_boc, d_actc, d_rec, d_vf, d_rec2, total);
             rec_r = d_rec2;
         }
         {
             LzHookScope hs(hook, "lz_spec");
-            lzp_spec_kernel<<<segs, 32, 0, stream>>>(d_in, d_pb, d_bos, extra ? 1 : 0, d_done, rec_r, d_logs, d_desc);
+            lzp_spec_kernel<<<(NS + 127) / 128, 128, 0, stream>>>(d_in, d_pb, d_bos, extra ? 1 : 0, d_acts, NS, rec_r, d_logs, d_desc);
         }
         {
             LzHookScope hs(hook, "lz_stitch");
-            lzp_stitch_kernel<<<nblocks, 32, 0, stream>>>(d_in, d_pb, (int)nblocks, extra ? 1 : 0, d_done, rec_r, d_logs, d_desc, d_fix, d_pieces, d_pstart, d_pst);
+            lzp_junction_kernel<<<(NS + 127) / 128, 128, 0, stream>>>(d_in, d_pb, d_bos, extra ? 1 : 0, d_acts, NS, rec_r, d_logs, d_desc, d_jfix, d_junc);
+            lzp_walk_kernel<<<NB, 256, 0, stream>>>(d_pb, d_actb, d_desc, d_junc, d_pieces, d_pstart, d_pst);
+            lzp_stitch_kernel<<<NB, 32, 0, stream>>>(d_in, d_pb, d_actb, extra ? 1 : 0, rec_r, d_logs, d_desc, d_fix, d_pieces, d_pstart, d_pst);
         }
         {
             LzHookScope hs(hook, "lz_derive");
-            lzp_flatten_kernel<<<dim3(64, nblocks), 256, 0, stream>>>(d_pb, d_done, d_pst, d_pieces, d_pstart, d_logs, d_fix, d_ml);
+            lzp_flatten_kernel<<<dim3(64, NB), 256, 0, stream>>>(d_pb, d_actb, d_pst, d_pieces, d_pstart, d_logs, d_jfix, d_fix, d_ml);
             cudaMemsetAsync(d_changed, 0, (size_t)nblocks * 4, stream);
-            lzp_derive_kernel<<<G, 256, 0, stream>>>(d_pb, d_boc, d_done, d_pst, d_ml, d_vf, d_vf2, d_changed, total);
+            lzp_derive_kernel<<<GA, 256, 0, stream>>>(d_pb, d_boc, d_actc, d_pst, d_ml, d_vf, d_vf2, d_changed, total);
         }
         e = cudaMemcpyAsync(h_changed.data(), d_changed, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, stream);
         if (e != cudaSuccess) return e;
@@ -574,16 +706,12 @@ cudaError_t lz_forward_parallel_sub(const uint8_t* d_in, uint8_t* d_out, const L
         if (e != cudaSuccess) return e;
         bool all = true;
         for (uint32_t b = 0; b < nblocks; b++) {
-            if (!h_done[b] && !h_changed[b]) h_done[b] = 1;  // vf' == vf: this round's match list is the parse
-            all = all && (h_done[b] || !pb[b].active);
+            if (!h_done[b] && !h_changed[b]) h_done[b] = 1, lists_stale = true;  // vf' == vf: this round's match list is the parse
+            all = all && h_done[b];
         }
-        e = cudaMemcpyAsync(d_done, h_done.data(), (size_t)nblocks * 4, cudaMemcpyHostToDevice, stream);
-        if (e != cudaSuccess) return e;
         if (all) break;
-        std::swap(d_vf, d_vf2);  // blocks that are done have identical halves
+        std::swap(d_vf, d_vf2);
     }
-    for (uint32_t b = 0; b < nblocks; b++)
-        if (!pb[b].active) h_done[b] = 1;
     e = cudaMemcpyAsync(d_done, h_done.data(), (size_t)nblocks * 4, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
     uint32_t max_tiles = 1;

@@ -421,6 +421,89 @@ KZL_HD uint32_t stitch_block(const Params& P, int nsegs, const SegDesc* desc, Se
     return np;
 }
 
+// ---- parallel stitch: one junction per segment -----------------------------------------------------------------------------------------
+// The serial stitch above only ever does one thing between two joins: starting from the state a segment's speculative log stopped in, it
+// parses on until it meets the log of the segment the cursor is in. That piece of work depends on nothing but the segment it starts from, so
+// every segment's junction is parsed at once (junction_parse, one lane each) and what remains serial is a walk over the junction records
+// (walk_junctions: a few loads per live segment). A junction that starts from a false state (its segment is never reached by the true parse:
+// a long match jumps over it) may wander; its fix-up log is capped, and a capped junction that turns out to be live sends the block to the
+// serial stitch.
+enum { J_JOINED = 0, J_TERMINAL = 1, J_OVERFLOW = 2 };
+struct Junction {
+    uint32_t status;  // J_*
+    uint32_t fix_n;   // fix-up matches parsed by this junction
+    uint32_t seg;     // J_JOINED: the segment whose log is joined ...
+    uint32_t idx;     // ... behind entry idx
+    int32_t anchor;   // J_TERMINAL: anchor behind the last match of the block
+};
+template <class SegLog>
+KZL_HD void junction_parse(const Params& P, int k0, int nsegs, const SegDesc* desc, SegLog seg_log, Match* fix, uint32_t fix_cap, Junction& J) {
+    const int seg_size = P.seg_size;
+    State st = desc[k0].fin;
+    J.status = J_TERMINAL, J.fix_n = 0, J.seg = 0, J.idx = 0, J.anchor = st.anchor;
+    if (desc[k0].end == END_BLOCK) return;  // the walk stops at this segment: no junction
+    uint32_t fn = 0;
+    int cur_seg = -1;
+    uint32_t cursor = 0;
+    while (st.src_idx < P.src_end) {
+        const int k = imin(st.src_idx / seg_size, nsegs - 1);
+        if (k != cur_seg) {
+            cur_seg = k;
+            cursor = 0;
+        }
+        const SegDesc& d = desc[k];
+        const Match* lg = seg_log(k);
+        while (cursor < d.n && (int)(lg[cursor].start + lg[cursor].len) < st.anchor) cursor++;
+        if (cursor >= 1 && cursor < d.n && (int)(lg[cursor].start + lg[cursor].len) == st.anchor && (int)lg[cursor].dist == st.repd0 &&
+            (int)lg[cursor - 1].dist == st.repd1) {
+            J.status = J_JOINED, J.fix_n = fn, J.seg = (uint32_t)k, J.idx = cursor;
+            return;
+        }
+        if (fn >= fix_cap) {
+            J.status = J_OVERFLOW, J.fix_n = fn;
+            return;
+        }
+        Match m;
+        if (parse_one(P, st, m) == R_END) break;
+        fix[fn++] = m;
+    }
+    J.status = J_TERMINAL, J.fix_n = fn, J.anchor = st.anchor;
+}
+// Walk over the junction records of one block. Pieces: spec 1 = entries [begin, end) of segment `seg`'s speculative log, spec 2 = entries
+// [begin, end) of junction `seg`'s fix-up log. Returns the number of pieces (at most 2 * nsegs), or 0xFFFFFFFF when a live junction overflowed.
+KZL_HD uint32_t walk_junctions(int nsegs, const SegDesc* desc, const Junction* junc, Piece* pieces, uint32_t* nmatch, int32_t* final_anchor) {
+    uint32_t np = 0, total = 0;
+    int k = 0;
+    uint32_t begin = 0;
+    for (;;) {
+        const uint32_t n = desc[k].n;
+        if (n > begin) {
+            pieces[np].spec = 1, pieces[np].seg = (uint32_t)k, pieces[np].begin = begin, pieces[np].end = n;
+            np++;
+            total += n - begin;
+        }
+        if (desc[k].end == END_BLOCK) {
+            *final_anchor = desc[k].fin.anchor;
+            break;
+        }
+        const Junction J = junc[k];
+        if (J.status == J_OVERFLOW) return 0xFFFFFFFFu;
+        if (J.fix_n) {
+            pieces[np].spec = 2, pieces[np].seg = (uint32_t)k, pieces[np].begin = 0, pieces[np].end = J.fix_n;
+            np++;
+            total += J.fix_n;
+        }
+        if (J.status == J_TERMINAL) {
+            *final_anchor = J.anchor;
+            break;
+        }
+        k = (int)J.seg;
+        begin = J.idx + 1;
+    }
+    *nmatch = total;
+    return np;
+}
+
 // ---- emission: sizes and bytes of one match of the final list (LZCodec.go:416-495) ---------------------------------------------------
 KZL_HD int length_bytes(int length) { return length < 254 ? 1 : (length < 65536 + 254 ? 3 : 4); }
 KZL_HD int emit_length(uint8_t* block, int length) {

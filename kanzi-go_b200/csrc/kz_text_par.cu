@@ -747,7 +747,10 @@ __global__ void __launch_bounds__(256) ti_ins_list_kernel(const TpBlock* __restr
     if (!(B.go & 0x100u)) return;
     const uint32_t nc = st[blockIdx.y].ncand;
     for (uint32_t k = blockIdx.x * 256 + threadIdx.x; k < nc; k += gridDim.x * 256)
-        if (ins[B.cand_off + k]) ins_list[B.cand_off + rank[B.cand_off + k]] = k;
+        if (ins[B.cand_off + k]) {
+            const uint32_t r = rank[B.cand_off + k];
+            if (r < nc) ins_list[B.cand_off + r] = k;  // r < nc always holds for consistent decisions; never write outside the block's list
+        }
 }
 // output of one token: its length; with `d` != nullptr also the bytes. Returns -1 on an anomaly.
 __device__ __forceinline__ int ti_token_out(const uint8_t* src, int p, bool is_crlf, const int32_t* prevq, const Candidate* cand, uint32_t nc, const uint32_t* rank,
@@ -788,7 +791,9 @@ __device__ __forceinline__ int ti_token_out(const uint8_t* src, int p, bool is_c
         }
         const uint32_t before = lo < nc ? rank[lo] : nins;
         if ((uint32_t)(idx - STATIC_WORDS) >= before) return -1;
-        const Candidate c = cand[ins_list[idx - STATIC_WORDS]];
+        const uint32_t ci = ins_list[idx - STATIC_WORDS];
+        if (ci >= nc) return -1;  // unsettled rounds leave holes in the list: an anomaly, never an out-of-bounds read
+        const Candidate c = cand[ci];
         w = src + c.start;
         wl = c.end - c.start;
     }
@@ -892,7 +897,7 @@ size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 cudaError_t dictionary_rounds(const uint8_t* d_in, const TpBlock* d_pb, const std::vector<TpBlock>& pb, TpState* d_st, std::vector<TpState>& h_st,
                               const Candidate* d_cand, uint8_t* d_ins, uint8_t* d_ins2, uint32_t mask, uint32_t slots, int32_t* d_owner, const int32_t* d_owner0,
                               const Entry* sd, const uint8_t* d_swords, uint32_t* d_ct, uint32_t* d_tot, uint32_t* d_rank, int32_t* d_focc, uint8_t* d_fflip,
-                              uint32_t max_nct, int inverse, cudaStream_t stream, uint64_t* launches) {
+                              uint32_t max_nct, int inverse, size_t ins_bytes /* size of d_ins / d_ins2 */, cudaStream_t stream, uint64_t* launches) {
     const uint32_t nblocks = (uint32_t)pb.size();
     const dim3 gc(max_nct, nblocks), gs(32, nblocks);
     uint8_t *cur = d_ins, *nxt = d_ins2;
@@ -913,10 +918,8 @@ cudaError_t dictionary_rounds(const uint8_t* d_in, const TpBlock* d_pb, const st
         std::swap(cur, nxt);  // the decisions of this round
     }
     // a converged block has identical decisions in both buffers; the inverse path reads them from d_ins
-    if (cur != d_ins) {
-        size_t bytes = 0;
-        for (const TpBlock& B : pb) bytes = std::max<size_t>(bytes, B.cand_off + (size_t)B.nct_cap * CT);
-        if ((e = cudaMemcpyAsync(d_ins, cur, bytes, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) return e;
+    if (cur != d_ins) {  // exactly the decision bytes: d_ins2 / d_rank follow d_ins in the workspace
+        if ((e = cudaMemcpyAsync(d_ins, cur, ins_bytes, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) return e;
     }
     return cudaGetLastError();
 }
@@ -1018,7 +1021,7 @@ cudaError_t text_forward_parallel(const uint8_t* d_in, uint8_t* d_out, const std
     // ---- B
     std::vector<TpState> h_st(nblocks);
     if ((e = dictionary_rounds(d_in, d_pb, pb, d_st, h_st, d_cand, d_ins, d_ins2, mask, slots, d_owner, d_owner0, sd, d_swords, d_ct, d_tot, d_rank, d_focc, d_fflip, max_nct,
-                               0, stream, launches)) != cudaSuccess)
+                               0, (size_t)cands, stream, launches)) != cudaSuccess)
         return e;
     // the last round confirmed `nxt` (== cur bytewise for converged blocks); rank / focc / fflip belong to it
     std::vector<uint32_t> h_tot(nblocks * 8);
@@ -1136,7 +1139,7 @@ cudaError_t text_inverse_parallel(const uint8_t* d_in, uint8_t* d_out, const std
     if (launches) *launches += 11;
     std::vector<TpState> h_st(nblocks);
     if ((e = dictionary_rounds(d_in, d_pb, pb, d_tst, h_st, d_cand, d_ins, d_ins2, mask, slots, d_owner, d_owner0, sd, d_swords, d_ct, d_tot, d_rank, d_focc, d_fflip, max_nct, 1,
-                               stream, launches)) != cudaSuccess)
+                               (size_t)cands, stream, launches)) != cudaSuccess)
         return e;
     ti_ins_list_kernel<<<gs, 256, 0, stream>>>(d_pb, d_tst, d_ins, d_rank, d_ins_list);
     ti_output_kernel<<<gp, 256, 0, stream>>>(d_in, d_ib, d_tst, d_ist, d_start, d_prevq, d_cand, d_rank, d_tot, d_ins_list, sd, d_swords, static_n, d_pt, 0, d_out);

@@ -9,9 +9,11 @@
 
 using namespace kz::lzp;
 
+static uint32_t g_jcap = 64;  // fix-up matches per junction (JCAP of kz_lz_par.cu)
 extern "C" {
+void lz_set_jcap(int v) { g_jcap = uint32_t(v); }
 // returns the encoded length, -1 when the transform declines. stats: [0] matches, [1] fix-up matches (true parse work of the stitch passes, all
-// rounds), [2] pieces, [3] rounds to the fixed point
+// rounds), [2] pieces, [3] rounds to the fixed point, [4] longest live junction, [5] rounds that needed the serial stitch
 int64_t lz_forward_par(int extra_i, int data_type, const uint8_t* src_in, int64_t n, uint8_t* dst, int64_t cap, int seg_size, int64_t* stats) {
     const int max_rounds = 64;
     if (n == 0) return 0;
@@ -50,7 +52,7 @@ int64_t lz_forward_par(int extra_i, int data_type, const uint8_t* src_in, int64_
     }
     P.seg_size = seg_size;
     const int nsegs = std::max(1, (P.src_end + seg_size - 1) / seg_size);
-    const int seg_cap = seg_size / 4 + 4;
+    const int seg_cap = std::min(seg_size, count) / 4 + 8;  // a match is at least 4 bytes long
     std::vector<Match> logs(size_t(nsegs) * seg_cap);
     std::vector<SegDesc> desc(nsegs);
     std::vector<Match> fix(size_t(count) / 4 + 16);
@@ -60,7 +62,8 @@ int64_t lz_forward_par(int extra_i, int data_type, const uint8_t* src_in, int64_
     uint32_t fix_n = 0, np = 0;
     int32_t final_anchor = 0;
     int rounds = 0;
-    int64_t fix_total = 0;
+    int64_t fix_total = 0, max_junction = 0, serial_stitches = 0;
+    const uint32_t JCAP = g_jcap;
     for (;; rounds++) {
         if (rounds >= max_rounds) return -4;
         // filter the candidates by the previous round's vf (round 0: vf = 0, nothing moves)
@@ -73,18 +76,33 @@ int64_t lz_forward_par(int extra_i, int data_type, const uint8_t* src_in, int64_
             spec_parse_segment(P, s0, s1, logs.data() + size_t(k) * seg_cap, desc[k]);
             if (int(desc[k].n) > seg_cap) return -2;
         }
-        // stitch
+        // stitch: one junction per segment (parallel on the GPU), then the walk over the junction records; a live junction that hit its
+        // cap sends the block to the serial stitch
         Match* lp = logs.data();
-        np = stitch_block(P, nsegs, desc.data(), [lp, seg_cap](int k) { return (const Match*)(lp + size_t(k) * seg_cap); }, fix.data(), pieces.data(), &fix_n,
-                          &final_anchor);
+        auto seg_log = [lp, seg_cap](int k) { return (const Match*)(lp + size_t(k) * seg_cap); };
+        std::vector<Junction> junc(nsegs);
+        std::vector<Match> jfix(size_t(nsegs) * JCAP);
+        for (int k = 0; k < nsegs; k++) junction_parse(P, k, nsegs, desc.data(), seg_log, jfix.data() + size_t(k) * JCAP, JCAP, junc[k]);
+        uint32_t nmatch = 0;
+        np = walk_junctions(nsegs, desc.data(), junc.data(), pieces.data(), &nmatch, &final_anchor);
+        const bool serial_stitch = np == 0xFFFFFFFFu;
+        if (serial_stitch) {
+            serial_stitches++;
+            np = stitch_block(P, nsegs, desc.data(), seg_log, fix.data(), pieces.data(), &fix_n, &final_anchor);
+        } else {
+            fix_n = 0;
+            for (uint32_t p = 0; p < np; p++)
+                if (pieces[p].spec == 2) fix_n += pieces[p].end - pieces[p].begin, max_junction = std::max<int64_t>(max_junction, pieces[p].end - pieces[p].begin);
+        }
         if (np > pieces.size()) return -5;
         fix_total += fix_n;
         // flatten
         ml.clear();
         for (uint32_t p = 0; p < np; p++) {
-            const Match* base = pieces[p].spec ? logs.data() + size_t(pieces[p].seg) * seg_cap : fix.data();
+            const Match* base = pieces[p].spec == 1 ? logs.data() + size_t(pieces[p].seg) * seg_cap : pieces[p].spec == 2 ? jfix.data() + size_t(pieces[p].seg) * JCAP : fix.data();
             for (uint32_t e = pieces[p].begin; e < pieces[p].end; e++) ml.push_back(base[e]);
         }
+        if (!serial_stitch && ml.size() != nmatch) return -6;
         // the table membership this parse implies
         bool same = true;
         for (int j = 0; j < count; j++) {
@@ -99,6 +117,8 @@ int64_t lz_forward_par(int extra_i, int data_type, const uint8_t* src_in, int64_
         stats[1] = fix_total;
         stats[2] = np;
         stats[3] = rounds + 1;
+        stats[4] = max_junction;
+        stats[5] = serial_stitches;
     }
     std::vector<uint8_t> tk(ml.size() + 8), mb(3 * ml.size() + 8), mlenb(4 * ml.size() + 8);
     size_t tk_idx = 0, m_idx = 0, mlen_idx = 0, dst_idx = 13;

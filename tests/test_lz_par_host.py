@@ -53,7 +53,7 @@ def cases(n, seed):
 def run(lz, extra, dt, x, seg):
     n = len(x)
     dst = np.zeros(n + n // 64 + 64, np.uint8)
-    stats = (C.c_int64 * 4)(0, 0, 0, 0)
+    stats = (C.c_int64 * 8)()
     r = lz.lz_forward_par(extra, dt, x.ctypes.data, n, dst.ctypes.data, len(dst), seg, stats)
     return r, dst, list(stats)
 
@@ -81,7 +81,7 @@ def test_large_blocks_and_stitch_work(lz):
             continue
         x = np.ascontiguousarray(x, np.uint8)
         want, _ = po.transform_forward(po.T_LZX, x, 0)
-        r, dst, st = run(lz, 1, 0, x, 16384)
+        r, dst, st = run(lz, 1, 0, x, 1024)  # SEG of kz_lz_par.cu
         if want is None:
             assert r == -1, cname
             continue
@@ -89,3 +89,23 @@ def test_large_blocks_and_stitch_work(lz):
         print(cname, "matches", st[0], "fix-up (all rounds)", st[1], "pieces", st[2], "rounds", st[3])
         if cname == "text":
             assert st[1] < st[0] // 10 and st[3] <= 4
+
+
+def test_junction_cap_falls_back_to_the_serial_stitch(lz):
+    """a junction that needs more fix-up matches than its cap sends the block to the serial stitch: same bytes"""
+    n = 300000
+    hit = 0
+    try:
+        lz.lz_set_jcap(1)
+        for cname, x in cases(n, 5):
+            x = np.ascontiguousarray(x, np.uint8)
+            want, _ = po.transform_forward(po.T_LZX, x, 0)
+            r, dst, st = run(lz, 1, 0, x, 1024)
+            if want is None:
+                assert r == -1, cname
+                continue
+            assert r == len(want) and np.array_equal(dst[:r], want), (cname, r, len(want), st)
+            hit += st[5]
+    finally:
+        lz.lz_set_jcap(64)
+    assert hit > 0
