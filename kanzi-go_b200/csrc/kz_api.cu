@@ -963,18 +963,46 @@ int apply_forward(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint64_t istride
     const uint32_t nblocks = (uint32_t)len.size();
     applied.assign(nblocks, 0);
     if (t == KZ_T_BWT) {
-        uint32_t max_len = 0;
-        for (uint32_t b = 0; b < nblocks; b++) max_len = std::max(max_len, len[b]);
-        CK(ctx->d_ws.ensure(bwt_forward_workspace(max_len)));
         CK(ctx->d_lens.ensure((size_t)nblocks * 4 + 64));
         uint32_t* d_post = ctx->d_lens.as<uint32_t>();
-        for (uint32_t b = 0; b < nblocks; b++) {
-            if (!active[b] || len[b] < 2) continue;
-            LaunchScope ls(ctx, "bwt_forward");
-            cudaError_t e = bwt_forward_device(d_in + b * istride, len[b], d_out + b * ostride, d_post + b, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap, ctx->stream,
-                                               &ctx->launches);
-            if (e == cudaSuccess) applied[b] = 1;
-            else if (e != cudaErrorInvalidValue) return ctx->cuda_fail(e, "bwt_forward");
+        static const bool one_by_one = [] {  // KZ_BWT_FWD=single: one suffix sort per block (round 1)
+            const char* e = getenv("KZ_BWT_FWD");
+            return e && e[0] == 's';
+        }();
+        if (one_by_one) {
+            uint32_t max_len = 0;
+            for (uint32_t b = 0; b < nblocks; b++) max_len = std::max(max_len, len[b]);
+            CK(ctx->d_ws.ensure(bwt_forward_workspace(max_len)));
+            for (uint32_t b = 0; b < nblocks; b++) {
+                if (!active[b] || len[b] < 2) continue;
+                LaunchScope ls(ctx, "bwt_forward");
+                cudaError_t e = bwt_forward_device(d_in + b * istride, len[b], d_out + b * ostride, d_post + b, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap, ctx->stream,
+                                                   &ctx->launches);
+                if (e == cudaSuccess) applied[b] = 1;
+                else if (e != cudaErrorInvalidValue) return ctx->cuda_fail(e, "bwt_forward");
+            }
+        } else {
+            // all blocks of a sub-batch are suffix-sorted together (kz_bwt.cu: bwt_forward_batch)
+            for (uint32_t b0 = 0; b0 < nblocks;) {
+                std::vector<uint64_t> so, dof;
+                std::vector<uint32_t> nn, num;
+                uint64_t total = 0;
+                uint32_t b = b0;
+                for (; b < nblocks; b++) {
+                    if (!active[b] || len[b] < 2) continue;
+                    if (!nn.empty() && (total + len[b] > bwt_forward_batch_max_total() || nn.size() >= bwt_forward_batch_max_blocks())) break;
+                    so.push_back(b * istride), dof.push_back(b * ostride), nn.push_back(len[b]), num.push_back(b);
+                    total += len[b];
+                }
+                b0 = b;
+                if (nn.empty()) continue;
+                CK(ctx->d_ws.ensure(bwt_forward_batch_workspace(total, (uint32_t)nn.size())));
+                LaunchScope ls(ctx, "bwt_forward");
+                cudaError_t e = bwt_forward_batch(d_in, d_out, so.data(), dof.data(), nn.data(), num.data(), (uint32_t)nn.size(), d_post, ctx->d_ws.as<uint8_t>(),
+                                                  ctx->d_ws.cap, ctx->stream, &ctx->launches);
+                if (e != cudaSuccess) return ctx->cuda_fail(e, "bwt_forward");
+                for (uint32_t k : num) applied[k] = 1;
+            }
         }
         std::vector<uint32_t> post(nblocks);
         CK(cudaMemcpyAsync(post.data(), d_post, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1468,23 +1496,34 @@ int apply_inverse(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint8_t* d_out, 
             lb[b].data_type = 0;
             lb[b].pad = 0;
         }
-        Packer pk;
-        const size_t o_lb = pk.add(lb.data(), lb.size() * sizeof(LzBlock));
-        const size_t o_len = pk.reserve((size_t)nblocks * 4);
-        const size_t o_st = pk.reserve((size_t)nblocks * 4);
-        int rc = upload(ctx, pk);
-        if (rc) return rc;
-        uint8_t* T = ctx->d_tables.as<uint8_t>();
-        {
-            LaunchScope ls(ctx, "lz_inverse");
-            lz_inverse_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_in, (LzBlock*)(T + o_lb), (int)nblocks, d_out, (uint32_t*)(T + o_len), (int32_t*)(T + o_st));
-        }
-        CK(cudaGetLastError());
         std::vector<uint32_t> hl(nblocks);
         std::vector<int32_t> hs(nblocks);
-        CK(cudaMemcpyAsync(hl.data(), T + o_len, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(hs.data(), T + o_st, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        static const bool serial_inverse = [] {  // KZ_LZ_INV=serial: the round-1 kernel (one warp per block copies match by match)
+            const char* e = getenv("KZ_LZ_INV");
+            return e && e[0] == 's';
+        }();
+        if (!serial_inverse) {
+            CtxLzWorkspace W(ctx);
+            CtxLzHook H(ctx);
+            cudaError_t e = lz_inverse_parallel(d_in, d_out, lb, W, ctx->stream, hl, hs, &H, &ctx->launches);
+            if (e != cudaSuccess) return ctx->cuda_fail(e, "lz_inverse");
+        } else {
+            Packer pk;
+            const size_t o_lb = pk.add(lb.data(), lb.size() * sizeof(LzBlock));
+            const size_t o_len = pk.reserve((size_t)nblocks * 4);
+            const size_t o_st = pk.reserve((size_t)nblocks * 4);
+            int rc = upload(ctx, pk);
+            if (rc) return rc;
+            uint8_t* T = ctx->d_tables.as<uint8_t>();
+            {
+                LaunchScope ls(ctx, "lz_inverse");
+                lz_inverse_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_in, (LzBlock*)(T + o_lb), (int)nblocks, d_out, (uint32_t*)(T + o_len), (int32_t*)(T + o_st));
+            }
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(hl.data(), T + o_len, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(hs.data(), T + o_st, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
         for (uint32_t b = 0; b < nblocks; b++) {
             if (!active[b] || len[b] == 0) continue;
             if (hs[b]) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "LZCodec inverse transform failed");

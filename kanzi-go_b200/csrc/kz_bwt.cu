@@ -16,6 +16,9 @@
 //   transform/BWTBlockCodec.go:78-136, :141-225: block header (mode byte + big-endian primaryIndex-1 per chunk).
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
+#include <vector>
+
 #include "kz_bwt.cuh"
 
 namespace kz {
@@ -361,6 +364,199 @@ cudaError_t bwt_forward_device(const uint8_t* d_src, uint32_t n, uint8_t* d_dst,
         (*launches)++;
         h *= 2;
         end_bit = 2 * (int)log_n;
+    }
+    return cudaErrorUnknown;
+}
+
+// ---- forward, all blocks of a batch in one position space ------------------------------------------------------------------------------------
+// A 4 MiB sort cannot fill a B200 and 48 of them one after another pay 48 x (rounds x (sort + 6 small kernels + a host sync)). Here the blocks
+// are laid end to end (block b = positions [base[b], base[b] + n[b])) and sorted together: the block index is the top of the first key
+// (block | 6 symbols x 9 bits), so ranks taken as global group heads fall into [base[b], base[b] + n[b]) and the doubled keys
+// (rank[i] << lg | rank[i + h] + 1, 0 past the END OF THE BLOCK) never mix blocks. One sort, one flag / scan / apply pass and one host
+// sync per round for the whole batch; the number of rounds is the maximum over the blocks.
+namespace {
+struct BwtBatchBlock {
+    uint64_t src_off, dst_off;
+    uint32_t base, n;
+    uint32_t header, pad;
+};
+const int BWT_BATCH_MAX = 1024;  // 10 bits of block index above 54 bits of symbols
+__device__ __forceinline__ uint32_t bwtb_find(const uint32_t* __restrict__ s_base, uint32_t nb, uint32_t i) {  // last block with base <= i
+    uint32_t lo = 0, hi = nb;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s_base[mid] <= i) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+__global__ void __launch_bounds__(256) bwtb_init_keys_kernel(const uint8_t* __restrict__ in, const BwtBatchBlock* __restrict__ blocks, uint32_t nb, uint32_t total,
+                                                              uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+    __shared__ uint32_t s_base[BWT_BATCH_MAX];
+    for (uint32_t k = threadIdx.x; k < nb; k += 256) s_base[k] = blocks[k].base;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    const uint32_t b = bwtb_find(s_base, nb, i);
+    const BwtBatchBlock B = blocks[b];
+    const uint8_t* src = in + B.src_off;
+    const uint32_t l = i - B.base;
+    uint64_t k = b;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        const uint32_t p = l + j;
+        const uint64_t sym = p < B.n ? (uint64_t)src[p] + 1 : 0;
+        k = (k << 9) | sym;
+    }
+    keys[i] = k;
+    idx[i] = i;
+}
+__global__ void __launch_bounds__(256) bwtb_double_keys_kernel(const uint32_t* __restrict__ rank, const BwtBatchBlock* __restrict__ blocks, uint32_t nb, uint32_t total,
+                                                                uint32_t h, uint32_t lg, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+    __shared__ uint32_t s_base[BWT_BATCH_MAX];
+    __shared__ uint32_t s_n[BWT_BATCH_MAX];
+    for (uint32_t k = threadIdx.x; k < nb; k += 256) s_base[k] = blocks[k].base, s_n[k] = blocks[k].n;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    const uint32_t b = bwtb_find(s_base, nb, i);
+    const uint64_t end = (uint64_t)s_base[b] + s_n[b];
+    const uint64_t hi = rank[i];
+    const uint64_t lo = (uint64_t)i + h < end ? (uint64_t)rank[i + h] + 1 : 0;  // <= total < 2^lg
+    keys[i] = (hi << lg) | lo;
+    idx[i] = i;
+}
+__global__ void __launch_bounds__(256) bwtb_emit_kernel(const uint8_t* __restrict__ in, const BwtBatchBlock* __restrict__ blocks, uint32_t nb, uint32_t total,
+                                                         const uint32_t* __restrict__ sa, const uint32_t* __restrict__ rank, uint8_t* __restrict__ out) {
+    __shared__ uint32_t s_base[BWT_BATCH_MAX];
+    for (uint32_t k = threadIdx.x; k < nb; k += 256) s_base[k] = blocks[k].base;
+    __syncthreads();
+    const uint32_t r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= total) return;
+    const uint32_t b = bwtb_find(s_base, nb, r);  // ranks of block b are [base, base + n) as well
+    const BwtBatchBlock B = blocks[b];
+    const uint8_t* src = in + B.src_off;
+    uint8_t* dst = out + B.dst_off + B.header;
+    const uint32_t rl = r - B.base;
+    if (rl == 0) dst[0] = src[B.n - 1];
+    const uint32_t s = sa[r] - B.base;
+    if (s == 0) return;
+    const uint32_t rank0 = rank[B.base] - B.base;
+    dst[rl < rank0 ? rl + 1 : rl] = src[s - 1];
+}
+// primary indexes + BWTBlockCodec header of every block (BWTBlockCodec.go:113-133); one thread per block
+__global__ void bwtb_header_kernel(const BwtBatchBlock* __restrict__ blocks, uint32_t nb, const uint32_t* __restrict__ rank, uint8_t* __restrict__ out,
+                                   uint32_t* __restrict__ out_len /* indexed by pad = caller's block number */) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const BwtBatchBlock B = blocks[b];
+    const uint32_t n = B.n;
+    uint8_t* dst = out + B.dst_off;
+    uint32_t log_bs = log2_floor(n);
+    if (n & (n - 1)) log_bs++;
+    const int pidx = (int)(log_bs + 7) >> 3;
+    const uint32_t chunks = bwt_chunks(n);
+    uint32_t step = n / chunks;
+    if (step * chunks != n) step++;
+    dst[0] = (uint8_t)((log2_floor(chunks) << 2) | (uint32_t)(pidx - 1));
+    uint32_t idx = 1;
+    for (uint32_t i = 0; i < chunks; i++) {
+        const uint32_t prim = ((uint64_t)i * step < n) ? rank[B.base + i * step] - B.base + 1 : 0;
+        const uint32_t p = prim - 1;
+        for (int shift = (pidx - 1) << 3; shift >= 0; shift -= 8) dst[idx++] = (uint8_t)(p >> shift);
+    }
+    out_len[B.pad] = n + chunks * pidx + 1;
+}
+}  // namespace
+
+size_t bwt_forward_batch_workspace(uint64_t total, uint32_t nblocks) {
+    size_t temp = 0;
+    cub::DoubleBuffer<uint64_t> k(nullptr, nullptr);
+    cub::DoubleBuffer<uint32_t> v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, k, v, (int64_t)total, 0, 64);
+    return (size_t)total * (8 * 2 + 4 * 2 + 4 + 4) + 4 * ((size_t)total / 2048 + 16) + (size_t)nblocks * sizeof(BwtBatchBlock) + 8 * 256 + temp + 4096;
+}
+// at most this many positions / blocks in one call (keys: 2 * lg bits with total < 2^lg; 10 bits of block index in the first key)
+uint64_t bwt_forward_batch_max_total() { return (1ull << 30) - 1; }
+uint32_t bwt_forward_batch_max_blocks() { return BWT_BATCH_MAX; }
+
+// BWTBlockCodec.Forward of blocks[k] = (src offset, dst offset, n >= 2, caller's block number): d_out_len[number] = n + header
+cudaError_t bwt_forward_batch(const uint8_t* d_in, uint8_t* d_out, const uint64_t* src_off, const uint64_t* dst_off, const uint32_t* n_of, const uint32_t* number,
+                              uint32_t nb, uint32_t* d_out_len, uint8_t* ws, size_t ws_bytes, cudaStream_t stream, uint64_t* launches) {
+    if (nb == 0) return cudaSuccess;
+    if (nb > (uint32_t)BWT_BATCH_MAX) return cudaErrorInvalidValue;
+    std::vector<BwtBatchBlock> hb(nb);
+    uint64_t total64 = 0;
+    for (uint32_t k = 0; k < nb; k++) {
+        const uint32_t n = n_of[k];
+        if (n < 2) return cudaErrorInvalidValue;
+        uint32_t log_bs = log2_floor(n);
+        if (n & (n - 1)) log_bs++;
+        const uint32_t pidx = (log_bs + 7) >> 3;
+        if (pidx == 0 || pidx >= 5) return cudaErrorInvalidValue;
+        hb[k].src_off = src_off[k], hb[k].dst_off = dst_off[k], hb[k].base = (uint32_t)total64, hb[k].n = n;
+        hb[k].header = (n < 256 ? 1u : 8u) * pidx + 1;
+        hb[k].pad = number[k];
+        total64 += n;
+    }
+    if (total64 > bwt_forward_batch_max_total()) return cudaErrorInvalidValue;
+    const uint32_t total = (uint32_t)total64;
+    auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
+    size_t off = 0;
+    uint64_t* keys_a = (uint64_t*)(ws + off); off = align(off + (size_t)total * 8);
+    uint64_t* keys_b = (uint64_t*)(ws + off); off = align(off + (size_t)total * 8);
+    uint32_t* idx_a = (uint32_t*)(ws + off); off = align(off + (size_t)total * 4);
+    uint32_t* idx_b = (uint32_t*)(ws + off); off = align(off + (size_t)total * 4);
+    uint32_t* rank = (uint32_t*)(ws + off); off = align(off + (size_t)total * 4);
+    uint32_t* head = (uint32_t*)(ws + off); off = align(off + (size_t)total * 4);
+    const uint32_t nscan = (total + 2047) / 2048;
+    uint32_t* block_max = (uint32_t*)(ws + off); off = align(off + (size_t)nscan * 4);
+    uint32_t* flags = (uint32_t*)(ws + off); off = align(off + 64);
+    BwtBatchBlock* d_blocks = (BwtBatchBlock*)(ws + off); off = align(off + (size_t)nb * sizeof(BwtBatchBlock));
+    void* temp = ws + off;
+    if (ws_bytes < off) return cudaErrorInvalidValue;
+    const size_t temp_bytes = ws_bytes - off;
+    cudaError_t e = cudaMemcpyAsync(d_blocks, hb.data(), (size_t)nb * sizeof(BwtBatchBlock), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    const uint32_t T = 256, G = (total + T - 1) / T;
+    uint32_t lg = 1;
+    while ((1ull << lg) <= total) lg++;
+    bwtb_init_keys_kernel<<<G, T, 0, stream>>>(d_in, d_blocks, nb, total, keys_a, idx_a);
+    (*launches)++;
+    uint32_t h = 6;
+    int end_bit = 64;
+    uint32_t max_n = 0;
+    for (uint32_t k = 0; k < nb; k++) max_n = std::max(max_n, hb[k].n);
+    for (int round = 0; round < 40; round++) {
+        cub::DoubleBuffer<uint64_t> k(keys_a, keys_b);
+        cub::DoubleBuffer<uint32_t> v(idx_a, idx_b);
+        size_t tb = temp_bytes;
+        e = cub::DeviceRadixSort::SortPairs(temp, tb, k, v, (int64_t)total, 0, end_bit, stream);
+        if (e != cudaSuccess) return e;
+        (*launches) += 8;
+        const uint64_t* sk = k.Current();
+        const uint32_t* sa = v.Current();
+        cudaMemsetAsync(flags, 0, 4, stream);
+        bwt_flag_kernel<<<G, T, 0, stream>>>(sk, total, head);
+        scan_max_local_kernel<<<nscan, 256, 0, stream>>>(head, total, block_max);
+        scan_max_blocks_kernel<<<1, 1024, 0, stream>>>(block_max, nscan);
+        bwt_apply_rank_kernel<<<G, T, 0, stream>>>(head, block_max, sa, total, rank, flags);
+        (*launches) += 4;
+        uint32_t unsorted = 0;
+        e = cudaMemcpyAsync(&unsorted, flags, 4, cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return e;
+        if (!unsorted || h >= max_n) {
+            bwtb_emit_kernel<<<G, T, 0, stream>>>(d_in, d_blocks, nb, total, sa, rank, d_out);
+            bwtb_header_kernel<<<(nb + 63) / 64, 64, 0, stream>>>(d_blocks, nb, rank, d_out, d_out_len);
+            (*launches) += 2;
+            return cudaGetLastError();
+        }
+        bwtb_double_keys_kernel<<<G, T, 0, stream>>>(rank, d_blocks, nb, total, h, lg, keys_a, idx_a);
+        (*launches)++;
+        h *= 2;
+        end_bit = 2 * (int)lg;
     }
     return cudaErrorUnknown;
 }

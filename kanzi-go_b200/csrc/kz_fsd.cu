@@ -355,12 +355,21 @@ __global__ void __launch_bounds__(32) fsd_final_kernel(const FsdBlock* __restric
     res[b] = r;
 }
 
-// ---- inverse: one thread per block ----
+// ---- inverse: one warp per block, 32 source bytes per round (FSDCodec.go:317-401) ----
+// out[o] = f(out[o - dist]) is `dist` interleaved chains; along a chain the delta tokens are a prefix sum (mod 256) and the rare escape
+// tokens (0xFF + payload: out = payload ^ previous) cut it. A round takes 32 source bytes, one per lane:
+//   * which 0xFF bytes are escape markers is a parity question inside runs of 0xFF (a marker's successor is a payload, whatever its value),
+//     answered with one ballot and a clz per lane; the marker state is carried into the next round;
+//   * every byte that is not a marker is one output token; the k-th token moves to lane k (fns on the ballot);
+//   * token values: inclusive shuffle scan with stride `dist` over the deltas (escape tokens count as 0) on top of the chain's last value
+//     of earlier rounds (the last 16 outputs live in the registers of lanes 0..15), then one correction per escape token of the round, in
+//     order: E = payload ^ value before it; every later token of its chain moves by E - tentative value;
+//   * one coalesced store. XOR coding is the same scan with xor and no escapes.
+// ~250 cycles per 32 bytes instead of ~140 per byte for the one-thread walk this replaces.
 __global__ void __launch_bounds__(32) fsd_inverse_kernel(const uint8_t* __restrict__ in, const FsdBlock* __restrict__ blocks, int nblocks, uint8_t* __restrict__ out,
                                                           FsdResult* __restrict__ res) {
-    __shared__ uint8_t ring[16];
-    const int b = blockIdx.x;
-    if (b >= nblocks || threadIdx.x != 0) return;
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (b >= nblocks) return;
     const FsdBlock blk = blocks[b];
     FsdResult r;
     r.status = 0;
@@ -371,7 +380,7 @@ __global__ void __launch_bounds__(32) fsd_inverse_kernel(const uint8_t* __restri
     const uint8_t* src = in + blk.src_off;
     uint8_t* dst = out + blk.dst_off;
     if (src_end == 0 || dst_end == 0) {
-        res[b] = r;
+        if (lane == 0) res[b] = r;
         return;
     }
     bool bad = src_end < 2;
@@ -384,51 +393,87 @@ __global__ void __launch_bounds__(32) fsd_inverse_kernel(const uint8_t* __restri
     }
     if (bad) {
         r.status = -KZ_E_PROCESS_BLOCK;
-        res[b] = r;
+        if (lane == 0) res[b] = r;
         return;
     }
-    uint32_t si = 2, di = 0;
-    for (uint32_t i = 0; i < dist; i++) {
-        const uint8_t v = src[si++];
-        dst[di] = v;
-        ring[di & 15] = v;
-        di++;
-    }
-    if (mode == 0) {
-        while (si < src_end && di < dst_end) {
-            const uint32_t t = src[si];
-            const uint32_t prv = ring[(di - dist) & 15];
-            uint8_t v;
-            if (t != 0xFF) {
-                const int z = (t & 1) ? -(int)((t + 1) >> 1) : (int)(t >> 1);  // _FSD_ZIGZAG2
-                v = (uint8_t)((int)prv + z);
-                si++;
-            } else {
-                si++;
-                if (si >= src_end) {
-                    bad = true;
-                    break;
-                }
-                v = (uint8_t)(src[si] ^ prv);
-                si++;
+    // the first `dist` bytes are copied; tail = the last 16 outputs so far, out[di - 16 + lane] in lanes 0..15
+    uint32_t si = 2 + dist, di = dist;
+    uint32_t tail = 0;
+    if (lane < 16 && (uint32_t)lane + dist >= 16u) tail = src[2 + lane + dist - 16];
+    if ((uint32_t)lane < dist) dst[lane] = src[2 + lane];
+    uint32_t pending = 0;  // the previous round ended with an escape marker: this round's first byte is its payload
+    const uint32_t below = (1u << lane) - 1u;
+    uint32_t nxt = si + lane < src_end ? src[si + lane] : 0u;
+    while (si < src_end && di < dst_end) {
+        const uint32_t t = nxt;
+        const uint32_t cnt = min(32u, src_end - si);
+        const uint32_t valid = cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u);
+        nxt = si + 32 + lane < src_end ? src[si + 32 + lane] : 0u;  // next round in flight
+        uint32_t marker = 0;
+        if (mode == 0) {
+            const uint32_t ff = __ballot_sync(0xFFFFFFFFu, t == 0xFFu) & valid;
+            const uint32_t nz = ~ff & below;                                   // bytes below this lane that are not 0xFF
+            const uint32_t s = nz ? 32u - (uint32_t)__clz((int)nz) : 0u;        // first lane of the run of 0xFF this lane is in
+            const uint32_t par = (s == 0 && pending) ? 1u : 0u;                 // a run that starts with a payload
+            const bool is_marker = ((ff >> lane) & 1u) && ((((uint32_t)lane - s) & 1u) == par);
+            marker = __ballot_sync(0xFFFFFFFFu, is_marker);
+        }
+        const uint32_t payload = ((marker << 1) | pending) & valid;  // bytes that follow a marker
+        const uint32_t tokens = valid & ~marker;                     // bytes that produce an output byte
+        const uint32_t m = (uint32_t)__popc(tokens);
+        if (di + m > dst_end) {  // the reference stops at dst_end with source bytes left: an error (:398-400)
+            bad = true;
+            break;
+        }
+        // token k -> lane k
+        const int from = (uint32_t)lane < m ? (int)__fns(tokens, 0, lane + 1) : 0;
+        const uint32_t tk = __shfl_sync(0xFFFFFFFFu, t, from);
+        const bool is_esc = (uint32_t)lane < m && ((payload >> from) & 1u);
+        uint32_t v;  // value to combine along the chain: the delta, or 0 for an escape token
+        if (mode == 0) v = is_esc ? 0u : ((tk & 1u) ? (0u - ((tk + 1u) >> 1)) : (tk >> 1));  // _FSD_ZIGZAG2
+        else v = tk;
+        if ((uint32_t)lane >= m) v = 0;
+        for (uint32_t d = dist; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, v, d);
+            if ((uint32_t)lane >= d) v = mode == 0 ? v + y : v ^ y;
+        }
+        // the chain's last value of earlier rounds: out[di + (lane % dist) - dist] = tail lane 16 + (lane % dist) - dist
+        const uint32_t head = (uint32_t)lane % dist;
+        const uint32_t base = __shfl_sync(0xFFFFFFFFu, tail, (int)(16u + head - dist));
+        v = (mode == 0 ? v + base : v ^ base) & 0xFFu;
+        if (mode == 0) {
+            uint32_t esc = __ballot_sync(0xFFFFFFFFu, is_esc);
+            while (esc) {  // escapes of the round in order: every earlier token already has its final value
+                const int e = __ffs((int)esc) - 1;
+                esc &= esc - 1;
+                const uint32_t prev_in = __shfl_sync(0xFFFFFFFFu, v, e >= (int)dist ? e - (int)dist : 0);
+                const uint32_t prev_old = __shfl_sync(0xFFFFFFFFu, tail, (int)(16u + (uint32_t)e - dist) & 31);
+                const uint32_t prev = e >= (int)dist ? prev_in : prev_old;
+                const uint32_t tent = __shfl_sync(0xFFFFFFFFu, v, e);
+                const uint32_t pay = __shfl_sync(0xFFFFFFFFu, tk, e);
+                const uint32_t delta = ((pay ^ prev) - tent) & 0xFFu;
+                if (lane >= e && ((uint32_t)(lane - e) % dist) == 0) v = (v + delta) & 0xFFu;
             }
-            dst[di] = v;
-            ring[di & 15] = v;
-            di++;
         }
-    } else {
-        while (si < src_end && di < dst_end) {
-            const uint8_t v = (uint8_t)(src[si] ^ ring[(di - dist) & 15]);
-            dst[di] = v;
-            ring[di & 15] = v;
-            di++;
-            si++;
+        if ((uint32_t)lane < m) dst[di + lane] = (uint8_t)v;
+        // new tail: out[di + m - 16 + j] for j = 0..15
+        {
+            const int j = lane & 15;
+            const int pos = (int)m - 16 + j;  // index into this round's outputs (negative: still in the old tail)
+            const uint32_t from_new = __shfl_sync(0xFFFFFFFFu, v, pos >= 0 ? pos : 0);
+            const uint32_t from_old = __shfl_sync(0xFFFFFFFFu, tail, pos >= 0 ? 0 : (pos + 16) & 15);
+            tail = pos >= 0 ? from_new : from_old;
         }
+        pending = (marker >> 31) & 1u;
+        if (cnt < 32) pending = (marker >> (cnt - 1)) & 1u;
+        di += m;
+        si += cnt;
     }
-    if (si != src_end) bad = true;  // :398-400
+    if (!bad && pending) bad = true;       // a marker was the last source byte (:380-383)
+    if (!bad && si != src_end) bad = true;  // :398-400
     r.out_len = di;
     if (bad) r.status = -KZ_E_PROCESS_BLOCK;
-    res[b] = r;
+    if (lane == 0) res[b] = r;
 }
 
 }  // namespace

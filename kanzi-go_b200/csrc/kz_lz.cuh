@@ -55,6 +55,11 @@ cudaError_t lz_forward_parallel(const uint8_t* d_in, uint8_t* d_out, const std::
 cudaError_t lz_forward_parallel_sub(const uint8_t* d_in, uint8_t* d_out, const LzBlock* lb, uint32_t nblocks, bool extra, LzWorkspace& W, cudaStream_t stream,
                                     LzResult* res, LzHook* hook);
 
+// LZ / LZX inverse of a batch (kz_lz_inv.cu): parse by prefix scans, pointer jumping instead of ordered copies; blocks that trip a check of the
+// reference go through lz_inverse_kernel. out_len[b] / status[b] as lz_inverse_kernel leaves them. Synchronises the stream.
+cudaError_t lz_inverse_parallel(const uint8_t* d_in, uint8_t* d_out, const std::vector<LzBlock>& lb, LzWorkspace& W, cudaStream_t stream, std::vector<uint32_t>& out_len,
+                                std::vector<int32_t>& status, LzHook* hook, uint64_t* launches);
+
 __global__ void lz_parse_kernel(const uint8_t* in, const LzBlock* blocks, int nblocks, int extra, int32_t* hashes_all, uint8_t* scratch_all, uint8_t* out,
                                 LzResult* res);
 __global__ void lz_gather_kernel(const uint8_t* in, const LzBlock* blocks, int nblocks, const uint8_t* scratch_all, const LzResult* res, uint8_t* out);

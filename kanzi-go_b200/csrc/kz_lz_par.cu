@@ -7,8 +7,9 @@
 //   info      common prefix / suffix lengths of (i, prev[i]), saturated at 255               [streaming compares]
 //   rounds to the fixed point of the table membership vf[] (kz_lz_par_core.cuh, 3.; two rounds for ordinary blocks):
 //     filter    candidates under the previous round's vf (round 0: as linked)
-//     spec      one LANE per 1 KiB segment: speculative parse from a guessed state -> match log of the segment
-//     junction  one lane per segment: from the state the segment's log stopped in, the parse until it meets the log of the segment it is in
+//     spec      one warp per 1 KiB segment (the lanes take the next 32 probes of a literal run): speculative parse from a guessed state ->
+//               match log of the segment
+//     junction  one warp per segment: from the state the segment's log stopped in, the parse until it meets the log of the segment it is in
 //     walk      one CTA per block: junction records staged in shared memory, one thread follows them -> piece list of the match list
 //     stitch    (only blocks with a live junction that hit its cap) one lane per block: the serial stitch of kz_lz_par_core.cuh
 //     flatten   pieces -> contiguous match list
@@ -28,7 +29,7 @@ using namespace lzp;
 
 namespace {
 
-const int SEG = 1024;                // bytes per speculative segment (one lane each)
+const int SEG = 1024;                // bytes per speculative segment (one warp each)
 const int SEG_CAP = SEG / 4 + 8;     // log entries per segment (a match is at least 4 bytes long)
 const int JCAP = 64;                 // fix-up matches per junction before it gives up (a live one that does sends the block to the serial stitch)
 const int WALK_WIN = 4096;           // junction records staged in shared memory per window of the walk
@@ -142,12 +143,62 @@ __global__ void __launch_bounds__(256) lzp_derive_kernel(const PBlock* __restric
     if (__syncthreads_or(diff ? 1 : 0) && threadIdx.x == 0) atomicOr(&changed[b], 1u);
 }
 
-// ---- pass 1: speculative segment parses (one lane per segment; act_segs lists the segments of the unfinished blocks) ---------------------
+// ---- warp-cooperative parse: the 32 lanes evaluate the next 32 probes of the literal run at once ------------------------------------------------
+// probe_first is a pure function of (position, the two repeat distances, candidates); the positions of the next probes follow from the run
+// counter (stride 1 + (src_inc >> 6)), so the lanes take one probe each, the lowest lane with a match wins and every lane then runs the
+// (uniform) second stage on the winner's values. One memory round trip per 32 probes of a literal run, and per match on compressible data.
+// All lanes hold the same `st` / `m` on entry and exit.
+__device__ __forceinline__ int parse_one_warp(const Params& P, State& st, Match& m) {
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        if (st.src_idx >= P.src_end) return R_END;
+        const int step = 1 + ((st.src_inc + lane) >> 6);
+        int incl = step;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        const int pos = st.src_idx + incl - step;
+        const bool valid = pos < P.src_end;
+        int best_len = 0, ref = 0, kind = 0, b = 0;
+        bool hit = false;
+        if (valid) {
+            const bool swapped = lane == 0 && st.repd_idx != 0;
+            hit = probe_first(P, pos, swapped ? st.repd1 : st.repd0, swapped ? st.repd0 : st.repd1, best_len, ref, kind, b);
+        }
+        const uint32_t hits = __ballot_sync(0xFFFFFFFFu, hit), vmask = __ballot_sync(0xFFFFFFFFu, valid);
+        if (hits == 0) {
+            const int nvalid = __popc(vmask);  // the valid lanes are a prefix
+            st.src_inc += nvalid;
+            st.repd_idx = 0;
+            if (nvalid < 32) {
+                st.src_idx = __shfl_sync(0xFFFFFFFFu, pos, nvalid);
+                return R_END;
+            }
+            st.src_idx = __shfl_sync(0xFFFFFFFFu, pos + step, 31);
+            continue;
+        }
+        const int w = __ffs((int)hits) - 1;
+        if (w > 0) st.repd_idx = 0;
+        st.src_inc += w;
+        st.src_idx = __shfl_sync(0xFFFFFFFFu, pos, w);
+        best_len = __shfl_sync(0xFFFFFFFFu, best_len, w);
+        ref = __shfl_sync(0xFFFFFFFFu, ref, w);
+        kind = __shfl_sync(0xFFFFFFFFu, kind, w);
+        b = __shfl_sync(0xFFFFFFFFu, b, w);
+        probe_finish(P, st, best_len, ref, kind, b, m);
+        return R_MATCH;
+    }
+}
+
+// ---- pass 1: speculative segment parses (one warp per segment; act_segs lists the segments of the unfinished blocks) ---------------------
 __global__ void __launch_bounds__(128) lzp_spec_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_seg, int extra,
                                                         const uint32_t* __restrict__ act_segs, uint32_t n_act, const Rec* __restrict__ rec, Match* __restrict__ logs,
                                                         SegDesc* __restrict__ desc) {
-    const uint32_t t = blockIdx.x * 128 + threadIdx.x;
+    const uint32_t t = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (t >= n_act) return;
+    const int lane = threadIdx.x & 31;
     const uint32_t s = act_segs[t];
     const uint32_t b = blk_of_seg[s];
     const PBlock& B = blocks[b];
@@ -155,30 +206,95 @@ __global__ void __launch_bounds__(128) lzp_spec_kernel(const uint8_t* __restrict
     const Params P = make_params(in, B, extra, rec);
     const int s0 = (int)(k * SEG);
     const int s1 = k == B.nsegs - 1 ? 0x7FFFFFFF : s0 + SEG;
-    SegDesc d;
-    spec_parse_segment(P, s0, s1, logs + (size_t)s * SEG_CAP, d);
-    desc[s] = d;
+    Match* log = logs + (size_t)s * SEG_CAP;
+    State st = initial_state(P.count, s0);  // spec_parse_segment of kz_lz_par_core.cuh with the warp-cooperative parse
+    uint32_t n = 0, end = END_BLOCK;
+    for (;;) {
+        Match m;
+        if (parse_one_warp(P, st, m) == R_END) break;
+        if (lane == 0) log[n] = m;
+        n++;
+        if (st.anchor >= s1) {
+            end = END_POST_MATCH;
+            break;
+        }
+    }
+    if (lane == 0) {
+        SegDesc d;
+        d.n = n, d.end = end, d.fin = st;
+        desc[s] = d;
+    }
 }
 
-// ---- pass 2: junctions (one lane per segment), the walk over them (one CTA per block), the serial stitch for what the walk could not do ---------
+// ---- pass 2: junctions (one warp per segment), the walk over them (one CTA per block), the serial stitch for what the walk could not do ---------
 struct SegLogAt {
     const Match* base;
     __device__ const Match* operator()(int k) const { return base + (size_t)k * SEG_CAP; }
 };
+// junction_parse of kz_lz_par_core.cuh with the warp-cooperative parse; the log of the segment the cursor is in is searched 32 entries at a time
 __global__ void __launch_bounds__(128) lzp_junction_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_seg, int extra,
                                                             const uint32_t* __restrict__ act_segs, uint32_t n_act, const Rec* __restrict__ rec, const Match* __restrict__ logs,
-                                                            const SegDesc* __restrict__ desc, Match* __restrict__ jfix, Junction* __restrict__ junc) {
-    const uint32_t t = blockIdx.x * 128 + threadIdx.x;
+                                                            const SegDesc* __restrict__ desc_all, Match* __restrict__ jfix, Junction* __restrict__ junc) {
+    const uint32_t t = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (t >= n_act) return;
+    const int lane = threadIdx.x & 31;
     const uint32_t s = act_segs[t];
     const uint32_t b = blk_of_seg[s];
     const PBlock& B = blocks[b];
     const Params P = make_params(in, B, extra, rec);
-    SegLogAt sl;
-    sl.base = logs + (size_t)B.seg_base * SEG_CAP;
+    const SegDesc* desc = desc_all + B.seg_base;
+    const Match* lbase = logs + (size_t)B.seg_base * SEG_CAP;
+    const int k0 = (int)(s - B.seg_base), nsegs = (int)B.nsegs;
+    Match* fix = jfix + (size_t)s * JCAP;
+    State st = desc[k0].fin;
     Junction J;
-    junction_parse(P, (int)(s - B.seg_base), (int)B.nsegs, desc + B.seg_base, sl, jfix + (size_t)s * JCAP, (uint32_t)JCAP, J);
-    junc[s] = J;
+    J.status = J_TERMINAL, J.fix_n = 0, J.seg = 0, J.idx = 0, J.anchor = st.anchor;
+    if (desc[k0].end != END_BLOCK) {
+        uint32_t fn = 0;
+        int cur_seg = -1;
+        uint32_t cursor = 0, dn = 0;
+        const Match* lg = lbase;
+        bool finished = false;
+        while (st.src_idx < P.src_end) {
+            const int k = imin(st.src_idx / SEG, nsegs - 1);
+            if (k != cur_seg) {
+                cur_seg = k;
+                cursor = 0;
+                dn = desc[k].n;
+                lg = lbase + (size_t)k * SEG_CAP;
+            }
+            // first entry at or behind the cursor that ends at or behind the anchor
+            while (cursor < dn) {
+                const uint32_t i = cursor + lane;
+                const bool ge = i < dn && (int)(lg[i].start + lg[i].len) >= st.anchor;
+                const uint32_t mk = __ballot_sync(0xFFFFFFFFu, ge);
+                if (mk) {
+                    cursor += (uint32_t)__ffs((int)mk) - 1u;
+                    break;
+                }
+                cursor = min(cursor + 32u, dn);
+            }
+            if (cursor >= 1 && cursor < dn) {
+                const Match c = lg[cursor], pm = lg[cursor - 1];
+                if ((int)(c.start + c.len) == st.anchor && (int)c.dist == st.repd0 && (int)pm.dist == st.repd1) {
+                    J.status = J_JOINED, J.fix_n = fn, J.seg = (uint32_t)k, J.idx = cursor;
+                    finished = true;
+                    break;
+                }
+            }
+            if (fn >= (uint32_t)JCAP) {
+                J.status = J_OVERFLOW, J.fix_n = fn;
+                finished = true;
+                break;
+            }
+            Match m;
+            if (parse_one_warp(P, st, m) == R_END) break;
+            if (lane == 0) fix[fn] = m;
+            fn++;
+        }
+        if (!finished) J.status = J_TERMINAL, J.fix_n = fn, J.anchor = st.anchor;
+    }
+    if (lane == 0) junc[s] = J;
 }
 // packed junction record of the walk: n (9 bits) | END_BLOCK << 9 | status << 10 | fix_n << 12 | idx << 19; second word: joined segment
 __global__ void __launch_bounds__(256) lzp_walk_kernel(const PBlock* __restrict__ blocks, const uint32_t* __restrict__ act_blocks, const SegDesc* __restrict__ desc_all,
@@ -686,11 +802,11 @@ cudaError_t lz_forward_parallel_sub(const uint8_t* d_in, uint8_t* d_out, const L
         }
         {
             LzHookScope hs(hook, "lz_spec");
-            lzp_spec_kernel<<<(NS + 127) / 128, 128, 0, stream>>>(d_in, d_pb, d_bos, extra ? 1 : 0, d_acts, NS, rec_r, d_logs, d_desc);
+            lzp_spec_kernel<<<(NS + 3) / 4, 128, 0, stream>>>(d_in, d_pb, d_bos, extra ? 1 : 0, d_acts, NS, rec_r, d_logs, d_desc);
         }
         {
             LzHookScope hs(hook, "lz_stitch");
-            lzp_junction_kernel<<<(NS + 127) / 128, 128, 0, stream>>>(d_in, d_pb, d_bos, extra ? 1 : 0, d_acts, NS, rec_r, d_logs, d_desc, d_jfix, d_junc);
+            lzp_junction_kernel<<<(NS + 3) / 4, 128, 0, stream>>>(d_in, d_pb, d_bos, extra ? 1 : 0, d_acts, NS, rec_r, d_logs, d_desc, d_jfix, d_junc);
             lzp_walk_kernel<<<NB, 256, 0, stream>>>(d_pb, d_actb, d_desc, d_junc, d_pieces, d_pstart, d_pst);
             lzp_stitch_kernel<<<NB, 32, 0, stream>>>(d_in, d_pb, d_actb, extra ? 1 : 0, rec_r, d_logs, d_desc, d_fix, d_pieces, d_pstart, d_pst);
         }

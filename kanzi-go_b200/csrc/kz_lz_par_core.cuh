@@ -228,104 +228,126 @@ KZL_HD uint32_t derive_vf(const Match* ml, uint32_t nm, int src_end, int j) {
     return j > (int)m.start ? m.start + m.len : VF_NEVER;
 }
 
-// Runs the parse from `st` to the next match. R_MATCH: m is the match, st the state behind it. R_END: the cursor reached srcEnd.
-KZL_HD int parse_one(const Params& P, State& st, Match& m) {
+// One probe of the parse at position src_idx, first stage (:339-366): the two repeat-distance checks (repd_first before repd_second), then the
+// table entry. Returns true when a match of at least min_match was found: kind 0 = repeat distance, 1 = table (b = stored suffix length).
+// A pure function of the position, the two distances and the candidates: the warp-cooperative parse evaluates 32 probes at once with it.
+KZL_HD bool probe_first(const Params& P, int src_idx, int repd_first, int repd_second, int& best_len, int& ref, int& kind, int& b) {
     const uint8_t* src = P.src;
     const int src_end = P.src_end, min_match = P.min_match;
-    while (st.src_idx < src_end) {
-        int src_idx = st.src_idx;
-        const int src_idx1 = src_idx + 1;
-        const int max_match = imin(src_end - src_idx1, MAX_MATCH);
-        const int min_ref = imax(src_idx - P.max_dist, 0);
-        const uint64_t p = ld64(src + src_idx);
-        int best_len = 0;
-        int ref = src_idx1 - (st.repd_idx ? st.repd1 : st.repd0);
-        if (ref > min_ref && (uint32_t)(p >> 8) == ld32(src + ref)) {
-            best_len = find_match(src, src_idx1, ref, max_match);
-        } else {
-            ref = src_idx1 - (st.repd_idx ? st.repd0 : st.repd1);
-            if (ref > min_ref && (uint32_t)(p >> 8) == ld32(src + ref)) best_len = find_match(src, src_idx1, ref, max_match);
-        }
-        if (best_len < min_match) {
-            int cand, t, b;
-            lookup(P, src_idx, cand, t, b);
-            bool found = false;
-            if (cand > min_ref && t >= 4) {
-                best_len = match_len(P, src_idx, cand, t, imin(src_end - src_idx, MAX_MATCH));
-                found = best_len >= min_match;
-            }
-            if (!found) {
-                st.src_idx = src_idx1 + (st.src_inc >> 6);
-                st.src_inc++;
-                st.repd_idx = 0;
-                continue;
-            }
+    const int src_idx1 = src_idx + 1;
+    const int max_match = imin(src_end - src_idx1, MAX_MATCH);
+    const int min_ref = imax(src_idx - P.max_dist, 0);
+    const uint64_t p = ld64(src + src_idx);
+    best_len = 0;
+    kind = 0;
+    b = 0;
+    ref = src_idx1 - repd_first;
+    if (ref > min_ref && (uint32_t)(p >> 8) == ld32(src + ref)) {
+        best_len = find_match(src, src_idx1, ref, max_match);
+    } else {
+        ref = src_idx1 - repd_second;
+        if (ref > min_ref && (uint32_t)(p >> 8) == ld32(src + ref)) best_len = find_match(src, src_idx1, ref, max_match);
+    }
+    if (best_len >= min_match) return true;
+    int cand, t;
+    lookup(P, src_idx, cand, t, b);
+    if (cand > min_ref && t >= 4) {
+        best_len = match_len(P, src_idx, cand, t, imin(src_end - src_idx, MAX_MATCH));
+        if (best_len >= min_match) {
             ref = cand;
-            int bsel = b, isel = src_idx;  // suffix length / position of the selected candidate pair
-            if (ref != src_idx - st.repd0 && ref != src_idx - st.repd1) {
-                int c1, t1, b1;
-                lookup(P, src_idx1, c1, t1, b1);
-                if (c1 > min_ref + 1) {
-                    const int m8 = max_match & ~7;
-                    if (m8 >= best_len && full_t(P, src_idx1, c1, t1, best_len + 1) >= best_len + 1) {
-                        const int tt = full_t(P, src_idx1, c1, t1, m8);
+            kind = 1;
+            return true;
+        }
+    }
+    return false;
+}
+// Second stage of a probe that found a match (:368-414): lazy checks at +1 / +2 and backward extension for a table match, the one byte
+// backward step of a repeat match. `st` is the state at the probe (st.src_idx = the probe's position); on return it stands behind the match.
+KZL_HD void probe_finish(const Params& P, State& st, int best_len, int ref, int kind, int b, Match& m) {
+    const uint8_t* src = P.src;
+    const int src_end = P.src_end;
+    int src_idx = st.src_idx;
+    const int src_idx1 = src_idx + 1;
+    const int max_match = imin(src_end - src_idx1, MAX_MATCH);
+    const int min_ref = imax(src_idx - P.max_dist, 0);
+    if (kind == 1) {
+        int bsel = b, isel = src_idx;  // suffix length / position of the selected candidate pair
+        if (ref != src_idx - st.repd0 && ref != src_idx - st.repd1) {
+            int c1, t1, b1;
+            lookup(P, src_idx1, c1, t1, b1);
+            if (c1 > min_ref + 1) {
+                const int m8 = max_match & ~7;
+                if (m8 >= best_len && full_t(P, src_idx1, c1, t1, best_len + 1) >= best_len + 1) {
+                    const int tt = full_t(P, src_idx1, c1, t1, m8);
+                    best_len = tt < m8 ? tt : m8;
+                    ref = c1;
+                    src_idx = src_idx1;
+                    bsel = b1;
+                    isel = src_idx1;
+                }
+            }
+            if (P.extra) {
+                const int src_idx2 = src_idx1 + 1;
+                int c2, t2, b2;
+                lookup(P, src_idx2, c2, t2, b2);
+                if (c2 > min_ref + 2) {
+                    const int m8 = imin(src_end - src_idx2, MAX_MATCH) & ~7;
+                    if (m8 >= best_len && full_t(P, src_idx2, c2, t2, best_len + 1) >= best_len + 1) {
+                        const int tt = full_t(P, src_idx2, c2, t2, m8);
                         best_len = tt < m8 ? tt : m8;
-                        ref = c1;
-                        src_idx = src_idx1;
-                        bsel = b1;
-                        isel = src_idx1;
+                        ref = c2;
+                        src_idx = src_idx2;
+                        bsel = b2;
+                        isel = src_idx2;
                     }
                 }
-                if (P.extra) {
-                    const int src_idx2 = src_idx1 + 1;
-                    int c2, t2, b2;
-                    lookup(P, src_idx2, c2, t2, b2);
-                    if (c2 > min_ref + 2) {
-                        const int m8 = imin(src_end - src_idx2, MAX_MATCH) & ~7;
-                        if (m8 >= best_len && full_t(P, src_idx2, c2, t2, best_len + 1) >= best_len + 1) {
-                            const int tt = full_t(P, src_idx2, c2, t2, m8);
-                            best_len = tt < m8 ? tt : m8;
-                            ref = c2;
-                            src_idx = src_idx2;
-                            bsel = b2;
-                            isel = src_idx2;
-                        }
-                    }
-                }
-            }
-            {  // extend backwards (:403-407)
-                const int room = imin(src_idx - st.anchor, ref - min_ref);
-                if (room > 0 && bsel > 0) {
-                    const int ext = imin(full_b(P, isel, ref, bsel, room), room);
-                    best_len += ext;
-                    ref -= ext;
-                    src_idx -= ext;
-                }
-            }
-            if (best_len > MAX_MATCH) {
-                src_idx += best_len - MAX_MATCH;
-                ref += best_len - MAX_MATCH;
-                best_len = MAX_MATCH;
-            }
-        } else {
-            if (src[src_idx] == src[ref - 1] && best_len < MAX_MATCH) {
-                best_len++;
-                ref--;
-            } else {
-                src_idx++;
             }
         }
-        const int dist = src_idx - ref;
-        m.start = (uint32_t)src_idx;
-        m.len = (uint32_t)best_len;
-        m.dist = (uint32_t)dist;
-        m.probe = (uint32_t)st.src_idx;
-        st.repd1 = st.repd0;
-        st.repd0 = dist;
-        st.repd_idx = 1;
-        st.src_inc = 0;
-        st.anchor = src_idx + best_len;
-        st.src_idx = st.anchor;
+        {  // extend backwards (:403-407)
+            const int room = imin(src_idx - st.anchor, ref - min_ref);
+            if (room > 0 && bsel > 0) {
+                const int ext = imin(full_b(P, isel, ref, bsel, room), room);
+                best_len += ext;
+                ref -= ext;
+                src_idx -= ext;
+            }
+        }
+        if (best_len > MAX_MATCH) {
+            src_idx += best_len - MAX_MATCH;
+            ref += best_len - MAX_MATCH;
+            best_len = MAX_MATCH;
+        }
+    } else {
+        if (src[src_idx] == src[ref - 1] && best_len < MAX_MATCH) {
+            best_len++;
+            ref--;
+        } else {
+            src_idx++;
+        }
+    }
+    const int dist = src_idx - ref;
+    m.start = (uint32_t)src_idx;
+    m.len = (uint32_t)best_len;
+    m.dist = (uint32_t)dist;
+    m.probe = (uint32_t)st.src_idx;
+    st.repd1 = st.repd0;
+    st.repd0 = dist;
+    st.repd_idx = 1;
+    st.src_inc = 0;
+    st.anchor = src_idx + best_len;
+    st.src_idx = st.anchor;
+}
+// Runs the parse from `st` to the next match. R_MATCH: m is the match, st the state behind it. R_END: the cursor reached srcEnd.
+KZL_HD int parse_one(const Params& P, State& st, Match& m) {
+    while (st.src_idx < P.src_end) {
+        int best_len, ref, kind, b;
+        if (!probe_first(P, st.src_idx, st.repd_idx ? st.repd1 : st.repd0, st.repd_idx ? st.repd0 : st.repd1, best_len, ref, kind, b)) {
+            st.src_idx = st.src_idx + 1 + (st.src_inc >> 6);
+            st.src_inc++;
+            st.repd_idx = 0;
+            continue;
+        }
+        probe_finish(P, st, best_len, ref, kind, b, m);
         return R_MATCH;
     }
     return R_END;
