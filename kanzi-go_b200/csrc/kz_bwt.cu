@@ -15,6 +15,8 @@
 //     pointer doubling, and a second parallel walk writes the bytes at their final offsets.
 //   transform/BWTBlockCodec.go:78-136, :141-225: block header (mode byte + big-endian primaryIndex-1 per chunk).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 #include <algorithm>
 #include <vector>
@@ -467,6 +469,55 @@ __global__ void bwtb_header_kernel(const BwtBatchBlock* __restrict__ blocks, uin
     }
     out_len[B.pad] = n + chunks * pidx + 1;
 }
+// ---- rounds over the unresolved part only -----------------------------------------------------------------------------------------------------
+// After a round every group of equal h-prefixes is a contiguous range of sorted positions and only groups with more than one member can
+// change. The members of those groups are compacted (sorted position, suffix), sorted by (group head, rank of the suffix h further), and
+// written back into the same positions: the work of a round is proportional to what is still unresolved, not to the batch.
+__global__ void __launch_bounds__(256) bwtu_flags_full_kernel(const uint32_t* __restrict__ head, uint32_t total, uint8_t* __restrict__ flags) {
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= total) return;
+    const uint32_t hj = head[j];
+    flags[j] = (hj != j || (j + 1 < total && head[j + 1] == hj)) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) bwtu_flags_kernel(const uint32_t* __restrict__ nhead, const uint32_t* __restrict__ cpos, uint32_t m, uint8_t* __restrict__ flags) {
+    const uint32_t u = blockIdx.x * 256 + threadIdx.x;
+    if (u >= m) return;
+    const uint32_t hu = nhead[u];
+    flags[u] = (hu != cpos[u] || (u + 1 < m && nhead[u + 1] == hu)) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) bwtu_keys_kernel(const uint32_t* __restrict__ rank, const uint32_t* __restrict__ cval, uint32_t m,
+                                                         const BwtBatchBlock* __restrict__ blocks, uint32_t nb, uint32_t h, uint32_t lg, uint64_t* __restrict__ keys) {
+    __shared__ uint32_t s_base[BWT_BATCH_MAX];
+    __shared__ uint32_t s_n[BWT_BATCH_MAX];
+    for (uint32_t k = threadIdx.x; k < nb; k += 256) s_base[k] = blocks[k].base, s_n[k] = blocks[k].n;
+    __syncthreads();
+    const uint32_t u = blockIdx.x * 256 + threadIdx.x;
+    if (u >= m) return;
+    const uint32_t i = cval[u];
+    const uint32_t b = bwtb_find(s_base, nb, i);
+    const uint64_t end = (uint64_t)s_base[b] + s_n[b];
+    const uint64_t hi = rank[i];
+    const uint64_t lo = (uint64_t)i + h < end ? (uint64_t)rank[i + h] + 1 : 0;
+    keys[u] = (hi << lg) | lo;
+}
+// candidate heads of the new groups: the sorted position of the first member (0 elsewhere; a max-scan spreads them)
+__global__ void __launch_bounds__(256) bwtu_heads_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cpos, uint32_t m, uint32_t* __restrict__ f) {
+    const uint32_t u = blockIdx.x * 256 + threadIdx.x;
+    if (u >= m) return;
+    f[u] = (u == 0 || keys[u] != keys[u - 1]) ? cpos[u] : 0u;
+}
+__global__ void __launch_bounds__(256) bwtu_apply_kernel(uint32_t* __restrict__ f, const uint32_t* __restrict__ block_max, const uint32_t* __restrict__ cpos,
+                                                          const uint32_t* __restrict__ cval, uint32_t m, uint32_t* __restrict__ sa, uint32_t* __restrict__ rank) {
+    const uint32_t u = blockIdx.x * 256 + threadIdx.x;
+    if (u >= m) return;
+    const uint32_t blk = u / (256 * 8);
+    uint32_t g = f[u];
+    if (blk > 0) g = max(g, block_max[blk - 1]);
+    f[u] = g;
+    const uint32_t v = cval[u];
+    sa[cpos[u]] = v;
+    rank[v] = g;
+}
 }  // namespace
 
 size_t bwt_forward_batch_workspace(uint64_t total, uint32_t nblocks) {
@@ -474,7 +525,9 @@ size_t bwt_forward_batch_workspace(uint64_t total, uint32_t nblocks) {
     cub::DoubleBuffer<uint64_t> k(nullptr, nullptr);
     cub::DoubleBuffer<uint32_t> v(nullptr, nullptr);
     cub::DeviceRadixSort::SortPairs(nullptr, temp, k, v, (int64_t)total, 0, 64);
-    return (size_t)total * (8 * 2 + 4 * 2 + 4 + 4) + 4 * ((size_t)total / 2048 + 16) + (size_t)nblocks * sizeof(BwtBatchBlock) + 8 * 256 + temp + 4096;
+    size_t temp2 = 0;
+    cub::DeviceSelect::Flagged(nullptr, temp2, (const uint32_t*)nullptr, (const uint8_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)total);
+    return (size_t)total * (8 * 2 + 4 * 2 + 4 + 4 + 4 * 4 + 1) + 4 * ((size_t)total / 2048 + 16) + (size_t)nblocks * sizeof(BwtBatchBlock) + 16 * 256 + std::max(temp, temp2) + 4096;
 }
 // at most this many positions / blocks in one call (keys: 2 * lg bits with total < 2^lg; 10 bits of block index in the first key)
 uint64_t bwt_forward_batch_max_total() { return (1ull << 30) - 1; }
@@ -513,6 +566,12 @@ cudaError_t bwt_forward_batch(const uint8_t* d_in, uint8_t* d_out, const uint64_
     uint32_t* block_max = (uint32_t*)(ws + off); off = align(off + (size_t)nscan * 4);
     uint32_t* flags = (uint32_t*)(ws + off); off = align(off + 64);
     BwtBatchBlock* d_blocks = (BwtBatchBlock*)(ws + off); off = align(off + (size_t)nb * sizeof(BwtBatchBlock));
+    uint32_t* cval_a = (uint32_t*)(ws + off); off = align(off + (size_t)total * 4);
+    uint32_t* cval_b = (uint32_t*)(ws + off); off = align(off + (size_t)total * 4);
+    uint32_t* cpos_a = (uint32_t*)(ws + off); off = align(off + (size_t)total * 4);
+    uint32_t* cpos_b = (uint32_t*)(ws + off); off = align(off + (size_t)total * 4);
+    uint8_t* uflags = ws + off; off = align(off + (size_t)total);
+    uint32_t* d_count = flags + 8;
     void* temp = ws + off;
     if (ws_bytes < off) return cudaErrorInvalidValue;
     const size_t temp_bytes = ws_bytes - off;
@@ -527,6 +586,12 @@ cudaError_t bwt_forward_batch(const uint8_t* d_in, uint8_t* d_out, const uint64_
     int end_bit = 64;
     uint32_t max_n = 0;
     for (uint32_t k = 0; k < nb; k++) max_n = std::max(max_n, hb[k].n);
+    static const bool full_rounds = [] {  // KZ_BWT_FWD=full: every round sorts the whole batch (first batched version)
+        const char* ev = getenv("KZ_BWT_FWD");
+        return ev && ev[0] == 'f';
+    }();
+    uint32_t* sa = nullptr;
+    // round 0 (and every round under KZ_BWT_FWD=full): the whole batch
     for (int round = 0; round < 40; round++) {
         cub::DoubleBuffer<uint64_t> k(keys_a, keys_b);
         cub::DoubleBuffer<uint32_t> v(idx_a, idx_b);
@@ -535,7 +600,7 @@ cudaError_t bwt_forward_batch(const uint8_t* d_in, uint8_t* d_out, const uint64_
         if (e != cudaSuccess) return e;
         (*launches) += 8;
         const uint64_t* sk = k.Current();
-        const uint32_t* sa = v.Current();
+        sa = v.Current();
         cudaMemsetAsync(flags, 0, 4, stream);
         bwt_flag_kernel<<<G, T, 0, stream>>>(sk, total, head);
         scan_max_local_kernel<<<nscan, 256, 0, stream>>>(head, total, block_max);
@@ -553,12 +618,66 @@ cudaError_t bwt_forward_batch(const uint8_t* d_in, uint8_t* d_out, const uint64_
             (*launches) += 2;
             return cudaGetLastError();
         }
+        if (!full_rounds) break;
         bwtb_double_keys_kernel<<<G, T, 0, stream>>>(rank, d_blocks, nb, total, h, lg, keys_a, idx_a);
         (*launches)++;
         h *= 2;
         end_bit = 2 * (int)lg;
     }
-    return cudaErrorUnknown;
+    if (full_rounds) return cudaErrorUnknown;
+    // later rounds: the members of groups with more than one suffix only
+    uint32_t m = 0;
+    {
+        bwtu_flags_full_kernel<<<G, T, 0, stream>>>(head, total, uflags);
+        size_t tb = temp_bytes;
+        e = cub::DeviceSelect::Flagged(temp, tb, cub::CountingInputIterator<uint32_t>(0), uflags, cpos_a, d_count, (int64_t)total, stream);
+        if (e != cudaSuccess) return e;
+        tb = temp_bytes;
+        e = cub::DeviceSelect::Flagged(temp, tb, (const uint32_t*)sa, uflags, cval_a, d_count, (int64_t)total, stream);
+        if (e != cudaSuccess) return e;
+        (*launches) += 5;
+        e = cudaMemcpyAsync(&m, d_count, 4, cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return e;
+    }
+    end_bit = 2 * (int)lg;
+    uint32_t* nhead = head;  // reused: new group heads of the compacted members
+    for (int round = 1; round < 48 && m > 0; round++) {
+        const uint32_t GM = (m + T - 1) / T, nscan_m = (m + 2047) / 2048;
+        bwtu_keys_kernel<<<GM, T, 0, stream>>>(rank, cval_a, m, d_blocks, nb, h, lg, keys_a);
+        cub::DoubleBuffer<uint64_t> k(keys_a, keys_b);
+        cub::DoubleBuffer<uint32_t> v(cval_a, cval_b);
+        size_t tb = temp_bytes;
+        e = cub::DeviceRadixSort::SortPairs(temp, tb, k, v, (int64_t)m, 0, end_bit, stream);
+        if (e != cudaSuccess) return e;
+        bwtu_heads_kernel<<<GM, T, 0, stream>>>(k.Current(), cpos_a, m, nhead);
+        scan_max_local_kernel<<<nscan_m, 256, 0, stream>>>(nhead, m, block_max);
+        scan_max_blocks_kernel<<<1, 1024, 0, stream>>>(block_max, nscan_m);
+        bwtu_apply_kernel<<<GM, T, 0, stream>>>(nhead, block_max, cpos_a, v.Current(), m, sa, rank);
+        (*launches) += 13;
+        h *= 2;
+        if (h >= 2 * (uint64_t)max_n) break;  // every suffix pair has been compared past the end of its block
+        bwtu_flags_kernel<<<GM, T, 0, stream>>>(nhead, cpos_a, m, uflags);
+        tb = temp_bytes;
+        e = cub::DeviceSelect::Flagged(temp, tb, (const uint32_t*)cpos_a, uflags, cpos_b, d_count, (int64_t)m, stream);
+        if (e != cudaSuccess) return e;
+        tb = temp_bytes;
+        uint32_t* other = v.Current() == cval_a ? cval_b : cval_a;
+        e = cub::DeviceSelect::Flagged(temp, tb, (const uint32_t*)v.Current(), uflags, other, d_count, (int64_t)m, stream);
+        if (e != cudaSuccess) return e;
+        (*launches) += 5;
+        e = cudaMemcpyAsync(&m, d_count, 4, cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return e;
+        std::swap(cpos_a, cpos_b);
+        if (other != cval_a) std::swap(cval_a, cval_b);  // the compacted suffixes are the next round's input
+    }
+    bwtb_emit_kernel<<<G, T, 0, stream>>>(d_in, d_blocks, nb, total, sa, rank, d_out);
+    bwtb_header_kernel<<<(nb + 63) / 64, 64, 0, stream>>>(d_blocks, nb, rank, d_out, d_out_len);
+    (*launches) += 2;
+    return cudaGetLastError();
 }
 
 size_t bwt_inverse_workspace(uint32_t n) {

@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(32) fsd_final_kernel(const FsdBlock* __restric
 // tokens (0xFF + payload: out = payload ^ previous) cut it. A round takes 32 source bytes, one per lane:
 //   * which 0xFF bytes are escape markers is a parity question inside runs of 0xFF (a marker's successor is a payload, whatever its value),
 //     answered with one ballot and a clz per lane; the marker state is carried into the next round;
-//   * every byte that is not a marker is one output token; the k-th token moves to lane k (fns on the ballot);
+//   * every byte that is not a marker is one output token; the k-th token moves to lane k (through 64 bytes of shared memory);
 //   * token values: inclusive shuffle scan with stride `dist` over the deltas (escape tokens count as 0) on top of the chain's last value
 //     of earlier rounds (the last 16 outputs live in the registers of lanes 0..15), then one correction per escape token of the round, in
 //     order: E = payload ^ value before it; every later token of its chain moves by E - tentative value;
@@ -368,6 +368,7 @@ __global__ void __launch_bounds__(32) fsd_final_kernel(const FsdBlock* __restric
 // ~250 cycles per 32 bytes instead of ~140 per byte for the one-thread walk this replaces.
 __global__ void __launch_bounds__(32) fsd_inverse_kernel(const uint8_t* __restrict__ in, const FsdBlock* __restrict__ blocks, int nblocks, uint8_t* __restrict__ out,
                                                           FsdResult* __restrict__ res) {
+    __shared__ uint16_t s_tok[32];
     const int b = blockIdx.x, lane = threadIdx.x;
     if (b >= nblocks) return;
     const FsdBlock blk = blocks[b];
@@ -425,10 +426,13 @@ __global__ void __launch_bounds__(32) fsd_inverse_kernel(const uint8_t* __restri
             bad = true;
             break;
         }
-        // token k -> lane k
-        const int from = (uint32_t)lane < m ? (int)__fns(tokens, 0, lane + 1) : 0;
-        const uint32_t tk = __shfl_sync(0xFFFFFFFFu, t, from);
-        const bool is_esc = (uint32_t)lane < m && ((payload >> from) & 1u);
+        // token k -> lane k (through shared memory: every token lane knows its output index by a popc)
+        if ((tokens >> lane) & 1u) s_tok[__popc(tokens & below)] = (uint16_t)(t | (((payload >> lane) & 1u) << 8));
+        __syncwarp();
+        const uint32_t tw = (uint32_t)lane < m ? s_tok[lane] : 0u;
+        __syncwarp();
+        const uint32_t tk = tw & 0xFFu;
+        const bool is_esc = (tw >> 8) != 0;
         uint32_t v;  // value to combine along the chain: the delta, or 0 for an escape token
         if (mode == 0) v = is_esc ? 0u : ((tk & 1u) ? (0u - ((tk + 1u) >> 1)) : (tk >> 1));  // _FSD_ZIGZAG2
         else v = tk;

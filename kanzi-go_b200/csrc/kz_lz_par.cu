@@ -32,6 +32,7 @@ namespace {
 const int SEG = 1024;                // bytes per speculative segment (one warp each)
 const int SEG_CAP = SEG / 4 + 8;     // log entries per segment (a match is at least 4 bytes long)
 const int JCAP = 64;                 // fix-up matches per junction before it gives up (a live one that does sends the block to the serial stitch)
+const int PROBE_CAP = 32;            // bytes a lane follows a match on its own before the warp takes over (a multiple of 8)
 const int WALK_WIN = 4096;           // junction records staged in shared memory per window of the walk
 const int MAX_ROUNDS = 96;
 const int TILE = 1024;               // matches per emission tile
@@ -161,11 +162,51 @@ __device__ __forceinline__ int parse_one_warp(const Params& P, State& st, Match&
         }
         const int pos = st.src_idx + incl - step;
         const bool valid = pos < P.src_end;
-        int best_len = 0, ref = 0, kind = 0, b = 0;
+        int best_len = 0, ref = 0, kind = 0, b = 0, ext = 0;
         bool hit = false;
+        Rec r1, r2;
+        r1.prev = r2.prev = NONE, r1.info = r2.info = 0;
         if (valid) {
+            // probe_first of kz_lz_par_core.cuh with every load issued before the first decision: one memory round trip per round
             const bool swapped = lane == 0 && st.repd_idx != 0;
-            hit = probe_first(P, pos, swapped ? st.repd1 : st.repd0, swapped ? st.repd0 : st.repd1, best_len, ref, kind, b);
+            const int rf = swapped ? st.repd1 : st.repd0, rs = swapped ? st.repd0 : st.repd1;
+            const uint8_t* src = P.src;
+            const int pos1 = pos + 1;
+            const int max_match = imin(P.src_end - pos1, MAX_MATCH);
+            const int min_ref = imax(pos - P.max_dist, 0);
+            const int ref_a = pos1 - rf, ref_b = pos1 - rs;
+            const uint64_t p = ld64(src + pos);
+            const Rec r0 = P.rec[pos];
+            r1 = P.rec[pos + 1];
+            r2 = P.rec[pos + 2];
+            const uint32_t wa = ref_a > min_ref ? ld32(src + ref_a) : 0u, wb = ref_b > min_ref ? ld32(src + ref_b) : 0u;
+            const uint32_t p4 = (uint32_t)(p >> 8);
+            // lengths are followed for PROBE_CAP bytes only here (enough for the decision); the winner's match is extended by the whole warp
+            const int capped = imin(max_match, PROBE_CAP);
+            ref = ref_a;
+            bool rep_probe = false;
+            if (ref_a > min_ref && p4 == wa) {
+                best_len = find_match(src, pos1, ref_a, capped);
+                rep_probe = true;
+            } else {
+                ref = ref_b;
+                if (ref_b > min_ref && p4 == wb) best_len = find_match(src, pos1, ref_b, capped), rep_probe = true;
+            }
+            if (rep_probe && capped < max_match && best_len == (capped & ~7)) ext = 1;  // no mismatch inside the cap
+            if (best_len >= P.min_match) {
+                hit = true;
+            } else {
+                ext = 0;
+                int cand, t;
+                unpack_rec(r0, cand, t, b);
+                if (cand > min_ref && t >= 4) {
+                    const int m8 = imin(P.src_end - pos, MAX_MATCH) & ~7;
+                    if (t < T_CAP || m8 <= T_CAP) best_len = t < m8 ? t : m8;  // match_len without the long compare
+                    else best_len = T_CAP, ext = 2;                              // saturated: at least T_CAP, the winner finds out
+                    if (best_len >= P.min_match) ref = cand, kind = 1, hit = true;
+                    else ext = 0;
+                }
+            }
         }
         const uint32_t hits = __ballot_sync(0xFFFFFFFFu, hit), vmask = __ballot_sync(0xFFFFFFFFu, valid);
         if (hits == 0) {
@@ -187,7 +228,17 @@ __device__ __forceinline__ int parse_one_warp(const Params& P, State& st, Match&
         ref = __shfl_sync(0xFFFFFFFFu, ref, w);
         kind = __shfl_sync(0xFFFFFFFFu, kind, w);
         b = __shfl_sync(0xFFFFFFFFu, b, w);
-        probe_finish(P, st, best_len, ref, kind, b, m);
+        r1.prev = __shfl_sync(0xFFFFFFFFu, r1.prev, w), r1.info = __shfl_sync(0xFFFFFFFFu, r1.info, w);
+        r2.prev = __shfl_sync(0xFFFFFFFFu, r2.prev, w), r2.info = __shfl_sync(0xFFFFFFFFu, r2.info, w);
+        ext = __shfl_sync(0xFFFFFFFFu, ext, w);
+        if (ext == 1) {  // repeat-distance match longer than the cap (findMatchLZX from the probe's successor)
+            best_len = find_match_w(P.src, st.src_idx + 1, ref, PROBE_CAP & ~7, imin(P.src_end - (st.src_idx + 1), MAX_MATCH));
+        } else if (ext == 2) {  // table match with a saturated prefix length
+            const int m8 = imin(P.src_end - st.src_idx, MAX_MATCH) & ~7;
+            const int tt = common_prefix_w(P.src, P.count, st.src_idx, ref, T_CAP & ~7, m8 + 8);
+            best_len = tt < m8 ? tt : m8;
+        }
+        probe_finish<true>(P, st, best_len, ref, kind, b, r1, r2, m);
         return R_MATCH;
     }
 }
@@ -801,17 +852,17 @@ cudaError_t lz_forward_parallel_sub(const uint8_t* d_in, uint8_t* d_out, const L
             rec_r = d_rec2;
         }
         {
-            LzHookScope hs(hook, "lz_spec");
+            LzHookScope hs(hook, round == 0 ? "lz_spec_r0" : (round == 1 ? "lz_spec_r1" : "lz_spec"));
             lzp_spec_kernel<<<(NS + 3) / 4, 128, 0, stream>>>(d_in, d_pb, d_bos, extra ? 1 : 0, d_acts, NS, rec_r, d_logs, d_desc);
         }
         {
-            LzHookScope hs(hook, "lz_stitch");
+            LzHookScope hs(hook, round == 0 ? "lz_stitch_r0" : (round == 1 ? "lz_stitch_r1" : "lz_stitch"));
             lzp_junction_kernel<<<(NS + 3) / 4, 128, 0, stream>>>(d_in, d_pb, d_bos, extra ? 1 : 0, d_acts, NS, rec_r, d_logs, d_desc, d_jfix, d_junc);
             lzp_walk_kernel<<<NB, 256, 0, stream>>>(d_pb, d_actb, d_desc, d_junc, d_pieces, d_pstart, d_pst);
             lzp_stitch_kernel<<<NB, 32, 0, stream>>>(d_in, d_pb, d_actb, extra ? 1 : 0, rec_r, d_logs, d_desc, d_fix, d_pieces, d_pstart, d_pst);
         }
         {
-            LzHookScope hs(hook, "lz_derive");
+            LzHookScope hs(hook, round == 0 ? "lz_derive_r0" : (round == 1 ? "lz_derive_r1" : "lz_derive"));
             lzp_flatten_kernel<<<dim3(64, NB), 256, 0, stream>>>(d_pb, d_actb, d_pst, d_pieces, d_pstart, d_logs, d_jfix, d_fix, d_ml);
             cudaMemsetAsync(d_changed, 0, (size_t)nblocks * 4, stream);
             lzp_derive_kernel<<<GA, 256, 0, stream>>>(d_pb, d_boc, d_actc, d_pst, d_ml, d_vf, d_vf2, d_changed, total);

@@ -150,6 +150,64 @@ KZL_HD int common_suffix(const uint8_t* src, int a, int b, int from, int limit) 
     return t;
 }
 
+#if defined(__CUDACC__)
+// Warp-uniform versions (every lane passes the same arguments): 32 x 8 bytes per step forwards, 32 bytes per step backwards. A match of
+// MAX_MATCH bytes costs 257 steps instead of 8 K dependent loads; the speculative parse meets such matches in every segment they cover.
+__device__ __forceinline__ int common_prefix_w(const uint8_t* src, int count, int a, int b, int from, int limit) {
+    limit = imin(limit, count - a);
+    const int lane = threadIdx.x & 31;
+    int t = from;
+    while (t < limit) {
+        const int o = t + 8 * lane;
+        uint64_t diff = 0;
+        if (o < limit) diff = ld64(src + a + o) ^ ld64(src + b + o);
+        const uint32_t mm = __ballot_sync(0xFFFFFFFFu, diff != 0);
+        if (mm) {
+            const int l = __ffs((int)mm) - 1;
+            const uint64_t d = __shfl_sync(0xFFFFFFFFu, diff, l);
+            t += 8 * l + (ctz64(d) >> 3);
+            break;
+        }
+        t += 256;
+    }
+    return imin(t, limit);
+}
+__device__ __forceinline__ int common_suffix_w(const uint8_t* src, int a, int b, int from, int limit) {
+    limit = imin(limit, b);
+    const int lane = threadIdx.x & 31;
+    int t = from;
+    while (t < limit) {
+        const int o = t + lane;
+        const bool ne = o < limit && src[a - 1 - o] != src[b - 1 - o];
+        const uint32_t mm = __ballot_sync(0xFFFFFFFFu, ne);
+        if (mm) {
+            t += __ffs((int)mm) - 1;
+            break;
+        }
+        t += 32;
+    }
+    return imin(t, limit);
+}
+// find_match continued from offset `from` (a multiple of 8 below which the two strings are equal)
+__device__ __forceinline__ int find_match_w(const uint8_t* src, int a, int b, int from, int maxm) {
+    const int lane = threadIdx.x & 31;
+    int best = from;
+    while (best + 8 <= maxm) {
+        const int o = best + 8 * lane;
+        uint64_t diff = 0;
+        if (o + 8 <= maxm) diff = ld64(src + a + o) ^ ld64(src + b + o);
+        const uint32_t mm = __ballot_sync(0xFFFFFFFFu, diff != 0);
+        if (mm) {
+            const int l = __ffs((int)mm) - 1;
+            const uint64_t d = __shfl_sync(0xFFFFFFFFu, diff, l);
+            return best + 8 * l + (ctz64(d) >> 3);
+        }
+        best += 256;
+    }
+    return imin(best, maxm & ~7);
+}
+#endif
+
 // ---- per position precomputation (position i, candidate c = prev[i]) -------------------------------------------------------------
 KZL_HD uint32_t make_info(const uint8_t* src, int count, int i, uint32_t c) {
     if (c == NONE) return 0;
@@ -166,12 +224,21 @@ KZL_HD void lookup(const Params& P, int i, int& cand, int& t, int& b) {
     cand = r.prev == NONE ? 0 : (int)r.prev;  // position 0 is never accepted (ref > minRef >= 0), like an empty table slot
 }
 // true prefix length as far as `limit` matters (the stored one saturates at T_CAP)
+// W: called with the same arguments by all lanes of a warp (the uniform second stage of the warp-cooperative parse): the long compares are shared
+template <bool W = false>
 KZL_HD int full_t(const Params& P, int i, int cand, int t, int limit) {
     if (t < T_CAP || limit <= T_CAP) return t;
+#if defined(__CUDA_ARCH__)
+    if (W) return common_prefix_w(P.src, P.count, i, cand, T_CAP & ~7, limit + 8);
+#endif
     return common_prefix(P.src, P.count, i, cand, T_CAP & ~7, limit + 8);
 }
+template <bool W = false>
 KZL_HD int full_b(const Params& P, int i, int cand, int b, int limit) {
     if (b < B_CAP || limit <= B_CAP) return b;
+#if defined(__CUDA_ARCH__)
+    if (W) return common_suffix_w(P.src, i, cand, B_CAP, limit);
+#endif
     return common_suffix(P.src, i, cand, B_CAP, limit);
 }
 // what findMatchLZX(src, i, cand, maxm) returns, from the prefix length
@@ -263,7 +330,14 @@ KZL_HD bool probe_first(const Params& P, int src_idx, int repd_first, int repd_s
 }
 // Second stage of a probe that found a match (:368-414): lazy checks at +1 / +2 and backward extension for a table match, the one byte
 // backward step of a repeat match. `st` is the state at the probe (st.src_idx = the probe's position); on return it stands behind the match.
-KZL_HD void probe_finish(const Params& P, State& st, int best_len, int ref, int kind, int b, Match& m) {
+KZL_HD void unpack_rec(const Rec& r, int& cand, int& t, int& b) {
+    t = (int)(r.info & 0xFF);
+    b = (int)((r.info >> 8) & 0xFF);
+    cand = r.prev == NONE ? 0 : (int)r.prev;
+}
+// rec1 / rec2: the table entries of the two positions behind the probe (the lazy checks), loaded by the caller together with everything else
+template <bool W = false>
+KZL_HD void probe_finish(const Params& P, State& st, int best_len, int ref, int kind, int b, const Rec& rec1, const Rec& rec2, Match& m) {
     const uint8_t* src = P.src;
     const int src_end = P.src_end;
     int src_idx = st.src_idx;
@@ -274,11 +348,11 @@ KZL_HD void probe_finish(const Params& P, State& st, int best_len, int ref, int 
         int bsel = b, isel = src_idx;  // suffix length / position of the selected candidate pair
         if (ref != src_idx - st.repd0 && ref != src_idx - st.repd1) {
             int c1, t1, b1;
-            lookup(P, src_idx1, c1, t1, b1);
+            unpack_rec(rec1, c1, t1, b1);
             if (c1 > min_ref + 1) {
                 const int m8 = max_match & ~7;
-                if (m8 >= best_len && full_t(P, src_idx1, c1, t1, best_len + 1) >= best_len + 1) {
-                    const int tt = full_t(P, src_idx1, c1, t1, m8);
+                if (m8 >= best_len && full_t<W>(P, src_idx1, c1, t1, best_len + 1) >= best_len + 1) {
+                    const int tt = full_t<W>(P, src_idx1, c1, t1, m8);
                     best_len = tt < m8 ? tt : m8;
                     ref = c1;
                     src_idx = src_idx1;
@@ -289,11 +363,11 @@ KZL_HD void probe_finish(const Params& P, State& st, int best_len, int ref, int 
             if (P.extra) {
                 const int src_idx2 = src_idx1 + 1;
                 int c2, t2, b2;
-                lookup(P, src_idx2, c2, t2, b2);
+                unpack_rec(rec2, c2, t2, b2);
                 if (c2 > min_ref + 2) {
                     const int m8 = imin(src_end - src_idx2, MAX_MATCH) & ~7;
-                    if (m8 >= best_len && full_t(P, src_idx2, c2, t2, best_len + 1) >= best_len + 1) {
-                        const int tt = full_t(P, src_idx2, c2, t2, m8);
+                    if (m8 >= best_len && full_t<W>(P, src_idx2, c2, t2, best_len + 1) >= best_len + 1) {
+                        const int tt = full_t<W>(P, src_idx2, c2, t2, m8);
                         best_len = tt < m8 ? tt : m8;
                         ref = c2;
                         src_idx = src_idx2;
@@ -306,7 +380,7 @@ KZL_HD void probe_finish(const Params& P, State& st, int best_len, int ref, int 
         {  // extend backwards (:403-407)
             const int room = imin(src_idx - st.anchor, ref - min_ref);
             if (room > 0 && bsel > 0) {
-                const int ext = imin(full_b(P, isel, ref, bsel, room), room);
+                const int ext = imin(full_b<W>(P, isel, ref, bsel, room), room);
                 best_len += ext;
                 ref -= ext;
                 src_idx -= ext;
@@ -347,7 +421,7 @@ KZL_HD int parse_one(const Params& P, State& st, Match& m) {
             st.repd_idx = 0;
             continue;
         }
-        probe_finish(P, st, best_len, ref, kind, b, m);
+        probe_finish(P, st, best_len, ref, kind, b, P.rec[st.src_idx + 1], P.rec[st.src_idx + 2], m);
         return R_MATCH;
     }
     return R_END;

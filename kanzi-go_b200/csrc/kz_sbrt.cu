@@ -429,6 +429,84 @@ __global__ void __launch_bounds__(32) sbrt_inverse_warp_kernel(const uint8_t* __
     }
 }
 
+// ---- inverse, branch-free variant of the warp-resident list (default for blocks <= 16 MiB) ------------------------------------------------
+// The ncu source view of the kernel above (profiles/r02_ncu_sbrt_inverse.md) shows one warp issuing ~77 instructions per rank at an IPC of
+// 0.33: a quarter of the stall samples sit on the loop / path branches and their targets, a tenth on an S2R + shared-memory address per
+// stored byte, the rest is the dependent issue latency of a single warp. This variant has no branch inside a round of 32 ranks: the round is
+// fully unrolled (the next rank is a shuffle from a constant lane), every rank — zero included — takes the same predicated move-up over the
+// 8 entries of every lane, and the decoded byte of step j is kept in a register of lane j. ~55 instructions per rank, no S2R, no LDC.
+template <bool RANK_MODE>
+__global__ void __launch_bounds__(32) sbrt_inverse_flat_kernel(const uint8_t* __restrict__ data, const SbrtBlock* __restrict__ blocks, int nblocks,
+                                                                uint8_t* __restrict__ out) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (b >= nblocks) return;
+    const SbrtBlock blk = blocks[b];
+    if (!blk.active) return;
+    const uint8_t* src = data + blk.src_off;
+    uint8_t* dst = out + blk.dst_off;
+    const uint32_t n = blk.len;
+    uint32_t Q[8], X[8];  // lane l holds ranks 8 l .. 8 l + 7: q and (p << 8 | symbol)
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        Q[k] = 0;
+        X[k] = (uint32_t)(8 * lane + k);
+    }
+    const uint32_t base = 8u * (uint32_t)lane;
+    auto step = [&](uint32_t r, uint32_t i) -> uint32_t {
+        // the entry of rank r: a select tree over the three low bits of r in every lane, one shuffle from the owner lane
+        const uint32_t up_q = __shfl_up_sync(0xFFFFFFFFu, Q[7], 1), up_x = __shfl_up_sync(0xFFFFFFFFu, X[7], 1);
+        const bool b0 = r & 1u, b1 = r & 2u, b2 = r & 4u;
+        const uint32_t a0 = b0 ? X[1] : X[0], a1 = b0 ? X[3] : X[2], a2 = b0 ? X[5] : X[4], a3 = b0 ? X[7] : X[6];
+        const uint32_t c0 = b1 ? a1 : a0, c1 = b1 ? a3 : a2;
+        const uint32_t x = __shfl_sync(0xFFFFFFFFu, b2 ? c1 : c0, (int)(r >> 3));
+        const uint32_t sym = x & 0xFFu;
+        const uint32_t qc = RANK_MODE ? (i + (x >> 8)) >> 1 : i;  // i, p < 2^24
+        const uint32_t fresh = (i << 8) | sym;
+        // local move-up rule (see above): position j <= r with q[j] <= qc takes the accessed symbol if q[j - 1] > qc, else the entry of j - 1
+        // d = r - base: slot k of this lane is at or below the accessed rank when k <= d
+        const int d = (int)r - (int)base;
+        bool gk = Q[7] > qc;
+#pragma unroll
+        for (int k = 7; k >= 1; k--) {
+            const bool gk1 = Q[k - 1] > qc;
+            const bool mv = k <= d && !gk;
+            const uint32_t xin = gk1 ? fresh : X[k - 1];
+            Q[k] = mv ? min(Q[k - 1], qc) : Q[k];  // g[k - 1] ? qc : Q[k - 1]
+            X[k] = mv ? xin : X[k];
+            gk = gk1;
+        }
+        {
+            const bool g_up = lane == 0 ? true : up_q > qc;
+            const bool mv = 0 <= d && !gk;
+            Q[0] = mv ? (g_up ? qc : up_q) : Q[0];
+            X[0] = mv ? (g_up ? fresh : up_x) : X[0];
+        }
+        return sym;
+    };
+    uint32_t nxt = (uint32_t)lane < n ? src[lane] : 0u;
+    uint32_t i0 = 0;
+    for (; i0 + 32 <= n; i0 += 32) {
+        const uint32_t mine = nxt;
+        nxt = i0 + 32 + lane < n ? src[i0 + 32 + lane] : 0u;  // next round's ranks in flight
+        uint32_t ob = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const uint32_t sym = step(__shfl_sync(0xFFFFFFFFu, mine, j), i0 + (uint32_t)j);
+            ob = lane == j ? sym : ob;
+        }
+        dst[i0 + lane] = (uint8_t)ob;
+    }
+    if (i0 < n) {  // last, partial round
+        const uint32_t mine = nxt;
+        uint32_t ob = 0;
+        for (uint32_t j = 0; i0 + j < n; j++) {
+            const uint32_t sym = step(__shfl_sync(0xFFFFFFFFu, mine, (int)j), i0 + j);
+            ob = (uint32_t)lane == j ? sym : ob;
+        }
+        if (i0 + lane < n) dst[i0 + lane] = (uint8_t)ob;
+    }
+}
+
 // host entry. KZ_SBRT_INV=lane selects the round-1 kernel (lane 0 walks the chain; kept for comparison); packed = every block < 128 MiB
 void sbrt_inverse_launch(const uint8_t* data, const SbrtBlock* d_blocks, int nblocks, int mode, uint8_t* out, bool packed, cudaStream_t stream) {
     static const bool old_kernel = [] {
@@ -452,7 +530,14 @@ void sbrt_inverse_launch_len(const uint8_t* data, const SbrtBlock* d_blocks, int
         sbrt_inverse_launch(data, d_blocks, nblocks, mode, out, max_len < (1u << 27), stream);
         return;
     }
-    if (max_len <= (1u << 24)) sbrt_inverse_warp_kernel<uint32_t><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, mode, out);
+    static const bool branchy = [] {  // KZ_SBRT_INV=warp: the first warp-resident kernel (run skipping, separate paths for ranks < 8)
+        const char* e = getenv("KZ_SBRT_INV");
+        return e && e[0] == 'w';
+    }();
+    if (max_len <= (1u << 24) && !branchy && (mode == 1 || mode == 2)) {
+        if (mode == 2) sbrt_inverse_flat_kernel<true><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, out);
+        else sbrt_inverse_flat_kernel<false><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, out);
+    } else if (max_len <= (1u << 24)) sbrt_inverse_warp_kernel<uint32_t><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, mode, out);
     else sbrt_inverse_warp_kernel<uint64_t><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, mode, out);
 }
 
