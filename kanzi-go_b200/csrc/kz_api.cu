@@ -1428,18 +1428,49 @@ int apply_inverse(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint8_t* d_out, 
         std::vector<uint8_t> heads((size_t)nblocks * 64, 0);
         CK(cudaMemcpy2DAsync(heads.data(), 64, d_in, stride, 33, nblocks, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        uint32_t max_len = 0;
-        for (uint32_t b = 0; b < nblocks; b++) max_len = std::max(max_len, len[b]);
-        CK(ctx->d_ws.ensure(bwt_inverse_workspace(max_len)));
-        for (uint32_t b = 0; b < nblocks; b++) {
-            if (!active[b]) continue;
-            uint32_t produced = 0;
-            LaunchScope ls(ctx, "bwt_inverse");
-            cudaError_t e = bwt_inverse_device(d_in + b * stride, &heads[(size_t)b * 64], len[b], d_out + b * stride, cap, &produced, ctx->d_ws.as<uint8_t>(),
-                                               ctx->d_ws.cap, ctx->stream, &ctx->launches);
-            if (e == cudaErrorInvalidValue) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "BWT inverse transform failed: invalid header");
-            if (e != cudaSuccess) return ctx->cuda_fail(e, "bwt_inverse");
-            len[b] = produced;
+        static const bool one_by_one = [] {  // KZ_BWT_INV=single: one set of launches per block (round 1)
+            const char* e = getenv("KZ_BWT_INV");
+            return e && e[0] == 's';
+        }();
+        if (one_by_one) {
+            uint32_t max_len = 0;
+            for (uint32_t b = 0; b < nblocks; b++) max_len = std::max(max_len, len[b]);
+            CK(ctx->d_ws.ensure(bwt_inverse_workspace(max_len)));
+            for (uint32_t b = 0; b < nblocks; b++) {
+                if (!active[b]) continue;
+                uint32_t produced = 0;
+                LaunchScope ls(ctx, "bwt_inverse");
+                cudaError_t e = bwt_inverse_device(d_in + b * stride, &heads[(size_t)b * 64], len[b], d_out + b * stride, cap, &produced, ctx->d_ws.as<uint8_t>(),
+                                                   ctx->d_ws.cap, ctx->stream, &ctx->launches);
+                if (e == cudaErrorInvalidValue) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "BWT inverse transform failed: invalid header");
+                if (e != cudaSuccess) return ctx->cuda_fail(e, "bwt_inverse");
+                len[b] = produced;
+            }
+        } else {
+            for (uint32_t b0 = 0; b0 < nblocks;) {
+                std::vector<uint64_t> so, dof;
+                std::vector<uint32_t> ll, num;
+                std::vector<uint8_t> hh;
+                uint64_t total = 0;
+                uint32_t b = b0;
+                for (; b < nblocks; b++) {
+                    if (!active[b]) continue;
+                    if (!ll.empty() && (total + len[b] > bwt_inverse_batch_max_total() || ll.size() >= bwt_inverse_batch_max_blocks())) break;
+                    so.push_back(b * stride), dof.push_back(b * stride), ll.push_back(len[b]), num.push_back(b);
+                    hh.insert(hh.end(), heads.begin() + (size_t)b * 64, heads.begin() + (size_t)(b + 1) * 64);
+                    total += len[b];
+                }
+                b0 = b;
+                if (ll.empty()) continue;
+                CK(ctx->d_ws.ensure(bwt_inverse_batch_workspace(total, (uint32_t)ll.size())));
+                std::vector<uint32_t> produced(ll.size(), 0);
+                LaunchScope ls(ctx, "bwt_inverse");
+                cudaError_t e = bwt_inverse_batch(d_in, d_out, so.data(), dof.data(), ll.data(), hh.data(), (uint32_t)ll.size(), cap, produced.data(),
+                                                  ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap, ctx->stream, &ctx->launches);
+                if (e == cudaErrorInvalidValue) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "BWT inverse transform failed: invalid header");
+                if (e != cudaSuccess) return ctx->cuda_fail(e, "bwt_inverse");
+                for (size_t k = 0; k < num.size(); k++) len[num[k]] = produced[k];
+            }
         }
     } else if (t == KZ_T_BWTS) {
         uint32_t max_len = 0;

@@ -770,6 +770,229 @@ cudaError_t bwt_inverse_device(const uint8_t* d_src, const uint8_t* h_header /*f
 }
 
 
+// ---- inverse, all blocks of a batch together ---------------------------------------------------------------------------------------------------
+// Same algorithm as bwt_inverse_device; one position space for the batch (block b = [base, base + n)), the block index above the byte in the
+// key of the stable sort (so the LF mapping of block b lands in its own range), one head list for all blocks, one set of launches: a 4 MiB
+// block is 17 pointer-doubling launches of a few hundred threads each, 48 blocks one after another were mostly launch latency.
+namespace {
+struct IbwtBatchBlock {
+    uint64_t src_off, dst_off;  // BWT bytes (behind the header) / output
+    uint32_t base, n;
+    uint32_t hbase, nstride;    // first head id of the block, heads on stride multiples (followed by the nprim primary heads)
+    uint32_t nprim, pad;
+    uint32_t prim[8];           // primary ranks (local), 0xFFFFFFFF when absent
+};
+const int IBWT_BATCH_MAX = 1024;
+__device__ __forceinline__ uint32_t ibwtb_find(const uint32_t* __restrict__ s_base, uint32_t nb, uint32_t i) {
+    uint32_t lo = 0, hi = nb;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s_base[mid] <= i) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+__global__ void __launch_bounds__(256) ibwtb_init_kernel(const uint8_t* __restrict__ in, const IbwtBatchBlock* __restrict__ blocks, uint32_t nb, uint32_t total,
+                                                          uint16_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    __shared__ uint32_t s_base[IBWT_BATCH_MAX];
+    for (uint32_t k = threadIdx.x; k < nb; k += 256) s_base[k] = blocks[k].base;
+    __syncthreads();
+    const uint32_t g = blockIdx.x * 256 + threadIdx.x;
+    if (g >= total) return;
+    const uint32_t b = ibwtb_find(s_base, nb, g);
+    const IbwtBatchBlock& B = blocks[b];
+    const uint32_t i = g - B.base;
+    const uint32_t pidx = B.prim[0] + 1;
+    keys[g] = (uint16_t)((b << 8) | in[B.src_off + i]);
+    vals[g] = i == 0 ? 0xFFFFFFFFu : B.base + (i < pidx ? i - 1 : i);
+}
+__device__ __forceinline__ bool ibwtb_is_head(uint32_t t_local, const IbwtBatchBlock& B) {
+    if ((t_local & (IBWT_STRIDE - 1)) == 0) return true;
+    for (uint32_t k = 0; k < B.nprim; k++)
+        if (t_local == B.prim[k]) return true;
+    return false;
+}
+__device__ __forceinline__ uint32_t ibwtb_head_id(uint32_t t_local, const IbwtBatchBlock& B) {
+    if ((t_local & (IBWT_STRIDE - 1)) == 0) return B.hbase + t_local / IBWT_STRIDE;
+    for (uint32_t k = 0; k < B.nprim; k++)
+        if (t_local == B.prim[k]) return B.hbase + B.nstride + k;
+    return 0xFFFFFFFFu;
+}
+__global__ void __launch_bounds__(256) ibwtb_measure_kernel(const uint32_t* __restrict__ next, const IbwtBatchBlock* __restrict__ blocks, uint32_t nb, uint32_t nheads,
+                                                             uint32_t* __restrict__ succ, uint32_t* __restrict__ len, uint64_t* __restrict__ dist0) {
+    __shared__ uint32_t s_hbase[IBWT_BATCH_MAX];
+    for (uint32_t k = threadIdx.x; k < nb; k += 256) s_hbase[k] = blocks[k].hbase;
+    __syncthreads();
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= nheads) return;
+    const uint32_t b = ibwtb_find(s_hbase, nb, j);
+    const IbwtBatchBlock B = blocks[b];
+    const uint32_t jl = j - B.hbase;
+    uint32_t t = jl < B.nstride ? jl * IBWT_STRIDE : B.prim[jl - B.nstride];
+    if (t >= B.n || (jl >= B.nstride && (t & (IBWT_STRIDE - 1)) == 0)) {  // duplicate head or out of range
+        succ[j] = 0xFFFFFFFEu;
+        len[j] = 0;
+        dist0[j] = 0;
+        return;
+    }
+    uint32_t l = 0;
+    uint32_t g = B.base + t;
+    for (;;) {
+        g = next[g];
+        l++;
+        if (g == 0xFFFFFFFFu) {
+            succ[j] = 0xFFFFFFFFu;
+            break;
+        }
+        const uint32_t tl = g - B.base;
+        if (g < B.base || tl >= B.n || l > B.n) {  // corrupt permutation
+            succ[j] = 0xFFFFFFFDu;
+            break;
+        }
+        if (ibwtb_is_head(tl, B)) {
+            succ[j] = ibwtb_head_id(tl, B);
+            break;
+        }
+    }
+    len[j] = l;
+    dist0[j] = l;
+}
+__global__ void __launch_bounds__(256) ibwtb_write_kernel(const uint32_t* __restrict__ next, const uint16_t* __restrict__ first, const IbwtBatchBlock* __restrict__ blocks,
+                                                           uint32_t nb, uint32_t nheads, const uint32_t* __restrict__ succ0, const uint32_t* __restrict__ len,
+                                                           const uint64_t* __restrict__ dist, uint8_t* __restrict__ out) {
+    __shared__ uint32_t s_hbase[IBWT_BATCH_MAX];
+    for (uint32_t k = threadIdx.x; k < nb; k += 256) s_hbase[k] = blocks[k].hbase;
+    __syncthreads();
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= nheads) return;
+    if (succ0[j] == 0xFFFFFFFEu) return;
+    const uint32_t b = ibwtb_find(s_hbase, nb, j);
+    const IbwtBatchBlock B = blocks[b];
+    const uint32_t jl = j - B.hbase;
+    const uint32_t t = jl < B.nstride ? jl * IBWT_STRIDE : B.prim[jl - B.nstride];
+    const uint64_t d = dist[j];
+    if (d > B.n) return;  // head not on the main list (corrupt input)
+    uint8_t* dst = out + B.dst_off;
+    const uint64_t off = (uint64_t)B.n - d;
+    const uint32_t l = len[j];
+    uint32_t g = B.base + t;
+    for (uint32_t i = 0; i < l; i++) {
+        if (off + i < B.n) dst[off + i] = (uint8_t)first[g];
+        g = next[g];
+        if (g - B.base >= B.n) break;
+    }
+}
+}  // namespace
+
+size_t bwt_inverse_batch_workspace(uint64_t total, uint32_t nblocks) {
+    size_t temp = 0;
+    cub::DoubleBuffer<uint16_t> k(nullptr, nullptr);
+    cub::DoubleBuffer<uint32_t> v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, k, v, (int64_t)total, 0, 16);
+    const size_t nheads = (size_t)total / IBWT_STRIDE + (size_t)nblocks * 10 + 16;
+    return (size_t)total * (2 * 2 + 4 * 2) + nheads * (4 * 4 + 8 * 2) + (size_t)nblocks * sizeof(IbwtBatchBlock) + 16 * 256 + temp + 4096;
+}
+uint64_t bwt_inverse_batch_max_total() { return (1ull << 31) - 1; }
+uint32_t bwt_inverse_batch_max_blocks() { return 256; }  // 8 bits of block index above the byte in a 16-bit key
+
+// BWTBlockCodec.Inverse of blocks k = 0..nb-1: stream at d_in + src_off[k] (len_of[k] bytes), h_headers + 64 k = its first 33 bytes on the host.
+// out_len[k] = decoded length. cudaErrorInvalidValue: a malformed header (checked before anything is launched).
+cudaError_t bwt_inverse_batch(const uint8_t* d_in, uint8_t* d_out, const uint64_t* src_off, const uint64_t* dst_off, const uint32_t* len_of, const uint8_t* h_headers,
+                              uint32_t nb, uint32_t cap, uint32_t* out_len, uint8_t* ws, size_t ws_bytes, cudaStream_t stream, uint64_t* launches) {
+    if (nb == 0) return cudaSuccess;
+    if (nb > bwt_inverse_batch_max_blocks()) return cudaErrorInvalidValue;
+    std::vector<IbwtBatchBlock> hb;
+    hb.reserve(nb);
+    uint64_t total64 = 0, heads64 = 0;
+    struct Tiny {
+        uint64_t src, dst;
+    };
+    std::vector<Tiny> singles;
+    for (uint32_t k = 0; k < nb; k++) {
+        const uint32_t len = len_of[k];
+        const uint8_t* hh = h_headers + (size_t)k * 64;
+        if (len < 2) return cudaErrorInvalidValue;
+        const uint8_t mode = hh[0];
+        const uint32_t log_chunks = (mode >> 2) & 7;
+        const int pidx_size = (int)(mode & 3) + 1;
+        const uint32_t chunks = 1u << log_chunks;
+        const uint32_t header = chunks * pidx_size + 1;
+        if (len < header || chunks > 8) return cudaErrorInvalidValue;
+        const uint32_t n = len - header;
+        if (chunks != (n < 256 ? 1u : 8u)) return cudaErrorInvalidValue;
+        out_len[k] = n;
+        if (n == 0) continue;
+        if (n > cap) return cudaErrorInvalidValue;
+        IbwtBatchBlock B;
+        for (uint32_t i = 0; i < 8; i++) B.prim[i] = 0xFFFFFFFFu;
+        for (uint32_t i = 0, idx = 1; i < chunks; i++) {
+            uint32_t p = 0;
+            for (int q = 0; q < pidx_size; q++) p = (p << 8) | hh[idx++];
+            const uint32_t pr = p + 1;
+            if (pr == 0 || pr > n) return cudaErrorInvalidValue;
+            B.prim[i] = pr - 1;
+        }
+        if (n == 1) {
+            singles.push_back(Tiny{src_off[k] + header, dst_off[k]});
+            continue;
+        }
+        B.src_off = src_off[k] + header, B.dst_off = dst_off[k], B.base = (uint32_t)total64, B.n = n;
+        B.hbase = (uint32_t)heads64, B.nstride = (n + IBWT_STRIDE - 1) / IBWT_STRIDE, B.nprim = chunks, B.pad = 0;
+        total64 += n;
+        heads64 += B.nstride + B.nprim;
+        hb.push_back(B);
+    }
+    cudaError_t e;
+    for (const Tiny& t : singles)
+        if ((e = cudaMemcpyAsync(d_out + t.dst, d_in + t.src, 1, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) return e;
+    if (hb.empty()) return cudaSuccess;
+    if (total64 > bwt_inverse_batch_max_total()) return cudaErrorInvalidValue;
+    const uint32_t total = (uint32_t)total64, nheads = (uint32_t)heads64, nbb = (uint32_t)hb.size();
+    auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
+    size_t off = 0;
+    uint16_t* keys_a = (uint16_t*)(ws + off); off = align(off + (size_t)total * 2);
+    uint16_t* keys_b = (uint16_t*)(ws + off); off = align(off + (size_t)total * 2);
+    uint32_t* val_a = (uint32_t*)(ws + off); off = align(off + (size_t)total * 4);
+    uint32_t* val_b = (uint32_t*)(ws + off); off = align(off + (size_t)total * 4);
+    uint32_t* succ_a = (uint32_t*)(ws + off); off = align(off + (size_t)nheads * 4);
+    uint32_t* succ_b = (uint32_t*)(ws + off); off = align(off + (size_t)nheads * 4);
+    uint32_t* succ0 = (uint32_t*)(ws + off); off = align(off + (size_t)nheads * 4);
+    uint32_t* lenv = (uint32_t*)(ws + off); off = align(off + (size_t)nheads * 4);
+    uint64_t* dist_a = (uint64_t*)(ws + off); off = align(off + (size_t)nheads * 8);
+    uint64_t* dist_b = (uint64_t*)(ws + off); off = align(off + (size_t)nheads * 8);
+    IbwtBatchBlock* d_blocks = (IbwtBatchBlock*)(ws + off); off = align(off + (size_t)nbb * sizeof(IbwtBatchBlock));
+    void* temp = ws + off;
+    if (ws_bytes < off) return cudaErrorInvalidValue;
+    const size_t temp_bytes = ws_bytes - off;
+    if ((e = cudaMemcpyAsync(d_blocks, hb.data(), (size_t)nbb * sizeof(IbwtBatchBlock), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+    const uint32_t T = 256, G = (total + T - 1) / T, GH = (nheads + T - 1) / T;
+    ibwtb_init_kernel<<<G, T, 0, stream>>>(d_in, d_blocks, nbb, total, keys_a, val_a);
+    cub::DoubleBuffer<uint16_t> k(keys_a, keys_b);
+    cub::DoubleBuffer<uint32_t> v(val_a, val_b);
+    size_t tb = temp_bytes;
+    int key_bits = 8;
+    while ((1u << (key_bits - 8)) < nbb) key_bits++;
+    if ((e = cub::DeviceRadixSort::SortPairs(temp, tb, k, v, (int64_t)total, 0, key_bits, stream)) != cudaSuccess) return e;  // stable: LF mapping per block
+    const uint16_t* first = k.Current();
+    const uint32_t* next = v.Current();
+    ibwtb_measure_kernel<<<GH, T, 0, stream>>>(next, d_blocks, nbb, nheads, succ0, lenv, dist_a);
+    if ((e = cudaMemcpyAsync(succ_a, succ0, (size_t)nheads * 4, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) return e;
+    (*launches) += 8;
+    uint32_t max_heads = 1;
+    for (const IbwtBatchBlock& B : hb) max_heads = std::max(max_heads, B.nstride + B.nprim);
+    uint32_t rounds = 1;
+    while ((1u << rounds) < max_heads) rounds++;
+    for (uint32_t r = 0; r < rounds + 1; r++) {
+        ibwt_jump_kernel<<<GH, T, 0, stream>>>(succ_a, dist_a, nheads, succ_b, dist_b);
+        std::swap(succ_a, succ_b);
+        std::swap(dist_a, dist_b);
+        (*launches)++;
+    }
+    ibwtb_write_kernel<<<GH, T, 0, stream>>>(next, first, d_blocks, nbb, nheads, succ0, lenv, dist_a, d_out);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // BWTS (bijective BWT, transform/BWTS.go:58-170 Forward, :211-288 Inverse).
 //

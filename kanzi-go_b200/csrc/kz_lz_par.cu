@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) lzp_info_kernel(const uint8_t* __restrict
 // candidates of a round: the first position of the prev[] chain that is in the table (vf) when the position is probed
 __global__ void __launch_bounds__(256) lzp_filter_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_chunk,
                                                           const uint32_t* __restrict__ act_chunks, const Rec* __restrict__ rec0, const uint32_t* __restrict__ vf,
-                                                          Rec* __restrict__ rec, uint64_t total) {
+                                                          Rec* __restrict__ rec, uint64_t total, int first_filter, uint32_t* __restrict__ dirty) {
     const uint64_t g = (uint64_t)act_chunks[blockIdx.x >> 2] * 1024 + (blockIdx.x & 3) * 256 + threadIdx.x;  // only chunks of unfinished blocks are launched
     if (g >= total) return;
     const uint32_t b = blk_of_chunk[g >> 10];
@@ -124,7 +124,28 @@ __global__ void __launch_bounds__(256) lzp_filter_kernel(const uint8_t* __restri
         rec[g] = rec0[g];
         return;
     }
-    rec[g] = filter_candidate(in + B.src_off, (int)B.count, rec0 + B.pos_off, vf + B.pos_off, (int)i);
+    const Rec r_new = filter_candidate(in + B.src_off, (int)B.count, rec0 + B.pos_off, vf + B.pos_off, (int)i);
+    const Rec r_old = first_filter ? rec0[g] : rec[g];  // what the previous round's parse saw at this position
+    if (r_new.prev != r_old.prev || r_new.info != r_old.info) dirty[B.seg_base + i / SEG] = 1;  // "changed": lzp_dirty_kernel spreads it
+    rec[g] = r_new;
+}
+// A segment's speculative parse reads the candidates from its first byte up to the end of its last match (it only stops behind a match
+// that ends at or behind the segment, however far the literal run before that match reaches): dirty[k] = a candidate changed anywhere in
+// the segments [k, segment of the last byte it read]. desc[] is the previous round's.
+__global__ void __launch_bounds__(128) lzp_dirty_kernel(const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_seg, const uint32_t* __restrict__ act_segs,
+                                                         uint32_t n_act, const SegDesc* __restrict__ desc, const uint32_t* __restrict__ changed,
+                                                         uint32_t* __restrict__ dirty) {
+    const uint32_t t = blockIdx.x * 128 + threadIdx.x;
+    if (t >= n_act) return;
+    const uint32_t s = act_segs[t];
+    const PBlock& B = blocks[blk_of_seg[s]];
+    const SegDesc d = desc[s];
+    const uint32_t last = B.seg_base + B.nsegs - 1;
+    uint32_t k_end = last;
+    if (d.end != END_BLOCK) k_end = min(last, B.seg_base + (uint32_t)(max(d.fin.anchor, 1) - 1) / SEG);
+    uint32_t any = 0;
+    for (uint32_t k = s; k <= k_end && !any; k++) any = changed[k];
+    dirty[s] = any;
 }
 // vf' of every position from the block's match list; changed[b] |= (vf' != vf)
 __global__ void __launch_bounds__(256) lzp_derive_kernel(const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_chunk, const uint32_t* __restrict__ act_chunks,
@@ -246,11 +267,12 @@ __device__ __forceinline__ int parse_one_warp(const Params& P, State& st, Match&
 // ---- pass 1: speculative segment parses (one warp per segment; act_segs lists the segments of the unfinished blocks) ---------------------
 __global__ void __launch_bounds__(128) lzp_spec_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_seg, int extra,
                                                         const uint32_t* __restrict__ act_segs, uint32_t n_act, const Rec* __restrict__ rec, Match* __restrict__ logs,
-                                                        SegDesc* __restrict__ desc) {
+                                                        SegDesc* __restrict__ desc, const uint32_t* __restrict__ dirty) {
     const uint32_t t = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (t >= n_act) return;
     const int lane = threadIdx.x & 31;
     const uint32_t s = act_segs[t];
+    if (!dirty[s]) return;  // same candidates as in the previous round: same log
     const uint32_t b = blk_of_seg[s];
     const PBlock& B = blocks[b];
     const uint32_t k = s - B.seg_base;
@@ -285,13 +307,25 @@ struct SegLogAt {
 // junction_parse of kz_lz_par_core.cuh with the warp-cooperative parse; the log of the segment the cursor is in is searched 32 entries at a time
 __global__ void __launch_bounds__(128) lzp_junction_kernel(const uint8_t* __restrict__ in, const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_seg, int extra,
                                                             const uint32_t* __restrict__ act_segs, uint32_t n_act, const Rec* __restrict__ rec, const Match* __restrict__ logs,
-                                                            const SegDesc* __restrict__ desc_all, Match* __restrict__ jfix, Junction* __restrict__ junc) {
+                                                            const SegDesc* __restrict__ desc_all, Match* __restrict__ jfix, Junction* __restrict__ junc,
+                                                            const uint32_t* __restrict__ dirty, int first_round) {
     const uint32_t t = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (t >= n_act) return;
     const int lane = threadIdx.x & 31;
     const uint32_t s = act_segs[t];
     const uint32_t b = blk_of_seg[s];
     const PBlock& B = blocks[b];
+    if (!first_round) {
+        // the junction read the state its segment stopped in, the logs and the candidates of the segments up to the one it joined: when none
+        // of those segments is dirty its record stands
+        const Junction old = junc[s];
+        if (old.status == J_JOINED) {
+            const uint32_t k_end = min(B.seg_base + old.seg, B.seg_base + B.nsegs - 1);
+            bool any = false;
+            for (uint32_t k = s + lane; k <= k_end; k += 32) any = any || dirty[k] != 0;
+            if (!__any_sync(0xFFFFFFFFu, any)) return;
+        }
+    }
     const Params P = make_params(in, B, extra, rec);
     const SegDesc* desc = desc_all + B.seg_base;
     const Match* lbase = logs + (size_t)B.seg_base * SEG_CAP;
@@ -762,7 +796,7 @@ cudaError_t lz_forward_parallel_sub(const uint8_t* d_in, uint8_t* d_out, const L
     const size_t o_fix = take(matches * sizeof(Match)), o_ml = take(matches * sizeof(Match)), o_runs = take(matches * sizeof(LzRun));
     const size_t o_pieces = take((size_t)pieces * sizeof(Piece)), o_pstart = take((size_t)pieces * 4), o_pst = take(nblocks * sizeof(PState));
     const size_t o_junc = take((size_t)segs * sizeof(Junction)), o_jfix = take((size_t)segs * JCAP * sizeof(Match));
-    const size_t o_actc = take(blk_of_chunk.size() * 4), o_acts = take((size_t)segs * 4), o_actb = take((size_t)nblocks * 4);
+    const size_t o_actc = take(blk_of_chunk.size() * 4), o_acts = take((size_t)segs * 4), o_actb = take((size_t)nblocks * 4), o_dirty = take((size_t)segs * 4), o_changed_seg = take((size_t)segs * 4);
     const size_t o_tiles = take((size_t)tiles * 16), o_res = take(nblocks * sizeof(LzResult));
     size_t cub_bytes = 0;
     {
@@ -820,7 +854,7 @@ cudaError_t lz_forward_parallel_sub(const uint8_t* d_in, uint8_t* d_out, const L
     }
     Junction* d_junc = (Junction*)(ws + o_junc);
     Match* d_jfix = (Match*)(ws + o_jfix);
-    uint32_t *d_actc = (uint32_t*)(ws + o_actc), *d_acts = (uint32_t*)(ws + o_acts), *d_actb = (uint32_t*)(ws + o_actb);
+    uint32_t *d_actc = (uint32_t*)(ws + o_actc), *d_acts = (uint32_t*)(ws + o_acts), *d_actb = (uint32_t*)(ws + o_actb), *d_dirty = (uint32_t*)(ws + o_dirty), *d_chseg = (uint32_t*)(ws + o_changed_seg);
     cudaMemsetAsync(d_pst, 0, nblocks * sizeof(PState), stream);
     std::vector<uint32_t> h_changed(nblocks), h_done(nblocks, 0);
     // the passes of a round run over the chunks / segments / blocks that have not reached their fixed point yet
@@ -846,18 +880,22 @@ cudaError_t lz_forward_parallel_sub(const uint8_t* d_in, uint8_t* d_out, const L
         }
         const uint32_t GA = (uint32_t)act_c.size() * 4, NS = (uint32_t)act_s.size(), NB = (uint32_t)act_b.size();
         const Rec* rec_r = d_rec;
+        // dirty[s]: the candidates a segment's parse reads differ from the previous round's (round 0: everything is new)
+        if (round == 0) cudaMemsetAsync(d_dirty, 0xFF, (size_t)segs * 4, stream);
         if (round > 0) {
             LzHookScope hs(hook, "lz_filter");
-            lzp_filter_kernel<<<GA, 256, 0, stream>>>(d_in, d_pb, d_boc, d_actc, d_rec, d_vf, d_rec2, total);
+            cudaMemsetAsync(d_chseg, 0, (size_t)segs * 4, stream);
+            lzp_filter_kernel<<<GA, 256, 0, stream>>>(d_in, d_pb, d_boc, d_actc, d_rec, d_vf, d_rec2, total, round == 1 ? 1 : 0, d_chseg);
+            lzp_dirty_kernel<<<(NS + 127) / 128, 128, 0, stream>>>(d_pb, d_bos, d_acts, NS, d_desc, d_chseg, d_dirty);
             rec_r = d_rec2;
         }
         {
             LzHookScope hs(hook, round == 0 ? "lz_spec_r0" : (round == 1 ? "lz_spec_r1" : "lz_spec"));
-            lzp_spec_kernel<<<(NS + 3) / 4, 128, 0, stream>>>(d_in, d_pb, d_bos, extra ? 1 : 0, d_acts, NS, rec_r, d_logs, d_desc);
+            lzp_spec_kernel<<<(NS + 3) / 4, 128, 0, stream>>>(d_in, d_pb, d_bos, extra ? 1 : 0, d_acts, NS, rec_r, d_logs, d_desc, d_dirty);
         }
         {
             LzHookScope hs(hook, round == 0 ? "lz_stitch_r0" : (round == 1 ? "lz_stitch_r1" : "lz_stitch"));
-            lzp_junction_kernel<<<(NS + 3) / 4, 128, 0, stream>>>(d_in, d_pb, d_bos, extra ? 1 : 0, d_acts, NS, rec_r, d_logs, d_desc, d_jfix, d_junc);
+            lzp_junction_kernel<<<(NS + 3) / 4, 128, 0, stream>>>(d_in, d_pb, d_bos, extra ? 1 : 0, d_acts, NS, rec_r, d_logs, d_desc, d_jfix, d_junc, d_dirty, round == 0 ? 1 : 0);
             lzp_walk_kernel<<<NB, 256, 0, stream>>>(d_pb, d_actb, d_desc, d_junc, d_pieces, d_pstart, d_pst);
             lzp_stitch_kernel<<<NB, 32, 0, stream>>>(d_in, d_pb, d_actb, extra ? 1 : 0, rec_r, d_logs, d_desc, d_fix, d_pieces, d_pstart, d_pst);
         }

@@ -507,6 +507,243 @@ __global__ void __launch_bounds__(32) sbrt_inverse_flat_kernel(const uint8_t* __
     }
 }
 
+// ---- inverse, the list mirrored in shared memory so that the NEXT rank's entry is known before the move-up is done ---------------------------
+// In the flat kernel every instruction of a step sits on the dependent chain: select tree + shuffle for the entry of rank r -> qc -> 40
+// instructions of move-up -> next step's select tree (177 cycles per rank measured, 70 instructions at IPC 0.4). Here the registers keep the
+// list for the move-up, and a copy in shared memory (2 KiB) serves the look-ups: after step j - 1 has stored its lanes' entries, the
+// candidates for the rank r2 of step j + 1 are loaded from the state BEFORE step j — entry r2 and entry r2 - 1 — and step j decides with two
+// compares which one (or its own fresh entry) stands at rank r2 afterwards (the move-up rule applied to that one position). The chain per
+// rank is qc -> 2 compares -> 2 selects -> next qc; the move-up, the stores and the loads for the step after next overlap it.
+template <bool RANK_MODE>
+__global__ void __launch_bounds__(32) sbrt_inverse_mirror_kernel(const uint8_t* __restrict__ data, const SbrtBlock* __restrict__ blocks, int nblocks,
+                                                                  uint8_t* __restrict__ out) {
+    __shared__ __align__(16) uint32_t s_q[256];
+    __shared__ __align__(16) uint32_t s_x[256];
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (b >= nblocks) return;
+    const SbrtBlock blk = blocks[b];
+    if (!blk.active) return;
+    const uint8_t* src = data + blk.src_off;
+    uint8_t* dst = out + blk.dst_off;
+    const uint32_t n = blk.len;
+    uint32_t Q[8], X[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        Q[k] = 0;
+        X[k] = (uint32_t)(8 * lane + k);
+        s_q[8 * lane + k] = 0;
+        s_x[8 * lane + k] = (uint32_t)(8 * lane + k);
+    }
+    __syncwarp();
+    const uint32_t base = 8u * (uint32_t)lane;
+    uint4* sq4 = reinterpret_cast<uint4*>(s_q) + 2 * lane;
+    uint4* sx4 = reinterpret_cast<uint4*>(s_x) + 2 * lane;
+    // candidates for the next rank, from the state before the current step
+    uint32_t a_q, a_x, b_q, b_x;
+    auto load_candidates = [&](uint32_t r2) {
+        const uint32_t r1 = r2 ? r2 - 1 : 0;
+        a_q = s_q[r2], a_x = s_x[r2], b_q = s_q[r1], b_x = s_x[r1];
+    };
+    // one rank: x = the entry at rank r (known to every lane), r2 = the next rank; returns the symbol, leaves the next entry in x.
+    // Instruction order matters (one warp, in-order issue): the decision about the next entry reads the candidates loaded at the end of the
+    // previous step, so it stands in the middle of the move-up — far enough behind those loads, early enough for the next step's qc.
+    auto step = [&](uint32_t r, uint32_t r2, uint32_t i, uint32_t& x) -> uint32_t {
+        const uint32_t up_q = __shfl_up_sync(0xFFFFFFFFu, Q[7], 1), up_x = __shfl_up_sync(0xFFFFFFFFu, X[7], 1);
+        const uint32_t sym = x & 0xFFu;
+        const uint32_t qc = RANK_MODE ? (i + (x >> 8)) >> 1 : i;  // i, p < 2^24
+        const uint32_t fresh = (i << 8) | sym;
+        const int d = (int)r - (int)base;
+        bool gk = Q[7] > qc;
+#pragma unroll
+        for (int k = 7; k >= 4; k--) {  // predicated moves (alu pipe: 2 compares + 1 min per slot; the moves can go to the fma pipe)
+            const bool gk1 = Q[k - 1] > qc;
+            uint32_t xin = X[k - 1];
+            if (gk1) xin = fresh;
+            if (k <= d && !gk) {
+                Q[k] = min(Q[k - 1], qc);
+                X[k] = xin;
+            }
+            gk = gk1;
+        }
+        {  // the entry at rank r2 after this step: the move-up rule for that one position
+            const bool mv = r2 <= r && !(a_q > qc);
+            const bool gb = r2 == 0 || b_q > qc;
+            x = mv ? (gb ? fresh : b_x) : a_x;
+        }
+#pragma unroll
+        for (int k = 3; k >= 1; k--) {
+            const bool gk1 = Q[k - 1] > qc;
+            uint32_t xin = X[k - 1];
+            if (gk1) xin = fresh;
+            if (k <= d && !gk) {
+                Q[k] = min(Q[k - 1], qc);
+                X[k] = xin;
+            }
+            gk = gk1;
+        }
+        {
+            const bool g_up = lane == 0 ? true : up_q > qc;
+            uint32_t qin = up_q, xin = up_x;
+            if (g_up) qin = qc, xin = fresh;
+            if (0 <= d && !gk) {
+                Q[0] = qin;
+                X[0] = xin;
+            }
+        }
+        sq4[0] = make_uint4(Q[0], Q[1], Q[2], Q[3]);
+        sq4[1] = make_uint4(Q[4], Q[5], Q[6], Q[7]);
+        sx4[0] = make_uint4(X[0], X[1], X[2], X[3]);
+        sx4[1] = make_uint4(X[4], X[5], X[6], X[7]);
+        __syncwarp();
+        return sym;
+    };
+    if (n == 0) return;
+    uint32_t mine = (uint32_t)lane < n ? src[lane] : 0u;
+    uint32_t nxt = 32u + lane < n ? src[32 + lane] : 0u;
+    uint32_t x = s_x[__shfl_sync(0xFFFFFFFFu, mine, 0)];  // entry of the first rank in the initial list
+    load_candidates(__shfl_sync(0xFFFFFFFFu, mine, 1));   // (rank 1 of a 1-byte block: lane 1 holds 0)
+    uint32_t i0 = 0;
+    for (; i0 + 32 <= n; i0 += 32) {
+        const uint32_t nn = i0 + 64 + lane < n ? src[i0 + 64 + lane] : 0u;  // the round after next in flight
+        uint32_t ob = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const uint32_t r = __shfl_sync(0xFFFFFFFFu, mine, j);
+            const uint32_t r2 = j < 31 ? __shfl_sync(0xFFFFFFFFu, mine, (j + 1) & 31) : __shfl_sync(0xFFFFFFFFu, nxt, 0);
+            const uint32_t r3 = j < 30 ? __shfl_sync(0xFFFFFFFFu, mine, (j + 2) & 31) : __shfl_sync(0xFFFFFFFFu, nxt, (j + 2) & 31);
+            const uint32_t sym = step(r, r2, i0 + (uint32_t)j, x);
+            load_candidates(r3);  // for the step after this one's successor: the state now is the state before step j + 1
+            ob = lane == j ? sym : ob;
+        }
+        dst[i0 + lane] = (uint8_t)ob;
+        mine = nxt;
+        nxt = nn;
+    }
+    if (i0 < n) {  // last, partial round (ranks past the end read as 0: harmless look-ups)
+        uint32_t ob = 0;
+        for (uint32_t j = 0; i0 + j < n; j++) {
+            const uint32_t r = __shfl_sync(0xFFFFFFFFu, mine, (int)j);
+            const uint32_t r2 = j < 31 ? __shfl_sync(0xFFFFFFFFu, mine, (int)((j + 1) & 31)) : 0u;
+            const uint32_t r3 = j < 30 ? __shfl_sync(0xFFFFFFFFu, mine, (int)((j + 2) & 31)) : 0u;
+            const uint32_t sym = step(r, r2, i0 + j, x);
+            load_candidates(r3);
+            ob = (uint32_t)lane == j ? sym : ob;
+        }
+        if (i0 + lane < n) dst[i0 + lane] = (uint8_t)ob;
+    }
+}
+
+// ---- inverse, the mirrored list spread over W warps (default W = 2) ------------------------------------------------------------------------------
+// The mirror kernel is bound by the ALU pipe of its one scheduler: ~50 integer / predicate instructions per rank at 2 cycles each (16 lanes
+// per cycle), 145 cycles per rank measured. With the list in shared memory for every look-up, nothing but the lane boundary ties the lanes
+// together, so the 256 entries are spread over W warps (8 / W entries per lane) that sit on different schedulers: every warp takes the same
+// decision about the next entry from the same shared-memory candidates, moves its own part of the list, stores it, and one CTA barrier per
+// rank publishes the stores; the entry that crosses a warp boundary is read from the mirror instead of a shuffle.
+template <bool RANK_MODE, int W>
+__global__ void __launch_bounds__(32 * W) sbrt_inverse_multi_kernel(const uint8_t* __restrict__ data, const SbrtBlock* __restrict__ blocks, int nblocks,
+                                                                     uint8_t* __restrict__ out) {
+    constexpr int S = 8 / W;  // entries per lane
+    // two copies, written alternately: a warp that runs ahead stores step j + 1 while another still reads the state after step j - 1 / j
+    __shared__ __align__(16) uint32_t s_q[2][256];
+    __shared__ __align__(16) uint32_t s_x[2][256];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (b >= nblocks) return;
+    const SbrtBlock blk = blocks[b];
+    if (!blk.active) return;
+    const uint8_t* src = data + blk.src_off;
+    uint8_t* dst = out + blk.dst_off;
+    const uint32_t n = blk.len;
+    if (n == 0) return;
+    uint32_t Q[S], X[S];
+    const uint32_t base = (uint32_t)(S * tid);
+#pragma unroll
+    for (int k = 0; k < S; k++) {
+        Q[k] = 0;
+        X[k] = base + k;
+        s_q[0][base + k] = s_q[1][base + k] = 0;
+        s_x[0][base + k] = s_x[1][base + k] = base + k;
+    }
+    __syncthreads();
+    uint32_t a_q, a_x, b_q, b_x;
+    auto load_candidates = [&](uint32_t r2, int par) {  // from the copy step `par` wrote
+        const uint32_t r1 = r2 ? r2 - 1 : 0;
+        a_q = s_q[par][r2], a_x = s_x[par][r2], b_q = s_q[par][r1], b_x = s_x[par][r1];
+    };
+    // par = parity of the step: it reads the copy of parity par ^ 1 (the state before it) and writes the copy of parity par
+    auto step = [&](uint32_t r, uint32_t r2, uint32_t i, int par, uint32_t& x) -> uint32_t {
+        // the entry above this lane's first one (state before the step): a shuffle inside the warp, the mirror across a warp boundary
+        uint32_t up_q = __shfl_up_sync(0xFFFFFFFFu, Q[S - 1], 1), up_x = __shfl_up_sync(0xFFFFFFFFu, X[S - 1], 1);
+        if (lane == 0 && warp > 0) up_q = s_q[par ^ 1][base - 1], up_x = s_x[par ^ 1][base - 1];
+        const uint32_t sym = x & 0xFFu;
+        const uint32_t qc = RANK_MODE ? (i + (x >> 8)) >> 1 : i;  // i, p < 2^24
+        const uint32_t fresh = (i << 8) | sym;
+        {  // the entry at rank r2 after this step (every warp computes the same)
+            const bool mv = r2 <= r && !(a_q > qc);
+            const bool gb = r2 == 0 || b_q > qc;
+            x = mv ? (gb ? fresh : b_x) : a_x;
+        }
+        const int d = (int)r - (int)base;
+        bool gk = Q[S - 1] > qc;
+#pragma unroll
+        for (int k = S - 1; k >= 1; k--) {
+            const bool gk1 = Q[k - 1] > qc;
+            const bool mv = k <= d && !gk;
+            const uint32_t xin = gk1 ? fresh : X[k - 1];
+            Q[k] = mv ? min(Q[k - 1], qc) : Q[k];
+            X[k] = mv ? xin : X[k];
+            gk = gk1;
+        }
+        {
+            const bool g_up = tid == 0 ? true : up_q > qc;
+            const bool mv = 0 <= d && !gk;
+            Q[0] = mv ? (g_up ? qc : up_q) : Q[0];
+            X[0] = mv ? (g_up ? fresh : up_x) : X[0];
+        }
+        if (S == 4) {
+            reinterpret_cast<uint4*>(s_q[par])[tid] = make_uint4(Q[0], Q[1], Q[S > 2 ? 2 : 0], Q[S > 3 ? 3 : 0]);
+            reinterpret_cast<uint4*>(s_x[par])[tid] = make_uint4(X[0], X[1], X[S > 2 ? 2 : 0], X[S > 3 ? 3 : 0]);
+        } else {
+            reinterpret_cast<uint2*>(s_q[par])[tid] = make_uint2(Q[0], Q[1]);
+            reinterpret_cast<uint2*>(s_x[par])[tid] = make_uint2(X[0], X[1]);
+        }
+        __syncthreads();
+        return sym;
+    };
+    uint32_t mine = (uint32_t)lane < n ? src[lane] : 0u;
+    uint32_t nxt = 32u + lane < n ? src[32 + lane] : 0u;
+    uint32_t x = s_x[1][__shfl_sync(0xFFFFFFFFu, mine, 0)];
+    load_candidates(__shfl_sync(0xFFFFFFFFu, mine, 1), 1);
+    uint32_t i0 = 0;
+    for (; i0 + 32 <= n; i0 += 32) {
+        const uint32_t nn = i0 + 64 + lane < n ? src[i0 + 64 + lane] : 0u;
+        uint32_t ob = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const uint32_t r = __shfl_sync(0xFFFFFFFFu, mine, j);
+            const uint32_t r2 = j < 31 ? __shfl_sync(0xFFFFFFFFu, mine, (j + 1) & 31) : __shfl_sync(0xFFFFFFFFu, nxt, 0);
+            const uint32_t r3 = j < 30 ? __shfl_sync(0xFFFFFFFFu, mine, (j + 2) & 31) : __shfl_sync(0xFFFFFFFFu, nxt, (j + 2) & 31);
+            const uint32_t sym = step(r, r2, i0 + (uint32_t)j, j & 1, x);  // i0 is a multiple of 32
+            load_candidates(r3, j & 1);
+            ob = lane == j ? sym : ob;
+        }
+        if (warp == 0) dst[i0 + lane] = (uint8_t)ob;
+        mine = nxt;
+        nxt = nn;
+    }
+    if (i0 < n) {
+        uint32_t ob = 0;
+        for (uint32_t j = 0; i0 + j < n; j++) {
+            const uint32_t r = __shfl_sync(0xFFFFFFFFu, mine, (int)j);
+            const uint32_t r2 = j < 31 ? __shfl_sync(0xFFFFFFFFu, mine, (int)((j + 1) & 31)) : 0u;
+            const uint32_t r3 = j < 30 ? __shfl_sync(0xFFFFFFFFu, mine, (int)((j + 2) & 31)) : 0u;
+            const uint32_t sym = step(r, r2, i0 + j, (int)(j & 1), x);
+            load_candidates(r3, (int)(j & 1));
+            ob = (uint32_t)lane == j ? sym : ob;
+        }
+        if (warp == 0 && i0 + lane < n) dst[i0 + lane] = (uint8_t)ob;
+    }
+}
+
 // host entry. KZ_SBRT_INV=lane selects the round-1 kernel (lane 0 walks the chain; kept for comparison); packed = every block < 128 MiB
 void sbrt_inverse_launch(const uint8_t* data, const SbrtBlock* d_blocks, int nblocks, int mode, uint8_t* out, bool packed, cudaStream_t stream) {
     static const bool old_kernel = [] {
@@ -534,9 +771,30 @@ void sbrt_inverse_launch_len(const uint8_t* data, const SbrtBlock* d_blocks, int
         const char* e = getenv("KZ_SBRT_INV");
         return e && e[0] == 'w';
     }();
+    static const bool flat = [] {  // KZ_SBRT_INV=flat: the branch-free kernel without the shared-memory mirror
+        const char* e = getenv("KZ_SBRT_INV");
+        return e && e[0] == 'f';
+    }();
     if (max_len <= (1u << 24) && !branchy && (mode == 1 || mode == 2)) {
-        if (mode == 2) sbrt_inverse_flat_kernel<true><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, out);
-        else sbrt_inverse_flat_kernel<false><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, out);
+        if (flat) {
+            if (mode == 2) sbrt_inverse_flat_kernel<true><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, out);
+            else sbrt_inverse_flat_kernel<false><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, out);
+        } else {
+            static const int warps = [] {  // KZ_SBRT_WARPS = 1 (mirror kernel), 2 (default) or 4
+                const char* e = getenv("KZ_SBRT_WARPS");
+                return e ? atoi(e) : 2;
+            }();
+            if (warps == 4) {
+                if (mode == 2) sbrt_inverse_multi_kernel<true, 4><<<nblocks, 128, 0, stream>>>(data, d_blocks, nblocks, out);
+                else sbrt_inverse_multi_kernel<false, 4><<<nblocks, 128, 0, stream>>>(data, d_blocks, nblocks, out);
+            } else if (warps == 2) {
+                if (mode == 2) sbrt_inverse_multi_kernel<true, 2><<<nblocks, 64, 0, stream>>>(data, d_blocks, nblocks, out);
+                else sbrt_inverse_multi_kernel<false, 2><<<nblocks, 64, 0, stream>>>(data, d_blocks, nblocks, out);
+            } else {
+                if (mode == 2) sbrt_inverse_mirror_kernel<true><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, out);
+                else sbrt_inverse_mirror_kernel<false><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, out);
+            }
+        }
     } else if (max_len <= (1u << 24)) sbrt_inverse_warp_kernel<uint32_t><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, mode, out);
     else sbrt_inverse_warp_kernel<uint64_t><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, mode, out);
 }

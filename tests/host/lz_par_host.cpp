@@ -59,6 +59,8 @@ int64_t lz_forward_par(int extra_i, int data_type, const uint8_t* src_in, int64_
     std::vector<Piece> pieces(size_t(2) * nsegs + 4);
     std::vector<uint32_t> vf(size_t(count) + 8, 0), vf2(size_t(count) + 8, 0);
     std::vector<Match> ml;
+    std::vector<Junction> junc;
+    std::vector<Match> jfix;
     uint32_t fix_n = 0, np = 0;
     int32_t final_anchor = 0;
     int rounds = 0;
@@ -66,23 +68,46 @@ int64_t lz_forward_par(int extra_i, int data_type, const uint8_t* src_in, int64_
     const uint32_t JCAP = g_jcap;
     for (;; rounds++) {
         if (rounds >= max_rounds) return -4;
-        // filter the candidates by the previous round's vf (round 0: vf = 0, nothing moves)
-        for (int i = 0; i < count; i++) rec[i] = rounds == 0 ? rec0[i] : filter_candidate(src, count, rec0.data(), vf.data(), i);
+        // filter the candidates by the previous round's vf (round 0: vf = 0, nothing moves); changed[k]: a candidate of segment k differs from
+        // what the previous round's parse saw
+        std::vector<uint8_t> changed(nsegs, rounds == 0 ? 1 : 0), dirty(nsegs, 1);
+        for (int i = 0; i < count; i++) {
+            const Rec r_new = rounds == 0 ? rec0[i] : filter_candidate(src, count, rec0.data(), vf.data(), i);
+            if (rounds > 0 && (r_new.prev != rec[i].prev || r_new.info != rec[i].info)) changed[std::min(i / seg_size, nsegs - 1)] = 1;
+            rec[i] = r_new;
+        }
         P.rec = rec.data();
-        // speculative parse of every segment
+        // dirty[k] (kz_lz_par.cu: lzp_dirty_kernel): something changed in the segments the previous parse of segment k read
+        if (rounds > 0) {
+            for (int k = 0; k < nsegs; k++) {
+                int k_end = nsegs - 1;
+                if (desc[k].end != END_BLOCK) k_end = std::min(nsegs - 1, (std::max(desc[k].fin.anchor, 1) - 1) / seg_size);
+                uint8_t any = 0;
+                for (int m = k; m <= k_end && !any; m++) any = changed[m];
+                dirty[k] = any;
+            }
+        }
+        // speculative parse of every dirty segment (clean ones keep their log)
         for (int k = 0; k < nsegs; k++) {
+            if (!dirty[k]) continue;
             const int s0 = k * seg_size;
             const int s1 = k == nsegs - 1 ? 0x7FFFFFFF : s0 + seg_size;
             spec_parse_segment(P, s0, s1, logs.data() + size_t(k) * seg_cap, desc[k]);
             if (int(desc[k].n) > seg_cap) return -2;
         }
         // stitch: one junction per segment (parallel on the GPU), then the walk over the junction records; a live junction that hit its
-        // cap sends the block to the serial stitch
+        // cap sends the block to the serial stitch. A junction is redone when a segment between its own and the one it joined is dirty.
         Match* lp = logs.data();
         auto seg_log = [lp, seg_cap](int k) { return (const Match*)(lp + size_t(k) * seg_cap); };
-        std::vector<Junction> junc(nsegs);
-        std::vector<Match> jfix(size_t(nsegs) * JCAP);
-        for (int k = 0; k < nsegs; k++) junction_parse(P, k, nsegs, desc.data(), seg_log, jfix.data() + size_t(k) * JCAP, JCAP, junc[k]);
+        if (junc.empty()) junc.resize(nsegs), jfix.resize(size_t(nsegs) * JCAP);
+        for (int k = 0; k < nsegs; k++) {
+            bool redo = rounds == 0 || junc[k].status != J_JOINED;
+            if (!redo) {
+                const int k_end = std::min<int>(int(junc[k].seg), nsegs - 1);
+                for (int m = k; m <= k_end && !redo; m++) redo = dirty[m];
+            }
+            if (redo) junction_parse(P, k, nsegs, desc.data(), seg_log, jfix.data() + size_t(k) * JCAP, JCAP, junc[k]);
+        }
         uint32_t nmatch = 0;
         np = walk_junctions(nsegs, desc.data(), junc.data(), pieces.data(), &nmatch, &final_anchor);
         const bool serial_stitch = np == 0xFFFFFFFFu;
