@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(32) sbrt_inverse_mirror_kernel(const uint8_t* 
     }
 }
 
-// ---- inverse, the mirrored list spread over W warps (default W = 2) ------------------------------------------------------------------------------
+// ---- inverse, the mirrored list spread over W warps (default W = 4) ------------------------------------------------------------------------------
 // The mirror kernel is bound by the ALU pipe of its one scheduler: ~50 integer / predicate instructions per rank at 2 cycles each (16 lanes
 // per cycle), 145 cycles per rank measured. With the list in shared memory for every look-up, nothing but the lane boundary ties the lanes
 // together, so the 256 entries are spread over W warps (8 / W entries per lane) that sit on different schedulers: every warp takes the same
@@ -780,9 +780,9 @@ void sbrt_inverse_launch_len(const uint8_t* data, const SbrtBlock* d_blocks, int
             if (mode == 2) sbrt_inverse_flat_kernel<true><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, out);
             else sbrt_inverse_flat_kernel<false><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, out);
         } else {
-            static const int warps = [] {  // KZ_SBRT_WARPS = 1 (mirror kernel), 2 (default) or 4
+            static const int warps = [] {  // KZ_SBRT_WARPS = 1 (mirror kernel), 2 or 4 (default)
                 const char* e = getenv("KZ_SBRT_WARPS");
-                return e ? atoi(e) : 2;
+                return e ? atoi(e) : 4;
             }();
             if (warps == 4) {
                 if (mode == 2) sbrt_inverse_multi_kernel<true, 4><<<nblocks, 128, 0, stream>>>(data, d_blocks, nblocks, out);
