@@ -1691,8 +1691,20 @@ int apply_inverse(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint8_t* d_out, 
         if (rc) return rc;
         uint8_t* T = ctx->d_tables.as<uint8_t>();
         {
+            static const bool warp_per_block = [] {  // KZ_MM_INV=warp: one warp per block walks the rounds (first data-parallel version)
+                const char* e = getenv("KZ_MM_INV");
+                return e && e[0] == 'w';
+            }();
             LaunchScope ls(ctx, "fsd_inverse");
-            cudaError_t e = fsd_inverse_batch(d_in, d_out, (const FsdBlock*)(T + o_fb), nblocks, (FsdResult*)(T + o_res), ctx->stream, &ctx->launches);
+            cudaError_t e;
+            if (warp_per_block) {
+                e = fsd_inverse_batch(d_in, d_out, (const FsdBlock*)(T + o_fb), nblocks, (FsdResult*)(T + o_res), ctx->stream, &ctx->launches);
+            } else {
+                uint64_t total_len = 0;
+                for (uint32_t b = 0; b < nblocks; b++) total_len += fb[b].len;
+                CK(ctx->d_ws.ensure(fsd_inverse_workspace(nblocks, total_len)));
+                e = fsd_inverse_tiles(d_in, d_out, fb.data(), nblocks, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap, (FsdResult*)(T + o_res), ctx->stream, &ctx->launches);
+            }
             if (e != cudaSuccess) return ctx->cuda_fail(e, "fsd_inverse");
         }
         std::vector<FsdResult> hr(nblocks);

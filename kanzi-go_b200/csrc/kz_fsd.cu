@@ -12,6 +12,8 @@
 #include <cmath>
 
 #include "kz_alias.cuh"
+#include <vector>
+
 #include "kz_fsd.cuh"
 
 namespace kz {
@@ -404,12 +406,15 @@ __global__ void __launch_bounds__(32) fsd_inverse_kernel(const uint8_t* __restri
     if ((uint32_t)lane < dist) dst[lane] = src[2 + lane];
     uint32_t pending = 0;  // the previous round ended with an escape marker: this round's first byte is its payload
     const uint32_t below = (1u << lane) - 1u;
-    uint32_t nxt = si + lane < src_end ? src[si + lane] : 0u;
+    // source bytes four rounds ahead (a round is ~500 cycles of shuffles and ballots, an HBM load ~800)
+    uint32_t n0 = si + lane < src_end ? src[si + lane] : 0u, n1 = si + 32 + lane < src_end ? src[si + 32 + lane] : 0u;
+    uint32_t n2 = si + 64 + lane < src_end ? src[si + 64 + lane] : 0u, n3 = si + 96 + lane < src_end ? src[si + 96 + lane] : 0u;
     while (si < src_end && di < dst_end) {
-        const uint32_t t = nxt;
+        const uint32_t t = n0;
         const uint32_t cnt = min(32u, src_end - si);
         const uint32_t valid = cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u);
-        nxt = si + 32 + lane < src_end ? src[si + 32 + lane] : 0u;  // next round in flight
+        n0 = n1, n1 = n2, n2 = n3;
+        n3 = si + 128 + lane < src_end ? src[si + 128 + lane] : 0u;
         uint32_t marker = 0;
         if (mode == 0) {
             const uint32_t ff = __ballot_sync(0xFFFFFFFFu, t == 0xFFu) & valid;
@@ -506,6 +511,328 @@ cudaError_t fsd_forward_batch(const uint8_t* d_in, uint8_t* d_out, const FsdBloc
     fsd_post_hist_kernel<<<dim3(SAMPLE_SLICES, nblocks), 256, 0, stream>>>(d_blocks, w.info, d_out, w.hpost);
     fsd_final_kernel<<<nblocks, 32, 0, stream>>>(d_blocks, (int)nblocks, w.info, w.hpost, w.log2tab, d_res);
     if (launches) *launches += 7;
+    return cudaGetLastError();
+}
+
+// ---- inverse over tiles of 32 source bytes, all tiles of all blocks at once (the default) ------------------------------------------------------
+// What a round of fsd_inverse_kernel carries into the next one is (a) whether its last byte was an escape marker, (b) the output offset,
+// (c) the last value of each of the `dist` chains. (a) and (b) are decided by a scan over tiles: a tile's marker pattern depends on the
+// incoming marker bit only through its leading run of 0xFF, so every tile is classified under both hypotheses (K1) and one warp per block
+// chains them (K2). (c): along a chain the deltas are a prefix sum and every escape replaces the value by payload ^ previous, which is not
+// a sum — but the escapes are few: each tile computes its chain totals and the list of its escapes with the delta sum in front of each
+// (K3), one warp per block (lane = chain) then walks the tiles once, O = (payload ^ (O + sum before)) - sum before per escape, + total per
+// tile, and leaves every tile its incoming chain values (K4). K5 is a round of fsd_inverse_kernel with all three carries given.
+namespace {
+const int FSD_ESC_SLOTS = 17;  // escapes of a tile: marker + payload take two bytes, plus one whose marker ended the tile before
+struct FsdiBlock {
+    uint64_t src_off, dst_off;
+    uint64_t tile_base;  // first tile of the block
+    uint32_t len, cap;
+    uint32_t ntiles, active;
+};
+struct FsdiState {  // per block, written by K2
+    uint32_t bad, total, ntiles_ok, pad;
+};
+__device__ __forceinline__ bool fsdi_header(const uint8_t* src, uint32_t len, uint32_t cap, uint32_t& mode, uint32_t& dist) {
+    if (len < 2) return false;
+    mode = src[0];
+    dist = src[1];
+    if (dist < 1 || (dist > 4 && dist != 8 && dist != 16)) return false;
+    if (len - 2 < dist || cap < dist || mode > 1) return false;
+    return true;
+}
+// marker / payload / token masks of a tile (lane = source byte) under an incoming marker bit
+__device__ __forceinline__ void fsdi_classify(uint32_t t, uint32_t cnt, uint32_t mode, uint32_t pending, uint32_t& marker, uint32_t& payload, uint32_t& tokens) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t valid = cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u);
+    marker = 0;
+    if (mode == 0) {
+        const uint32_t below = (1u << lane) - 1u;
+        const uint32_t ff = __ballot_sync(0xFFFFFFFFu, t == 0xFFu) & valid;
+        const uint32_t nz = ~ff & below;
+        const uint32_t s = nz ? 32u - (uint32_t)__clz((int)nz) : 0u;
+        const uint32_t par = (s == 0 && pending) ? 1u : 0u;
+        const bool is_marker = ((ff >> lane) & 1u) && ((((uint32_t)lane - s) & 1u) == par);
+        marker = __ballot_sync(0xFFFFFFFFu, is_marker);
+    }
+    payload = ((marker << 1) | pending) & valid;
+    tokens = valid & ~marker;
+}
+// K1: one warp per tile: token count and outgoing marker bit under both hypotheses
+__global__ void __launch_bounds__(128) fsdi_k1_kernel(const uint8_t* __restrict__ in, const FsdiBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_group,
+                                                       uint32_t* __restrict__ rec) {
+    const uint32_t gw = blockIdx.x * 4 + (threadIdx.x >> 5);  // global tile index; groups of 4 tiles never straddle blocks (tile_base % 4 == 0)
+    const int lane = threadIdx.x & 31;
+    const FsdiBlock& B = blocks[blk_of_group[blockIdx.x]];
+    const uint32_t tl = gw - (uint32_t)B.tile_base;
+    if (!B.active || tl >= B.ntiles) return;
+    const uint8_t* src = in + B.src_off;
+    uint32_t mode, dist;
+    if (!fsdi_header(src, B.len, B.cap, mode, dist)) return;
+    const uint32_t si = 2 + dist + 32 * tl;
+    if (si >= B.len) return;
+    const uint32_t cnt = min(32u, B.len - si);
+    const uint32_t t = (uint32_t)lane < cnt ? src[si + lane] : 0u;
+    uint32_t m0, p0, k0, m1, p1, k1;
+    fsdi_classify(t, cnt, mode, 0, m0, p0, k0);
+    fsdi_classify(t, cnt, mode, 1, m1, p1, k1);
+    if (lane == 0) rec[gw] = (uint32_t)__popc(k0) | ((uint32_t)__popc(k1) << 8) | (((m0 >> (cnt - 1)) & 1u) << 16) | (((m1 >> (cnt - 1)) & 1u) << 17);
+}
+// K2: one warp per block chains the tiles: incoming marker bit (bit 31 of start[]) and output offset of every tile
+__global__ void __launch_bounds__(32) fsdi_k2_kernel(const uint8_t* __restrict__ in, const FsdiBlock* __restrict__ blocks, int nblocks, const uint32_t* __restrict__ rec,
+                                                      uint32_t* __restrict__ start, FsdiState* __restrict__ st, uint8_t* __restrict__ out) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (b >= nblocks) return;
+    const FsdiBlock B = blocks[b];
+    FsdiState S;
+    S.bad = 0, S.total = 0, S.ntiles_ok = 0, S.pad = 0;
+    if (!B.active) {
+        if (lane == 0) st[b] = S;
+        return;
+    }
+    const uint8_t* src = in + B.src_off;
+    uint32_t mode, dist;
+    if (!fsdi_header(src, B.len, B.cap, mode, dist)) {
+        S.bad = 1;
+        if (lane == 0) st[b] = S;
+        return;
+    }
+    if ((uint32_t)lane < dist) out[B.dst_off + lane] = src[2 + lane];  // the first `dist` bytes are copied (:355-359)
+    const uint32_t nt = (B.len - 2 - dist + 31) / 32;
+    const uint32_t* r = rec + B.tile_base;
+    uint32_t* sp = start + B.tile_base;
+    uint32_t p = 0, di = dist, ok = nt;
+    bool bad = false;
+    uint32_t nxt = (uint32_t)lane < nt ? r[lane] : 0u;
+    for (uint32_t t0 = 0; t0 < nt && !bad; t0 += 32) {
+        const uint32_t mine = nxt;
+        nxt = t0 + 32 + lane < nt ? r[t0 + 32 + lane] : 0u;
+        uint32_t my_start = 0;
+        const uint32_t n = min(32u, nt - t0);
+        for (uint32_t j = 0; j < n; j++) {  // uniform: every lane tracks (p, di)
+            const uint32_t w = __shfl_sync(0xFFFFFFFFu, mine, (int)j);
+            const uint32_t tok = p ? (w >> 8) & 0xFFu : w & 0xFFu;
+            if (di + tok > B.cap) {  // the reference stops at dstEnd with source bytes left: an error (:398-400)
+                bad = true;
+                ok = t0 + j;
+                break;
+            }
+            if ((uint32_t)lane == j) my_start = di | (p << 31);
+            di += tok;
+            p = (w >> (16 + p)) & 1u;
+        }
+        if (t0 + lane < min(ok, nt)) sp[t0 + lane] = my_start;
+    }
+    if (!bad && p) bad = true;  // a marker was the last source byte (:380-383)
+    S.bad = bad ? 1u : 0u;
+    S.total = di;
+    S.ntiles_ok = bad ? ok : nt;
+    if (lane == 0) st[b] = S;
+}
+// tokens of a tile in output order: lane k = token k (tk, is_esc) and its chain prefix (deltas on its chain inside the tile, escapes count 0)
+__device__ __forceinline__ uint32_t fsdi_tokens(uint32_t t, uint32_t cnt, uint32_t mode, uint32_t dist, uint32_t pending, uint16_t* s_tok, uint32_t& tk, bool& is_esc,
+                                                 uint32_t& prefix) {
+    const int lane = threadIdx.x & 31;
+    uint32_t marker, payload, tokens;
+    fsdi_classify(t, cnt, mode, pending, marker, payload, tokens);
+    const uint32_t m = (uint32_t)__popc(tokens);
+    const uint32_t below = (1u << lane) - 1u;
+    if ((tokens >> lane) & 1u) s_tok[__popc(tokens & below)] = (uint16_t)(t | (((payload >> lane) & 1u) << 8));
+    __syncwarp();
+    const uint32_t tw = (uint32_t)lane < m ? s_tok[lane] : 0u;
+    __syncwarp();
+    tk = tw & 0xFFu;
+    is_esc = (tw >> 8) != 0;
+    uint32_t v;
+    if (mode == 0) v = is_esc ? 0u : ((tk & 1u) ? (0u - ((tk + 1u) >> 1)) : (tk >> 1));  // _FSD_ZIGZAG2
+    else v = tk;
+    if ((uint32_t)lane >= m) v = 0;
+    for (uint32_t d = dist; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if ((uint32_t)lane >= d) v = mode == 0 ? v + y : v ^ y;
+    }
+    prefix = v & 0xFFu;
+    return m;
+}
+// K3: chain totals and escape list of every tile
+__global__ void __launch_bounds__(128) fsdi_k3_kernel(const uint8_t* __restrict__ in, const FsdiBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_group,
+                                                       const FsdiState* __restrict__ st, const uint32_t* __restrict__ start, uint8_t* __restrict__ totals /*16 per tile*/,
+                                                       uint32_t* __restrict__ esc /*FSD_ESC_SLOTS per tile*/, uint8_t* __restrict__ nesc) {
+    __shared__ uint16_t s_tok_all[4][32];
+    const uint32_t gw = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const uint32_t bi = blk_of_group[blockIdx.x];
+    const FsdiBlock& B = blocks[bi];
+    const uint32_t tl = gw - (uint32_t)B.tile_base;
+    if (!B.active || tl >= st[bi].ntiles_ok) return;
+    const uint8_t* src = in + B.src_off;
+    const uint32_t mode = src[0], dist = src[1];
+    const uint32_t si = 2 + dist + 32 * tl;
+    const uint32_t cnt = min(32u, B.len - si);
+    const uint32_t t = (uint32_t)lane < cnt ? src[si + lane] : 0u;
+    const uint32_t sw = start[gw];
+    uint32_t tk, prefix;
+    bool is_esc;
+    const uint32_t m = fsdi_tokens(t, cnt, mode, dist, sw >> 31, s_tok_all[threadIdx.x >> 5], tk, is_esc, prefix);
+    const uint32_t di0 = sw & 0x7FFFFFFFu;
+    // totals: the last token of each chain holds the chain's sum; chains without a token in the tile: 0
+    if (lane < 16) totals[(size_t)gw * 16 + lane] = 0;
+    __syncwarp();
+    if ((uint32_t)lane < m && (uint32_t)lane + dist >= m) totals[(size_t)gw * 16 + (di0 + lane) % dist] = (uint8_t)prefix;
+    const uint32_t em = __ballot_sync(0xFFFFFFFFu, is_esc);
+    if (is_esc) esc[(size_t)gw * FSD_ESC_SLOTS + __popc(em & ((1u << lane) - 1u))] = ((di0 + lane) % dist) | (tk << 8) | (prefix << 16);  // chain, payload, deltas before it
+    if (lane == 0) nesc[gw] = (uint8_t)__popc(em);
+}
+// K4: one warp per block, lane = chain: the value every chain has when a tile starts
+__global__ void __launch_bounds__(32) fsdi_k4_kernel(const uint8_t* __restrict__ in, const FsdiBlock* __restrict__ blocks, int nblocks, const FsdiState* __restrict__ st,
+                                                      const uint32_t* __restrict__ start, const uint8_t* __restrict__ totals, const uint32_t* __restrict__ esc,
+                                                      const uint8_t* __restrict__ nesc, uint8_t* __restrict__ snap /*16 per tile*/) {
+    (void)start;
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (b >= nblocks) return;
+    const FsdiBlock B = blocks[b];
+    const uint32_t nt = st[b].ntiles_ok;
+    if (!B.active || nt == 0) return;
+    const uint8_t* src = in + B.src_off;
+    const uint32_t mode = src[0], dist = src[1];
+    const uint32_t r = (uint32_t)lane & 15u;  // chain of this lane (lanes 16..31 mirror 0..15 and hold the second half of the escape slots)
+    uint32_t R = r < dist ? src[2 + r] : 0u;
+    const size_t tb = B.tile_base;
+    const int G = 8;  // tiles per group; the next group's totals / escape words / counts are loaded while this one is walked
+    uint32_t Tn[G], En[G], Mn[G];
+    auto load_group = [&](uint32_t t0) {
+#pragma unroll
+        for (int j = 0; j < G; j++) {
+            const uint32_t t = t0 + j;
+            const bool in_range = t < nt;
+            Tn[j] = in_range ? totals[(tb + t) * 16 + r] : 0u;
+            En[j] = (in_range && lane < FSD_ESC_SLOTS) ? esc[(tb + t) * FSD_ESC_SLOTS + lane] : 0u;
+            Mn[j] = in_range ? (uint32_t)nesc[tb + t] : 0u;
+        }
+    };
+    load_group(0);
+    for (uint32_t t0 = 0; t0 < nt; t0 += G) {
+        uint32_t Tc[G], Ec[G], Mc[G];
+#pragma unroll
+        for (int j = 0; j < G; j++) Tc[j] = Tn[j], Ec[j] = En[j], Mc[j] = Mn[j];
+        load_group(t0 + G);
+#pragma unroll
+        for (int j = 0; j < G; j++) {
+            if (t0 + j >= nt) break;
+            if (lane < 16) snap[(tb + t0 + j) * 16 + lane] = (uint8_t)R;
+            const uint32_t ne = Mc[j];  // escapes of the tile
+            uint32_t O = R;
+            for (uint32_t e = 0; e < ne; e++) {
+                const uint32_t w = __shfl_sync(0xFFFFFFFFu, Ec[j], (int)e);
+                const uint32_t pay = (w >> 8) & 0xFFu, pl = (w >> 16) & 0xFFu;
+                if ((w & 0xFFu) == r) O = ((pay ^ ((O + pl) & 0xFFu)) - pl) & 0xFFu;
+            }
+            R = mode == 0 ? (O + Tc[j]) & 0xFFu : (O ^ Tc[j]);
+        }
+    }
+}
+// K5: the bytes of every tile
+__global__ void __launch_bounds__(128) fsdi_k5_kernel(const uint8_t* __restrict__ in, const FsdiBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_group,
+                                                       const FsdiState* __restrict__ st, const uint32_t* __restrict__ start, const uint8_t* __restrict__ snap,
+                                                       uint8_t* __restrict__ out) {
+    __shared__ uint16_t s_tok_all[4][32];
+    const uint32_t gw = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const uint32_t bi = blk_of_group[blockIdx.x];
+    const FsdiBlock& B = blocks[bi];
+    const uint32_t tl = gw - (uint32_t)B.tile_base;
+    if (!B.active || st[bi].bad || tl >= st[bi].ntiles_ok) return;
+    const uint8_t* src = in + B.src_off;
+    const uint32_t mode = src[0], dist = src[1];
+    const uint32_t si = 2 + dist + 32 * tl;
+    const uint32_t cnt = min(32u, B.len - si);
+    const uint32_t t = (uint32_t)lane < cnt ? src[si + lane] : 0u;
+    const uint32_t sw = start[gw];
+    uint32_t tk, prefix;
+    bool is_esc;
+    const uint32_t m = fsdi_tokens(t, cnt, mode, dist, sw >> 31, s_tok_all[threadIdx.x >> 5], tk, is_esc, prefix);
+    const uint32_t di0 = sw & 0x7FFFFFFFu;
+    const uint32_t base = snap[(size_t)gw * 16 + (di0 + lane) % dist];
+    uint32_t v = (mode == 0 ? prefix + base : prefix ^ base) & 0xFFu;
+    if (mode == 0) {
+        uint32_t em = __ballot_sync(0xFFFFFFFFu, is_esc);
+        while (em) {  // escapes of the tile in order (as in fsd_inverse_kernel)
+            const int e = __ffs((int)em) - 1;
+            em &= em - 1;
+            const uint32_t prev_in = __shfl_sync(0xFFFFFFFFu, v, e >= (int)dist ? e - (int)dist : 0);
+            const uint32_t prev_old = __shfl_sync(0xFFFFFFFFu, base, e);  // lane e's chain value at the tile start
+            const uint32_t prev = e >= (int)dist ? prev_in : prev_old;
+            const uint32_t tent = __shfl_sync(0xFFFFFFFFu, v, e);
+            const uint32_t pay = __shfl_sync(0xFFFFFFFFu, tk, e);
+            const uint32_t delta = ((pay ^ prev) - tent) & 0xFFu;
+            if (lane >= e && ((uint32_t)(lane - e) % dist) == 0) v = (v + delta) & 0xFFu;
+        }
+    }
+    if ((uint32_t)lane < m) out[B.dst_off + di0 + lane] = (uint8_t)v;
+}
+__global__ void fsdi_result_kernel(const FsdiBlock* __restrict__ blocks, int nblocks, const FsdiState* __restrict__ st, FsdResult* __restrict__ res) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    FsdResult r;
+    r.status = 0, r.out_len = 0, r.data_type = 0, r.mode = 0;
+    if (blocks[b].active) {
+        r.out_len = st[b].total;
+        if (st[b].bad) r.status = -KZ_E_PROCESS_BLOCK;
+    }
+    res[b] = r;
+}
+}  // namespace
+
+size_t fsd_inverse_workspace(uint32_t nblocks, uint64_t total_len) {
+    const size_t tiles = (size_t)total_len / 32 + 8 * (size_t)nblocks + 8;
+    return tiles * (4 + 4 + 16 + 16 + 1 + 4 * FSD_ESC_SLOTS + 1) + (size_t)nblocks * (sizeof(FsdiBlock) + sizeof(FsdiState)) + 16 * 256 + 4096;
+}
+
+// FSDCodec.Inverse of a batch over tiles (kernels above); h_blocks: the descriptors on the host. KZ_MM_INV=warp: fsd_inverse_kernel (one warp per block).
+cudaError_t fsd_inverse_tiles(const uint8_t* d_in, uint8_t* d_out, const FsdBlock* h_blocks, uint32_t nblocks, uint8_t* ws, size_t ws_bytes, FsdResult* d_res,
+                              cudaStream_t stream, uint64_t* launches) {
+    if (nblocks == 0) return cudaSuccess;
+    std::vector<FsdiBlock> hb(nblocks);
+    std::vector<uint32_t> blk_of_group;
+    uint64_t tiles = 0;
+    for (uint32_t b = 0; b < nblocks; b++) {
+        FsdiBlock& B = hb[b];
+        B.src_off = h_blocks[b].src_off, B.dst_off = h_blocks[b].dst_off, B.len = h_blocks[b].len, B.cap = h_blocks[b].cap;
+        B.active = (h_blocks[b].len != 0 && h_blocks[b].cap != 0) ? 1u : 0u;
+        B.ntiles = B.active ? (B.len + 31) / 32 : 0;  // upper bound (the header and the first `dist` bytes are not tiled)
+        B.tile_base = tiles;
+        const uint32_t groups = (B.ntiles + 3) / 4;
+        for (uint32_t g = 0; g < groups; g++) blk_of_group.push_back(b);
+        tiles += (uint64_t)groups * 4;
+    }
+    auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
+    size_t off = 0;
+    FsdiBlock* d_b = (FsdiBlock*)(ws + off); off = align(off + nblocks * sizeof(FsdiBlock));
+    FsdiState* d_st = (FsdiState*)(ws + off); off = align(off + nblocks * sizeof(FsdiState));
+    uint32_t* d_bog = (uint32_t*)(ws + off); off = align(off + (blk_of_group.size() + 1) * 4);
+    uint32_t* d_rec = (uint32_t*)(ws + off); off = align(off + (tiles + 4) * 4);
+    uint32_t* d_start = (uint32_t*)(ws + off); off = align(off + (tiles + 4) * 4);
+    uint8_t* d_tot = ws + off; off = align(off + (tiles + 4) * 16);
+    uint8_t* d_snap = ws + off; off = align(off + (tiles + 4) * 16);
+    uint8_t* d_nesc = ws + off; off = align(off + (tiles + 4));
+    uint32_t* d_esc = (uint32_t*)(ws + off); off = align(off + (tiles + 4) * 4 * FSD_ESC_SLOTS);
+    if (off > ws_bytes) return cudaErrorInvalidValue;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d_b, hb.data(), nblocks * sizeof(FsdiBlock), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+    const uint32_t groups = (uint32_t)blk_of_group.size();
+    if (groups) {
+        if ((e = cudaMemcpyAsync(d_bog, blk_of_group.data(), (size_t)groups * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        fsdi_k1_kernel<<<groups, 128, 0, stream>>>(d_in, d_b, d_bog, d_rec);
+    }
+    fsdi_k2_kernel<<<nblocks, 32, 0, stream>>>(d_in, d_b, (int)nblocks, d_rec, d_start, d_st, d_out);
+    if (groups) {
+        fsdi_k3_kernel<<<groups, 128, 0, stream>>>(d_in, d_b, d_bog, d_st, d_start, d_tot, d_esc, d_nesc);
+        fsdi_k4_kernel<<<nblocks, 32, 0, stream>>>(d_in, d_b, (int)nblocks, d_st, d_start, d_tot, d_esc, d_nesc, d_snap);
+        fsdi_k5_kernel<<<groups, 128, 0, stream>>>(d_in, d_b, d_bog, d_st, d_start, d_snap, d_out);
+    }
+    fsdi_result_kernel<<<(nblocks + 127) / 128, 128, 0, stream>>>(d_b, (int)nblocks, d_st, d_res);
+    if (launches) *launches += 6;
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;  // hb / blk_of_group go out of scope
     return cudaGetLastError();
 }
 

@@ -94,6 +94,10 @@ __global__ void __launch_bounds__(32) lzi_parse_kernel(const uint8_t* __restrict
         const bool live = (uint32_t)lane < n;
         const uint32_t tok = tok_next;
         tok_next = t0 + 32 + lane < tk_n ? src[tk0 + t0 + 32 + lane] : 0u;
+        {  // the three byte streams are consumed front to back: pull the next lines into L1 so the chased loads below hit
+            const int64_t pf = lane < 4 ? lit_pos + 128 * (lane + 1) : (lane < 6 ? m_pos + 128 * (lane - 3) : mlen_pos + 128 * (lane - 5));
+            if (lane < 8 && pf < count) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + pf));
+        }
         const bool last = live && t0 + lane == tk_n - 1;  // the final token: literals only
         const uint32_t lit_code = live ? tok >> 5 : 0u;
         const bool lit_ext = live && tok >= 0xE0u;

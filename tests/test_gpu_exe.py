@@ -97,3 +97,16 @@ def test_stream_parity_level4_chain(gpu, oracle, synth, kz, bs):
     m = min(len(got), len(want))
     assert len(got) == len(want) and np.array_equal(got, want), (bs, len(got), len(want), int(np.argmax(got[:m] != want[:m])))
     assert np.array_equal(gpu.decompress(want, n + 64), x), bs
+
+
+@pytest.mark.parametrize("n,seed", [(4096, 1), (65536, 3), (1 << 20, 5)])
+def test_exe_x86_blocks_of_the_independent_pin(gpu, oracle, kz, n, seed):
+    """the blocks tests/test_oracle_exe_independent.py pins the oracle with (a third, Python statement of EXECodec.go's x86 path): GPU == that statement"""
+    from test_oracle_exe_independent import forward_x86, make_block
+
+    x = make_block(n, seed)
+    want = forward_x86(x)
+    got, _ = gpu.transform_forward(kz.TRANSFORM_IDS["EXE"], x)
+    assert want is not None and got is not None and len(got) == len(want) and np.array_equal(got, want)
+    back = gpu.transform_inverse(kz.TRANSFORM_IDS["EXE"], want, n + 64)
+    assert np.array_equal(back, x)
