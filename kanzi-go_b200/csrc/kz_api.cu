@@ -990,6 +990,16 @@ int apply_forward(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint64_t istride
                 uint32_t b = b0;
                 for (; b < nblocks; b++) {
                     if (!active[b] || len[b] < 2) continue;
+                    if (len[b] > bwt_forward_batch_max_total()) {  // a block the batch's key layout cannot hold (1 GiB): its own suffix sort
+                        if (!nn.empty()) break;                    // flush what has been collected first
+                        CK(ctx->d_ws.ensure(bwt_forward_workspace(len[b])));
+                        LaunchScope ls(ctx, "bwt_forward");
+                        cudaError_t e = bwt_forward_device(d_in + b * istride, len[b], d_out + b * ostride, d_post + b, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap,
+                                                           ctx->stream, &ctx->launches);
+                        if (e == cudaSuccess) applied[b] = 1;
+                        else if (e != cudaErrorInvalidValue) return ctx->cuda_fail(e, "bwt_forward");
+                        continue;
+                    }
                     if (!nn.empty() && (total + len[b] > bwt_forward_batch_max_total() || nn.size() >= bwt_forward_batch_max_blocks())) break;
                     so.push_back(b * istride), dof.push_back(b * ostride), nn.push_back(len[b]), num.push_back(b);
                     total += len[b];
