@@ -967,7 +967,7 @@ int apply_forward(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint64_t istride
         uint32_t* d_post = ctx->d_lens.as<uint32_t>();
         static const bool one_by_one = [] {  // KZ_BWT_FWD=single: one suffix sort per block (round 1)
             const char* e = getenv("KZ_BWT_FWD");
-            return e && e[0] == 's';
+            return e && e[0] == 's' && e[1] == 'i';
         }();
         if (one_by_one) {
             uint32_t max_len = 0;
@@ -1477,7 +1477,7 @@ int apply_inverse(kz_ctx* ctx, uint64_t t, const uint8_t* d_in, uint8_t* d_out, 
                 LaunchScope ls(ctx, "bwt_inverse");
                 cudaError_t e = bwt_inverse_batch(d_in, d_out, so.data(), dof.data(), ll.data(), hh.data(), (uint32_t)ll.size(), cap, produced.data(),
                                                   ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap, ctx->stream, &ctx->launches);
-                if (e == cudaErrorInvalidValue) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "BWT inverse transform failed: invalid header");
+                if (e == cudaErrorInvalidValue) return ctx->fail(KZ_ERR_PROCESS_BLOCK, "BWT inverse transform failed: invalid header or data");
                 if (e != cudaSuccess) return ctx->cuda_fail(e, "bwt_inverse");
                 for (size_t k = 0; k < num.size(); k++) len[num[k]] = produced[k];
             }

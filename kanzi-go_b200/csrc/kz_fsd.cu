@@ -731,10 +731,131 @@ __global__ void __launch_bounds__(32) fsdi_k4_kernel(const uint8_t* __restrict__
         }
     }
 }
+// K3b: per block, exclusive prefix over the tiles of (a) the escape counts and (b) the 16 chain totals (bytes: add modulo 256, or xor) — one CTA
+// per block, 256 tiles per step, the 16 bytes of a tile scanned as four words of four byte lanes
+__device__ __forceinline__ uint32_t fsdi_add4(uint32_t a, uint32_t b) {  // four independent byte additions
+    return ((a & 0x7F7F7F7Fu) + (b & 0x7F7F7F7Fu)) ^ ((a ^ b) & 0x80808080u);
+}
+__global__ void __launch_bounds__(256) fsdi_k3b_kernel(const uint8_t* __restrict__ in, const FsdiBlock* __restrict__ blocks, int nblocks, const FsdiState* __restrict__ st,
+                                                        const uint8_t* __restrict__ totals, const uint8_t* __restrict__ nesc, uint8_t* __restrict__ ptile /*16 per tile*/,
+                                                        uint32_t* __restrict__ esc_base, uint32_t* __restrict__ esc_total) {
+    __shared__ uint4 s_w[8];
+    __shared__ uint32_t s_c[8];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (b >= nblocks) return;
+    const FsdiBlock B = blocks[b];
+    const uint32_t nt = st[b].ntiles_ok;
+    if (!B.active || nt == 0) {
+        if (tid == 0) esc_total[b] = 0;
+        return;
+    }
+    const bool is_xor = in[B.src_off] != 0;
+    const size_t tb = B.tile_base;
+    uint4 carry = make_uint4(0, 0, 0, 0);
+    uint32_t ccount = 0;
+    auto comb = [&](uint4 a, uint4 c) {
+        return is_xor ? make_uint4(a.x ^ c.x, a.y ^ c.y, a.z ^ c.z, a.w ^ c.w) : make_uint4(fsdi_add4(a.x, c.x), fsdi_add4(a.y, c.y), fsdi_add4(a.z, c.z), fsdi_add4(a.w, c.w));
+    };
+    for (uint32_t t0 = 0; t0 < nt; t0 += 256) {
+        const uint32_t t = t0 + tid;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        uint32_t c = 0;
+        if (t < nt) {
+            v = *reinterpret_cast<const uint4*>(totals + (tb + t) * 16);
+            c = nesc[tb + t];
+        }
+        uint4 iv = v;
+        uint32_t ic = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint4 y;
+            y.x = __shfl_up_sync(0xFFFFFFFFu, iv.x, d), y.y = __shfl_up_sync(0xFFFFFFFFu, iv.y, d), y.z = __shfl_up_sync(0xFFFFFFFFu, iv.z, d), y.w = __shfl_up_sync(0xFFFFFFFFu, iv.w, d);
+            const uint32_t yc = __shfl_up_sync(0xFFFFFFFFu, ic, d);
+            if (lane >= d) iv = comb(iv, y), ic += yc;
+        }
+        if (lane == 31) s_w[warp] = iv, s_c[warp] = ic;
+        __syncthreads();
+        uint4 pre = carry;
+        uint32_t prec = ccount;
+        uint4 tot = carry;
+        uint32_t totc = ccount;
+        for (int w = 0; w < 8; w++) {
+            if (w < warp) pre = comb(pre, s_w[w]), prec += s_c[w];
+            tot = comb(tot, s_w[w]), totc += s_c[w];
+        }
+        // exclusive: everything before this tile
+        uint4 ev;
+        ev.x = __shfl_up_sync(0xFFFFFFFFu, iv.x, 1), ev.y = __shfl_up_sync(0xFFFFFFFFu, iv.y, 1), ev.z = __shfl_up_sync(0xFFFFFFFFu, iv.z, 1), ev.w = __shfl_up_sync(0xFFFFFFFFu, iv.w, 1);
+        uint32_t ec = __shfl_up_sync(0xFFFFFFFFu, ic, 1);
+        if (lane == 0) ev = make_uint4(0, 0, 0, 0), ec = 0;
+        if (t < nt) {
+            *reinterpret_cast<uint4*>(ptile + (tb + t) * 16) = comb(pre, ev);
+            esc_base[tb + t] = prec + ec;
+        }
+        __syncthreads();
+        carry = tot;
+        ccount = totc;
+    }
+    if (tid == 0) esc_total[b] = ccount;
+}
+// K3c: the escapes of every tile into the block's flat list (two words: chain | payload << 8 | deltas before << 16, tile)
+__global__ void __launch_bounds__(256) fsdi_k3c_kernel(const FsdiBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_group, const FsdiState* __restrict__ st,
+                                                        const uint32_t* __restrict__ esc, const uint8_t* __restrict__ nesc, const uint32_t* __restrict__ esc_base,
+                                                        uint2* __restrict__ flat) {
+    const uint32_t gt = blockIdx.x * 4 + (threadIdx.x >> 6);  // 64 threads per tile slot group: thread j < nesc copies escape j
+    const int j = threadIdx.x & 63;
+    const uint32_t bi = blk_of_group[blockIdx.x];
+    const FsdiBlock& B = blocks[bi];
+    const uint32_t tl = gt - (uint32_t)B.tile_base;
+    if (!B.active || tl >= st[bi].ntiles_ok) return;
+    if (j < (int)nesc[gt]) flat[(size_t)B.tile_base * FSD_ESC_SLOTS + esc_base[gt] + j] = make_uint2(esc[(size_t)gt * FSD_ESC_SLOTS + j], tl);
+}
+// K4 (escape list version): one warp per block walks the block's ESCAPES only; corr[c] = what has to be added to
+// (first value of chain c + chain prefix) behind the escapes so far. After every escape the 16 corrections are stored.
+__global__ void __launch_bounds__(32) fsdi_k4e_kernel(const uint8_t* __restrict__ in, const FsdiBlock* __restrict__ blocks, int nblocks, const FsdiState* __restrict__ st,
+                                                       const uint2* __restrict__ flat, const uint32_t* __restrict__ esc_total, const uint8_t* __restrict__ ptile,
+                                                       uint8_t* __restrict__ corrvec /*16 per escape*/) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (b >= nblocks) return;
+    const FsdiBlock B = blocks[b];
+    const uint32_t ne = esc_total[b];
+    if (!B.active || st[b].ntiles_ok == 0 || ne == 0) return;
+    const uint8_t* src = in + B.src_off;
+    const uint32_t dist = src[1];
+    const uint32_t c = (uint32_t)lane & 15u;
+    const uint32_t r0 = c < dist ? src[2 + c] : 0u;
+    const size_t tb = B.tile_base, eb0 = (size_t)B.tile_base * FSD_ESC_SLOTS;  // first tile / first escape slot of the block
+    uint32_t corr = 0;
+    auto fetch = [&](uint32_t e0, uint32_t& w, uint32_t& pt) {
+        w = 0, pt = 0;
+        if (e0 + lane < ne) {
+            const uint2 f = flat[eb0 + e0 + lane];
+            w = f.x;
+            pt = ptile[(tb + f.y) * 16 + (f.x & 0xFFu)];
+        }
+    };
+    uint32_t wn, ptn;
+    fetch(0, wn, ptn);
+    for (uint32_t e0 = 0; e0 < ne; e0 += 32) {
+        const uint32_t wc = wn, ptc = ptn;
+        fetch(e0 + 32, wn, ptn);  // next 32 escapes in flight
+        const uint32_t n = min(32u, ne - e0);
+        for (uint32_t j = 0; j < n; j++) {
+            const uint32_t w = __shfl_sync(0xFFFFFFFFu, wc, (int)j), pt = __shfl_sync(0xFFFFFFFFu, ptc, (int)j);
+            const uint32_t pay = (w >> 8) & 0xFFu, pl = (w >> 16) & 0xFFu;
+            if ((w & 0xFFu) == c) {
+                const uint32_t lin = (r0 + pt + pl) & 0xFFu;           // value before the escape without corrections
+                corr = ((pay ^ ((lin + corr) & 0xFFu)) - lin) & 0xFFu;  // the escape's value is payload ^ (value before it)
+            }
+            if (lane < 16) corrvec[(eb0 + e0 + j) * 16 + lane] = (uint8_t)corr;
+        }
+    }
+}
+
 // K5: the bytes of every tile
 __global__ void __launch_bounds__(128) fsdi_k5_kernel(const uint8_t* __restrict__ in, const FsdiBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_group,
-                                                       const FsdiState* __restrict__ st, const uint32_t* __restrict__ start, const uint8_t* __restrict__ snap,
-                                                       uint8_t* __restrict__ out) {
+                                                       const FsdiState* __restrict__ st, const uint32_t* __restrict__ start, const uint8_t* __restrict__ ptile,
+                                                       const uint32_t* __restrict__ esc_base, const uint8_t* __restrict__ corrvec, uint8_t* __restrict__ out) {
     __shared__ uint16_t s_tok_all[4][32];
     const uint32_t gw = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -752,7 +873,12 @@ __global__ void __launch_bounds__(128) fsdi_k5_kernel(const uint8_t* __restrict_
     bool is_esc;
     const uint32_t m = fsdi_tokens(t, cnt, mode, dist, sw >> 31, s_tok_all[threadIdx.x >> 5], tk, is_esc, prefix);
     const uint32_t di0 = sw & 0x7FFFFFFFu;
-    const uint32_t base = snap[(size_t)gw * 16 + (di0 + lane) % dist];
+    // the chain's value when the tile starts: first value of the chain, chain totals of the tiles before, corrections of the escapes before
+    const uint32_t ch = (di0 + lane) % dist;
+    const uint32_t pt = ptile[(size_t)gw * 16 + ch];
+    const uint32_t eb = esc_base[gw];
+    const uint32_t cr = eb ? corrvec[((size_t)B.tile_base * FSD_ESC_SLOTS + eb - 1) * 16 + ch] : 0u;
+    const uint32_t base = mode == 0 ? (src[2 + ch] + pt + cr) & 0xFFu : (src[2 + ch] ^ pt);
     uint32_t v = (mode == 0 ? prefix + base : prefix ^ base) & 0xFFu;
     if (mode == 0) {
         uint32_t em = __ballot_sync(0xFFFFFFFFu, is_esc);
@@ -785,7 +911,7 @@ __global__ void fsdi_result_kernel(const FsdiBlock* __restrict__ blocks, int nbl
 
 size_t fsd_inverse_workspace(uint32_t nblocks, uint64_t total_len) {
     const size_t tiles = (size_t)total_len / 32 + 8 * (size_t)nblocks + 8;
-    return tiles * (4 + 4 + 16 + 16 + 1 + 4 * FSD_ESC_SLOTS + 1) + (size_t)nblocks * (sizeof(FsdiBlock) + sizeof(FsdiState)) + 16 * 256 + 4096;
+    return tiles * (4 + 4 + 16 + 16 + 1 + 4 * FSD_ESC_SLOTS + 1 + 4 + (8 + 16) * FSD_ESC_SLOTS) + (size_t)nblocks * (sizeof(FsdiBlock) + sizeof(FsdiState) + 4) + 24 * 256 + 4096;
 }
 
 // FSDCodec.Inverse of a batch over tiles (kernels above); h_blocks: the descriptors on the host. KZ_MM_INV=warp: fsd_inverse_kernel (one warp per block).
@@ -816,6 +942,10 @@ cudaError_t fsd_inverse_tiles(const uint8_t* d_in, uint8_t* d_out, const FsdBloc
     uint8_t* d_snap = ws + off; off = align(off + (tiles + 4) * 16);
     uint8_t* d_nesc = ws + off; off = align(off + (tiles + 4));
     uint32_t* d_esc = (uint32_t*)(ws + off); off = align(off + (tiles + 4) * 4 * FSD_ESC_SLOTS);
+    uint32_t* d_ebase = (uint32_t*)(ws + off); off = align(off + (tiles + 4) * 4);
+    uint32_t* d_etot = (uint32_t*)(ws + off); off = align(off + (size_t)nblocks * 4 + 64);
+    uint2* d_flat = (uint2*)(ws + off); off = align(off + (tiles + 4) * 8 * FSD_ESC_SLOTS);
+    uint8_t* d_corr = ws + off; off = align(off + (tiles + 4) * 16 * FSD_ESC_SLOTS);
     if (off > ws_bytes) return cudaErrorInvalidValue;
     cudaError_t e;
     if ((e = cudaMemcpyAsync(d_b, hb.data(), nblocks * sizeof(FsdiBlock), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
@@ -827,11 +957,13 @@ cudaError_t fsd_inverse_tiles(const uint8_t* d_in, uint8_t* d_out, const FsdBloc
     fsdi_k2_kernel<<<nblocks, 32, 0, stream>>>(d_in, d_b, (int)nblocks, d_rec, d_start, d_st, d_out);
     if (groups) {
         fsdi_k3_kernel<<<groups, 128, 0, stream>>>(d_in, d_b, d_bog, d_st, d_start, d_tot, d_esc, d_nesc);
-        fsdi_k4_kernel<<<nblocks, 32, 0, stream>>>(d_in, d_b, (int)nblocks, d_st, d_start, d_tot, d_esc, d_nesc, d_snap);
-        fsdi_k5_kernel<<<groups, 128, 0, stream>>>(d_in, d_b, d_bog, d_st, d_start, d_snap, d_out);
+        fsdi_k3b_kernel<<<nblocks, 256, 0, stream>>>(d_in, d_b, (int)nblocks, d_st, d_tot, d_nesc, d_snap /* = chain prefixes per tile */, d_ebase, d_etot);
+        fsdi_k3c_kernel<<<groups, 256, 0, stream>>>(d_b, d_bog, d_st, d_esc, d_nesc, d_ebase, d_flat);
+        fsdi_k4e_kernel<<<nblocks, 32, 0, stream>>>(d_in, d_b, (int)nblocks, d_st, d_flat, d_etot, d_snap, d_corr);
+        fsdi_k5_kernel<<<groups, 128, 0, stream>>>(d_in, d_b, d_bog, d_st, d_start, d_snap, d_ebase, d_corr, d_out);
     }
     fsdi_result_kernel<<<(nblocks + 127) / 128, 128, 0, stream>>>(d_b, (int)nblocks, d_st, d_res);
-    if (launches) *launches += 6;
+    if (launches) *launches += 8;
     if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;  // hb / blk_of_group go out of scope
     return cudaGetLastError();
 }

@@ -33,7 +33,8 @@ const int SEG = 1024;                // bytes per speculative segment (one warp 
 const int SEG_CAP = SEG / 4 + 8;     // log entries per segment (a match is at least 4 bytes long)
 const int JCAP = 64;                 // fix-up matches per junction before it gives up (a live one that does sends the block to the serial stitch)
 const int PROBE_CAP = 32;            // bytes a lane follows a match on its own before the warp takes over (a multiple of 8)
-const int WALK_WIN = 4096;           // junction records staged in shared memory per window of the walk
+const int WALK_WIN = 4096;
+const int WALKP_MAX_SERIAL_FROM = 4096;  // blocks with more segments than this take the windowed serial walk (= WALKP_MAX)           // junction records staged in shared memory per window of the walk
 const int MAX_ROUNDS = 96;
 const int TILE = 1024;               // matches per emission tile
 const uint32_t LONG_RUN = 4096;      // literal runs above this length are copied by all warps of the block's CTAs together
@@ -151,16 +152,29 @@ __global__ void __launch_bounds__(128) lzp_dirty_kernel(const PBlock* __restrict
 __global__ void __launch_bounds__(256) lzp_derive_kernel(const PBlock* __restrict__ blocks, const uint32_t* __restrict__ blk_of_chunk, const uint32_t* __restrict__ act_chunks,
                                                           const PState* __restrict__ pst, const Match* __restrict__ ml_all, const uint32_t* __restrict__ vf,
                                                           uint32_t* __restrict__ vf2, uint32_t* __restrict__ changed, uint64_t total) {
-    const uint64_t g = (uint64_t)act_chunks[blockIdx.x >> 2] * 1024 + (blockIdx.x & 3) * 256 + threadIdx.x;
-    const uint32_t b = blk_of_chunk[min(g, total - 1) >> 10];  // a chunk of 1024 positions belongs to one block: uniform per CTA
+    // one CTA per chunk of 1024 positions, four consecutive positions per thread: one search in the match list, then it only moves forward
+    const uint64_t g0 = (uint64_t)act_chunks[blockIdx.x] * 1024 + threadIdx.x * 4;
+    const uint32_t b = blk_of_chunk[act_chunks[blockIdx.x]];
+    const PBlock& B = blocks[b];
     bool diff = false;
-    if (g < total) {
-        const PBlock& B = blocks[b];
-        const uint32_t i = (uint32_t)(g - B.pos_off);
-        uint32_t v = 0;
-        if (B.active && i < B.count) v = derive_vf(ml_all + B.match_off, pst[b].nmatch, (int)B.src_end, (int)i);
-        vf2[g] = v;
-        diff = v != vf[g];
+    if (g0 < total) {  // total is a multiple of 1024
+        const Match* ml = ml_all + B.match_off;
+        const uint32_t nm = pst[b].nmatch;
+        const uint32_t i0 = (uint32_t)(g0 - B.pos_off);
+        uint32_t v[4] = {0, 0, 0, 0};
+        if (B.active && i0 < B.count) {
+            uint32_t t = matches_ended(ml, nm, (int)i0);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t i = i0 + k;
+                if (i >= B.count) break;
+                while (t < nm && (int)(ml[t].start + ml[t].len) <= (int)i) t++;
+                v[k] = derive_vf_at(ml, nm, (int)B.src_end, (int)i, t);
+            }
+        }
+        const uint4 old = *reinterpret_cast<const uint4*>(vf + g0);
+        *reinterpret_cast<uint4*>(vf2 + g0) = make_uint4(v[0], v[1], v[2], v[3]);
+        diff = v[0] != old.x || v[1] != old.y || v[2] != old.z || v[3] != old.w;
     }
     if (__syncthreads_or(diff ? 1 : 0) && threadIdx.x == 0) atomicOr(&changed[b], 1u);
 }
@@ -384,7 +398,7 @@ __global__ void __launch_bounds__(128) lzp_junction_kernel(const uint8_t* __rest
 // packed junction record of the walk: n (9 bits) | END_BLOCK << 9 | status << 10 | fix_n << 12 | idx << 19; second word: joined segment
 __global__ void __launch_bounds__(256) lzp_walk_kernel(const PBlock* __restrict__ blocks, const uint32_t* __restrict__ act_blocks, const SegDesc* __restrict__ desc_all,
                                                         const Junction* __restrict__ junc_all, Piece* __restrict__ pieces, uint32_t* __restrict__ piece_start,
-                                                        PState* __restrict__ pst) {
+                                                        PState* __restrict__ pst, int skip_small) {
     __shared__ uint32_t s_w0[WALK_WIN], s_w1[WALK_WIN];
     __shared__ int s_k, s_stop;
     const uint32_t b = act_blocks[blockIdx.x];
@@ -397,6 +411,7 @@ __global__ void __launch_bounds__(256) lzp_walk_kernel(const PBlock* __restrict_
         }
         return;
     }
+    if (skip_small && B.nsegs <= (uint32_t)WALKP_MAX_SERIAL_FROM) return;  // lzp_walk_par_kernel does these
     const SegDesc* desc = desc_all + B.seg_base;
     const Junction* junc = junc_all + B.seg_base;
     Piece* pc = pieces + B.piece_off;
@@ -467,6 +482,128 @@ __global__ void __launch_bounds__(256) lzp_walk_kernel(const PBlock* __restrict_
         S.final_anchor = final_anchor;
         S.m_total = S.mlen_total = S.lit_total = S.too_many = 0;
         ps[np] = total;
+        pst[b] = S;
+    }
+}
+// The same walk for blocks of up to WALKP_MAX segments without the serial loop: the junction records are a linked list next[k] > k from
+// segment 0; the live segments are marked by pointer doubling (13 rounds over shared memory), every live segment then knows where its log
+// is entered (one scatter), and its pieces and match counts are placed by a block-wide scan in segment order — which is list order.
+const int WALKP_MAX = 4096;
+__global__ void __launch_bounds__(256) lzp_walk_par_kernel(const PBlock* __restrict__ blocks, const uint32_t* __restrict__ act_blocks, const SegDesc* __restrict__ desc_all,
+                                                            const Junction* __restrict__ junc_all, Piece* __restrict__ pieces, uint32_t* __restrict__ piece_start,
+                                                            PState* __restrict__ pst) {
+    __shared__ uint16_t s_next[WALKP_MAX], s_ja[WALKP_MAX], s_jb[WALKP_MAX], s_begin[WALKP_MAX];
+    __shared__ uint8_t s_ma[WALKP_MAX], s_mb[WALKP_MAX];
+    __shared__ uint32_t s_wp[8], s_wm[8];
+    __shared__ uint32_t s_over, s_anchor;
+    const uint32_t b = act_blocks[blockIdx.x];
+    const PBlock B = blocks[b];
+    if (!B.active || B.nsegs > (uint32_t)WALKP_MAX) return;  // larger blocks: lzp_walk_kernel
+    const int n = (int)B.nsegs, tid = threadIdx.x;
+    const SegDesc* desc = desc_all + B.seg_base;
+    const Junction* junc = junc_all + B.seg_base;
+    const uint16_t TERM = 0xFFFF;
+    if (tid == 0) s_over = 0, s_anchor = 0;
+    for (int k = tid; k < n; k += 256) {
+        const bool last = desc[k].end == END_BLOCK;
+        const uint32_t st = last ? (uint32_t)J_TERMINAL : junc[k].status;
+        s_next[k] = st == J_JOINED ? (uint16_t)junc[k].seg : TERM;
+        s_ja[k] = s_next[k];
+        s_ma[k] = k == 0 ? 1 : 0;
+        s_mb[k] = k == 0 ? 1 : 0;
+        s_begin[k] = 0;
+    }
+    __syncthreads();
+    // live[k]: k is on the list from 0. Round d: every marked k marks jump[k] (2^d links ahead), then jump doubles.
+    uint16_t *ja = s_ja, *jb = s_jb;
+    uint8_t *ma = s_ma, *mb = s_mb;
+    for (int d = 0; (1 << d) < n; d++) {
+        for (int k = tid; k < n; k += 256) {
+            const uint16_t j = ja[k];
+            if (ma[k]) {
+                mb[k] = 1;
+                if (j != TERM) mb[j] = 1;
+            }
+            jb[k] = j == TERM ? TERM : ja[j];
+        }
+        __syncthreads();
+        uint16_t* tj = ja; ja = jb; jb = tj;
+        uint8_t* tm = ma; ma = mb; mb = tm;
+        for (int k = tid; k < n; k += 256) mb[k] = ma[k];  // the other copy catches up (marks only grow)
+        __syncthreads();
+    }
+    // where a live segment's log is entered: behind the entry its predecessor joined
+    for (int k = tid; k < n; k += 256)
+        if (ma[k] && s_next[k] != TERM) s_begin[s_next[k]] = (uint16_t)(junc[k].idx + 1);
+    __syncthreads();
+    // pieces and match counts per live segment, 16 consecutive segments per thread, block-wide exclusive scan
+    uint32_t cp = 0, cm = 0;
+    const int k0 = tid * 16;
+    for (int k = k0; k < min(k0 + 16, n); k++) {
+        if (!ma[k]) continue;
+        const uint32_t nk = desc[k].n, bg = s_begin[k];
+        if (nk > bg) cp++, cm += nk - bg;
+        if (desc[k].end == END_BLOCK) continue;
+        const Junction J = junc[k];
+        if (J.status == J_OVERFLOW) {
+            s_over = 1;
+            continue;
+        }
+        if (J.fix_n) cp++, cm += J.fix_n;
+    }
+    uint32_t ip = cp, im = cm;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t yp = __shfl_up_sync(0xFFFFFFFFu, ip, d), ym = __shfl_up_sync(0xFFFFFFFFu, im, d);
+        if (lane >= d) ip += yp, im += ym;
+    }
+    if (lane == 31) s_wp[warp] = ip, s_wm[warp] = im;
+    __syncthreads();
+    uint32_t op = 0, om = 0, tp = 0, tm2 = 0;
+    for (int w = 0; w < 8; w++) {
+        if (w < warp) op += s_wp[w], om += s_wm[w];
+        tp += s_wp[w], tm2 += s_wm[w];
+    }
+    uint32_t at = op + ip - cp, total = om + im - cm;  // first piece index / first match index of this thread's segments
+    Piece* pc = pieces + B.piece_off;
+    uint32_t* ps = piece_start + B.piece_off;
+    for (int k = k0; k < min(k0 + 16, n); k++) {
+        if (!ma[k]) continue;
+        const uint32_t nk = desc[k].n, bg = s_begin[k];
+        if (nk > bg) {
+            Piece p;
+            p.spec = 1, p.seg = (uint32_t)k, p.begin = bg, p.end = nk;
+            pc[at] = p;
+            ps[at] = total;
+            at++;
+            total += nk - bg;
+        }
+        if (desc[k].end == END_BLOCK) {
+            s_anchor = (uint32_t)desc[k].fin.anchor;  // the list ends here
+            continue;
+        }
+        const Junction J = junc[k];
+        if (J.status == J_OVERFLOW) continue;
+        if (J.fix_n) {
+            Piece p;
+            p.spec = 2, p.seg = (uint32_t)k, p.begin = 0, p.end = J.fix_n;
+            pc[at] = p;
+            ps[at] = total;
+            at++;
+            total += J.fix_n;
+        }
+        if (J.status == J_TERMINAL) s_anchor = (uint32_t)J.anchor;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        PState S;
+        S.np = s_over ? 0xFFFFFFFFu : tp;
+        S.fix_n = 0;
+        S.nmatch = tm2;
+        S.final_anchor = (int32_t)s_anchor;
+        S.m_total = S.mlen_total = S.lit_total = S.too_many = 0;
+        ps[tp] = tm2;
         pst[b] = S;
     }
 }
@@ -896,14 +1033,19 @@ cudaError_t lz_forward_parallel_sub(const uint8_t* d_in, uint8_t* d_out, const L
         {
             LzHookScope hs(hook, round == 0 ? "lz_stitch_r0" : (round == 1 ? "lz_stitch_r1" : "lz_stitch"));
             lzp_junction_kernel<<<(NS + 3) / 4, 128, 0, stream>>>(d_in, d_pb, d_bos, extra ? 1 : 0, d_acts, NS, rec_r, d_logs, d_desc, d_jfix, d_junc, d_dirty, round == 0 ? 1 : 0);
-            lzp_walk_kernel<<<NB, 256, 0, stream>>>(d_pb, d_actb, d_desc, d_junc, d_pieces, d_pstart, d_pst);
+            static const bool serial_walk = [] {  // KZ_LZ_WALK=serial: the one-thread walk for every block
+                const char* ev = getenv("KZ_LZ_WALK");
+                return ev && ev[0] == 's';
+            }();
+            if (!serial_walk) lzp_walk_par_kernel<<<NB, 256, 0, stream>>>(d_pb, d_actb, d_desc, d_junc, d_pieces, d_pstart, d_pst);
+            lzp_walk_kernel<<<NB, 256, 0, stream>>>(d_pb, d_actb, d_desc, d_junc, d_pieces, d_pstart, d_pst, serial_walk ? 0 : 1);
             lzp_stitch_kernel<<<NB, 32, 0, stream>>>(d_in, d_pb, d_actb, extra ? 1 : 0, rec_r, d_logs, d_desc, d_fix, d_pieces, d_pstart, d_pst);
         }
         {
             LzHookScope hs(hook, round == 0 ? "lz_derive_r0" : (round == 1 ? "lz_derive_r1" : "lz_derive"));
             lzp_flatten_kernel<<<dim3(64, NB), 256, 0, stream>>>(d_pb, d_actb, d_pst, d_pieces, d_pstart, d_logs, d_jfix, d_fix, d_ml);
             cudaMemsetAsync(d_changed, 0, (size_t)nblocks * 4, stream);
-            lzp_derive_kernel<<<GA, 256, 0, stream>>>(d_pb, d_boc, d_actc, d_pst, d_ml, d_vf, d_vf2, d_changed, total);
+            lzp_derive_kernel<<<GA / 4, 256, 0, stream>>>(d_pb, d_boc, d_actc, d_pst, d_ml, d_vf, d_vf2, d_changed, total);
         }
         e = cudaMemcpyAsync(h_changed.data(), d_changed, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, stream);
         if (e != cudaSuccess) return e;

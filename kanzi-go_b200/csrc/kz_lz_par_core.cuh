@@ -276,14 +276,17 @@ KZL_HD bool run_offset_probed(uint32_t d) {
     return (d - 32u * g * (g + 1)) % (g + 1) == 0;
 }
 // vf of position j given the block's final match list ml[0..nm) (ascending): see the header comment
-KZL_HD uint32_t derive_vf(const Match* ml, uint32_t nm, int src_end, int j) {
-    uint32_t lo = 0, hi = nm;  // t = number of matches that end at or before j
+// t = number of matches that end at or before j
+KZL_HD uint32_t matches_ended(const Match* ml, uint32_t nm, int j) {
+    uint32_t lo = 0, hi = nm;
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
         if ((int)(ml[mid].start + ml[mid].len) <= j) lo = mid + 1;
         else hi = mid;
     }
-    const uint32_t t = lo;
+    return lo;
+}
+KZL_HD uint32_t derive_vf_at(const Match* ml, uint32_t nm, int src_end, int j, uint32_t t) {
     const int a = t ? (int)(ml[t - 1].start + ml[t - 1].len) : 0;
     if (t == nm) {
         if (j >= src_end) return 0;
@@ -294,6 +297,7 @@ KZL_HD uint32_t derive_vf(const Match* ml, uint32_t nm, int src_end, int j) {
     if (run_offset_probed((uint32_t)(j - a))) return 0;
     return j > (int)m.start ? m.start + m.len : VF_NEVER;
 }
+KZL_HD uint32_t derive_vf(const Match* ml, uint32_t nm, int src_end, int j) { return derive_vf_at(ml, nm, src_end, j, matches_ended(ml, nm, j)); }
 
 // One probe of the parse at position src_idx, first stage (:339-366): the two repeat-distance checks (repd_first before repd_second), then the
 // table entry. Returns true when a match of at least min_match was found: kind 0 = repeat distance, 1 = table (b = stored suffix length).

@@ -702,9 +702,12 @@ __global__ void __launch_bounds__(32 * W) sbrt_inverse_multi_kernel(const uint8_
         if (S == 4) {
             reinterpret_cast<uint4*>(s_q[par])[tid] = make_uint4(Q[0], Q[1], Q[S > 2 ? 2 : 0], Q[S > 3 ? 3 : 0]);
             reinterpret_cast<uint4*>(s_x[par])[tid] = make_uint4(X[0], X[1], X[S > 2 ? 2 : 0], X[S > 3 ? 3 : 0]);
+        } else if (S == 2) {
+            reinterpret_cast<uint2*>(s_q[par])[tid] = make_uint2(Q[0], Q[S > 1 ? 1 : 0]);
+            reinterpret_cast<uint2*>(s_x[par])[tid] = make_uint2(X[0], X[S > 1 ? 1 : 0]);
         } else {
-            reinterpret_cast<uint2*>(s_q[par])[tid] = make_uint2(Q[0], Q[1]);
-            reinterpret_cast<uint2*>(s_x[par])[tid] = make_uint2(X[0], X[1]);
+            s_q[par][tid] = Q[0];
+            s_x[par][tid] = X[0];
         }
         __syncthreads();
         return sym;
@@ -780,11 +783,14 @@ void sbrt_inverse_launch_len(const uint8_t* data, const SbrtBlock* d_blocks, int
             if (mode == 2) sbrt_inverse_flat_kernel<true><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, out);
             else sbrt_inverse_flat_kernel<false><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, out);
         } else {
-            static const int warps = [] {  // KZ_SBRT_WARPS = 1 (mirror kernel), 2 or 4 (default)
+            static const int warps = [] {  // KZ_SBRT_WARPS = 1 (mirror kernel), 2, 4 (default) or 8
                 const char* e = getenv("KZ_SBRT_WARPS");
                 return e ? atoi(e) : 4;
             }();
-            if (warps == 4) {
+            if (warps == 8) {
+                if (mode == 2) sbrt_inverse_multi_kernel<true, 8><<<nblocks, 256, 0, stream>>>(data, d_blocks, nblocks, out);
+                else sbrt_inverse_multi_kernel<false, 8><<<nblocks, 256, 0, stream>>>(data, d_blocks, nblocks, out);
+            } else if (warps == 4) {
                 if (mode == 2) sbrt_inverse_multi_kernel<true, 4><<<nblocks, 128, 0, stream>>>(data, d_blocks, nblocks, out);
                 else sbrt_inverse_multi_kernel<false, 4><<<nblocks, 128, 0, stream>>>(data, d_blocks, nblocks, out);
             } else if (warps == 2) {

@@ -78,3 +78,21 @@ def test_config4_block_32mb(gpu, oracle, synth, kz):
     assert np.array_equal(gpu.decompress(got, n + 64), x)
     want = oracle.compress(x, "BWT", "ANS0", block_size=n, jobs=1, input_size=n)
     assert len(got) == len(want) and np.array_equal(got, want)
+
+
+def test_bwt_inverse_corrupt_payload_is_reported_or_decoded(gpu, oracle, synth, kz):
+    """a payload whose LF permutation is not one list through all ranks (flipped primary index / data bytes) is an error, never stale device memory"""
+    x = synth.markov_text(100000, seed=3)
+    enc, _ = oracle.transform_forward(kz.T_BWT, x)
+    rng = np.random.default_rng(5)
+    for trial in range(16):
+        bad = enc.copy()
+        pos = 1 + trial if trial < 8 else int(rng.integers(40, len(bad)))  # the 8 primary index fields, then data bytes
+        bad[pos] ^= 1 << int(rng.integers(0, 8))
+        try:
+            y = gpu.transform_inverse(kz.T_BWT, bad, len(x) + 64)
+            assert len(y) == len(x)
+        except kz.KanziError:
+            pass
+    back = gpu.transform_inverse(kz.T_BWT, enc, len(x) + 64)  # and the engine is fine afterwards
+    assert np.array_equal(back, x)
