@@ -578,56 +578,91 @@ __global__ void __launch_bounds__(128) fsdi_k1_kernel(const uint8_t* __restrict_
     fsdi_classify(t, cnt, mode, 1, m1, p1, k1);
     if (lane == 0) rec[gw] = (uint32_t)__popc(k0) | ((uint32_t)__popc(k1) << 8) | (((m0 >> (cnt - 1)) & 1u) << 16) | (((m1 >> (cnt - 1)) & 1u) << 17);
 }
-// K2: one warp per block chains the tiles: incoming marker bit (bit 31 of start[]) and output offset of every tile
-__global__ void __launch_bounds__(32) fsdi_k2_kernel(const uint8_t* __restrict__ in, const FsdiBlock* __restrict__ blocks, int nblocks, const uint32_t* __restrict__ rec,
-                                                      uint32_t* __restrict__ start, FsdiState* __restrict__ st, uint8_t* __restrict__ out) {
-    const int b = blockIdx.x, lane = threadIdx.x;
+// K2: one CTA per block chains the tiles: a tile maps the incoming marker bit p to (outgoing bit, tokens) — a function with two cases,
+// closed under composition — so the chain is a scan over those functions, 256 tiles per step. start[t] = output offset | p << 31.
+struct FsdiFn {
+    uint32_t po;      // bit p = outgoing marker bit for incoming bit p
+    uint32_t c0, c1;  // tokens for incoming bit 0 / 1
+};
+__device__ __forceinline__ FsdiFn fsdi_then(const FsdiFn& a, const FsdiFn& b) {  // first a, then b
+    FsdiFn r;
+    const uint32_t a0 = a.po & 1u, a1 = (a.po >> 1) & 1u;
+    r.po = ((b.po >> a0) & 1u) | (((b.po >> a1) & 1u) << 1);
+    r.c0 = a.c0 + (a0 ? b.c1 : b.c0);
+    r.c1 = a.c1 + (a1 ? b.c1 : b.c0);
+    return r;
+}
+__global__ void __launch_bounds__(256) fsdi_k2_kernel(const uint8_t* __restrict__ in, const FsdiBlock* __restrict__ blocks, int nblocks, const uint32_t* __restrict__ rec,
+                                                       uint32_t* __restrict__ start, FsdiState* __restrict__ st, uint8_t* __restrict__ out) {
+    __shared__ FsdiFn s_w[8];
+    __shared__ uint32_t s_ok;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (b >= nblocks) return;
     const FsdiBlock B = blocks[b];
     FsdiState S;
     S.bad = 0, S.total = 0, S.ntiles_ok = 0, S.pad = 0;
     if (!B.active) {
-        if (lane == 0) st[b] = S;
+        if (tid == 0) st[b] = S;
         return;
     }
     const uint8_t* src = in + B.src_off;
     uint32_t mode, dist;
     if (!fsdi_header(src, B.len, B.cap, mode, dist)) {
         S.bad = 1;
-        if (lane == 0) st[b] = S;
+        if (tid == 0) st[b] = S;
         return;
     }
-    if ((uint32_t)lane < dist) out[B.dst_off + lane] = src[2 + lane];  // the first `dist` bytes are copied (:355-359)
+    if ((uint32_t)tid < dist) out[B.dst_off + tid] = src[2 + tid];  // the first `dist` bytes are copied (:355-359)
     const uint32_t nt = (B.len - 2 - dist + 31) / 32;
     const uint32_t* r = rec + B.tile_base;
     uint32_t* sp = start + B.tile_base;
-    uint32_t p = 0, di = dist, ok = nt;
-    bool bad = false;
-    uint32_t nxt = (uint32_t)lane < nt ? r[lane] : 0u;
-    for (uint32_t t0 = 0; t0 < nt && !bad; t0 += 32) {
-        const uint32_t mine = nxt;
-        nxt = t0 + 32 + lane < nt ? r[t0 + 32 + lane] : 0u;
-        uint32_t my_start = 0;
-        const uint32_t n = min(32u, nt - t0);
-        for (uint32_t j = 0; j < n; j++) {  // uniform: every lane tracks (p, di)
-            const uint32_t w = __shfl_sync(0xFFFFFFFFu, mine, (int)j);
-            const uint32_t tok = p ? (w >> 8) & 0xFFu : w & 0xFFu;
-            if (di + tok > B.cap) {  // the reference stops at dstEnd with source bytes left: an error (:398-400)
-                bad = true;
-                ok = t0 + j;
-                break;
-            }
-            if ((uint32_t)lane == j) my_start = di | (p << 31);
-            di += tok;
-            p = (w >> (16 + p)) & 1u;
+    if (tid == 0) s_ok = 0xFFFFFFFFu;
+    FsdiFn carry;
+    carry.po = 2u, carry.c0 = 0, carry.c1 = 0;  // identity
+    __syncthreads();
+    for (uint32_t t0 = 0; t0 < nt; t0 += 256) {
+        const uint32_t t = t0 + tid;
+        FsdiFn f;
+        f.po = 2u, f.c0 = 0, f.c1 = 0;
+        if (t < nt) {
+            const uint32_t w = r[t];
+            f.po = (w >> 16) & 3u, f.c0 = w & 0xFFu, f.c1 = (w >> 8) & 0xFFu;
         }
-        if (t0 + lane < min(ok, nt)) sp[t0 + lane] = my_start;
+        FsdiFn inc = f;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            FsdiFn y;
+            y.po = __shfl_up_sync(0xFFFFFFFFu, inc.po, d), y.c0 = __shfl_up_sync(0xFFFFFFFFu, inc.c0, d), y.c1 = __shfl_up_sync(0xFFFFFFFFu, inc.c1, d);
+            if (lane >= d) inc = fsdi_then(y, inc);
+        }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        FsdiFn pre = carry, tot = carry;
+        for (int w = 0; w < 8; w++) {
+            if (w < warp) pre = fsdi_then(pre, s_w[w]);
+            tot = fsdi_then(tot, s_w[w]);
+        }
+        FsdiFn ex;
+        ex.po = __shfl_up_sync(0xFFFFFFFFu, inc.po, 1), ex.c0 = __shfl_up_sync(0xFFFFFFFFu, inc.c0, 1), ex.c1 = __shfl_up_sync(0xFFFFFFFFu, inc.c1, 1);
+        if (lane == 0) ex.po = 2u, ex.c0 = 0, ex.c1 = 0;
+        const FsdiFn before = fsdi_then(pre, ex);  // everything before this tile, from the block's start (incoming bit 0)
+        if (t < nt) {
+            const uint32_t p = before.po & 1u, di = dist + before.c0;
+            sp[t] = di | (p << 31);
+            const uint32_t tok = p ? f.c1 : f.c0;
+            if ((uint64_t)di + tok > B.cap) atomicMin(&s_ok, t);  // the reference stops at dstEnd with source bytes left: an error (:398-400)
+        }
+        __syncthreads();
+        carry = tot;
     }
-    if (!bad && p) bad = true;  // a marker was the last source byte (:380-383)
-    S.bad = bad ? 1u : 0u;
-    S.total = di;
-    S.ntiles_ok = bad ? ok : nt;
-    if (lane == 0) st[b] = S;
+    if (tid == 0) {
+        const bool over = s_ok != 0xFFFFFFFFu;
+        const bool bad = over || (carry.po & 1u);  // ... or a marker was the last source byte (:380-383)
+        S.bad = bad ? 1u : 0u;
+        S.total = over ? (sp[s_ok] & 0x7FFFFFFFu) : dist + carry.c0;
+        S.ntiles_ok = over ? s_ok : nt;
+        st[b] = S;
+    }
 }
 // tokens of a tile in output order: lane k = token k (tk, is_esc) and its chain prefix (deltas on its chain inside the tile, escapes count 0)
 __device__ __forceinline__ uint32_t fsdi_tokens(uint32_t t, uint32_t cnt, uint32_t mode, uint32_t dist, uint32_t pending, uint16_t* s_tok, uint32_t& tk, bool& is_esc,
@@ -954,7 +989,7 @@ cudaError_t fsd_inverse_tiles(const uint8_t* d_in, uint8_t* d_out, const FsdBloc
         if ((e = cudaMemcpyAsync(d_bog, blk_of_group.data(), (size_t)groups * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
         fsdi_k1_kernel<<<groups, 128, 0, stream>>>(d_in, d_b, d_bog, d_rec);
     }
-    fsdi_k2_kernel<<<nblocks, 32, 0, stream>>>(d_in, d_b, (int)nblocks, d_rec, d_start, d_st, d_out);
+    fsdi_k2_kernel<<<nblocks, 256, 0, stream>>>(d_in, d_b, (int)nblocks, d_rec, d_start, d_st, d_out);
     if (groups) {
         fsdi_k3_kernel<<<groups, 128, 0, stream>>>(d_in, d_b, d_bog, d_st, d_start, d_tot, d_esc, d_nesc);
         fsdi_k3b_kernel<<<nblocks, 256, 0, stream>>>(d_in, d_b, (int)nblocks, d_st, d_tot, d_nesc, d_snap /* = chain prefixes per tile */, d_ebase, d_etot);
