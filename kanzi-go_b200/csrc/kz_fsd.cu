@@ -520,8 +520,9 @@ cudaError_t fsd_forward_batch(const uint8_t* d_in, uint8_t* d_out, const FsdBloc
 // incoming marker bit only through its leading run of 0xFF, so every tile is classified under both hypotheses (K1) and one warp per block
 // chains them (K2). (c): along a chain the deltas are a prefix sum and every escape replaces the value by payload ^ previous, which is not
 // a sum — but the escapes are few: each tile computes its chain totals and the list of its escapes with the delta sum in front of each
-// (K3), one warp per block (lane = chain) then walks the tiles once, O = (payload ^ (O + sum before)) - sum before per escape, + total per
-// tile, and leaves every tile its incoming chain values (K4). K5 is a round of fsd_inverse_kernel with all three carries given.
+// (K3); the chain totals are scanned over the tiles (K3b), the escapes are compacted into one list per block (K3c) and one warp per block (lane =
+// chain) walks that list only: corr = (payload ^ (linear value before + corr)) - linear value before (K4e). K5 is a round of fsd_inverse_kernel
+// with all three carries given.
 namespace {
 const int FSD_ESC_SLOTS = 17;  // escapes of a tile: marker + payload take two bytes, plus one whose marker ended the tile before
 struct FsdiBlock {
@@ -717,54 +718,6 @@ __global__ void __launch_bounds__(128) fsdi_k3_kernel(const uint8_t* __restrict_
     const uint32_t em = __ballot_sync(0xFFFFFFFFu, is_esc);
     if (is_esc) esc[(size_t)gw * FSD_ESC_SLOTS + __popc(em & ((1u << lane) - 1u))] = ((di0 + lane) % dist) | (tk << 8) | (prefix << 16);  // chain, payload, deltas before it
     if (lane == 0) nesc[gw] = (uint8_t)__popc(em);
-}
-// K4: one warp per block, lane = chain: the value every chain has when a tile starts
-__global__ void __launch_bounds__(32) fsdi_k4_kernel(const uint8_t* __restrict__ in, const FsdiBlock* __restrict__ blocks, int nblocks, const FsdiState* __restrict__ st,
-                                                      const uint32_t* __restrict__ start, const uint8_t* __restrict__ totals, const uint32_t* __restrict__ esc,
-                                                      const uint8_t* __restrict__ nesc, uint8_t* __restrict__ snap /*16 per tile*/) {
-    (void)start;
-    const int b = blockIdx.x, lane = threadIdx.x;
-    if (b >= nblocks) return;
-    const FsdiBlock B = blocks[b];
-    const uint32_t nt = st[b].ntiles_ok;
-    if (!B.active || nt == 0) return;
-    const uint8_t* src = in + B.src_off;
-    const uint32_t mode = src[0], dist = src[1];
-    const uint32_t r = (uint32_t)lane & 15u;  // chain of this lane (lanes 16..31 mirror 0..15 and hold the second half of the escape slots)
-    uint32_t R = r < dist ? src[2 + r] : 0u;
-    const size_t tb = B.tile_base;
-    const int G = 8;  // tiles per group; the next group's totals / escape words / counts are loaded while this one is walked
-    uint32_t Tn[G], En[G], Mn[G];
-    auto load_group = [&](uint32_t t0) {
-#pragma unroll
-        for (int j = 0; j < G; j++) {
-            const uint32_t t = t0 + j;
-            const bool in_range = t < nt;
-            Tn[j] = in_range ? totals[(tb + t) * 16 + r] : 0u;
-            En[j] = (in_range && lane < FSD_ESC_SLOTS) ? esc[(tb + t) * FSD_ESC_SLOTS + lane] : 0u;
-            Mn[j] = in_range ? (uint32_t)nesc[tb + t] : 0u;
-        }
-    };
-    load_group(0);
-    for (uint32_t t0 = 0; t0 < nt; t0 += G) {
-        uint32_t Tc[G], Ec[G], Mc[G];
-#pragma unroll
-        for (int j = 0; j < G; j++) Tc[j] = Tn[j], Ec[j] = En[j], Mc[j] = Mn[j];
-        load_group(t0 + G);
-#pragma unroll
-        for (int j = 0; j < G; j++) {
-            if (t0 + j >= nt) break;
-            if (lane < 16) snap[(tb + t0 + j) * 16 + lane] = (uint8_t)R;
-            const uint32_t ne = Mc[j];  // escapes of the tile
-            uint32_t O = R;
-            for (uint32_t e = 0; e < ne; e++) {
-                const uint32_t w = __shfl_sync(0xFFFFFFFFu, Ec[j], (int)e);
-                const uint32_t pay = (w >> 8) & 0xFFu, pl = (w >> 16) & 0xFFu;
-                if ((w & 0xFFu) == r) O = ((pay ^ ((O + pl) & 0xFFu)) - pl) & 0xFFu;
-            }
-            R = mode == 0 ? (O + Tc[j]) & 0xFFu : (O ^ Tc[j]);
-        }
-    }
 }
 // K3b: per block, exclusive prefix over the tiles of (a) the escape counts and (b) the 16 chain totals (bytes: add modulo 256, or xor) — one CTA
 // per block, 256 tiles per step, the 16 bytes of a tile scanned as four words of four byte lanes
