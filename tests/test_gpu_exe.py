@@ -110,3 +110,15 @@ def test_exe_x86_blocks_of_the_independent_pin(gpu, oracle, kz, n, seed):
     assert want is not None and got is not None and len(got) == len(want) and np.array_equal(got, want)
     back = gpu.transform_inverse(kz.TRANSFORM_IDS["EXE"], want, n + 64)
     assert np.array_equal(back, x)
+
+
+@pytest.mark.parametrize("n,seed", [(4096, 21), (300004, 23)])
+def test_exe_arm64_blocks_of_the_independent_pin(gpu, oracle, kz, n, seed):
+    from test_oracle_exe_independent import forward_arm, make_arm_block
+
+    x = make_arm_block(n, seed)
+    want = forward_arm(x)
+    got, _ = gpu.transform_forward(kz.TRANSFORM_IDS["EXE"], x)
+    assert want is not None and got is not None and len(got) == len(want) and np.array_equal(got, want)
+    back = gpu.transform_inverse(kz.TRANSFORM_IDS["EXE"], want, n + 64)
+    assert np.array_equal(back, x)

@@ -11,33 +11,133 @@ from oracle import pyoracle as po
 ESC, PREFIX, MASK_ADDR, ADDR_MASK = 0x9B, 0x0F, 0xF0F0F0F0, (1 << 24) - 1
 
 
-def detect_is_x86(src):
-    """detectExeType for a block whose first bytes are no known magic: the ad-hoc thresholds (:734-810). src = block[:count-4], code = [0, count-8)."""
+def detect(src):
+    """detectExeType for a block whose first bytes are no known magic: the ad-hoc thresholds (:734-810). src = block[:count-4], code = [0, count-8).
+    Returns "x86", "arm64" or None."""
     end = len(src) - 4
     histo = [0] * 256
-    jumps = 0
+    jumps_x86 = jumps_arm = 0
     i = 0
     while i < end:
         histo[src[i]] += 1
+        counted = False
         if (src[i] & 0xFE) == 0xE8:
             if src[i + 4] in (0, 0xFF):
-                jumps += 1
-                i += 1
-                continue
+                jumps_x86 += 1
+                counted = True
         elif src[i] == PREFIX:
             i += 1
             if src[i] in (0x38, 0x3A):
                 i += 1
             if (src[i] & 0xF0) == 0x80:
-                jumps += 1
-                i += 1
-                continue
-        i += 1  # (the ARM count does not matter once the x86 threshold is met)
+                jumps_x86 += 1
+                counted = True
+        if not counted and (i & 3) == 0:
+            instr = int.from_bytes(bytes(src[i: i + 4]), "little")
+            if (instr & 0xFC000000) in (0x14000000, 0x94000000) or (instr & 0x7F000000) in (0x34000000, 0x3500000):
+                jumps_arm += 1
+        i += 1
     if sum(1 for h in histo if h) != 256:  # DetectSimpleType: anything but "all 256 values present" is not DT_BIN here
-        return False
+        return None
     if histo[0] < end // 10 or sum(histo[:16]) > end // 2 or histo[255] < end // 100:
-        return False
-    return jumps >= end // 200
+        return None
+    if jumps_x86 >= end // 200:
+        return "x86"
+    if jumps_arm >= end // 200:
+        return "arm64"
+    return None
+
+
+def detect_is_x86(src):
+    return detect(src) == "x86"
+
+
+def forward_arm(src):
+    """forwardARM (:507-613) with codeStart = 0, codeEnd = count - 8."""
+    count = len(src)
+    code_end = count - 8
+    dst = bytearray(count + count // 32 + 64)
+    dst_end = len(dst) - 8
+    dst[0] = 0x20
+    s, d, matches = 0, 9, 0
+    while s + 4 <= code_end and d < dst_end:
+        instr = int.from_bytes(bytes(src[s: s + 4]), "little")
+        opcode1 = instr & 0xFC000000
+        if opcode1 not in (0x14000000, 0x94000000):
+            dst[d: d + 4] = bytes(src[s: s + 4])
+            s += 4
+            d += 4
+            continue
+        offset = instr & 0x03FFFFFF
+        if instr & (1 << 25) == 0:
+            addr = s + 4 * offset
+        else:
+            addr = s - 4 * ((-offset) & 0x03FFFFFF)
+        if addr < 0:
+            addr = 0
+        val = (opcode1 | (addr >> 2)) & 0xFFFFFFFF
+        dst[d: d + 4] = val.to_bytes(4, "little")
+        if addr == 0:  # 0 address as escape: the original instruction follows
+            dst[d + 4: d + 8] = bytes(src[s: s + 4])
+            s += 4
+            d += 8
+            continue
+        s += 4
+        d += 4
+        matches += 1
+    if matches < 16:
+        return None
+    if (s + 4 <= code_end and d >= dst_end) or d + (count - s) > dst_end:
+        return None
+    dst[1:5] = (0).to_bytes(4, "little")
+    dst[5:9] = d.to_bytes(4, "little")
+    dst[d: d + count - s] = bytes(src[s:count])
+    d += count - s
+    if d > count + count // 50:
+        return None
+    return np.frombuffer(bytes(dst[:d]), np.uint8)
+
+
+def inverse_arm(enc, cap):
+    code_end = int.from_bytes(bytes(enc[5:9]), "little")
+    out = bytearray()
+    s = 9
+    while s < code_end:
+        instr = int.from_bytes(bytes(enc[s: s + 4]), "little")
+        opcode1 = instr & 0xFC000000
+        if opcode1 not in (0x14000000, 0x94000000):
+            out += bytes(enc[s: s + 4])
+            s += 4
+            continue
+        addr = (instr & 0x03FFFFFF) << 2
+        if addr == 0:
+            out += bytes(enc[s + 4: s + 8])
+            s += 8
+            continue
+        offset = (addr - len(out)) >> 2
+        out += ((opcode1 | (offset & 0x03FFFFFF)) & 0xFFFFFFFF).to_bytes(4, "little")
+        s += 4
+    out += bytes(enc[s:])
+    assert len(out) <= cap
+    return np.frombuffer(bytes(out), np.uint8)
+
+
+def make_arm_block(n, seed):
+    """AArch64-like words without an executable header: B / BL with small offsets, every byte value present, enough zeros and 0xFF bytes."""
+    r = np.random.default_rng(seed)
+    x = r.integers(0, 256, n).astype(np.uint8)
+    x[r.random(n) < 0.15] = 0
+    x[r.random(n) < 0.03] = 0xFF
+    x[:256] = np.arange(256, dtype=np.uint8)
+    x[0:4] = [0xFD, 0x7B, 0xBF, 0xA9]  # stp x29, x30, [sp, #-16]!: no magic number
+    for pos in range(0, n - 3, 4):
+        if pos >= 512 and pos < n - 32 and r.random() < 0.08:
+            off = int(r.integers(-(pos >> 2) + 1, 1 << 18)) & 0x03FFFFFF  # targets inside the block or ahead of it (address 0 is the escape)
+            instr = (0x94000000 if r.random() < 0.7 else 0x14000000) | off
+            x[pos: pos + 4] = np.frombuffer(instr.to_bytes(4, "little"), np.uint8)
+        elif pos >= 256 and (int(x[pos + 3]) & 0xFC) in (0x14, 0x94) and r.random() < 0.9:
+            x[pos + 3] ^= 0x40  # most accidental B / BL patterns of the filler go away (the rest exercises the escapes)
+    return x
 
 
 def forward_x86(src):
@@ -205,3 +305,17 @@ def test_oracle_exe_declines_like_the_independent_statement():
     # random words hold enough ARM64 B / BL opcode patterns (2 of 64 values of the top six bits) to pass the ARM threshold: the block is
     # either declined or coded as ARM64 (mode byte 0x20, not restated here) — never as x86
     assert got is None or got[0] == 0x20
+
+
+@pytest.mark.parametrize("n,seed", [(4096, 21), (65536, 22), (300004, 23)])
+def test_oracle_exe_arm64_matches_the_independent_statement(n, seed):
+    x = make_arm_block(n, seed)
+    assert detect(x[: n - 4]) == "arm64", "the generator must produce blocks the detector takes for AArch64 code"
+    want = forward_arm(x)
+    got, dt = po.transform_forward(po.T_EXE, x)
+    assert (want is None) == (got is None)
+    assert want is not None, "the block should be transformed"
+    assert len(got) == len(want) and np.array_equal(got, want), int(np.argmax(got[: min(len(got), len(want))] != want[: min(len(got), len(want))]))
+    back = po.transform_inverse(po.T_EXE, want, n + 64)
+    assert np.array_equal(back, x)
+    assert np.array_equal(inverse_arm(want, n + 64), x)
