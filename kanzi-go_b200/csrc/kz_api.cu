@@ -2004,22 +2004,33 @@ int inverse_stage(kz_ctx* ctx, const TransformPlan& plan, std::vector<DecJob>& j
             lb[b].data_type = 0;
             lb[b].pad = 0;
         }
-        Packer pk;
-        const size_t o_lb = pk.add(lb.data(), lb.size() * sizeof(LzBlock));
-        const size_t o_len = pk.reserve((size_t)nblocks * 4);
-        const size_t o_st = pk.reserve((size_t)nblocks * 4);
-        int rc = upload(ctx, pk);
-        if (rc) return rc;
-        uint8_t* T = ctx->d_tables.as<uint8_t>();
-        {
-            LaunchScope ls(ctx, "lz_inverse");
-            lz_inverse_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_pre, (LzBlock*)(T + o_lb), (int)nblocks, d_dst, (uint32_t*)(T + o_len), (int32_t*)(T + o_st));
-        }
         std::vector<uint32_t> hl(nblocks);
         std::vector<int32_t> hs(nblocks);
-        CK(cudaMemcpyAsync(hl.data(), T + o_len, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(hs.data(), T + o_st, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        static const bool serial_inverse = [] {  // KZ_LZ_INV=serial: the round-1 kernel (one warp per block copies match by match)
+            const char* e = getenv("KZ_LZ_INV");
+            return e && e[0] == 's';
+        }();
+        if (!serial_inverse) {  // the stream's only stage is LZ / LZX (kanzi -l 1): the same data-parallel inverse as inside a sequence
+            CtxLzWorkspace W(ctx);
+            CtxLzHook H(ctx);
+            cudaError_t e = lz_inverse_parallel(d_pre, d_dst, lb, W, ctx->stream, hl, hs, &H, &ctx->launches);
+            if (e != cudaSuccess) return ctx->cuda_fail(e, "lz_inverse");
+        } else {
+            Packer pk;
+            const size_t o_lb = pk.add(lb.data(), lb.size() * sizeof(LzBlock));
+            const size_t o_len = pk.reserve((size_t)nblocks * 4);
+            const size_t o_st = pk.reserve((size_t)nblocks * 4);
+            int rc = upload(ctx, pk);
+            if (rc) return rc;
+            uint8_t* T = ctx->d_tables.as<uint8_t>();
+            {
+                LaunchScope ls(ctx, "lz_inverse");
+                lz_inverse_kernel<<<nblocks, 32, 0, ctx->stream>>>(d_pre, (LzBlock*)(T + o_lb), (int)nblocks, d_dst, (uint32_t*)(T + o_len), (int32_t*)(T + o_st));
+            }
+            CK(cudaMemcpyAsync(hl.data(), T + o_len, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(hs.data(), T + o_st, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
         uint64_t off = 0;
         for (uint32_t b = 0; b < nblocks; b++) {
             const bool skip = jobs[b].copy || (jobs[b].skip_flags & 0x80);
