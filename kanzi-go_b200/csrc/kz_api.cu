@@ -1934,28 +1934,47 @@ int forward_stage(kz_ctx* ctx, const TransformPlan& plan, const uint8_t* d_src, 
         *d_data = ctx->d_tmp.as<uint8_t>();
         return 0;
     }
-    // ---- BWT (BWTBlockCodec.Forward): one block at a time, the suffix sort uses the whole GPU
+    // ---- BWT (BWTBlockCodec.Forward): the blocks of the batch are suffix-sorted together (kz_bwt.cu: bwt_forward_batch)
     const uint64_t tstride = ((uint64_t)max_len + 33 + 64 + 15) & ~15ull;
     CK(ctx->d_tmp.ensure(tstride * nblocks + 64));
-    const size_t wsz = bwt_forward_workspace(max_len);
-    CK(ctx->d_ws.ensure(wsz));
     CK(ctx->d_lens.ensure((size_t)nblocks * 4 + 64));
     uint8_t* tmp = ctx->d_tmp.as<uint8_t>();
     uint32_t* d_post = ctx->d_lens.as<uint32_t>();
     std::vector<uint8_t> ok(nblocks, 0);
-    for (uint32_t b = 0; b < nblocks; b++) {
-        const uint8_t* src = d_src + (uint64_t)b * stride;
-        uint8_t* dst = tmp + (uint64_t)b * tstride;
-        if (!jobs[b].copy && blen[b] >= 2) {
-            LaunchScope ls(ctx, "bwt_forward");
-            cudaError_t e = bwt_forward_device(src, blen[b], dst, d_post + b, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap, ctx->stream, &ctx->launches);
-            if (e == cudaSuccess) {
-                ok[b] = 1;
+    for (uint32_t b0 = 0; b0 < nblocks;) {
+        std::vector<uint64_t> so, dof;
+        std::vector<uint32_t> nn, num;
+        uint64_t total = 0;
+        uint32_t b = b0;
+        for (; b < nblocks; b++) {
+            const uint8_t* src = d_src + (uint64_t)b * stride;
+            uint8_t* dst = tmp + (uint64_t)b * tstride;
+            if (jobs[b].copy || blen[b] < 2) {
+                if (blen[b]) CK(cudaMemcpyAsync(dst, src, blen[b], cudaMemcpyDeviceToDevice, ctx->stream));  // transform skipped: data unchanged
                 continue;
             }
-            if (e != cudaErrorInvalidValue) return ctx->cuda_fail(e, "bwt_forward");
+            if (blen[b] > bwt_forward_batch_max_total()) {  // 1 GiB block: its own suffix sort
+                if (!nn.empty()) break;
+                CK(ctx->d_ws.ensure(bwt_forward_workspace(blen[b])));
+                LaunchScope ls(ctx, "bwt_forward");
+                cudaError_t e = bwt_forward_device(src, blen[b], dst, d_post + b, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap, ctx->stream, &ctx->launches);
+                if (e == cudaSuccess) ok[b] = 1;
+                else if (e != cudaErrorInvalidValue) return ctx->cuda_fail(e, "bwt_forward");
+                else CK(cudaMemcpyAsync(dst, src, blen[b], cudaMemcpyDeviceToDevice, ctx->stream));
+                continue;
+            }
+            if (!nn.empty() && (total + blen[b] > bwt_forward_batch_max_total() || nn.size() >= bwt_forward_batch_max_blocks())) break;
+            so.push_back((uint64_t)b * stride), dof.push_back((uint64_t)b * tstride), nn.push_back(blen[b]), num.push_back(b);
+            total += blen[b];
         }
-        if (blen[b]) CK(cudaMemcpyAsync(dst, src, blen[b], cudaMemcpyDeviceToDevice, ctx->stream));  // transform skipped: data unchanged
+        b0 = b;
+        if (nn.empty()) continue;
+        CK(ctx->d_ws.ensure(bwt_forward_batch_workspace(total, (uint32_t)nn.size())));
+        LaunchScope ls(ctx, "bwt_forward");
+        cudaError_t e = bwt_forward_batch(d_src, tmp, so.data(), dof.data(), nn.data(), num.data(), (uint32_t)nn.size(), d_post, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap,
+                                          ctx->stream, &ctx->launches);
+        if (e != cudaSuccess) return ctx->cuda_fail(e, "bwt_forward");
+        for (uint32_t k : num) ok[k] = 1;
     }
     std::vector<uint32_t> post(nblocks);
     CK(cudaMemcpyAsync(post.data(), d_post, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -2055,10 +2074,28 @@ int inverse_stage(kz_ctx* ctx, const TransformPlan& plan, std::vector<DecJob>& j
     std::vector<uint8_t> heads((size_t)nblocks * 64, 0);
     CK(cudaMemcpy2DAsync(heads.data(), 64, d_pre, pstride, 33, nblocks, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    uint32_t max_len = 0;
-    for (auto& j : jobs) max_len = std::max(max_len, j.pre_len);
-    CK(ctx->d_ws.ensure(bwt_inverse_workspace(max_len)));
+    // output offsets follow from the block headers (decoded length = stream length - header), so all blocks can be inverted together
     uint64_t off = 0;
+    std::vector<uint64_t> so, dof;
+    std::vector<uint32_t> ll, num;
+    std::vector<uint8_t> hh;
+    uint64_t batch_total = 0;
+    auto flush = [&]() -> int {
+        if (ll.empty()) return 0;
+        CK(ctx->d_ws.ensure(bwt_inverse_batch_workspace(batch_total, (uint32_t)ll.size())));
+        std::vector<uint32_t> produced(ll.size(), 0);
+        LaunchScope ls(ctx, "bwt_inverse");
+        cudaError_t e = bwt_inverse_batch(d_pre, d_dst, so.data(), dof.data(), ll.data(), hh.data(), (uint32_t)ll.size(), 0xFFFFFFFFu, produced.data(),
+                                          ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap, ctx->stream, &ctx->launches);
+        if (e == cudaErrorInvalidValue) {
+            for (uint32_t k : num) jobs[k].status = -KZ_ERR_PROCESS_BLOCK;
+            return ctx->fail(KZ_ERR_PROCESS_BLOCK, "BWT inverse transform failed: invalid header or data");
+        }
+        if (e != cudaSuccess) return ctx->cuda_fail(e, "bwt_inverse");
+        so.clear(), dof.clear(), ll.clear(), num.clear(), hh.clear();
+        batch_total = 0;
+        return 0;
+    };
     for (uint32_t b = 0; b < nblocks; b++) {
         DecJob& j = jobs[b];
         const uint8_t* src = d_pre + (uint64_t)b * pstride;
@@ -2068,18 +2105,31 @@ int inverse_stage(kz_ctx* ctx, const TransformPlan& plan, std::vector<DecJob>& j
             CK(cudaMemcpyAsync(d_dst + off, src, j.pre_len, cudaMemcpyDeviceToDevice, ctx->stream));
             out_len[b] = j.pre_len;
         } else {
-            uint32_t produced = 0;
-            LaunchScope ls(ctx, "bwt_inverse");
-            cudaError_t e = bwt_inverse_device(src, &heads[(size_t)b * 64], j.pre_len, d_dst + off, (uint32_t)std::min<uint64_t>(cap - off, 0xFFFFFFFFu),
-                                               &produced, ctx->d_ws.as<uint8_t>(), ctx->d_ws.cap, ctx->stream, &ctx->launches);
-            if (e == cudaErrorInvalidValue) {
+            const uint8_t* h = &heads[(size_t)b * 64];
+            const uint32_t header = (1u << ((h[0] >> 2) & 7)) * ((uint32_t)(h[0] & 3) + 1) + 1;
+            if (j.pre_len < 2 || j.pre_len < header) {
                 j.status = -KZ_ERR_PROCESS_BLOCK;
                 return ctx->fail(KZ_ERR_PROCESS_BLOCK, "BWT inverse transform failed: invalid header");
             }
-            if (e != cudaSuccess) return ctx->cuda_fail(e, "bwt_inverse");
+            const uint32_t produced = j.pre_len - header;
+            if (off + produced > cap) {
+                j.status = -KZ_ERR_PROCESS_BLOCK;
+                return ctx->fail(KZ_ERR_PROCESS_BLOCK, "BWT inverse transform failed: invalid header");
+            }
+            if (!ll.empty() && (batch_total + j.pre_len > bwt_inverse_batch_max_total() || ll.size() >= bwt_inverse_batch_max_blocks())) {
+                int rc = flush();
+                if (rc) return rc;
+            }
+            so.push_back((uint64_t)b * pstride), dof.push_back(off), ll.push_back(j.pre_len), num.push_back(b);
+            hh.insert(hh.end(), h, h + 64);
+            batch_total += j.pre_len;
             out_len[b] = produced;
         }
         off += out_len[b];
+    }
+    {
+        int rc = flush();
+        if (rc) return rc;
     }
     *total = off;
     return 0;
