@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(256) utf_hist_kernel(const uint8_t* __restrict
     for (uint32_t i = lo + threadIdx.x; i < hi; i += 256) {
         const uint32_t cur = p[i], prv = i ? p[i - 1] : 0u;
         atomicAdd(&h[cur], 1u);
-        atomicAdd(&h1[(prv << 8) | cur], 1u);
+        // validate_utf reads only the rows of the lead bytes C2..F4: the other digrams are not counted
+        if (prv >= 0xC2u) atomicAdd(&h1[(prv << 8) | cur], 1u);
         if (i < checked && forbidden_byte((uint8_t)cur)) f++;
     }
     if (f) atomicAdd(&s_forb, f);
