@@ -4,10 +4,14 @@
 Default workload at N=1 = the configuration BASELINE.json's `metric` is quoted on: a 200,000,000-byte silesia.tar-shaped
 slab (kanzi-go_b200/synth.py: silesia_shaped), 4 MiB blocks (48 blocks), compressed and decompressed at
 kanzi `-l 3` (TEXT+UTF+PACK+MM+LZX & HUFFMAN) AND `-l 5` (TEXT+UTF+BWT+RANK+ZRLT & ANS0) (app/BlockCompressor.go:665-700).
-A "step" is one pass of the hot path over that slab: compress + decompress at -l 3, then compress + decompress at -l 5.
+A "step" is one pass of the hot path over that slab: compress + decompress at -l 3 and compress + decompress at -l 5. The
+two round trips belong to two contexts (one CUDA stream each) driven by two host threads: -l 5 compresses, and while it
+decompresses - its serial RANK inverse chains occupy 48 of the 148 SMs for most of that time - the -l 3 round trip runs beside
+it on the other SMs; a step ends when both have ended.
 
   value  = uncompressed bytes through the four passes per second (MB = 1e6 B), inputs resident in HBM (device API);
-           config.levels holds encode / decode / combined MB/s of each level
+           "sequential" = the same steps with the levels one after the other (the schedule of the lines before r02_h);
+           "levels" holds encode / decode / combined MB/s of each level on its own, and inside the side-by-side steps
   e2e    = the same through the host-buffer C ABI (kz_compress_stream / kz_decompress_stream) from pinned host
            memory, host<->device copies inside the timed region
   roofline: the kernel with the largest share of the step; achieved = algorithmic bytes of its stage (stage input +
@@ -232,6 +236,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "MB/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(args.warmup, 1),
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": static_config(args.workload, passes, BLOCK, NBLOCKS, n, world), "levels": r["levels"],
+                "schedule": "levels one after the other, every pass on all %d worker threads (side by side they would only share the same cores)" % r["cores"],
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         emit(line)
@@ -254,12 +259,15 @@ def main():
     P = [(label, kz.transform_type(tr), kz.entropy_type(en)) for label, tr, en in passes]
 
     # ---------------- device-resident pass (value) ----------------
+    # one context (= one CUDA stream + its workspaces) and one host thread per level: the round trips of a step run side by side, the way two
+    # callers of the C ABI would drive one GPU; the same steps with the levels one after the other are timed as well ("sequential")
+    ctxs = [ctx] + [kz.Context(local_rank) for _ in P[1:]]
+    ext = [torch.cuda.ExternalStream(c.cuda_stream()) for c in ctxs]
     d_src = torch.empty(n + 256, dtype=torch.uint8, device="cuda")
     d_cmp = [torch.zeros(cap + 256, dtype=torch.uint8, device="cuda") for _ in P]
-    d_dec = torch.empty(n + 256, dtype=torch.uint8, device="cuda")
+    d_dec = [torch.empty(n + 256, dtype=torch.uint8, device="cuda") for _ in P]
     d_src[:n].copy_(torch.from_numpy(x))
     torch.cuda.synchronize()
-    ext = torch.cuda.ExternalStream(ctx.cuda_stream())
 
     def barrier():
         torch.cuda.synchronize()
@@ -268,78 +276,138 @@ def main():
         torch.cuda.synchronize()
 
     m = [0] * len(P)
-    for _ in range(args.warmup):
+
+    def device_round_trip(i, enc, dec, before=None, between=None):
+        label, t48, et = P[i]
+        with torch.cuda.stream(ext[i]):
+            a, b, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if before:
+                before()
+            a.record()
+            m[i] = ctxs[i].compress_device(d_src.data_ptr(), n, d_cmp[i].data_ptr(), cap, t48, et, BLOCK, 0, n)
+            b.record()
+            if between:
+                between()
+            k = ctxs[i].decompress_device(d_cmp[i].data_ptr(), m[i], d_dec[i].data_ptr(), n)
+            c.record()
+            c.synchronize()
+        assert k == n, "decoded %d of %d bytes at %s" % (k, n, label)
+        enc[i] += a.elapsed_time(b)
+        dec[i] += b.elapsed_time(c)
+
+    def timed_region(steps, one, side_by_side):
+        """`steps` steps of one(i, enc, dec) for every level i; device milliseconds of the whole region and per level."""
+        enc, dec = [0.0] * len(P), [0.0] * len(P)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        errors = []
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(ext[0])
+        if side_by_side and len(P) > 1:
+            gate = threading.Barrier(len(P))
+            coded = [threading.Event() for _ in range(steps)]  # step k: the anchor level has written its stream
+
+            def worker(i):
+                try:
+                    torch.cuda.set_device(local_rank)
+                    for k in range(steps):
+                        gate.wait()  # a step starts when every level finished the previous one
+                        if i == anchor:
+                            one(i, enc, dec, None, coded[k].set)
+                        else:  # beside the anchor's decode
+                            one(i, enc, dec, lambda: coded[k].wait(120.0) or gate.abort(), None)
+                except BaseException as e:  # noqa: B902 - reported by the main thread
+                    errors.append(e)
+                    gate.abort()
+                    for ev in coded:
+                        ev.set()
+
+            th = [threading.Thread(target=worker, args=(i,)) for i in range(len(P))]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+        else:
+            for _ in range(steps):
+                for i in range(len(P)):
+                    one(i, enc, dec)
+        e1.record(ext[0])  # every level synchronised its own stream at the end of its round trip: the streams are idle here
+        barrier()
+        if errors:
+            raise errors[0]
+        return e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3, enc, dec
+
+    anchor = 0
+    seq_steps = max(1, min(args.steps, 3))
+    for w in range(args.warmup):
+        for d in d_dec:
+            d.zero_()
+        _, _, _, w_dec = timed_region(1, device_round_trip, w > 0)
         for i, (label, t48, et) in enumerate(P):
-            m[i] = ctx.compress_device(d_src.data_ptr(), n, d_cmp[i].data_ptr(), cap, t48, et, BLOCK, 0, n)
-            d_dec.zero_()
-            k = ctx.decompress_device(d_cmp[i].data_ptr(), m[i], d_dec.data_ptr(), n)
-            assert k == n and torch.equal(d_dec[:n], d_src[:n]), "round trip mismatch at %s" % label
+            assert torch.equal(d_dec[i][:n], d_src[:n]), "round trip mismatch at %s" % label
+        if w == 0:
+            # the level with the longest decode (-l 5: the serial RANK inverse chains on 48 SMs) is the anchor of a step: the other levels run their
+            # round trips beside its decode, after its encode
+            anchor = max(range(len(P)), key=lambda i: w_dec[i])
+    seq_ms, _, seq_enc, seq_dec = timed_region(seq_steps, device_round_trip, False)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ctx.profile(True)
-    ctx.profile_reset()
-    ctx.launch_count(reset=True)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    enc_ms = [0.0] * len(P)
-    dec_ms = [0.0] * len(P)
-    with torch.cuda.stream(ext):
-        e0.record()
-        for _ in range(args.steps):
-            for i, (label, t48, et) in enumerate(P):
-                a, b, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                m[i] = ctx.compress_device(d_src.data_ptr(), n, d_cmp[i].data_ptr(), cap, t48, et, BLOCK, 0, n)
-                b.record()
-                ctx.decompress_device(d_cmp[i].data_ptr(), m[i], d_dec.data_ptr(), n)
-                c.record()
-                c.synchronize()
-                enc_ms[i] += a.elapsed_time(b)
-                dec_ms[i] += b.elapsed_time(c)
-        e1.record()
-    barrier()
-    dev_ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count(reset=True)
+    for c in ctxs:
+        c.profile(True)
+        c.profile_reset()
+        c.launch_count(reset=True)
+    dev_ms, _, enc_ms, dec_ms = timed_region(args.steps, device_round_trip, True)
+    launches = sum(c.launch_count(reset=True) for c in ctxs)
     kern = {}
-    for name in ctx.profile_names():
-        if name.startswith("stage:"):
-            continue
-        cnt, ms = ctx.kernel_time(name)
-        if cnt:
-            kern[name] = {"launches": cnt, "ms_avg": ms / cnt, "ms_per_step": ms / args.steps}
     stages = {}
-    for name in ctx.profile_names():
-        if name.startswith("stage:"):
-            cnt, bi, bo = ctx.stage_bytes(name)
+    for c in ctxs:
+        for name in c.profile_names():
+            if name.startswith("stage:"):
+                cnt, bi, bo = c.stage_bytes(name)
+                if cnt:
+                    st = stages.setdefault(name[6:], {"bytes_in": 0.0, "bytes_out": 0.0, "batches_per_step": 0.0})
+                    st["bytes_in"] += bi
+                    st["bytes_out"] += bo
+                    st["batches_per_step"] += cnt
+                continue
+            cnt, ms = c.kernel_time(name)
             if cnt:
-                stages[name[6:]] = {"bytes_in": bi / cnt, "bytes_out": bo / cnt, "batches_per_step": cnt / args.steps}
-    ctx.profile(False)
+                kk = kern.setdefault(name, {"launches": 0, "ms_avg": 0.0, "ms_per_step": 0.0})
+                kk["launches"] += cnt
+                kk["ms_per_step"] += ms
+        c.profile(False)
+    for kk in kern.values():
+        kk["ms_avg"] = kk["ms_per_step"] / kk["launches"]
+        kk["ms_per_step"] /= args.steps
+    for st in stages.values():
+        cnt = st["batches_per_step"]
+        st["bytes_in"] /= cnt
+        st["bytes_out"] /= cnt
+        st["batches_per_step"] = cnt / args.steps
 
     # ---------------- end-to-end pass through the host-buffer C ABI (pinned host memory) ----------------
     e2e_ms, e2e_wall_ms, e2e_steps = 0.0, 0.0, 0
     if not args.no_e2e:
         h_src = torch.empty(n, dtype=torch.uint8).pin_memory()
         h_cmp = [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in P]
-        h_dec = torch.empty(n + 64, dtype=torch.uint8).pin_memory()
+        h_dec = [torch.empty(n + 64, dtype=torch.uint8).pin_memory() for _ in P]
         h_src.numpy()[:] = x
         e2e_steps = max(1, min(args.steps, 3))
+
+        def host_round_trip(i, enc, dec, before=None, between=None):
+            label, t48, et = P[i]
+            if before:
+                before()
+            mm = ctxs[i].compress_host(h_src.data_ptr(), n, h_cmp[i].data_ptr(), cap, t48, et, BLOCK, 0, n)
+            if between:
+                between()
+            kk = ctxs[i].decompress_host(h_cmp[i].data_ptr(), mm, h_dec[i].data_ptr(), n + 64)
+            assert kk == n and mm == m[i], "e2e round trip: %d bytes coded, %d decoded at %s" % (mm, kk, label)
+
+        timed_region(1, host_round_trip, True)
         for i, (label, t48, et) in enumerate(P):
-            mm = ctx.compress_host(h_src.data_ptr(), n, h_cmp[i].data_ptr(), cap, t48, et, BLOCK, 0, n)
-            kk = ctx.decompress_host(h_cmp[i].data_ptr(), mm, h_dec.data_ptr(), n + 64)
-            assert kk == n and np.array_equal(h_dec.numpy()[:n], x), "e2e round trip mismatch"
-        barrier()
-        t0 = time.perf_counter()
-        with torch.cuda.stream(ext):
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for _ in range(e2e_steps):
-                for i, (label, t48, et) in enumerate(P):
-                    mm = ctx.compress_host(h_src.data_ptr(), n, h_cmp[i].data_ptr(), cap, t48, et, BLOCK, 0, n)
-                    ctx.decompress_host(h_cmp[i].data_ptr(), mm, h_dec.data_ptr(), n + 64)
-            f1.record()
-        barrier()
-        e2e_ms = f0.elapsed_time(f1)
-        e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+            assert np.array_equal(h_dec[i].numpy()[:n], x), "e2e round trip mismatch at %s" % label
+        e2e_ms, e2e_wall_ms, _, _ = timed_region(e2e_steps, host_round_trip, True)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -398,12 +466,13 @@ def main():
                               "for decompression (kz_stream_index_device, windows scattered, kz_decompress_fragment_device, decoded ranges gathered)" % n}
 
     # ---------------- max over ranks ----------------
-    vals = torch.tensor([dev_ms, e2e_ms] + enc_ms + dec_ms, dtype=torch.float64, device="cuda")
+    vals = torch.tensor([dev_ms, e2e_ms, seq_ms] + enc_ms + dec_ms + seq_enc + seq_dec, dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
     vals = [float(v) for v in vals.tolist()]
-    dev_ms, e2e_ms = vals[0], vals[1]
-    enc_ms, dec_ms = vals[2:2 + len(P)], vals[2 + len(P):]
+    dev_ms, e2e_ms, seq_ms = vals[0], vals[1], vals[2]
+    L = len(P)
+    enc_ms, dec_ms, seq_enc, seq_dec = vals[3:3 + L], vals[3 + L:3 + 2 * L], vals[3 + 2 * L:3 + 3 * L], vals[3 + 3 * L:3 + 4 * L]
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -417,9 +486,17 @@ def main():
     peak, peak_src = peaks()
     levels = {}
     for i, (label, t48, et) in enumerate(P):
+        # a level's own rates: timed with the levels one after the other (nothing else on the GPU); "side_by_side" = inside the timed steps of `value`
         levels[label] = {"transform": passes[i][1], "entropy": passes[i][2], "compressed_bytes": int(m[i]), "ratio": m[i] / n,
-                         "encode_MBps": n * world * args.steps / (enc_ms[i] / 1e3) / 1e6, "decode_MBps": n * world * args.steps / (dec_ms[i] / 1e3) / 1e6,
-                         "MBps": 2.0 * n * world * args.steps / ((enc_ms[i] + dec_ms[i]) / 1e3) / 1e6}
+                         "encode_MBps": n * world * seq_steps / (seq_enc[i] / 1e3) / 1e6, "decode_MBps": n * world * seq_steps / (seq_dec[i] / 1e3) / 1e6,
+                         "MBps": 2.0 * n * world * seq_steps / ((seq_enc[i] + seq_dec[i]) / 1e3) / 1e6}
+        if npass > 1:
+            levels[label]["side_by_side"] = {"encode_MBps": n * world * args.steps / (enc_ms[i] / 1e3) / 1e6, "decode_MBps": n * world * args.steps / (dec_ms[i] / 1e3) / 1e6}
+    schedule = ("one context (CUDA stream + workspaces) and one host thread per level; a step = %s compress, then %s decompress with the round trip(s) of %s beside "
+                "it on the GPU; the step ends when all of them have" % (P[anchor][0], P[anchor][0], ", ".join(P[i][0] for i in range(npass) if i != anchor))) \
+        if npass > 1 else "one context, one level"
+    sequential = {"value": total_bytes * seq_steps / (seq_ms / 1e3) / 1e6, "unit": "MB/s", "ms_per_step": seq_ms / seq_steps, "steps": seq_steps,
+                  "what": "the same steps with the levels one after the other on the GPU (the schedule of the earlier bench lines)"}
     # dominant kernel of the step = largest ms_per_step among device kernels
     roof = None
     dev_kern = {k: v for k, v in kern.items() if not k.startswith("host:")}
@@ -446,6 +523,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": static_config(args.workload, passes, BLOCK, NBLOCKS, n, world), "levels": levels,
+        "schedule": schedule, "sequential": sequential,
         "clocks": sampler.summary(),
         "gpu_launches": int(launches),
         "kernels": dict(sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])),
@@ -454,7 +532,7 @@ def main():
     if e2e_steps:
         line["e2e"] = {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": int(n * npass + sum(m)), "d2h_bytes_per_step": int(sum(m) + n * npass),
                        "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": e2e_wall_ms / e2e_steps,
-                       "api": "kz_compress_stream + kz_decompress_stream per level, pinned host buffers"}
+                       "api": "kz_compress_stream + kz_decompress_stream per level, pinned host buffers; same schedule as `value`"}
     if roof:
         line["roofline"] = roof
     if sharded is not None:

@@ -761,6 +761,33 @@ void sbrt_inverse_launch(const uint8_t* data, const SbrtBlock* d_blocks, int nbl
     else sbrt_inverse_kernel_t<false><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, mode, out);
 }
 
+// A chain is serial and latency-bound: a CTA that shares its SM with another chain's CTA runs at a fraction of its speed for the whole launch, and
+// the block scheduler does pack CTAs (six per SM were seen: 1.6 s instead of 0.26 s) when kernels of other streams occupy the GPU at launch time.
+// Dynamic shared memory that nobody touches caps the chains per SM at ceil(nblocks / SMs): the chains spread over the GPU whatever runs beside them.
+// KZ_SBRT_SMEM_KB overrides the amount for nblocks <= SMs (A/B measurements).
+template <typename K>
+static size_t spread_chains(K kernel, int nblocks) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 0;
+    const int per = (nblocks + sms - 1) / sms;
+    if (per > 5) return 0;  // small blocks in large numbers: several chains per SM overlap their latencies, no cap
+    const size_t sm_bytes = 228 * 1024;
+    size_t dyn = sm_bytes / (size_t)(per + 1);
+    if (per == 1) {
+        static const int kb = [] {
+            const char* e = getenv("KZ_SBRT_SMEM_KB");
+            return e ? atoi(e) : -1;
+        }();
+        if (kb >= 0) dyn = (size_t)kb * 1024;
+    }
+    if (dyn == 0) return 0;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return dyn;
+}
+
 void sbrt_inverse_launch_len(const uint8_t* data, const SbrtBlock* d_blocks, int nblocks, int mode, uint8_t* out, uint32_t max_len, cudaStream_t stream) {
     static const bool old_kernel = [] {
         const char* e = getenv("KZ_SBRT_INV");
@@ -788,17 +815,17 @@ void sbrt_inverse_launch_len(const uint8_t* data, const SbrtBlock* d_blocks, int
                 return e ? atoi(e) : 4;
             }();
             if (warps == 8) {
-                if (mode == 2) sbrt_inverse_multi_kernel<true, 8><<<nblocks, 256, 0, stream>>>(data, d_blocks, nblocks, out);
-                else sbrt_inverse_multi_kernel<false, 8><<<nblocks, 256, 0, stream>>>(data, d_blocks, nblocks, out);
+                if (mode == 2) sbrt_inverse_multi_kernel<true, 8><<<nblocks, 256, spread_chains(sbrt_inverse_multi_kernel<true, 8>, nblocks), stream>>>(data, d_blocks, nblocks, out);
+                else sbrt_inverse_multi_kernel<false, 8><<<nblocks, 256, spread_chains(sbrt_inverse_multi_kernel<false, 8>, nblocks), stream>>>(data, d_blocks, nblocks, out);
             } else if (warps == 4) {
-                if (mode == 2) sbrt_inverse_multi_kernel<true, 4><<<nblocks, 128, 0, stream>>>(data, d_blocks, nblocks, out);
-                else sbrt_inverse_multi_kernel<false, 4><<<nblocks, 128, 0, stream>>>(data, d_blocks, nblocks, out);
+                if (mode == 2) sbrt_inverse_multi_kernel<true, 4><<<nblocks, 128, spread_chains(sbrt_inverse_multi_kernel<true, 4>, nblocks), stream>>>(data, d_blocks, nblocks, out);
+                else sbrt_inverse_multi_kernel<false, 4><<<nblocks, 128, spread_chains(sbrt_inverse_multi_kernel<false, 4>, nblocks), stream>>>(data, d_blocks, nblocks, out);
             } else if (warps == 2) {
-                if (mode == 2) sbrt_inverse_multi_kernel<true, 2><<<nblocks, 64, 0, stream>>>(data, d_blocks, nblocks, out);
-                else sbrt_inverse_multi_kernel<false, 2><<<nblocks, 64, 0, stream>>>(data, d_blocks, nblocks, out);
+                if (mode == 2) sbrt_inverse_multi_kernel<true, 2><<<nblocks, 64, spread_chains(sbrt_inverse_multi_kernel<true, 2>, nblocks), stream>>>(data, d_blocks, nblocks, out);
+                else sbrt_inverse_multi_kernel<false, 2><<<nblocks, 64, spread_chains(sbrt_inverse_multi_kernel<false, 2>, nblocks), stream>>>(data, d_blocks, nblocks, out);
             } else {
-                if (mode == 2) sbrt_inverse_mirror_kernel<true><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, out);
-                else sbrt_inverse_mirror_kernel<false><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, out);
+                if (mode == 2) sbrt_inverse_mirror_kernel<true><<<nblocks, 32, spread_chains(sbrt_inverse_mirror_kernel<true>, nblocks), stream>>>(data, d_blocks, nblocks, out);
+                else sbrt_inverse_mirror_kernel<false><<<nblocks, 32, spread_chains(sbrt_inverse_mirror_kernel<false>, nblocks), stream>>>(data, d_blocks, nblocks, out);
             }
         }
     } else if (max_len <= (1u << 24)) sbrt_inverse_warp_kernel<uint32_t><<<nblocks, 32, 0, stream>>>(data, d_blocks, nblocks, mode, out);

@@ -280,10 +280,13 @@ cudaError_t text_forward_batch(const uint8_t* d_in, uint8_t* d_out, const TextBl
         for (uint32_t b = 0; b < nblocks; b++) any = any || fallback[b];
         if (!any) return cudaGetLastError();
         std::vector<uint32_t> go(nblocks);
-        if ((e = cudaMemcpy(go.data(), w.go, nblocks * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+        // on the context's own (non-blocking) stream: a plain cudaMemcpy would neither wait for it nor leave other contexts alone
+        if ((e = cudaMemcpyAsync(go.data(), w.go, nblocks * 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
         for (uint32_t b = 0; b < nblocks; b++)
             if (!fallback[b]) go[b] = 0;
-        if ((e = cudaMemcpy(w.go, go.data(), nblocks * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(w.go, go.data(), nblocks * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;  // `go` is a local
     }
     text_init_kernel<<<dim3(INIT_SLICES, nblocks), 256, 0, stream>>>(w.go, w.sdict, S.n, w.map, w.log, w.list);
     text_forward_walk_kernel<<<nblocks, 32, 0, stream>>>(d_in, d_blocks, (int)nblocks, w.go, S.n, w.swords, w.map, w.log, w.list, d_out, d_res);
