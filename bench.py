@@ -349,41 +349,51 @@ def main():
             # the level with the longest decode (-l 5: the serial RANK inverse chains on 48 SMs) is the anchor of a step: the other levels run their
             # round trips beside its decode, after its encode
             anchor = max(range(len(P)), key=lambda i: w_dec[i])
+
+    def profiling(on):
+        for c in ctxs:
+            c.profile(on)
+            c.profile_reset()
+            c.launch_count(reset=True)
+
+    def collect(steps):
+        """CUDA-event times of the kernels and byte counts of the stages since profiling(True), over all contexts."""
+        kern, stages = {}, {}
+        for c in ctxs:
+            for name in c.profile_names():
+                if name.startswith("stage:"):
+                    cnt, bi, bo = c.stage_bytes(name)
+                    if cnt:
+                        st = stages.setdefault(name[6:], {"bytes_in": 0.0, "bytes_out": 0.0, "batches_per_step": 0.0})
+                        st["bytes_in"] += bi
+                        st["bytes_out"] += bo
+                        st["batches_per_step"] += cnt
+                    continue
+                cnt, ms = c.kernel_time(name)
+                if cnt:
+                    kk = kern.setdefault(name, {"launches": 0, "ms_avg": 0.0, "ms_per_step": 0.0})
+                    kk["launches"] += cnt
+                    kk["ms_per_step"] += ms
+        for kk in kern.values():
+            kk["ms_avg"] = kk["ms_per_step"] / kk["launches"]
+            kk["ms_per_step"] /= steps
+        for st in stages.values():
+            cnt = st["batches_per_step"]
+            st["bytes_in"] /= cnt
+            st["bytes_out"] /= cnt
+            st["batches_per_step"] = cnt / steps
+        return kern, stages
+
+    profiling(True)
     seq_ms, _, seq_enc, seq_dec = timed_region(seq_steps, device_round_trip, False)
+    seq_kern, _ = collect(seq_steps)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for c in ctxs:
-        c.profile(True)
-        c.profile_reset()
-        c.launch_count(reset=True)
+    profiling(True)
     dev_ms, _, enc_ms, dec_ms = timed_region(args.steps, device_round_trip, True)
     launches = sum(c.launch_count(reset=True) for c in ctxs)
-    kern = {}
-    stages = {}
-    for c in ctxs:
-        for name in c.profile_names():
-            if name.startswith("stage:"):
-                cnt, bi, bo = c.stage_bytes(name)
-                if cnt:
-                    st = stages.setdefault(name[6:], {"bytes_in": 0.0, "bytes_out": 0.0, "batches_per_step": 0.0})
-                    st["bytes_in"] += bi
-                    st["bytes_out"] += bo
-                    st["batches_per_step"] += cnt
-                continue
-            cnt, ms = c.kernel_time(name)
-            if cnt:
-                kk = kern.setdefault(name, {"launches": 0, "ms_avg": 0.0, "ms_per_step": 0.0})
-                kk["launches"] += cnt
-                kk["ms_per_step"] += ms
-        c.profile(False)
-    for kk in kern.values():
-        kk["ms_avg"] = kk["ms_per_step"] / kk["launches"]
-        kk["ms_per_step"] /= args.steps
-    for st in stages.values():
-        cnt = st["batches_per_step"]
-        st["bytes_in"] /= cnt
-        st["bytes_out"] /= cnt
-        st["batches_per_step"] = cnt / args.steps
+    kern, stages = collect(args.steps)
+    profiling(False)
 
     # ---------------- end-to-end pass through the host-buffer C ABI (pinned host memory) ----------------
     e2e_ms, e2e_wall_ms, e2e_steps = 0.0, 0.0, 0
@@ -515,6 +525,10 @@ def main():
         roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "algorithmic_bytes": how, "ms_per_launch": dev_kern[top]["ms_avg"],
                 "share_of_step": dev_kern[top]["ms_per_step"] / ms_per_step}
+        if npass > 1 and top in seq_kern:
+            # with the levels one after the other (how a profiler's serialised launch list sees the step): the kernel alone on the GPU
+            roof["sequential"] = {"ms_per_launch": seq_kern[top]["ms_avg"], "achieved": alg / (seq_kern[top]["ms_avg"] / 1e3) / 1e9,
+                                  "share_of_step": seq_kern[top]["ms_per_step"] / (seq_ms / seq_steps)}
         t = measured_traffic(top)
         if t:
             roof["traffic"] = t[0]

@@ -12,6 +12,13 @@
  *   - no entry point aborts or throws; kz_last_error() gives the message of the last failure on that context;
  *   - there is NO CPU fallback: if no CUDA device is usable kz_init fails with -ERR_CREATE_COMPRESSOR.
  *   - entropy type ids (entropy/EntropyCodecFactory.go:26-35): NONE 0, HUFFMAN 1, RANGE 4, ANS0 5, ANS1 8.
+ *   - threads: a context is used by ONE host thread at a time; different contexts are independent (own CUDA stream, own scratch) and may be
+ *     driven by different threads (goroutines locked to OS threads or not: every call selects its device itself) on the same GPU at the same
+ *     time - their kernels run side by side (tests/test_gpu_contexts.py; bench.py times the -l 3 and -l 5 round trips of a step that way);
+ *   - subsets of the v6 format the decoders accept (anything else answers an error, never wrong bytes; the Go caller keeps its own path then):
+ *     ANS0 / ANS1 log range <= 12 (what every kanzi encoder writes; the format allows 8..15, entropy/ANSRangeCodec.go:606-609), ROLZ
+ *     logPosChecks = 4 (what `-t ROLZ` writes), TEXT encoding 2 only (entropy NONE / ANS0 / HUFFMAN / RANGE, transform/Factory.go:99-119),
+ *     bitstream version 6;
  *   - transform ids (transform/Factory.go:31-50): NONE 0, BWT 1, BWTS 2, LZ 3, ZRLT 6, MTFT 7, RANK 8, ROLZ 11, LZX 16; a "transform48"
  *     word packs up to 8 six-bit ids, first transform in the top 6 bits (Factory.go:26-54).
  */
