@@ -40,6 +40,15 @@ var cases = []goldenCase{
 	{"rolz_none", "ROLZ", "NONE", 65536, 0, 300000},
 	{"bwt_rank_zrlt_ans0", "BWT+RANK+ZRLT", "ANS0", 65536, 0, 300000},
 	{"bwt_mtft_zrlt_huffman", "BWT+MTFT+ZRLT", "HUFFMAN", 65536, 0, 300000},
+	// the complete level chains of app/BlockCompressor.go:665-700
+	{"l1", "LZX", "NONE", 65536, 0, 300000},
+	{"l2", "DNA+LZ", "HUFFMAN", 65536, 0, 300000},
+	{"l3", "TEXT+UTF+PACK+MM+LZX", "HUFFMAN", 65536, 0, 300000},
+	{"l4", "TEXT+UTF+EXE+PACK+MM+ROLZ", "NONE", 65536, 0, 300000},
+	{"l5", "TEXT+UTF+BWT+RANK+ZRLT", "ANS0", 65536, 32, 300000},
+	{"text_none", "TEXT", "NONE", 65536, 0, 300000},
+	{"pack_none", "PACK", "NONE", 65536, 0, 300000},
+	{"mm_none", "MM", "NONE", 65536, 0, 300000},
 }
 
 // goldenInput must match golden_input() in tests/test_oracle_pins.py: xorshift32 seeded with 0x4B414E5A, each output byte is
