@@ -45,7 +45,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed")
     os.replace(tmp, OUT)
     with open(os.path.join(HERE, "ptxas_info.txt"), "w") as f:
-        f.write(r.stderr)
+        f.write("".join(ln for ln in r.stderr.splitlines(True) if "Compile time" not in ln))  # registers / spills / smem per kernel, reproducible
     return OUT
 
 
