@@ -1,6 +1,7 @@
 """Contexts are independent: several of them (one CUDA stream and one set of workspaces each), driven by several host threads,
 may work on one GPU at the same time - the way goroutines of the Go side would call the C ABI (integration/go/gpu). The streams
 they write are the oracle's, whatever runs beside them (bench.py times the -l 3 and -l 5 round trips of a step side by side)."""
+import os
 import threading
 
 import numpy as np
@@ -12,7 +13,7 @@ JOBS = [("TEXT+UTF+PACK+MM+LZX", "HUFFMAN"), ("TEXT+UTF+BWT+RANK+ZRLT", "ANS0"),
 
 
 def test_contexts_side_by_side(kz, oracle, synth):
-    n = 6_000_000
+    n = int(os.environ.get("KZ_TEST_CONTEXTS_BYTES", "6000000"))  # smaller under compute-sanitizer
     x = synth.silesia_shaped(n, seed=synth.SEED + 7)
     want = [oracle.compress(x, tr, en, block_size=1 << 20, jobs=8, input_size=n) for tr, en in JOBS]
     ctxs = [kz.Context(0) for _ in JOBS]
