@@ -58,6 +58,7 @@ WORKLOADS = {
     "l4": ([("l4", "TEXT+UTF+EXE+PACK+MM+ROLZ", "NONE")], 4 << 20, 200_000_000, "silesia", "encode+decode MB/s, 200 MB silesia-shaped slab, kanzi -l 4"),
     "l3": ([L3], 4 << 20, 48 * (4 << 20), "text", "encode+decode MB/s (kanzi -l 3, 48x4MiB markov text blocks)"),
     "l5": ([L5], 4 << 20, 16 * (4 << 20), "text", "encode+decode MB/s (kanzi -l 5, 16x4MiB markov text blocks)"),
+    "tiny": ([L3, L5], 256 << 10, 2_000_000, "silesia", "encode+decode MB/s, 2 MB silesia-shaped slab, kanzi -l 3 and -l 5, 256 KiB blocks (contract test of the line, not a measurement)"),
 }
 for _bs in (1, 2, 4, 8, 16, 32, 64):  # BASELINE.json configs[4]: ANS1 block-size sweep over 256 MiB of order-1 text
     WORKLOADS["ans1_%dm" % _bs] = ([("ans1", "NONE", "ANS1")], _bs << 20, 256 << 20, "text",
