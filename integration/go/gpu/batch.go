@@ -49,6 +49,8 @@ func (c *Context) EncodeBlocks(transformType uint64, entropyType uint32, ckBits 
 	for i := 0; i < n && len(listeners) > 0; i++ { // the checksum is not known yet: the reference computes it before this event, here it follows
 		notify(listeners, kanzi.NewEvent(kanzi.EVT_BEFORE_TRANSFORM, firstBlockID+i, int64(lens[i]), 0, kanzi.EVT_HASH_NONE, t0))
 	}
+	c.mu.Lock()
+	defer c.mu.Unlock()
 	rc := C.kz_encode_blocks(c.h, C.uint64_t(transformType), C.uint32_t(entropyType), C.uint32_t(ckBits),
 		(*C.uint8_t)(unsafe.Pointer(&slab[0])), C.uint64_t(stride), (*C.uint32_t)(unsafe.Pointer(&lens[0])), C.uint32_t(n),
 		(*C.uint8_t)(unsafe.Pointer(&out[0])), C.uint64_t(outStride), &bits[0], &status[0])
@@ -94,6 +96,8 @@ func (c *Context) DecodeBlocks(transformType uint64, entropyType uint32, ckBits 
 	n := len(off)
 	outLen := make([]uint32, n)
 	status := make([]C.int32_t, n)
+	c.mu.Lock()
+	defer c.mu.Unlock()
 	rc := C.kz_decode_blocks(c.h, C.uint64_t(transformType), C.uint32_t(entropyType), C.uint32_t(ckBits), (*C.uint8_t)(unsafe.Pointer(&in[0])),
 		(*C.uint64_t)(unsafe.Pointer(&off[0])), (*C.uint64_t)(unsafe.Pointer(&bits[0])), C.uint32_t(n), C.uint32_t(blockSize),
 		(*C.uint8_t)(unsafe.Pointer(&out[0])), C.uint64_t(outStride), (*C.uint32_t)(unsafe.Pointer(&outLen[0])), &status[0])

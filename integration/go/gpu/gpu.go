@@ -11,14 +11,21 @@ import "C"
 import (
 	"errors"
 	"fmt"
+	"sync"
 	"unsafe"
 
 	kanzi "github.com/flanglet/kanzi-go/v2"
 	"github.com/flanglet/kanzi-go/v2/internal"
 )
 
-// Context wraps kz_ctx: one per GPU, shared by all codec instances of the process.
-type Context struct{ h *C.kz_ctx }
+// Context wraps kz_ctx (one CUDA stream + device scratch). The C side serves one caller at a time per context, so every call below holds mu:
+// the per-block goroutines of Writer / Reader may share one Context (their calls queue up; the batch entry points of batch.go are the
+// efficient way to give the GPU all blocks at once). Streams that are compressed or decompressed concurrently should each get their own
+// Context: different contexts run side by side on the GPU (include/kanzi_b200.h, "threads").
+type Context struct {
+	h  *C.kz_ctx
+	mu sync.Mutex
+}
 
 func NewContext(device int) (*Context, error) {
 	var h *C.kz_ctx
@@ -27,7 +34,14 @@ func NewContext(device int) (*Context, error) {
 	}
 	return &Context{h: h}, nil
 }
-func (c *Context) Close()          { C.kz_destroy(c.h) }
+func (c *Context) Close() {
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	C.kz_destroy(c.h)
+	c.h = nil
+}
+
+// err is called with mu held (kz_last_error belongs to the failed call)
 func (c *Context) err(rc C.int) error {
 	return errors.New(C.GoString(C.kz_last_error(c.h)))
 }
@@ -49,6 +63,8 @@ func (e *EntropyEncoder) Write(block []byte) (int, error) {
 		e.buf = make([]byte, need)
 	}
 	var bits C.uint64_t
+	e.ctx.mu.Lock()
+	defer e.ctx.mu.Unlock()
 	rc := C.kz_entropy_encode(e.ctx.h, C.uint32_t(e.typ), (*C.uint8_t)(unsafe.Pointer(&block[0])), C.size_t(len(block)),
 		(*C.uint8_t)(unsafe.Pointer(&e.buf[0])), C.size_t(len(e.buf)), &bits)
 	if rc != 0 {
@@ -92,6 +108,8 @@ func (d *EntropyDecoder) Read(block []byte) (int, error) {
 		return 0, nil
 	}
 	var used C.uint64_t
+	d.ctx.mu.Lock()
+	defer d.ctx.mu.Unlock()
 	rc := C.kz_entropy_decode(d.ctx.h, C.uint32_t(d.typ), (*C.uint8_t)(unsafe.Pointer(&d.data[d.off])), C.size_t(len(d.data)-d.off),
 		(*C.uint8_t)(unsafe.Pointer(&block[0])), C.size_t(len(block)), &used)
 	if rc != 0 {
@@ -121,6 +139,8 @@ type Transform struct {
 func (t *Transform) Forward(src, dst []byte) (uint, uint, error) {
 	var n C.size_t
 	dt := C.int(*t.dt)
+	t.ctx.mu.Lock()
+	defer t.ctx.mu.Unlock()
 	rc := C.kz_transform_forward(t.ctx.h, C.uint64_t(t.typ), &dt, (*C.uint8_t)(unsafe.Pointer(&src[0])), C.size_t(len(src)),
 		(*C.uint8_t)(unsafe.Pointer(&dst[0])), C.size_t(len(dst)), &n)
 	if rc == 1 {
@@ -134,6 +154,8 @@ func (t *Transform) Forward(src, dst []byte) (uint, uint, error) {
 }
 func (t *Transform) Inverse(src, dst []byte) (uint, uint, error) {
 	var n C.size_t
+	t.ctx.mu.Lock()
+	defer t.ctx.mu.Unlock()
 	rc := C.kz_transform_inverse(t.ctx.h, C.uint64_t(t.typ), (*C.uint8_t)(unsafe.Pointer(&src[0])), C.size_t(len(src)),
 		(*C.uint8_t)(unsafe.Pointer(&dst[0])), C.size_t(len(dst)), &n)
 	if rc != 0 {
